@@ -1,0 +1,141 @@
+/* lsl.h — C ABI of the B200-native LineSLAM line front end (liblsl_b200.so).
+ *
+ * Drop-in boundary for the reference's hot path. The reference has no FFI;
+ * these entry points are what a maintainer binds from the C++ symbols listed beside each
+ * function (see INTEGRATION.md for the adapter code). POD only, no exceptions, no exit():
+ * every call returns 0 or a negative lsl_status. All entry points are re-entrant per context.
+ *
+ * RNG contract: the process-global rand() of the reference becomes an explicit
+ * seed per call; the library replays glibc's TYPE_3 generator from that seed in the serial
+ * order of a single-threaded reference run.
+ */
+#ifndef LSL_H_
+#define LSL_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum lsl_status {
+  LSL_OK = 0,
+  LSL_ERR_ARG = -1,        /* NULL / out-of-range argument */
+  LSL_ERR_CUDA = -2,       /* CUDA runtime error (lsl_last_error has the text) */
+  LSL_ERR_CAPACITY = -3,   /* caller buffer or internal table too small */
+  LSL_ERR_NO_DEVICE = -4,  /* no CUDA device: there is NO CPU fallback */
+  LSL_ERR_NCCL = -5
+} lsl_status;
+
+/* Parameters: src/parameter_server.cpp:160-199 + SystemParameters::init (src/line/lineslam.cpp:577-640)
+ * + the LSD constants of lsd_scale() (external/lsd/lsd.cpp:2070-2091). Layout is shared with the
+ * test oracle; keep doubles first, then ints. */
+typedef struct lsl_params {
+  double lsd_scale, lsd_sigma_scale, lsd_quant, lsd_ang_th, lsd_eps, lsd_density_th, lsd_max_grad;
+  double line_2d_len_thres, msld_sample_interval, line_3d_len_thres_m, collin_pts_ratio, line_sample_interval;
+  double pt2line_mahdist_extractline, ratio_support_pts_on_line, stdev_sample_pt_imgline;
+  double depth_stdev_coeff_c1, depth_stdev_coeff_c2, depth_stdev_coeff_c3, depth_scaling;
+  double max_mah_dist_for_inliers, g2o_line_error_weight, g2o_BA_kernel_delta;
+  double pt2line3d_dist_relmotion, line3d_angle_relmotion;
+  int32_t lsd_n_bins, line_sample_max_num, line_sample_min_num, line3d_mle_iter_num;
+  int32_t ransac_iters_extract_line, num_cells_lineseg_range;
+  int32_t ransac_iters_line_motion, adjacent_linematch_window, line_match_number_weight;
+  int32_t min_feature_matches, min_matches_loopclose, g2o_BA_use_kernel;
+} lsl_params;
+
+/* One 3D line of a frame: FrameLine + RandomLine3d (src/line/lineslam.h:84-151). 1040 bytes. */
+typedef struct lsl_line_rec {
+  double p[2], q[2], lineEq2d[3], r[2], des[72];
+  double A[3], B[3], covA[9], covB[9], DU_A[9], DU_B[9], Wsqrt_A[3], Wsqrt_B[3];
+  int32_t lid, haveDepth;
+} lsl_line_rec;
+
+/* cv::DMatch subset used by the path */
+typedef struct lsl_match { int32_t queryIdx, trainIdx; float distance; } lsl_match;
+
+/* Result of one pair registration; fixed 128-byte record (the unit of lsl_allgather_poses).
+ * tf maps query(newer) -> train(older) coordinates, row-major Matrix4f (motion.cpp:534). */
+typedef struct lsl_pose_rec {
+  int32_t id_train, id_query, found, n_line_matches, n_ransac_inliers, n_inliers;
+  float rmse;
+  float tf[16];
+  int32_t best_iter;
+  int32_t pad[8];
+} lsl_pose_rec;
+
+typedef struct lsl_ctx lsl_ctx;     /* owns device, stream, scratch */
+typedef struct lsl_frame lsl_frame; /* library-owned: device-resident line records + host mirror */
+
+void lsl_params_default(lsl_params* p);
+const char* lsl_strerror(int status);
+const char* lsl_last_error(const lsl_ctx* ctx);
+
+/* max_batch frames / pairs can be in flight per call; scratch is sized at creation. */
+int lsl_ctx_create(lsl_ctx** out, const lsl_params* params, int cuda_device, int max_batch, int max_w, int max_h);
+void lsl_ctx_destroy(lsl_ctx* ctx);
+
+/* Node::detect3DLines (src/node.h:286-287, src/line/lineslam.cpp:200-357) for one frame.
+ * img: u8, channels = 1 (gray, as detect3DLines receives it) or 3 (interleaved, memory-order
+ * CV_RGB2GRAY like src/node.cpp:191-196). depth: f32 metres*depth_scaling, 0/NaN invalid.
+ * K: row-major 3x3 (global K of src/node.cpp:200-206). asynch_dt: Node::asynch_time_diff_sec_. */
+int lsl_extract(lsl_ctx* ctx, const uint8_t* img, int channels, const float* depth, int W, int H,
+                const double K[9], double asynch_dt_s, uint32_t rand_seed, lsl_frame** out);
+/* Same for n frames in one launch sequence (the Node constructors of a stream). Host buffers:
+ * imgs[i] / depths[i] point to frame i. */
+int lsl_extract_batch(lsl_ctx* ctx, int n, const uint8_t* const* imgs, int channels,
+                      const float* const* depths, int W, int H, const double K[9],
+                      double asynch_dt_s, const uint32_t* rand_seeds, lsl_frame** out);
+/* Inputs already resident in device memory: d_imgs = n*H*W*channels u8, d_depths = n*H*W f32. */
+int lsl_extract_batch_dev(lsl_ctx* ctx, int n, const uint8_t* d_imgs, int channels, const float* d_depths,
+                          int W, int H, const double K[9], double asynch_dt_s, const uint32_t* rand_seeds,
+                          lsl_frame** out);
+
+int lsl_frame_num_lines(const lsl_frame* f);
+int lsl_frame_lines(const lsl_frame* f, lsl_line_rec* dst, int cap, int* n);
+/* LSD output (ntuple_list of lsd(), external/lsd/lsd.h): n x 5 doubles x1,y1,x2,y2,width */
+int lsl_frame_segments(const lsl_frame* f, double* dst, int cap, int* n);
+/* Builds a frame from caller-supplied records (e.g. features cached by the host). */
+int lsl_frame_from_lines(lsl_ctx* ctx, const lsl_line_rec* recs, int n, lsl_frame** out);
+void lsl_frame_free(lsl_frame* f);
+
+/* Node::lineMatching (src/node.h:288, src/node.cpp:1619-1694): query = this, train = other. */
+int lsl_match_lines(lsl_ctx* ctx, const lsl_frame* query, const lsl_frame* train, int adjacent,
+                    lsl_match* out, int cap, int* n);
+
+/* getTransform_PtsLines_ransac (src/line/utils.h:147-153, src/line/motion.cpp:605-849), line
+ * matches only in this round (npt must be 0; point features are a "next" row).
+ * inliers_out receives output_line_inlier_matches; ransac_inliers_out (optional) the
+ * max_line_inlier_set of the best hypothesis. */
+int lsl_pose_ransac(lsl_ctx* ctx, const lsl_frame* train, const lsl_frame* query, int id_train, int id_query,
+                    const lsl_match* pt_matches, int npt, const lsl_match* ln_matches, int nln, uint32_t seed,
+                    lsl_pose_rec* rec, lsl_match* inliers_out, int cap, int* n_inl,
+                    lsl_match* ransac_inliers_out, int cap2, int* n_rinl);
+
+/* Node::matchNodePair (src/node.h:107, src/node.cpp:1494-1545) for npairs independent pairs, the
+ * unit GraphManager::nodeComparisons maps over (src/graph_manager.cpp:555): lineMatching +
+ * pose RANSAC + refinement on the device, one 128-byte record per pair back. */
+int lsl_match_pair_batch(lsl_ctx* ctx, int npairs, const lsl_frame* const* queries, const lsl_frame* const* trains,
+                         const int32_t* id_query, const int32_t* id_train, const uint32_t* seeds,
+                         lsl_pose_rec* out);
+
+/* Graph-insert-time exchange: all ranks contribute nlocal records and receive
+ * nranks*nlocal. nccl_comm is an ncclComm_t created by the host; NCCL is resolved with dlopen. */
+int lsl_allgather_poses(lsl_ctx* ctx, void* nccl_comm, int nranks, const lsl_pose_rec* local_recs, int nlocal,
+                        lsl_pose_rec* all_recs);
+
+/* Stage counters of the last call (segments, lines, matches, LM iterations, kernel launches). */
+typedef struct lsl_stats {
+  int64_t kernel_launches, frames, segments, lines3d, pairs, matches, h2d_bytes, d2h_bytes;
+} lsl_stats;
+int lsl_get_stats(const lsl_ctx* ctx, lsl_stats* out);
+/* Device-time of the region-growing kernel of the last extract call in ms (CUDA events on the
+ * context stream), and of the whole last call. */
+int lsl_last_timing(const lsl_ctx* ctx, float* ms_total, float* ms_region_grow);
+
+/* Stage-wise read-back for parity tests (frame 0 of the last extract call):
+ * what: 0 gray u8[H*W], 1 scaled f64[sh*sw], 2 angles f64, 3 modgrad f64, 4 seeds i32 (x|y<<16),
+ *       5 gx i16[H*W], 6 gy i16[H*W]. Returns the number of elements copied (or <0). */
+int64_t lsl_debug_read(lsl_ctx* ctx, int what, void* dst, int64_t cap_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSL_H_ */

@@ -1,0 +1,512 @@
+// oracle_pair.cpp — CPU restatement of the pair-registration path (TEST INFRASTRUCTURE):
+// Node::lineMatching (src/node.cpp:1619-1694), getTransform_PtsLines_ransac with line-only
+// input (src/line/motion.cpp:605-849), getTransform_Line_svd / computeRelativeMotion_svd
+// (motion.cpp:581-603, 315-365) and a native restatement of the g2o refinement
+// getTransformFromHybridMatchesG2O (src/transformation_estimation.cpp:218-461, line edges
+// src/line/edge_se3_lineendpts.cpp:146-189). g2o itself is not in the container: the LM
+// follows SURVEY.md Appendix C.3 from memory -> parity UNPINNED for that stage (Tier-T).
+#include "oracle.h"
+#include <math.h>
+#include <float.h>
+#include <string.h>
+#include <algorithm>
+#include "../lineslam_b200/csrc/shared/lsl_math.h"
+#include "../lineslam_b200/csrc/shared/lsl_linalg.h"
+
+using namespace lslm;
+
+namespace orc {
+
+static double cvnorm_diff72(const double* a, const double* b) {  // cv::norm(a - b), see oracle_extract.cpp:cvnorm
+  double result = 0;
+  for (int i = 0; i < 72; i += 4) {
+    double v0 = a[i] - b[i], v1 = a[i + 1] - b[i + 1];
+    result += v0 * v0 + v1 * v1;
+    v0 = a[i + 2] - b[i + 2]; v1 = a[i + 3] - b[i + 3];
+    result += v0 * v0 + v1 * v1;
+  }
+  return sqrt(result);
+}
+// pt_to_line_dist2d (utils.cpp:1250-1264)
+static double pt_to_line_dist2d(const double p[2], const double l[3]) {
+  double a = l[0], b = l[1], c = l[2], x = p[0], y = p[1];
+  return fabs((a * x + b * y + c)) / sqrt(a * a + b * b);
+}
+// line_to_line_dist2d (utils.cpp:1265-1273)
+static double line_to_line_dist2d(const Line& a, const Line& b) {
+  return 0.25 * pt_to_line_dist2d(a.p, b.lineEq2d) + 0.25 * pt_to_line_dist2d(a.q, b.lineEq2d) +
+         0.25 * pt_to_line_dist2d(b.p, a.lineEq2d) + 0.25 * pt_to_line_dist2d(b.q, a.lineEq2d);
+}
+static double norm2(double x, double y) { return sqrt(x * x + y * y); }
+// projectPt2d_to_line2d (utils.cpp:1612-1618)
+static double project2d(const double X[2], const double A[2], const double B[2]) {
+  double BX[2] = {X[0] - B[0], X[1] - B[1]}, BA[2] = {A[0] - B[0], A[1] - B[1]};
+  double n = norm2(BA[0], BA[1]);
+  return (BX[0] * BA[0] + BX[1] * BA[1]) / n / n;
+}
+// lineSegmentOverlap (utils.cpp:1620-1638)
+static double lineSegmentOverlap(const Line& a, const Line& b) {
+  double la = norm2(a.p[0] - a.q[0], a.p[1] - a.q[1]), lb = norm2(b.p[0] - b.q[0], b.p[1] - b.q[1]);
+  if (la < lb) {
+    double lp = project2d(a.p, b.p, b.q), lq = project2d(a.q, b.p, b.q);
+    if ((lp < 0 && lq < 0) || (lp > 1 && lq > 1)) return -1;
+    return fabs(lp - lq) * lb;
+  } else {
+    double lp = project2d(b.p, a.p, a.q), lq = project2d(b.q, a.p, a.q);
+    if ((lp < 0 && lq < 0) || (lp > 1 && lq > 1)) return -1;
+    return fabs(lp - lq) * la;
+  }
+}
+
+void lineMatching(const std::vector<Line>& f1, const std::vector<Line>& f2, bool adjacent,
+                  std::vector<Match>& matches, int omp_threads) {
+  const double PI_T = 3.14159265;  // lineslam.h:38
+  double lineDistThresh, lineAngleThresh, descDiffThresh, lineOverlapThresh, ratio;
+  if (adjacent) { lineDistThresh = 45; lineAngleThresh = 30 * PI_T / 180; descDiffThresh = 0.85; lineOverlapThresh = 0; ratio = 0.7; }
+  else { lineDistThresh = 80; lineAngleThresh = 30 * PI_T / 180; descDiffThresh = 0.7; lineOverlapThresh = -1; ratio = 0.7; }
+  int n1 = (int)f1.size(), n2 = (int)f2.size();
+  if (n1 == 0 || n2 == 0) return;
+  double cosT = lsl_cos(lineAngleThresh);
+  std::vector<double> D((size_t)n1 * n2, 100.0);
+#pragma omp parallel for num_threads(omp_threads) if (omp_threads > 1)
+  for (int i = 0; i < n1; ++i)
+    for (int j = 0; j < n2; ++j)
+      if ((f1[i].r[0] * f2[j].r[0] + f1[i].r[1] * f2[j].r[1] > cosT) &&
+          (line_to_line_dist2d(f1[i], f2[j]) < lineDistThresh) &&
+          (lineSegmentOverlap(f1[i], f2[j]) > lineOverlapThresh))
+        D[(size_t)i * n2 + j] = cvnorm_diff72(f1[i].des, f2[j].des);
+  for (int i = 0; i < n1; ++i) {
+    double minVal = D[(size_t)i * n2]; int minX = 0;       // cv::minMaxLoc: first minimum
+    for (int j = 1; j < n2; ++j) if (D[(size_t)i * n2 + j] < minVal) { minVal = D[(size_t)i * n2 + j]; minX = j; }
+    if (minVal < descDiffThresh) {
+      double minV = D[minX]; int minY = 0;
+      for (int j = 1; j < n1; ++j) if (D[(size_t)j * n2 + minX] < minV) { minV = D[(size_t)j * n2 + minX]; minY = j; }
+      if (i == minY) {
+        double rowmin2 = 100, colmin2 = 100;
+        for (int j = 0; j < n2; ++j) { if (j == minX) continue; if (rowmin2 > D[(size_t)i * n2 + j]) rowmin2 = D[(size_t)i * n2 + j]; }
+        for (int j = 0; j < n1; ++j) { if (j == minY) continue; if (colmin2 > D[(size_t)j * n2 + minX]) colmin2 = D[(size_t)j * n2 + minX]; }
+        if (rowmin2 * ratio > minVal && colmin2 * ratio > minVal) {
+          Match m; m.queryIdx = i; m.trainIdx = minX; m.distance = (float)minVal;
+          if (f1[i].haveDepth && f2[minX].haveDepth) matches.push_back(m);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------- minimal solver ----
+static void cross3(const double a[3], const double b[3], double c[3]) {
+  c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
+}
+static void q2r(const double q[4], double R[9]) {  // utils.cpp:1659-1694
+  double a = q[0], b = q[1], c = q[2], d = q[3];
+  double nm = sqrt(a * a + b * b + c * c + d * d);
+  a = a / nm; b = b / nm; c = c / nm; d = d / nm;
+  R[0] = a * a + b * b - c * c - d * d; R[1] = 2 * b * c - 2 * a * d; R[2] = 2 * b * d + 2 * a * c;
+  R[3] = 2 * b * c + 2 * a * d; R[4] = a * a - b * b + c * c - d * d; R[5] = 2 * c * d - 2 * a * b;
+  R[6] = 2 * b * d - 2 * a * c; R[7] = 2 * c * d + 2 * a * b; R[8] = a * a - b * b - c * c + d * d;
+}
+static void skew(const double v[3], double m[9]) {  // vec2SkewMat utils.cpp:1649
+  m[0] = 0; m[1] = -v[2]; m[2] = v[1]; m[3] = v[2]; m[4] = 0; m[5] = -v[0]; m[6] = -v[1]; m[7] = v[0]; m[8] = 0;
+}
+// computeRelativeMotion_svd (motion.cpp:315-365). a = query lines, b = train lines; x_b = R x_a + t.
+bool relmotion_svd(const double* aA, const double* aB, const double* bA, const double* bB, int n, double R[9], double t[3]) {
+  if (n < 2) return false;
+  std::vector<double> au(3 * n), ad(3 * n), bu(3 * n), bd(3 * n);
+  for (int i = 0; i < n; ++i) {
+    for (int s = 0; s < 2; ++s) {
+      const double* A = s ? bA + 3 * i : aA + 3 * i;
+      const double* B = s ? bB + 3 * i : aB + 3 * i;
+      double* u = s ? &bu[3 * i] : &au[3 * i];
+      double* d = s ? &bd[3 * i] : &ad[3 * i];
+      double l[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]};
+      double m[3] = {(A[0] + B[0]) * 0.5, (A[1] + B[1]) * 0.5, (A[2] + B[2]) * 0.5};
+      double inv = 1 / sqrt(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]);
+      u[0] = l[0] * inv; u[1] = l[1] * inv; u[2] = l[2] * inv;
+      cross3(u, m, d);
+    }
+  }
+  double A[16];
+  for (int i = 0; i < 16; ++i) A[i] = 0;
+  for (int i = 0; i < n; ++i) {
+    double Ai[16];
+    for (int k = 0; k < 16; ++k) Ai[k] = 0;
+    double dm[3] = {au[3 * i] - bu[3 * i], au[3 * i + 1] - bu[3 * i + 1], au[3 * i + 2] - bu[3 * i + 2]};
+    double dp[3] = {au[3 * i] + bu[3 * i], au[3 * i + 1] + bu[3 * i + 1], au[3 * i + 2] + bu[3 * i + 2]};
+    double dn[3] = {bu[3 * i] - au[3 * i], bu[3 * i + 1] - au[3 * i + 1], bu[3 * i + 2] - au[3 * i + 2]};
+    Ai[1] = dm[0]; Ai[2] = dm[1]; Ai[3] = dm[2];
+    Ai[4] = dn[0]; Ai[8] = dn[1]; Ai[12] = dn[2];
+    double S[9]; skew(dp, S);
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Ai[(r + 1) * 4 + c + 1] = S[r * 3 + c];
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) {
+        double s = 0;
+        for (int k = 0; k < 4; ++k) s += Ai[k * 4 + r] * Ai[k * 4 + c];
+        A[r * 4 + c] = A[r * 4 + c] + s;
+      }
+  }
+  double w[4], V[16];
+  jacobi_sym<4>(A, w, V);
+  double q[4] = {V[3], V[7], V[11], V[15]};  // svd.u.col(3): smallest singular value
+  q2r(q, R);
+  double uu[9], udr[3] = {0, 0, 0};
+  for (int i = 0; i < 9; ++i) uu[i] = 0;
+  for (int i = 0; i < n; ++i) {
+    double S[9]; skew(&bu[3 * i], S);
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        double s = 0;
+        for (int k = 0; k < 3; ++k) s += S[r * 3 + k] * S[c * 3 + k];  // S * S^T
+        uu[r * 3 + c] = uu[r * 3 + c] + s;
+      }
+    double Rad[3], v[3];
+    for (int r = 0; r < 3; ++r) Rad[r] = R[r * 3] * ad[3 * i] + R[r * 3 + 1] * ad[3 * i + 1] + R[r * 3 + 2] * ad[3 * i + 2];
+    for (int r = 0; r < 3; ++r) v[r] = bd[3 * i + r] - Rad[r];
+    for (int r = 0; r < 3; ++r) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += S[k * 3 + r] * v[k];  // S^T * v
+      udr[r] = udr[r] + s;
+    }
+  }
+  double ui[9];
+  inv3(uu, ui);
+  for (int r = 0; r < 3; ++r) t[r] = ui[r * 3] * udr[0] + ui[r * 3 + 1] * udr[1] + ui[r * 3 + 2] * udr[2];
+  return true;
+}
+
+// Eigen Matrix4f * Vector4f, column-wise accumulation in float, rows 0..2
+static void tf_apply_f(const float tf[16], const float v[4], double out[3]) {
+  for (int r = 0; r < 3; ++r) {
+    float acc = tf[r * 4 + 0] * v[0];
+    acc = tf[r * 4 + 1] * v[1] + acc;
+    acc = tf[r * 4 + 2] * v[2] + acc;
+    acc = tf[r * 4 + 3] * v[3] + acc;
+    out[r] = (double)acc;
+  }
+}
+
+struct Score { std::vector<int> inl; double sse; };
+// the line half of the scoring loops at motion.cpp:688-699 / :800-813
+static void score_lines(const std::vector<Line>& train, const std::vector<Line>& query, const std::vector<Match>& ms,
+                        const float tf[16], double thr, Score& sc, bool float_sse) {
+  sc.inl.clear();
+  float sse_f = 0; double sse_d = 0;
+  for (size_t i = 0; i < ms.size(); ++i) {
+    const Line& q = query[ms[i].queryIdx];
+    const Line& t = train[ms[i].trainIdx];
+    float qa[4] = {(float)q.A[0], (float)q.A[1], (float)q.A[2], 1.f}, qb[4] = {(float)q.B[0], (float)q.B[1], (float)q.B[2], 1.f};
+    double qA[3], qB[3];
+    tf_apply_f(tf, qa, qA);
+    tf_apply_f(tf, qb, qB);
+    double da = mah_dist3d_pt_line(t.A, t.DU_A, qA, qB);
+    double db = mah_dist3d_pt_line(t.B, t.DU_B, qA, qB);
+    if (da < thr && db < thr) {
+      sc.inl.push_back((int)i);
+      if (float_sse) sse_f += da * da + db * db; else sse_d += da * da + db * db;
+    }
+  }
+  sc.sse = float_sse ? (double)sse_f : sse_d;
+}
+
+// ------------------------------------------------- g2o-style refinement ----
+// Unknowns: cam1 pose (VertexSE3, right-multiplied increment [t, qxyz]) and one free
+// 6-vector of endpoints per line match (VertexLineEndpts, additive), initialised with the
+// newer frame's endpoints. Each match carries two EdgeSE3LineEndpts (newer: identity pose,
+// fixed; older: cam1). Numeric central-difference Jacobians (delta 1e-9), Huber(delta),
+// Levenberg-Marquardt with g2o's lambda policy; the arrow-shaped normal equations are
+// solved exactly by eliminating the per-line 6x6 blocks (same solution as the full
+// Cholesky up to rounding).
+struct Iso { double R[9], t[3]; };
+static void iso_mul(const Iso& a, const Iso& b, Iso& c) {
+  for (int r = 0; r < 3; ++r) {
+    for (int k = 0; k < 3; ++k) c.R[r * 3 + k] = a.R[r * 3] * b.R[k] + a.R[r * 3 + 1] * b.R[3 + k] + a.R[r * 3 + 2] * b.R[6 + k];
+    c.t[r] = a.R[r * 3] * b.t[0] + a.R[r * 3 + 1] * b.t[1] + a.R[r * 3 + 2] * b.t[2] + a.t[r];
+  }
+}
+static void iso_inv(const Iso& a, Iso& c) {
+  for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) c.R[r * 3 + k] = a.R[k * 3 + r];
+  for (int r = 0; r < 3; ++r) c.t[r] = -(c.R[r * 3] * a.t[0] + c.R[r * 3 + 1] * a.t[1] + c.R[r * 3 + 2] * a.t[2]);
+}
+static void iso_oplus(const Iso& est, const double u[6], Iso& out) {  // VertexSE3::oplusImpl, fromVectorMQT
+  double w2 = 1. - (u[3] * u[3] + u[4] * u[4] + u[5] * u[5]);
+  double q[4] = {w2 > 0 ? sqrt(w2) : 0.0, u[3], u[4], u[5]};
+  Iso inc;
+  q2r(q, inc.R);
+  inc.t[0] = u[0]; inc.t[1] = u[1]; inc.t[2] = u[2];
+  iso_mul(est, inc, out);
+}
+// EdgeSE3LineEndpts::computeError (edge_se3_lineendpts.cpp:146-189); w2n = pose^-1
+static void edge_error(const Iso& w2n, const double L[6], const double meas[6], const double AffA[9], const double AffB[9], double e[6]) {
+  double ptA[3], ptB[3];
+  for (int r = 0; r < 3; ++r) {
+    ptA[r] = w2n.R[r * 3] * L[0] + w2n.R[r * 3 + 1] * L[1] + w2n.R[r * 3 + 2] * L[2] + w2n.t[r];
+    ptB[r] = w2n.R[r * 3] * L[3] + w2n.R[r * 3 + 1] * L[4] + w2n.R[r * 3 + 2] * L[5] + w2n.t[r];
+  }
+  for (int h = 0; h < 2; ++h) {
+    const double* Af = h ? AffB : AffA;
+    const double* mp = meas + 3 * h;
+    double dA[3] = {ptA[0] - mp[0], ptA[1] - mp[1], ptA[2] - mp[2]}, dB[3] = {ptB[0] - mp[0], ptB[1] - mp[1], ptB[2] - mp[2]};
+    double Ap[3], Bp[3], BA[3];
+    for (int r = 0; r < 3; ++r) {
+      Ap[r] = Af[r * 3] * dA[0] + Af[r * 3 + 1] * dA[1] + Af[r * 3 + 2] * dA[2];
+      Bp[r] = Af[r * 3] * dB[0] + Af[r * 3 + 1] * dB[1] + Af[r * 3 + 2] * dB[2];
+    }
+    for (int r = 0; r < 3; ++r) BA[r] = Bp[r] - Ap[r];
+    double tt = -(Ap[0] * BA[0] + Ap[1] * BA[1] + Ap[2] * BA[2]) / (BA[0] * BA[0] + BA[1] * BA[1] + BA[2] * BA[2]);
+    for (int r = 0; r < 3; ++r) e[3 * h + r] = Ap[r] + tt * BA[r];
+  }
+}
+// endpt_AffnMat = D^-1/2 U^T (transformation_estimation.cpp:349-372)
+static void affn(const double cov[9], double Af[9]) {
+  double A[9], w[3], V[9];
+  for (int i = 0; i < 9; ++i) A[i] = cov[i];
+  jacobi_sym<3>(A, w, V);
+  for (int i = 0; i < 3; ++i) {
+    double d = sqrt(1 / w[i]);
+    for (int j = 0; j < 3; ++j) Af[i * 3 + j] = d * V[j * 3 + i];
+  }
+}
+static void huber(double e2, double delta, double rho[3]) {  // g2o RobustKernelHuber::robustify
+  double dsqr = delta * delta;
+  if (e2 <= dsqr) { rho[0] = e2; rho[1] = 1.; rho[2] = 0.; }
+  else { double sqrte = sqrt(e2); rho[0] = 2 * sqrte * delta - dsqr; rho[1] = delta / sqrte; rho[2] = -0.5 * rho[1] / e2; }
+}
+
+void refine_pose_lines(const std::vector<Line>& train, const std::vector<Line>& query, const std::vector<Match>& ms,
+                       float tf[16], int iterations, const Params& P) {
+  int n = (int)ms.size();
+  if (n == 0) return;
+  // tfinv = tf.inverse() (Matrix4f general inverse) -> cam1 = SE3Quat(Quaterniond(R), t). The rigid
+  // inverse in double and a quaternion round trip are restated as: cam1 = [R^T, -R^T t] in double.
+  Iso tfd, cam1;
+  for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) tfd.R[r * 3 + c] = (double)tf[r * 4 + c]; tfd.t[r] = (double)tf[r * 4 + 3]; }
+  iso_inv(tfd, cam1);
+  Iso ident; for (int i = 0; i < 9; ++i) ident.R[i] = (i % 4 == 0) ? 1 : 0; ident.t[0] = ident.t[1] = ident.t[2] = 0;
+  std::vector<double> L(6 * n), measN(6 * n), measO(6 * n), AfN(18 * n), AfO(18 * n);
+  for (int i = 0; i < n; ++i) {
+    const Line& q = query[ms[i].queryIdx];
+    const Line& t = train[ms[i].trainIdx];
+    for (int k = 0; k < 3; ++k) { measN[6 * i + k] = q.A[k]; measN[6 * i + 3 + k] = q.B[k]; measO[6 * i + k] = t.A[k]; measO[6 * i + 3 + k] = t.B[k]; }
+    for (int k = 0; k < 6; ++k) L[6 * i + k] = measN[6 * i + k];
+    affn(q.covA, &AfN[18 * i]); affn(q.covB, &AfN[18 * i + 9]);
+    affn(t.covA, &AfO[18 * i]); affn(t.covB, &AfO[18 * i + 9]);
+  }
+  const double w = P.g2o_line_error_weight, hdelta = P.g2o_BA_kernel_delta;
+  const bool robust = P.g2o_BA_use_kernel != 0;
+  auto chi2_all = [&](const Iso& c1, const std::vector<double>& Lv) {
+    Iso w2n; iso_inv(c1, w2n);
+    double chi = 0;
+    for (int i = 0; i < n; ++i) {
+      double e[6];
+      for (int side = 0; side < 2; ++side) {
+        edge_error(side ? w2n : ident, &Lv[6 * i], side ? &measO[6 * i] : &measN[6 * i], side ? &AfO[18 * i] : &AfN[18 * i],
+                   side ? &AfO[18 * i + 9] : &AfN[18 * i + 9], e);
+        double c2 = 0; for (int k = 0; k < 6; ++k) c2 += e[k] * w * e[k];
+        if (robust) { double rho[3]; huber(c2, hdelta, rho); chi += rho[0]; } else chi += c2;
+      }
+    }
+    return chi;
+  };
+  double lambda = 0, ni = 2;
+  const double tau = 1e-5, lowS = 1. / 3., upS = 2. / 3.;
+  const double del = 1e-9, scalar = 1 / (2 * del);
+  std::vector<double> Hll(36 * n), Hpl(36 * n), bl(6 * n), dl(6 * n), HllInv(36 * n);
+  for (int it = 0; it < iterations; ++it) {
+    double currentChi = chi2_all(cam1, L);
+    // ---- build system
+    double Hpp[36], bp[6];
+    for (int i = 0; i < 36; ++i) Hpp[i] = 0;
+    for (int i = 0; i < 6; ++i) bp[i] = 0;
+    Iso w2n; iso_inv(cam1, w2n);
+    for (int i = 0; i < n; ++i) {
+      double* hll = &Hll[36 * i]; double* hpl = &Hpl[36 * i]; double* b = &bl[6 * i];
+      for (int k = 0; k < 36; ++k) { hll[k] = 0; hpl[k] = 0; }
+      for (int k = 0; k < 6; ++k) b[k] = 0;
+      for (int side = 0; side < 2; ++side) {
+        const double* meas = side ? &measO[6 * i] : &measN[6 * i];
+        const double* A1 = side ? &AfO[18 * i] : &AfN[18 * i];
+        const double* A2 = A1 + 9;
+        double e[6], Jl[36], Jp[36];
+        // numeric Jacobian wrt the line vertex (additive)
+        for (int d = 0; d < 6; ++d) {
+          double Lp[6], e1[6], e2[6];
+          for (int k = 0; k < 6; ++k) Lp[k] = L[6 * i + k];
+          Lp[d] = L[6 * i + d] + del;
+          edge_error(side ? w2n : ident, Lp, meas, A1, A2, e1);
+          Lp[d] = L[6 * i + d] + (-del);
+          edge_error(side ? w2n : ident, Lp, meas, A1, A2, e2);
+          for (int k = 0; k < 6; ++k) Jl[k * 6 + d] = scalar * (e1[k] - e2[k]);
+        }
+        if (side) {  // numeric Jacobian wrt cam1
+          for (int d = 0; d < 6; ++d) {
+            double u[6] = {0, 0, 0, 0, 0, 0}, e1[6], e2[6];
+            Iso c, ci;
+            u[d] = del; iso_oplus(cam1, u, c); iso_inv(c, ci); edge_error(ci, &L[6 * i], meas, A1, A2, e1);
+            u[d] = -del; iso_oplus(cam1, u, c); iso_inv(c, ci); edge_error(ci, &L[6 * i], meas, A1, A2, e2);
+            for (int k = 0; k < 6; ++k) Jp[k * 6 + d] = scalar * (e1[k] - e2[k]);
+          }
+        }
+        edge_error(side ? w2n : ident, &L[6 * i], meas, A1, A2, e);
+        double c2 = 0; for (int k = 0; k < 6; ++k) c2 += e[k] * w * e[k];
+        double wgt = w;
+        if (robust) { double rho[3]; huber(c2, hdelta, rho); wgt = rho[1] * w; }
+        for (int a = 0; a < 6; ++a) {
+          double s = 0; for (int k = 0; k < 6; ++k) s += Jl[k * 6 + a] * (wgt * e[k]);
+          b[a] -= s;
+          for (int c = 0; c < 6; ++c) { double h = 0; for (int k = 0; k < 6; ++k) h += Jl[k * 6 + a] * wgt * Jl[k * 6 + c]; hll[a * 6 + c] += h; }
+        }
+        if (side) {
+          for (int a = 0; a < 6; ++a) {
+            double s = 0; for (int k = 0; k < 6; ++k) s += Jp[k * 6 + a] * (wgt * e[k]);
+            bp[a] -= s;
+            for (int c = 0; c < 6; ++c) {
+              double h = 0, g = 0;
+              for (int k = 0; k < 6; ++k) { h += Jp[k * 6 + a] * wgt * Jp[k * 6 + c]; g += Jp[k * 6 + a] * wgt * Jl[k * 6 + c]; }
+              Hpp[a * 6 + c] += h;
+              hpl[a * 6 + c] += g;
+            }
+          }
+        }
+      }
+    }
+    if (it == 0) {  // computeLambdaInit: tau * max diagonal entry
+      double maxDiag = 0;
+      for (int a = 0; a < 6; ++a) maxDiag = std::max(fabs(Hpp[a * 6 + a]), maxDiag);
+      for (int i = 0; i < n; ++i) for (int a = 0; a < 6; ++a) maxDiag = std::max(fabs(Hll[36 * i + a * 6 + a]), maxDiag);
+      lambda = tau * maxDiag;
+      ni = 2;
+    }
+    double rho = 0;
+    int qmax = 0;
+    do {
+      // solve (H + lambda I) x = b by eliminating the line blocks
+      double S[36], rhs[6], dp[6];
+      for (int k = 0; k < 36; ++k) S[k] = Hpp[k];
+      for (int a = 0; a < 6; ++a) { S[a * 6 + a] += lambda; rhs[a] = bp[a]; }
+      bool ok = true;
+      for (int i = 0; i < n; ++i) {
+        double M[36];
+        for (int k = 0; k < 36; ++k) M[k] = Hll[36 * i + k];
+        for (int a = 0; a < 6; ++a) M[a * 6 + a] += lambda;
+        if (!inv_lu<6>(M, &HllInv[36 * i])) ok = false;
+        const double* hi = &HllInv[36 * i]; const double* hpl = &Hpl[36 * i];
+        double T[36];  // Hpl * Hll^-1
+        for (int a = 0; a < 6; ++a) for (int c = 0; c < 6; ++c) { double s = 0; for (int k = 0; k < 6; ++k) s += hpl[a * 6 + k] * hi[k * 6 + c]; T[a * 6 + c] = s; }
+        for (int a = 0; a < 6; ++a) {
+          double s = 0; for (int k = 0; k < 6; ++k) s += T[a * 6 + k] * bl[6 * i + k];
+          rhs[a] -= s;
+          for (int c = 0; c < 6; ++c) { double h = 0; for (int k = 0; k < 6; ++k) h += T[a * 6 + k] * hpl[c * 6 + k]; S[a * 6 + c] -= h; }
+        }
+      }
+      double Si[36];
+      if (!inv_lu<6>(S, Si)) ok = false;
+      for (int a = 0; a < 6; ++a) { double s = 0; for (int k = 0; k < 6; ++k) s += Si[a * 6 + k] * rhs[k]; dp[a] = s; }
+      double scale = 0;
+      for (int a = 0; a < 6; ++a) scale += dp[a] * (lambda * dp[a] + bp[a]);
+      for (int i = 0; i < n; ++i) {
+        const double* hi = &HllInv[36 * i]; const double* hpl = &Hpl[36 * i];
+        double r[6];
+        for (int a = 0; a < 6; ++a) { double s = 0; for (int k = 0; k < 6; ++k) s += hpl[k * 6 + a] * dp[k]; r[a] = bl[6 * i + a] - s; }
+        for (int a = 0; a < 6; ++a) { double s = 0; for (int k = 0; k < 6; ++k) s += hi[a * 6 + k] * r[k]; dl[6 * i + a] = s; }
+        for (int a = 0; a < 6; ++a) scale += dl[6 * i + a] * (lambda * dl[6 * i + a] + bl[6 * i + a]);
+      }
+      Iso camNew; iso_oplus(cam1, dp, camNew);
+      std::vector<double> Lnew(L);
+      for (int k = 0; k < 6 * n; ++k) Lnew[k] += dl[k];
+      double tempChi = chi2_all(camNew, Lnew);
+      if (!ok) tempChi = DBL_MAX;
+      rho = (currentChi - tempChi);
+      scale += 1e-3;
+      rho /= scale;
+      if (rho > 0 && std::isfinite(tempChi)) {
+        double alpha = 1. - (2 * rho - 1) * (2 * rho - 1) * (2 * rho - 1);
+        alpha = std::min(alpha, upS);
+        double scaleFactor = std::max(lowS, alpha);
+        lambda *= scaleFactor;
+        ni = 2;
+        currentChi = tempChi;
+        cam1 = camNew; L.swap(Lnew);
+      } else {
+        lambda *= ni;
+        ni *= 2;
+      }
+      qmax++;
+    } while (rho < 0 && qmax < 10);
+    if (qmax == 10 || rho == 0) break;
+  }
+  Iso out; iso_inv(cam1, out);  // estimate().inverse(), cast to float
+  for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) tf[r * 4 + c] = (float)out.R[r * 3 + c]; tf[r * 4 + 3] = (float)out.t[r]; }
+  tf[12] = 0; tf[13] = 0; tf[14] = 0; tf[15] = 1;
+}
+
+// ---------------------------------------------------- pose RANSAC (lines) ----
+void getTransform_Lines_ransac(const std::vector<Line>& train, const std::vector<Line>& query, int id_train, int id_query,
+                               const std::vector<Match>& all_ln, uint32_t seed, const Params& P, PoseResult& out) {
+  out = PoseResult();
+  for (int i = 0; i < 16; ++i) out.tf[i] = out.tf_ransac[i] = (i % 5 == 0) ? 1.f : 0.f;
+  int nPt = 0, nLn = (int)all_ln.size();
+  int min_inlier_nmb = P.min_feature_matches, line_weight = P.line_match_number_weight;
+  if (nPt + nLn * line_weight < min_inlier_nmb) { out.rmse = 1e9f; return; }
+  if (min_inlier_nmb > 0.7 * (nPt + nLn * line_weight)) min_inlier_nmb = 0.7 * (nPt + nLn * line_weight);
+  if (abs(id_train - id_query) > 50) min_inlier_nmb = P.min_matches_loopclose;
+  std::vector<int> indexes(nPt + nLn);
+  for (size_t i = 0; i < indexes.size(); ++i) indexes[i] = (int)i;
+  int maxIter = P.ransac_iters_line_motion;
+  double thr = P.max_mah_dist_for_inliers;
+  GlibcRand rng; rng.seed(seed);
+  float sum_squared_error = 1e9f;
+  std::vector<int> best_inl;
+  float tf_best[16];
+  for (int i = 0; i < 16; ++i) tf_best[i] = 0;
+  int iter = 0;
+  while (iter < maxIter) {
+    ++iter;
+    int left = (int)indexes.size();
+    for (int k = 0; k < 3; ++k) { int r = rng.next() % left; std::swap(indexes[k], indexes[k + r]); --left; }
+    double qA[9], qB[9], tA[9], tB[9];
+    for (int k = 0; k < 3; ++k) {
+      const Match& m = all_ln[indexes[k] - nPt];
+      for (int c = 0; c < 3; ++c) {
+        qA[3 * k + c] = query[m.queryIdx].A[c]; qB[3 * k + c] = query[m.queryIdx].B[c];
+        tA[3 * k + c] = train[m.trainIdx].A[c]; tB[3 * k + c] = train[m.trainIdx].B[c];
+      }
+    }
+    double R[9], t[3];
+    if (!relmotion_svd(qA, qB, tA, tB, 3, R, t)) continue;
+    float tf[16];
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) tf[r * 4 + c] = (float)R[r * 3 + c]; tf[r * 4 + 3] = (float)t[r]; }
+    tf[12] = tf[13] = tf[14] = 0; tf[15] = 1;
+    Score sc;
+    score_lines(train, query, all_ln, tf, thr, sc, true);
+    if ((int)(line_weight * sc.inl.size()) > (int)(line_weight * best_inl.size())) {
+      best_inl = sc.inl;
+      memcpy(tf_best, tf, sizeof(tf));
+      sum_squared_error = (float)sc.sse;
+      out.best_iter = iter - 1;
+    }
+  }
+  if (best_inl.size() < 3) return;
+  for (int i : best_inl) out.ransac_inliers.push_back(all_ln[i]);
+  memcpy(out.tf_ransac, tf_best, sizeof(tf_best));
+  float refined_tf[16];
+  memcpy(refined_tf, tf_best, sizeof(tf_best));
+  refine_pose_lines(train, query, out.ransac_inliers, refined_tf, 25, P);
+  double refined_rmse = sqrt(sum_squared_error / (double)(best_inl.size()));
+  std::vector<Match> refined;
+  for (int it = 0; it < 20; ++it) {
+    Score sc;
+    score_lines(train, query, all_ln, refined_tf, thr, sc, false);
+    if (sc.inl.size() * P.line_match_number_weight > refined.size() * P.line_match_number_weight) {
+      refined.clear();
+      for (int i : sc.inl) refined.push_back(all_ln[i]);
+      refined_rmse = sqrt(sc.sse / (double)(sc.inl.size()));
+      refine_pose_lines(train, query, refined, refined_tf, 20, P);
+    } else break;
+  }
+  out.inliers = refined;
+  out.rmse = (float)refined_rmse;
+  memcpy(out.tf, refined_tf, sizeof(refined_tf));
+  out.found = (int)(line_weight * refined.size()) >= min_inlier_nmb;
+}
+
+}  // namespace orc

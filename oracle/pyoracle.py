@@ -1,0 +1,139 @@
+"""ctypes binding of the CPU oracle (TEST INFRASTRUCTURE).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; the product package lineslam_b200 never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+from lineslam_b200.records import Params, LINE_DTYPE, MATCH_DTYPE, POSE_DTYPE, ptr
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    if force or not os.path.exists(so):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    if os.path.isdir("/root/reference/external/lsd/lsd-1.5"):
+        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        L = _LIB
+        for n in "exp log log10 sin cos sinh".split():
+            f = getattr(L, "orc_m_" + n); f.restype = C.c_double; f.argtypes = [C.c_double]
+        for n in "atan2 pow".split():
+            f = getattr(L, "orc_m_" + n); f.restype = C.c_double; f.argtypes = [C.c_double, C.c_double]
+        L.orc_stream_step.restype = C.c_double
+    return _LIB
+
+
+def default_params():
+    p = Params()
+    lib().orc_params_default(C.byref(p))
+    return p
+
+
+def rand(seed, n):
+    out = np.zeros(n, np.int32)
+    lib().orc_rand(C.c_uint32(seed), n, ptr(out))
+    return out
+
+
+def gray(img):
+    H, W, _ = img.shape
+    g = np.zeros((H, W), np.uint8)
+    lib().orc_gray(ptr(np.ascontiguousarray(img)), W, H, ptr(g))
+    return g
+
+
+def lsd(gray_img, params=None, debug=False):
+    p = params or default_params()
+    g = np.ascontiguousarray(gray_img, np.uint8)
+    H, W = g.shape
+    cap = 8192
+    segs = np.zeros((cap, 5))
+    if not debug:
+        n = lib().orc_lsd(ptr(g), W, H, C.byref(p), ptr(segs), cap, None, None, None, None, None, None, None)
+        return segs[:n].copy()
+    sw, sh = int(np.floor(W * p.lsd_scale)), int(np.floor(H * p.lsd_scale))
+    scaled = np.zeros((sh, sw)); ang = np.zeros((sh, sw)); mod = np.zeros((sh, sw))
+    seeds = np.zeros(sh * sw, np.int32); ns = C.c_int(0); a = C.c_int(0); b = C.c_int(0)
+    n = lib().orc_lsd(ptr(g), W, H, C.byref(p), ptr(segs), cap, ptr(scaled), ptr(ang), ptr(mod), ptr(seeds),
+                      C.byref(ns), C.byref(a), C.byref(b))
+    return segs[:n].copy(), dict(scaled=scaled, angles=ang, modgrad=mod, seeds=seeds[:ns.value].copy())
+
+
+def sobel5(gray_img):
+    g = np.ascontiguousarray(gray_img, np.uint8)
+    H, W = g.shape
+    gx = np.zeros((H, W)); gy = np.zeros((H, W))
+    lib().orc_sobel5(ptr(g), W, H, ptr(gx), ptr(gy))
+    return gx, gy
+
+
+def detect3DLines(img, depth, K, seed=1, params=None, dt=0.0, omp_threads=1, debug=False):
+    p = params or default_params()
+    img = np.ascontiguousarray(img, np.uint8)
+    depth = np.ascontiguousarray(depth, np.float32)
+    H, W = depth.shape
+    ch = 3 if img.ndim == 3 else 1
+    cap = 4096
+    out = np.zeros(cap, LINE_DTYPE)
+    Kc = np.ascontiguousarray(K, np.float64)
+    if not debug:
+        n = lib().orc_detect3DLines(ptr(img), ch, ptr(depth), W, H, ptr(Kc), C.c_double(dt), C.c_uint32(seed),
+                                    C.byref(p), ptr(out), cap, omp_threads, None, None, None, None, None, None, None, 0)
+        return out[:n].copy()
+    sol = np.zeros(cap, np.int32); ninl = np.zeros(cap, np.int32); idx = np.full((cap, 101), -1, np.int32)
+    a0b0 = np.zeros((cap, 6)); its = np.zeros(cap, np.int32); nsegs = C.c_int(0); segs = np.zeros((8192, 5))
+    n = lib().orc_detect3DLines(ptr(img), ch, ptr(depth), W, H, ptr(Kc), C.c_double(dt), C.c_uint32(seed), C.byref(p),
+                                ptr(out), cap, omp_threads, ptr(sol), ptr(ninl), ptr(idx), ptr(a0b0), ptr(its),
+                                C.byref(nsegs), ptr(segs), 8192)
+    return out[:n].copy(), dict(seg_of_line=sol[:n].copy(), n_inl=ninl[:n].copy(), inl_idx=idx[:n].copy(),
+                                a0b0=a0b0[:n].copy(), lm_iters=its[:n].copy(), segs=segs[:nsegs.value].copy())
+
+
+def lineMatching(f1, f2, adjacent=True, omp_threads=1):
+    f1 = np.ascontiguousarray(f1, LINE_DTYPE); f2 = np.ascontiguousarray(f2, LINE_DTYPE)
+    cap = max(len(f1), 1)
+    out = np.zeros(cap, MATCH_DTYPE)
+    n = lib().orc_lineMatching(ptr(f1), len(f1), ptr(f2), len(f2), int(adjacent), ptr(out), cap, omp_threads)
+    return out[:n].copy()
+
+
+def pose_ransac(train, query, matches, id_train=0, id_query=1, seed=1, params=None):
+    p = params or default_params()
+    train = np.ascontiguousarray(train, LINE_DTYPE); query = np.ascontiguousarray(query, LINE_DTYPE)
+    m = np.ascontiguousarray(matches, MATCH_DTYPE)
+    rec = np.zeros(1, POSE_DTYPE)
+    cap = max(len(m), 1)
+    inl = np.zeros(cap, MATCH_DTYPE); rinl = np.zeros(cap, MATCH_DTYPE)
+    n1 = C.c_int(0); n2 = C.c_int(0); tfr = np.zeros(16, np.float32)
+    lib().orc_pose_ransac(ptr(train), len(train), ptr(query), len(query), id_train, id_query, ptr(m), len(m),
+                          C.c_uint32(seed), C.byref(p), ptr(rec), ptr(inl), cap, C.byref(n1), ptr(rinl), cap,
+                          C.byref(n2), ptr(tfr))
+    return rec[0].copy(), inl[:n1.value].copy(), rinl[:n2.value].copy(), tfr.reshape(4, 4)
+
+
+def stream_step(img, depth, K, seed, prev_lines, params=None, omp_threads=1):
+    """One reference CPU step (extract + match against prev + RANSAC pose); returns (seconds, lines, pose)."""
+    p = params or default_params()
+    img = np.ascontiguousarray(img, np.uint8); depth = np.ascontiguousarray(depth, np.float32)
+    H, W = depth.shape
+    ch = 3 if img.ndim == 3 else 1
+    cap = 4096
+    cur = np.zeros(cap, LINE_DTYPE); ncur = C.c_int(0); rec = np.zeros(1, POSE_DTYPE)
+    prev = np.ascontiguousarray(prev_lines, LINE_DTYPE) if prev_lines is not None else np.zeros(0, LINE_DTYPE)
+    Kc = np.ascontiguousarray(K, np.float64)
+    sec = lib().orc_stream_step(ptr(img), ch, ptr(depth), W, H, ptr(Kc), C.c_uint32(seed), C.byref(p), ptr(prev),
+                                len(prev), ptr(cur), cap, C.byref(ncur), ptr(rec), omp_threads)
+    return sec, cur[:ncur.value].copy(), rec[0].copy()
