@@ -1,0 +1,277 @@
+"""Host-side mirror of the reference's interface for the line front end, on top of the C ABI
+(include/lsl.h -> liblsl_b200.so). Names follow the reference:
+
+  Node(...)                       src/node.h:71-77   (constructor runs detect3DLines, src/node.cpp:214-215)
+  Node.lineMatching(other, adj)   src/node.h:288     (src/node.cpp:1619-1694)
+  Node.matchNodePair(older)       src/node.h:107     (src/node.cpp:1494-1545)
+  getTransform_PtsLines_ransac    src/line/utils.h:147-153 (src/line/motion.cpp:605-849)
+  MatchingResult                  src/matching_result.h
+
+There is no CPU path here: if liblsl_b200.so is missing or no CUDA device is present every call
+raises. torch is not involved; device buffers may be handed in as raw pointers (see
+Context.extract_batch_dev).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .records import LINE_DTYPE, MATCH_DTYPE, POSE_DTYPE, Params, Stats, ptr
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblsl_b200.so")
+_LIB = None
+
+
+class LslError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads liblsl_b200.so (built by __graft_entry__.build() / make -C lineslam_b200/csrc)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise LslError(f"{LIB_PATH} not built: run `make -C lineslam_b200/csrc` (there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.lsl_strerror.restype = C.c_char_p
+        L.lsl_last_error.restype = C.c_char_p
+        L.lsl_last_error.argtypes = [C.c_void_p]
+        L.lsl_debug_read.restype = C.c_int64
+        L.lsl_debug_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
+        L.lsl_ctx_destroy.argtypes = [C.c_void_p]
+        L.lsl_ctx_destroy.restype = None
+        L.lsl_frame_free.argtypes = [C.c_void_p]
+        L.lsl_frame_free.restype = None
+        L.lsl_frame_num_lines.argtypes = [C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def default_params() -> Params:
+    p = Params()
+    lib().lsl_params_default(C.byref(p))
+    return p
+
+
+def _check(rc, ctx=None):
+    if rc < 0:
+        msg = lib().lsl_strerror(rc).decode()
+        if ctx is not None:
+            extra = lib().lsl_last_error(ctx).decode()
+            if extra:
+                msg += ": " + extra
+        raise LslError(msg)
+    return rc
+
+
+@dataclass
+class MatchingResult:
+    """src/matching_result.h: the subset the line path fills."""
+    all_line_matches: np.ndarray = field(default_factory=lambda: np.zeros(0, MATCH_DTYPE))
+    inlier_line_matches: np.ndarray = field(default_factory=lambda: np.zeros(0, MATCH_DTYPE))
+    ransac_line_inliers: np.ndarray = field(default_factory=lambda: np.zeros(0, MATCH_DTYPE))
+    ransac_trafo: np.ndarray = field(default_factory=lambda: np.eye(4, dtype=np.float32))
+    final_trafo: np.ndarray = field(default_factory=lambda: np.eye(4, dtype=np.float32))
+    rmse: float = 1e9
+    found: bool = False
+    id1: int = -1   # edge.id1 = older node, edge.id2 = newer node (src/node.cpp:1535-1537)
+    id2: int = -1
+    informationMatrix: np.ndarray = field(default_factory=lambda: np.eye(6))
+
+
+class Context:
+    """Owns the device workspace (lsl_ctx). max_batch frames can be extracted per call."""
+
+    def __init__(self, params: Params | None = None, device: int = 0, max_batch: int = 1, max_w: int = 640,
+                 max_h: int = 480):
+        self.params = params if params is not None else default_params()
+        self._h = C.c_void_p()
+        _check(lib().lsl_ctx_create(C.byref(self._h), C.byref(self.params), device, max_batch, max_w, max_h))
+        self.max_batch = max_batch
+
+    def close(self):
+        if self._h:
+            lib().lsl_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- extraction -----------------------------------------------------------------------
+    def extract_batch(self, imgs, depths, K, seeds=None, dt=0.0):
+        """imgs: (n,H,W,3) or (n,H,W) u8 host array; depths: (n,H,W) f32. Returns [Frame]."""
+        imgs = np.ascontiguousarray(imgs, np.uint8)
+        depths = np.ascontiguousarray(depths, np.float32)
+        n, H, W = depths.shape
+        ch = 3 if imgs.ndim == 4 else 1
+        ip = (C.c_void_p * n)(*[imgs[i].ctypes.data for i in range(n)])
+        dp = (C.c_void_p * n)(*[depths[i].ctypes.data for i in range(n)])
+        sd = np.ascontiguousarray(seeds if seeds is not None else np.ones(n), np.uint32)
+        Kc = np.ascontiguousarray(K, np.float64)
+        out = (C.c_void_p * n)()
+        _check(lib().lsl_extract_batch(self._h, n, ip, ch, dp, W, H, ptr(Kc), C.c_double(dt), ptr(sd), out), self._h)
+        return [Frame(self, out[i]) for i in range(n)]
+
+    def extract_batch_dev(self, d_imgs: int, channels: int, d_depths: int, n: int, W: int, H: int, K, seeds=None,
+                          dt=0.0):
+        """Same with inputs already in device memory (raw device pointers, e.g. tensor.data_ptr())."""
+        sd = np.ascontiguousarray(seeds if seeds is not None else np.ones(n), np.uint32)
+        Kc = np.ascontiguousarray(K, np.float64)
+        out = (C.c_void_p * n)()
+        _check(lib().lsl_extract_batch_dev(self._h, n, C.c_void_p(d_imgs), channels, C.c_void_p(d_depths), W, H,
+                                           ptr(Kc), C.c_double(dt), ptr(sd), out), self._h)
+        return [Frame(self, out[i]) for i in range(n)]
+
+    def frame_from_lines(self, recs):
+        recs = np.ascontiguousarray(recs, LINE_DTYPE)
+        h = C.c_void_p()
+        _check(lib().lsl_frame_from_lines(self._h, ptr(recs), len(recs), C.byref(h)), self._h)
+        return Frame(self, h)
+
+    # ---- pair registration ----------------------------------------------------------------
+    def match_lines(self, query: "Frame", train: "Frame", adjacent: bool):
+        cap = max(query.num_lines, 1)
+        out = np.zeros(cap, MATCH_DTYPE)
+        n = C.c_int(0)
+        _check(lib().lsl_match_lines(self._h, query._h, train._h, int(adjacent), ptr(out), cap, C.byref(n)), self._h)
+        return out[:n.value].copy()
+
+    def pose_ransac(self, train: "Frame", query: "Frame", ln_matches, id_train=0, id_query=1, seed=1):
+        m = np.ascontiguousarray(ln_matches, MATCH_DTYPE)
+        rec = np.zeros(1, POSE_DTYPE)
+        cap = max(len(m), 1)
+        inl = np.zeros(cap, MATCH_DTYPE)
+        rinl = np.zeros(cap, MATCH_DTYPE)
+        n1, n2 = C.c_int(0), C.c_int(0)
+        _check(lib().lsl_pose_ransac(self._h, train._h, query._h, id_train, id_query, None, 0, ptr(m), len(m),
+                                     C.c_uint32(seed), ptr(rec), ptr(inl), cap, C.byref(n1), ptr(rinl), cap,
+                                     C.byref(n2)), self._h)
+        return rec[0].copy(), inl[:n1.value].copy(), rinl[:n2.value].copy()
+
+    def match_pair_batch(self, queries, trains, id_query, id_train, seeds):
+        n = len(queries)
+        q = (C.c_void_p * n)(*[f._h.value if isinstance(f._h, C.c_void_p) else f._h for f in queries])
+        t = (C.c_void_p * n)(*[f._h.value if isinstance(f._h, C.c_void_p) else f._h for f in trains])
+        iq = np.ascontiguousarray(id_query, np.int32)
+        it = np.ascontiguousarray(id_train, np.int32)
+        sd = np.ascontiguousarray(seeds, np.uint32)
+        out = np.zeros(n, POSE_DTYPE)
+        _check(lib().lsl_match_pair_batch(self._h, n, q, t, ptr(iq), ptr(it), ptr(sd), ptr(out)), self._h)
+        return out
+
+    # ---- introspection --------------------------------------------------------------------
+    def stats(self) -> Stats:
+        s = Stats()
+        _check(lib().lsl_get_stats(self._h, C.byref(s)))
+        return s
+
+    def last_timing(self):
+        a, b = C.c_float(0), C.c_float(0)
+        _check(lib().lsl_last_timing(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def debug_read(self, what: int, dtype, count: int):
+        buf = np.zeros(count, dtype)
+        n = _check(lib().lsl_debug_read(self._h, what, ptr(buf), buf.nbytes), self._h)
+        return buf[:n]
+
+
+class Frame:
+    """lsl_frame handle: the `lines` member of a reference Node, resident on the device."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self._h = handle if isinstance(handle, C.c_void_p) else C.c_void_p(handle)
+
+    @property
+    def num_lines(self) -> int:
+        return _check(lib().lsl_frame_num_lines(self._h))
+
+    def lines(self) -> np.ndarray:
+        n = self.num_lines
+        out = np.zeros(max(n, 1), LINE_DTYPE)
+        k = C.c_int(0)
+        _check(lib().lsl_frame_lines(self._h, ptr(out), len(out), C.byref(k)))
+        return out[:k.value].copy()
+
+    def segments(self) -> np.ndarray:
+        k = C.c_int(0)
+        lib().lsl_frame_segments(self._h, None, 0, C.byref(k))
+        out = np.zeros((max(k.value, 1), 5))
+        _check(lib().lsl_frame_segments(self._h, ptr(out), len(out), C.byref(k)))
+        return out[:k.value].copy()
+
+    def debug(self):
+        n = self.num_lines
+        npts = np.zeros(max(n, 1), np.int32)
+        idx = np.full((max(n, 1), 101), -1, np.int32)
+        seg = np.zeros(max(n, 1), np.int32)
+        lm = np.zeros(max(n, 1), np.int32)
+        _check(lib().lsl_frame_debug(self._h, ptr(npts), ptr(idx), ptr(seg), ptr(lm)))
+        return dict(n_inl=npts[:n], inl_idx=idx[:n], seg_of_line=seg[:n], lm_iters=lm[:n])
+
+    def free(self):
+        if self._h:
+            lib().lsl_frame_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Node:
+    """One RGB-D frame (src/node.h). The constructor runs Node::detect3DLines on the device."""
+
+    def __init__(self, ctx: Context, visual, depth, K, node_id: int = 0, seed: int = 1, frame: Frame | None = None):
+        self.ctx = ctx
+        self.id_ = node_id
+        self.seed = seed
+        if frame is None:
+            frame = ctx.extract_batch(np.asarray(visual)[None], np.asarray(depth)[None], K, [seed])[0]
+        self.frame = frame
+
+    @property
+    def lines(self) -> np.ndarray:
+        return self.frame.lines()
+
+    def lineMatching(self, other: "Node", adjacentFrame: bool) -> np.ndarray:
+        return self.ctx.match_lines(self.frame, other.frame, adjacentFrame)
+
+    def matchNodePair(self, older: "Node", seed: int | None = None) -> MatchingResult:
+        """src/node.cpp:1494-1545 (USE_LINES, line features only): lineMatching -> RANSAC -> edge."""
+        P = self.ctx.params
+        mr = MatchingResult()
+        adjacent = abs(self.id_ - older.id_) <= P.adjacent_linematch_window
+        mr.all_line_matches = self.lineMatching(older, adjacent)
+        if len(mr.all_line_matches) * P.line_match_number_weight < P.min_feature_matches:
+            return mr
+        rec, inl, rinl = getTransform_PtsLines_ransac(older, self, None, mr.all_line_matches,
+                                                      seed if seed is not None else self.seed)
+        mr.inlier_line_matches, mr.ransac_line_inliers = inl, rinl
+        mr.rmse = float(rec["rmse"])
+        mr.found = bool(rec["found"])
+        if mr.found:
+            mr.final_trafo = rec["tf"].reshape(4, 4).copy()
+            mr.ransac_trafo = mr.final_trafo
+            mr.id1, mr.id2 = older.id_, self.id_
+            w = len(inl) * P.line_match_number_weight
+            mr.informationMatrix = np.eye(6) * (w / (mr.rmse * mr.rmse))
+        return mr
+
+
+def getTransform_PtsLines_ransac(trainNode: Node, queryNode: Node, all_point_matches, all_line_matches, seed: int = 1):
+    """src/line/motion.cpp:605-849, line matches only (point features are a later row of the scope table)."""
+    if all_point_matches is not None and len(all_point_matches):
+        raise LslError("point matches are not supported by this build (line-only path)")
+    return trainNode.ctx.pose_ransac(trainNode.frame, queryNode.frame, all_line_matches, trainNode.id_,
+                                     queryNode.id_, seed)

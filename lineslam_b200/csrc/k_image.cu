@@ -1,0 +1,239 @@
+// k_image.cu — dense image passes of the front end for a batch of frames (sm_100a).
+//   K1a gray_kernel        cvtColor CV_RGB2GRAY, OpenCV 2.4 fixed point (src/node.cpp:191-196)
+//   K1b xpass/ypass        LSD gaussian_sampler (external/lsd/lsd.cpp:529-646)
+//   K2  ll_angle_kernel    LSD ll_angle gradient / level-line angle / bins (lsd.cpp:670-794)
+//   K2b seed_list_kernel   ordered bin concatenation == list_p (lsd.cpp:756-787)
+//   K4  sobel5_kernel      cv::Sobel ksize 5, both derivatives (src/line/lineslam.cpp:313-314)
+// All of these are HBM/L2-streaming stencils; arithmetic follows the reference's operation order
+// exactly (compiled with --fmad=false) so every plane is bit-identical to the CPU path.
+#include "lsl_internal.h"
+#include "shared/lsl_math.h"
+
+using namespace lslm;
+
+// ---------------------------------------------------------------- taps ----
+// gaussian_kernel (lsd.cpp:466-489) evaluated once per output coordinate, as the reference does.
+__global__ void taps_kernel(double* __restrict__ k, int* __restrict__ c, int nout, double scale, double sigma, int h) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= nout) return;
+  double xx = (double)x / scale;
+  int xc = (int)floor(xx + 0.5);
+  double mean = (double)h + xx - (double)xc;
+  int n = 1 + 2 * h;
+  double v[8], sum = 0.0;
+  for (int i = 0; i < n; ++i) {
+    double val = ((double)i - mean) / sigma;
+    v[i] = lsl_exp(-0.5 * val * val);
+    sum += v[i];
+  }
+  if (sum >= 0.0)
+    for (int i = 0; i < n; ++i) v[i] /= sum;
+  for (int i = 0; i < 8; ++i) k[x * 8 + i] = i < n ? v[i] : 0.0;
+  c[x] = xc;
+}
+
+int lsl_prepare_taps(lsl_ctx* ctx) {
+  const lsl_params& P = ctx->P;
+  LslDims& d = ctx->dims;
+  double sigma = P.lsd_scale < 1.0 ? P.lsd_sigma_scale / P.lsd_scale : P.lsd_sigma_scale;
+  // h = ceil(sigma * sqrt(2 * 3 * ln 10)); ln 10 to double precision is enough for the ceil
+  int h = (int)ceil(sigma * sqrt(2.0 * 3.0 * 2.302585092994046));
+  if (1 + 2 * h > 8) { ctx->err = "gaussian kernel wider than 8 taps"; return LSL_ERR_ARG; }
+  ctx->taps.h = h; ctx->taps.n = 1 + 2 * h;
+  taps_kernel<<<(d.sw + 127) / 128, 128, 0, ctx->stream>>>(ctx->taps.kx, ctx->taps.xc, d.sw, P.lsd_scale, sigma, h);
+  taps_kernel<<<(d.sh + 127) / 128, 128, 0, ctx->stream>>>(ctx->taps.ky, ctx->taps.yc, d.sh, P.lsd_scale, sigma, h);
+  ctx->stats.kernel_launches += 2;
+  LSL_CUDA(cudaGetLastError());
+  return LSL_OK;
+}
+
+// ---------------------------------------------------------------- gray ----
+// 4 pixels per thread: 12 interleaved bytes in (3 x 32-bit loads), one 32-bit store.
+__global__ void gray_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ gray, long npix4) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix4) return;
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(img) + i * 3;
+  uint32_t a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+  uint32_t by[12] = {a & 255, (a >> 8) & 255, (a >> 16) & 255, a >> 24, b & 255, (b >> 8) & 255,
+                     (b >> 16) & 255, b >> 24, c & 255, (c >> 8) & 255, (c >> 16) & 255, c >> 24};
+  uint32_t out = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint32_t g = (by[3 * k] * 4899u + by[3 * k + 1] * 9617u + by[3 * k + 2] * 1868u + 8192u) >> 14;
+    out |= (g & 255u) << (8 * k);
+  }
+  reinterpret_cast<uint32_t*>(gray)[i] = out;
+}
+
+// ------------------------------------------------------------- sampler ----
+__device__ __forceinline__ int sym_index(int j, int n) {  // lsd.cpp:596-599 symmetric boundary
+  int n2 = 2 * n;
+  while (j < 0) j += n2;
+  while (j >= n2) j -= n2;
+  if (j >= n) j = n2 - 1 - j;
+  return j;
+}
+__global__ void xpass_kernel(const uint8_t* __restrict__ gray, double* __restrict__ aux, const double* __restrict__ kx,
+                             const int* __restrict__ xc, int W, int H, int sw, int h, int ntap) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+  if (x >= sw) return;
+  const uint8_t* row = gray + ((size_t)f * H + y) * W;
+  int c = xc[x];
+  double sum = 0.0;
+  for (int i = 0; i < ntap; ++i) {
+    int j = sym_index(c - h + i, W);
+    sum += (double)row[j] * kx[x * 8 + i];
+  }
+  aux[((size_t)f * H + y) * sw + x] = sum;
+}
+__global__ void ypass_kernel(const double* __restrict__ aux, double* __restrict__ out, const double* __restrict__ ky,
+                             const int* __restrict__ yc, int H, int sw, int sh, int h, int ntap) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+  if (x >= sw) return;
+  const double* a = aux + (size_t)f * H * sw;
+  int c = yc[y];
+  double sum = 0.0;
+  for (int i = 0; i < ntap; ++i) {
+    int j = sym_index(c - h + i, H);
+    sum += a[(size_t)j * sw + x] * ky[y * 8 + i];
+  }
+  out[((size_t)f * sh + y) * sw + x] = sum;
+}
+
+// ------------------------------------------------------------ ll_angle ----
+__global__ void ll_angle_kernel(const double* __restrict__ in, double* __restrict__ angles, double* __restrict__ modgrad,
+                                double2* __restrict__ cs, uint16_t* __restrict__ binT, int p, int n, double threshold,
+                                int n_bins, double max_grad) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+  if (x >= p) return;
+  size_t base = (size_t)f * p * n, adr = (size_t)y * p + x;
+  double ang = LSL_NOTDEF, norm = 0.0;
+  uint16_t bin = 0xFFFF;
+  double2 c2 = make_double2(2.0, 0.0);
+  if (x < p - 1 && y < n - 1) {
+    const double* I = in + base;
+    double com1 = I[adr + p + 1] - I[adr];
+    double com2 = I[adr + 1] - I[adr + p];
+    double gx = com1 + com2, gy = com1 - com2;
+    double norm2 = gx * gx + gy * gy;
+    norm = sqrt(norm2 / 4.0);
+    if (!(norm <= threshold)) {
+      ang = lsl_atan2(gx, -gy);
+      unsigned i = (unsigned)(norm * (double)n_bins / max_grad);
+      if (i >= (unsigned)n_bins) i = n_bins - 1;
+      bin = (uint16_t)i;
+      double s, c;
+      lsl_sincos(ang, &s, &c);
+      c2 = make_double2(c, s);
+    }
+  }
+  angles[base + adr] = ang;
+  modgrad[base + adr] = norm;
+  cs[base + adr] = c2;
+  binT[base + (size_t)x * n + y] = bin;
+}
+
+// ---------------------------------------------------------- seed list ----
+// One CTA per frame. Pass A: histogram of bins (smem atomics, order-free). Pass B (warp 0): walk the
+// pixels in the reference's x-outer / y-inner order and scatter stably, bins 1023 .. 1 concatenated
+// (lsd.cpp:777-787; bin 0 would only be appended if it were the highest non-empty bin, which needs
+// norm < max_grad/n_bins <= threshold and therefore never holds a seed).
+__global__ void seed_list_kernel(const uint16_t* __restrict__ binT, int32_t* __restrict__ seeds, int32_t* __restrict__ nseeds,
+                                 int p, int n, int n_bins) {
+  extern __shared__ int s_cnt[];  // n_bins counters, then cursors
+  int f = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  const uint16_t* B = binT + (size_t)f * p * n;
+  int32_t* S = seeds + (size_t)f * p * n;
+  int total = p * n;
+  for (int i = tid; i < n_bins; i += nthr) s_cnt[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < total; i += nthr) {
+    uint16_t b = B[i];
+    if (b != 0xFFFF && b != 0) atomicAdd(&s_cnt[b], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int b = n_bins - 1; b >= 1; --b) { int c = s_cnt[b]; s_cnt[b] = run; run += c; }
+    nseeds[f] = run;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    unsigned lt = (1u << tid) - 1u;
+    for (int i0 = 0; i0 < total; i0 += 32) {
+      int i = i0 + tid;
+      uint16_t b = i < total ? B[i] : (uint16_t)0xFFFF;
+      bool valid = (b != 0xFFFF && b != 0);
+      unsigned vm = __ballot_sync(0xffffffffu, valid);
+      if (valid) {
+        unsigned grp = __match_any_sync(vm, (unsigned)b);
+        int pos = s_cnt[b] + __popc(grp & lt);
+        int x = i / n, y = i - x * n;
+        S[pos] = x | (y << 16);
+        __syncwarp(vm);
+        if ((grp & lt) == 0) s_cnt[b] += __popc(grp);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// --------------------------------------------------------------- Sobel ----
+__device__ __forceinline__ int reflect101(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return i;
+}
+__global__ void sobel5_kernel(const uint8_t* __restrict__ gray, int16_t* __restrict__ gx, int16_t* __restrict__ gy, int W, int H) {
+  __shared__ uint8_t t[20][36 + 4];
+  int f = blockIdx.z;
+  const uint8_t* G = gray + (size_t)f * W * H;
+  int x0 = blockIdx.x * 32, y0 = blockIdx.y * 16;
+  for (int i = threadIdx.y * 32 + threadIdx.x; i < 20 * 36; i += 32 * 16) {
+    int ty = i / 36, tx = i - ty * 36;
+    int yy = reflect101(y0 + ty - 2, H), xx = reflect101(x0 + tx - 2, W);
+    t[ty][tx] = G[(size_t)yy * W + xx];
+  }
+  __syncthreads();
+  int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const int dv[5] = {-1, -2, 0, 2, 1}, sm[5] = {1, 4, 6, 4, 1};
+  int sx = 0, sy = 0;
+#pragma unroll
+  for (int j = 0; j < 5; ++j)
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      int v = t[threadIdx.y + j][threadIdx.x + i];
+      sx += sm[j] * dv[i] * v;
+      sy += dv[j] * sm[i] * v;
+    }
+  gx[(size_t)f * W * H + (size_t)y * W + x] = (int16_t)sx;
+  gy[(size_t)f * W * H + (size_t)y * W + x] = (int16_t)sy;
+}
+
+// Copies channel 0 when the caller already has a gray plane (channels == 1).
+int lsl_launch_image(lsl_ctx* ctx, int n, const uint8_t* d_img, int channels) {
+  const LslDims& d = ctx->dims;
+  const lsl_params& P = ctx->P;
+  LslWork& w = ctx->wk;
+  cudaStream_t st = ctx->stream;
+  size_t npix = (size_t)d.W * d.H;
+  if (channels == 3) {
+    long n4 = (long)(npix * n / 4);
+    gray_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(d_img, w.gray, n4);
+  } else {
+    LSL_CUDA(cudaMemcpyAsync(w.gray, d_img, npix * n, cudaMemcpyDeviceToDevice, st));
+  }
+  dim3 bx(128), gxp((d.sw + 127) / 128, d.H, n), gyp((d.sw + 127) / 128, d.sh, n);
+  xpass_kernel<<<gxp, bx, 0, st>>>(w.gray, w.aux, ctx->taps.kx, ctx->taps.xc, d.W, d.H, d.sw, ctx->taps.h, ctx->taps.n);
+  ypass_kernel<<<gyp, bx, 0, st>>>(w.aux, w.scaled, ctx->taps.ky, ctx->taps.yc, d.H, d.sw, d.sh, ctx->taps.h, ctx->taps.n);
+  double prec = LSL_PI * P.lsd_ang_th / 180.0;
+  double rho = P.lsd_quant / lsl_sin(prec);
+  ll_angle_kernel<<<gyp, bx, 0, st>>>(w.scaled, w.angles, w.modgrad, w.cs, w.binT, d.sw, d.sh, rho, P.lsd_n_bins, P.lsd_max_grad);
+  seed_list_kernel<<<n, 256, P.lsd_n_bins * sizeof(int), st>>>(w.binT, w.seeds, w.nseeds, d.sw, d.sh, P.lsd_n_bins);
+  dim3 bs(32, 16), gs((d.W + 31) / 32, (d.H + 15) / 16, n);
+  sobel5_kernel<<<gs, bs, 0, st>>>(w.gray, w.gx, w.gy, d.W, d.H);
+  ctx->stats.kernel_launches += 6;
+  LSL_CUDA(cudaGetLastError());
+  return LSL_OK;
+}

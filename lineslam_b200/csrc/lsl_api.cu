@@ -1,0 +1,312 @@
+// lsl_api.cu — C ABI of liblsl_b200 (include/lsl.h): contexts, frames, batched extraction.
+// There is no CPU fallback anywhere in this library: without a CUDA device every entry point
+// that computes returns LSL_ERR_NO_DEVICE.
+#include "lsl_internal.h"
+#include "shared/lsl_params_default.h"
+#include <string.h>
+#include <stdlib.h>
+#include <new>
+
+extern "C" void lsl_params_default(lsl_params* p) { if (p) lsl_params_default_impl(p); }
+
+extern "C" const char* lsl_strerror(int s) {
+  switch (s) {
+    case LSL_OK: return "ok";
+    case LSL_ERR_ARG: return "invalid argument";
+    case LSL_ERR_CUDA: return "CUDA error";
+    case LSL_ERR_CAPACITY: return "capacity exceeded";
+    case LSL_ERR_NO_DEVICE: return "no CUDA device (liblsl_b200 has no CPU fallback)";
+    case LSL_ERR_NCCL: return "NCCL error";
+    default: return "unknown status";
+  }
+}
+extern "C" const char* lsl_last_error(const lsl_ctx* ctx) { return ctx ? ctx->err.c_str() : ""; }
+
+static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// carve the per-frame work arrays out of one allocation
+static int carve(lsl_ctx* ctx, bool measure, size_t* total) {
+  const int B = ctx->max_batch;
+  const size_t npix = (size_t)ctx->max_w * ctx->max_h;
+  const size_t sw = (size_t)floor(ctx->max_w * ctx->P.lsd_scale), sh = (size_t)floor(ctx->max_h * ctx->P.lsd_scale);
+  const size_t spix = sw * sh;
+  size_t off = 0;
+  uint8_t* base = (uint8_t*)ctx->wk_block;
+  LslWork& w = ctx->wk;
+#define CARVE(field, type, count)                               \
+  do {                                                          \
+    if (!measure) w.field = (type*)(base + off);                \
+    off += align_up(sizeof(type) * (size_t)(count));            \
+  } while (0)
+  CARVE(img, uint8_t, B * npix * 3);
+  CARVE(depth, float, B * npix);
+  CARVE(gray, uint8_t, B * npix);
+  CARVE(aux, double, B * (size_t)ctx->max_h * sw);
+  CARVE(scaled, double, B * spix);
+  CARVE(angles, double, B * spix);
+  CARVE(modgrad, double, B * spix);
+  CARVE(cs, double2, B * spix);
+  CARVE(binT, uint16_t, B * spix);
+  CARVE(used, uint8_t, B * spix);
+  CARVE(seeds, int32_t, B * spix);
+  CARVE(nseeds, int32_t, B);
+  CARVE(reg, int32_t, B * spix);
+  CARVE(segs, double, (size_t)B * LSL_MAX_SEGS * 5);
+  CARVE(nsegs, int32_t, B);
+  CARVE(gx, int16_t, B * npix);
+  CARVE(gy, int16_t, B * npix);
+  CARVE(cand_seg, int32_t, (size_t)B * LSL_MAX_SEGS);
+  CARVE(ncand, int32_t, B);
+  CARVE(keep_cand, int32_t, (size_t)B * LSL_MAX_LINES);
+  CARVE(nlines, int32_t, B);
+  CARVE(npts, int32_t, (size_t)B * LSL_MAX_LINES);
+  CARVE(pts, double, (size_t)B * LSL_MAX_LINES * LSL_MAX_SMP * 3);
+  CARVE(inl_idx, int32_t, (size_t)B * LSL_MAX_LINES * LSL_MAX_SMP);
+  CARVE(lines, lsl_line_rec, (size_t)B * LSL_MAX_LINES);
+  CARVE(seeds_rng, uint32_t, B);
+  CARVE(rng_state, int32_t, (size_t)B * 36);
+  CARVE(lm_iters, int32_t, (size_t)B * LSL_MAX_LINES);
+  // tap tables
+  if (!measure) ctx->taps.kx = (double*)(base + off); off += align_up(sizeof(double) * sw * 8);
+  if (!measure) ctx->taps.xc = (int*)(base + off); off += align_up(sizeof(int) * sw);
+  if (!measure) ctx->taps.ky = (double*)(base + off); off += align_up(sizeof(double) * sh * 8);
+  if (!measure) ctx->taps.yc = (int*)(base + off); off += align_up(sizeof(int) * sh);
+#undef CARVE
+  *total = off;
+  return LSL_OK;
+}
+
+extern "C" int lsl_ctx_create(lsl_ctx** out, const lsl_params* params, int cuda_device, int max_batch, int max_w, int max_h) {
+  if (!out || max_batch < 1 || max_w < 16 || max_h < 16 || (max_w & 3)) return LSL_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return LSL_ERR_NO_DEVICE;
+  if (cuda_device < 0 || cuda_device >= ndev) return LSL_ERR_ARG;
+  lsl_ctx* ctx = new (std::nothrow) lsl_ctx();
+  if (!ctx) return LSL_ERR_ARG;
+  if (params) ctx->P = *params; else lsl_params_default_impl(&ctx->P);
+  ctx->device = cuda_device; ctx->max_batch = max_batch; ctx->max_w = max_w; ctx->max_h = max_h;
+  ctx->wk_block = nullptr; ctx->pair_block = nullptr; ctx->pair_bytes = 0; ctx->pair_cap = 0;
+  ctx->h_pin = nullptr; ctx->h_pin_bytes = 0;
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  memset(&ctx->dims, 0, sizeof(ctx->dims));
+  ctx->ms_total = ctx->ms_rg = 0.f;
+  if (ctx->P.lsd_n_bins > 4096 || ctx->P.line_sample_max_num + 1 > LSL_MAX_SMP) { delete ctx; return LSL_ERR_ARG; }
+  cudaError_t e = cudaSetDevice(cuda_device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev2);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev3);
+  size_t total = 0;
+  carve(ctx, true, &total);
+  ctx->wk_bytes = total;
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->wk_block, total);
+  if (e != cudaSuccess) { delete ctx; return LSL_ERR_CUDA; }
+  carve(ctx, false, &total);
+  *out = ctx;
+  return LSL_OK;
+}
+
+extern "C" void lsl_ctx_destroy(lsl_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->wk_block) cudaFree(ctx->wk_block);
+  if (ctx->pair_block) cudaFree(ctx->pair_block);
+  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+static int set_dims(lsl_ctx* ctx, int W, int H) {
+  if (W > ctx->max_w || H > ctx->max_h || W < 16 || H < 16 || (W & 3)) { ctx->err = "image size outside context limits"; return LSL_ERR_ARG; }
+  if (ctx->dims.W == W && ctx->dims.H == H) return LSL_OK;
+  ctx->dims.W = W; ctx->dims.H = H;
+  ctx->dims.sw = (int)floor(W * ctx->P.lsd_scale);
+  ctx->dims.sh = (int)floor(H * ctx->P.lsd_scale);
+  ctx->dims.msld_s = (int)(5 * W / 800.0);
+  if (ctx->dims.sw >= 65536 || ctx->dims.sh >= 32768) return LSL_ERR_ARG;
+  return lsl_prepare_taps(ctx);
+}
+
+static int ensure_pinned(lsl_ctx* ctx, size_t bytes) {
+  if (ctx->h_pin_bytes >= bytes) return LSL_OK;
+  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  ctx->h_pin = nullptr; ctx->h_pin_bytes = 0;
+  LSL_CUDA(cudaMallocHost((void**)&ctx->h_pin, bytes));
+  ctx->h_pin_bytes = bytes;
+  return LSL_OK;
+}
+
+// Runs all extraction kernels for n frames whose inputs are on the device, then builds the handles.
+static int extract_device(lsl_ctx* ctx, int n, const uint8_t* d_imgs, int channels, const float* d_depths, int W, int H,
+                          const double K[9], double dt, const uint32_t* seeds, lsl_frame** out) {
+  int rc = set_dims(ctx, W, H);
+  if (rc) return rc;
+  LslWork& w = ctx->wk;
+  cudaStream_t st = ctx->stream;
+  std::vector<uint32_t> sd(n);
+  for (int i = 0; i < n; ++i) sd[i] = seeds ? seeds[i] : 1u;
+  LSL_CUDA(cudaMemcpyAsync(w.seeds_rng, sd.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+  cudaEventRecord(ctx->ev0, st);
+  if ((rc = lsl_launch_image(ctx, n, d_imgs, channels))) return rc;
+  if ((rc = lsl_launch_lsd(ctx, n))) return rc;
+  if ((rc = lsl_launch_lines(ctx, n, d_depths, K, dt))) return rc;
+  cudaEventRecord(ctx->ev3, st);
+  // ---- results back: counts, then the records actually produced
+  std::vector<int32_t> nsegs(n), nlines(n);
+  LSL_CUDA(cudaMemcpyAsync(nsegs.data(), w.nsegs, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  LSL_CUDA(cudaMemcpyAsync(nlines.data(), w.nlines, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  LSL_CUDA(cudaStreamSynchronize(st));
+  ctx->stats.d2h_bytes += 8 * n;
+  for (int f = 0; f < n; ++f) {
+    if (nsegs[f] > LSL_MAX_SEGS || nlines[f] > LSL_MAX_LINES) { ctx->err = "per-frame segment/line table overflow"; return LSL_ERR_CAPACITY; }
+    lsl_frame* fr = new (std::nothrow) lsl_frame();
+    if (!fr) return LSL_ERR_ARG;
+    fr->ctx = ctx; fr->nlines = nlines[f]; fr->nsegs = nsegs[f]; fr->d_lines = nullptr;
+    fr->lines.resize(fr->nlines); fr->segs.resize((size_t)fr->nsegs * 5);
+    fr->dbg_npts.resize(fr->nlines); fr->dbg_inl.resize((size_t)fr->nlines * LSL_MAX_SMP);
+    fr->dbg_seg.resize(fr->nlines); fr->dbg_lm.resize(fr->nlines);
+    if (fr->nsegs)
+      LSL_CUDA(cudaMemcpyAsync(fr->segs.data(), w.segs + (size_t)f * LSL_MAX_SEGS * 5, sizeof(double) * 5 * fr->nsegs, cudaMemcpyDeviceToHost, st));
+    if (fr->nlines) {
+      size_t lb = sizeof(lsl_line_rec) * fr->nlines;
+      LSL_CUDA(cudaMalloc((void**)&fr->d_lines, lb));
+      LSL_CUDA(cudaMemcpyAsync(fr->d_lines, w.lines + (size_t)f * LSL_MAX_LINES, lb, cudaMemcpyDeviceToDevice, st));
+      LSL_CUDA(cudaMemcpyAsync(fr->lines.data(), w.lines + (size_t)f * LSL_MAX_LINES, lb, cudaMemcpyDeviceToHost, st));
+      LSL_CUDA(cudaMemcpyAsync(fr->dbg_npts.data(), w.npts + (size_t)f * LSL_MAX_LINES, 4 * fr->nlines, cudaMemcpyDeviceToHost, st));
+      LSL_CUDA(cudaMemcpyAsync(fr->dbg_inl.data(), w.inl_idx + (size_t)f * LSL_MAX_LINES * LSL_MAX_SMP, 4 * (size_t)fr->nlines * LSL_MAX_SMP, cudaMemcpyDeviceToHost, st));
+      LSL_CUDA(cudaMemcpyAsync(fr->dbg_seg.data(), w.keep_cand + (size_t)f * LSL_MAX_LINES, 4 * fr->nlines, cudaMemcpyDeviceToHost, st));
+      LSL_CUDA(cudaMemcpyAsync(fr->dbg_lm.data(), w.lm_iters + (size_t)f * LSL_MAX_LINES, 4 * fr->nlines, cudaMemcpyDeviceToHost, st));
+      ctx->stats.d2h_bytes += lb;
+    }
+    ctx->stats.d2h_bytes += sizeof(double) * 5 * fr->nsegs;
+    ctx->stats.segments += fr->nsegs; ctx->stats.lines3d += fr->nlines;
+    out[f] = fr;
+  }
+  LSL_CUDA(cudaStreamSynchronize(st));
+  ctx->stats.frames += n;
+  cudaEventElapsedTime(&ctx->ms_total, ctx->ev0, ctx->ev3);
+  cudaEventElapsedTime(&ctx->ms_rg, ctx->ev1, ctx->ev2);
+  return LSL_OK;
+}
+
+extern "C" int lsl_extract_batch_dev(lsl_ctx* ctx, int n, const uint8_t* d_imgs, int channels, const float* d_depths, int W,
+                                     int H, const double K[9], double dt, const uint32_t* seeds, lsl_frame** out) {
+  if (!ctx || !d_imgs || !d_depths || !K || !out || n < 1 || (channels != 1 && channels != 3)) return LSL_ERR_ARG;
+  if (n > ctx->max_batch) { ctx->err = "batch larger than the context's max_batch"; return LSL_ERR_CAPACITY; }
+  cudaSetDevice(ctx->device);
+  return extract_device(ctx, n, d_imgs, channels, d_depths, W, H, K, dt, seeds, out);
+}
+
+extern "C" int lsl_extract_batch(lsl_ctx* ctx, int n, const uint8_t* const* imgs, int channels, const float* const* depths,
+                                 int W, int H, const double K[9], double dt, const uint32_t* seeds, lsl_frame** out) {
+  if (!ctx || !imgs || !depths || !K || !out || n < 1 || (channels != 1 && channels != 3)) return LSL_ERR_ARG;
+  if (n > ctx->max_batch) { ctx->err = "batch larger than the context's max_batch"; return LSL_ERR_CAPACITY; }
+  cudaSetDevice(ctx->device);
+  int rc = set_dims(ctx, W, H);
+  if (rc) return rc;
+  const size_t ib = (size_t)W * H * channels, db = (size_t)W * H * sizeof(float);
+  // stage through pinned memory so the copies are truly asynchronous (inputs may be pageable)
+  if ((rc = ensure_pinned(ctx, (ib + db) * n))) return rc;
+  uint8_t* hp = ctx->h_pin;
+  for (int i = 0; i < n; ++i) {
+    if (!imgs[i] || !depths[i]) return LSL_ERR_ARG;
+    memcpy(hp + ib * i, imgs[i], ib);
+    memcpy(hp + ib * n + db * i, depths[i], db);
+  }
+  LSL_CUDA(cudaMemcpyAsync(ctx->wk.img, hp, ib * n, cudaMemcpyHostToDevice, ctx->stream));
+  LSL_CUDA(cudaMemcpyAsync(ctx->wk.depth, hp + ib * n, db * n, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->stats.h2d_bytes += (ib + db) * n;
+  return extract_device(ctx, n, ctx->wk.img, channels, ctx->wk.depth, W, H, K, dt, seeds, out);
+}
+
+extern "C" int lsl_extract(lsl_ctx* ctx, const uint8_t* img, int channels, const float* depth, int W, int H,
+                           const double K[9], double dt, uint32_t seed, lsl_frame** out) {
+  return lsl_extract_batch(ctx, 1, &img, channels, &depth, W, H, K, dt, &seed, out);
+}
+
+extern "C" int lsl_frame_num_lines(const lsl_frame* f) { return f ? f->nlines : LSL_ERR_ARG; }
+extern "C" int lsl_frame_lines(const lsl_frame* f, lsl_line_rec* dst, int cap, int* n) {
+  if (!f || !n) return LSL_ERR_ARG;
+  *n = f->nlines;
+  if (cap < f->nlines || (!dst && f->nlines)) return LSL_ERR_CAPACITY;
+  if (f->nlines) memcpy(dst, f->lines.data(), sizeof(lsl_line_rec) * f->nlines);
+  return LSL_OK;
+}
+extern "C" int lsl_frame_segments(const lsl_frame* f, double* dst, int cap, int* n) {
+  if (!f || !n) return LSL_ERR_ARG;
+  *n = f->nsegs;
+  if (cap < f->nsegs || (!dst && f->nsegs)) return LSL_ERR_CAPACITY;
+  if (f->nsegs) memcpy(dst, f->segs.data(), sizeof(double) * 5 * f->nsegs);
+  return LSL_OK;
+}
+extern "C" int lsl_frame_from_lines(lsl_ctx* ctx, const lsl_line_rec* recs, int n, lsl_frame** out) {
+  if (!ctx || !out || n < 0 || (n && !recs) || n > LSL_MAX_LINES) return LSL_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  lsl_frame* fr = new (std::nothrow) lsl_frame();
+  if (!fr) return LSL_ERR_ARG;
+  fr->ctx = ctx; fr->nlines = n; fr->nsegs = 0; fr->d_lines = nullptr;
+  fr->lines.assign(recs, recs + n);
+  if (n) {
+    LSL_CUDA(cudaMalloc((void**)&fr->d_lines, sizeof(lsl_line_rec) * n));
+    LSL_CUDA(cudaMemcpyAsync(fr->d_lines, recs, sizeof(lsl_line_rec) * n, cudaMemcpyHostToDevice, ctx->stream));
+    LSL_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.h2d_bytes += sizeof(lsl_line_rec) * n;
+  }
+  *out = fr;
+  return LSL_OK;
+}
+extern "C" void lsl_frame_free(lsl_frame* f) {
+  if (!f) return;
+  if (f->d_lines) { cudaSetDevice(f->ctx->device); cudaFree(f->d_lines); }
+  delete f;
+}
+// parity-test read-back of per-line intermediates (inlier sample indices of the 3D-line RANSAC etc.)
+extern "C" int lsl_frame_debug(const lsl_frame* f, int32_t* npts, int32_t* inl_idx, int32_t* seg_of_line, int32_t* lm_iters) {
+  if (!f) return LSL_ERR_ARG;
+  if (npts) memcpy(npts, f->dbg_npts.data(), 4 * f->dbg_npts.size());
+  if (inl_idx) memcpy(inl_idx, f->dbg_inl.data(), 4 * f->dbg_inl.size());
+  if (seg_of_line) memcpy(seg_of_line, f->dbg_seg.data(), 4 * f->dbg_seg.size());
+  if (lm_iters) memcpy(lm_iters, f->dbg_lm.data(), 4 * f->dbg_lm.size());
+  return LSL_OK;
+}
+
+extern "C" int lsl_get_stats(const lsl_ctx* ctx, lsl_stats* out) {
+  if (!ctx || !out) return LSL_ERR_ARG;
+  *out = ctx->stats;
+  return LSL_OK;
+}
+extern "C" int lsl_last_timing(const lsl_ctx* ctx, float* ms_total, float* ms_rg) {
+  if (!ctx) return LSL_ERR_ARG;
+  if (ms_total) *ms_total = ctx->ms_total;
+  if (ms_rg) *ms_rg = ctx->ms_rg;
+  return LSL_OK;
+}
+
+extern "C" int64_t lsl_debug_read(lsl_ctx* ctx, int what, void* dst, int64_t cap_bytes) {
+  if (!ctx || !dst) return LSL_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  const LslDims& d = ctx->dims;
+  const LslWork& w = ctx->wk;
+  const void* src = nullptr;
+  int64_t count = 0, esz = 1;
+  int32_t ns = 0;
+  switch (what) {
+    case 0: src = w.gray; count = (int64_t)d.W * d.H; esz = 1; break;
+    case 1: src = w.scaled; count = (int64_t)d.sw * d.sh; esz = 8; break;
+    case 2: src = w.angles; count = (int64_t)d.sw * d.sh; esz = 8; break;
+    case 3: src = w.modgrad; count = (int64_t)d.sw * d.sh; esz = 8; break;
+    case 4:
+      if (cudaMemcpy(&ns, w.nseeds, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return LSL_ERR_CUDA;
+      src = w.seeds; count = ns; esz = 4; break;
+    case 5: src = w.gx; count = (int64_t)d.W * d.H; esz = 2; break;
+    case 6: src = w.gy; count = (int64_t)d.W * d.H; esz = 2; break;
+    default: return LSL_ERR_ARG;
+  }
+  if (count * esz > cap_bytes) return LSL_ERR_CAPACITY;
+  if (count && cudaMemcpy(dst, src, count * esz, cudaMemcpyDeviceToHost) != cudaSuccess) return LSL_ERR_CUDA;
+  return count;
+}

@@ -1,0 +1,102 @@
+// lsl_internal.h — context / frame / workspace layout of liblsl_b200 (product code, CUDA only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/lsl.h"
+
+#define LSL_MAX_SEGS 2048      // LSD segments per frame (ntuple_list rows)
+#define LSL_MAX_LINES 1024     // 3D lines kept per frame
+#define LSL_MAX_SMP 101        // samples per line (line_sample_max_num + 1)
+#define LSL_NOTDEF (-1024.0)   // external/lsd/lsd.cpp:102
+#define LSL_MAX_MATCH 1024     // line matches per pair
+
+struct LslDims {
+  int W, H;      // input image
+  int sw, sh;    // LSD scaled image (floor(W*scale), floor(H*scale))
+  int msld_s;    // int(5*W/800.0)
+};
+
+// Gaussian sampler tap tables (one set per context, depend on W,H,scale,sigma_scale only)
+struct LslTaps {
+  double* kx;  // [sw][8]  7 normalised taps (+pad) per output column  (lsd.cpp:581-585)
+  int* xc;     // [sw]     centre pixel per output column
+  double* ky;  // [sh][8]
+  int* yc;     // [sh]
+  int h, n;    // half width, taps (3, 7 for sigma 0.75)
+};
+
+// Per-frame device scratch; frame f lives at base + f * stride for each array.
+struct LslWork {
+  uint8_t* img;     // [B][H*W*3]  (only used by the host-buffer path)
+  float* depth;     // [B][H*W]
+  uint8_t* gray;    // [B][H*W]
+  double* aux;      // [B][H*sw]   x-pass of the sampler
+  double* scaled;   // [B][sh*sw]
+  double* angles;   // [B][sh*sw]
+  double* modgrad;  // [B][sh*sw]
+  double2* cs;      // [B][sh*sw]  (cos, sin) of the level-line angle; x = 2.0 marks NOTDEF
+  uint16_t* binT;   // [B][sw*sh]  gradient bin, column-major (x*sh+y); 0xFFFF = not a seed
+  uint8_t* used;    // [B][sh*sw]
+  int32_t* seeds;   // [B][sh*sw]  x | y<<16 in list_p order
+  int32_t* nseeds;  // [B]
+  int32_t* reg;     // [B][sh*sw]  region pixel list x | y<<16
+  double* segs;     // [B][LSL_MAX_SEGS*5]
+  int32_t* nsegs;   // [B]
+  int16_t* gx;      // [B][H*W]  Sobel 5x5 d/dx (exact integers, |v| <= 6570)
+  int16_t* gy;      // [B][H*W]
+  // per-frame line tables
+  int32_t* cand_seg;   // [B][LSL_MAX_SEGS] segment index of candidate c (len > thres)
+  int32_t* ncand;      // [B]
+  int32_t* keep_cand;  // [B][LSL_MAX_LINES] candidate index of kept line k
+  int32_t* nlines;     // [B]
+  int32_t* npts;       // [B][LSL_MAX_LINES] inlier count of kept line
+  double* pts;         // [B][LSL_MAX_LINES][LSL_MAX_SMP*3] inlier points xyz
+  int32_t* inl_idx;    // [B][LSL_MAX_LINES][LSL_MAX_SMP] inlier sample indices (debug / parity)
+  lsl_line_rec* lines; // [B][LSL_MAX_LINES]
+  uint32_t* seeds_rng; // [B]
+  int32_t* rng_state;  // [B][36] glibc TYPE_3 state carried from the RANSAC stage to the MSLD stage
+  int32_t* lm_iters;   // [B][LSL_MAX_LINES]
+};
+
+struct lsl_frame {
+  lsl_ctx* ctx;
+  int nlines, nsegs;
+  lsl_line_rec* d_lines;            // device copy (owned)
+  std::vector<lsl_line_rec> lines;  // host mirror
+  std::vector<double> segs;         // host mirror of LSD output (5 per row)
+  std::vector<int32_t> dbg_npts, dbg_inl, dbg_seg, dbg_lm;
+};
+
+struct lsl_ctx {
+  lsl_params P;
+  int device, max_batch, max_w, max_h;
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1, ev2, ev3;
+  LslDims dims;   // dims the workspace / taps were last prepared for
+  LslTaps taps;
+  LslWork wk;
+  void* wk_block; size_t wk_bytes;
+  // pair workspace
+  void* pair_block; size_t pair_bytes; int pair_cap;
+  uint8_t* h_pin; size_t h_pin_bytes;   // pinned staging
+  std::string err;
+  lsl_stats stats;
+  float ms_total, ms_rg;
+};
+
+#define LSL_CUDA(call)                                                                  \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                    \
+      return LSL_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+// kernel launchers (one per .cu)
+int lsl_launch_image(lsl_ctx* ctx, int n, const uint8_t* d_img, int channels);
+int lsl_launch_lsd(lsl_ctx* ctx, int n);
+int lsl_launch_lines(lsl_ctx* ctx, int n, const float* d_depth, const double K[9], double dt);
+int lsl_prepare_taps(lsl_ctx* ctx);

@@ -167,4 +167,43 @@ LSL_HD void pt3d_cov(const double pt[3], double f, double sigma_impt, double c1,
     }
 }
 
+// jac_rpt2ln_mahvec_wrt_ln (src/line/utils.cpp:1086-1115), structured form of the generated
+// expressions: u = DU(x-a), e = DU(x-a) - DU(x-b), s = u.e, n = e.e, cu_j = DU(:,j).u, ce_j = DU(:,j).e
+//   d/da_j [k] = DU_kj - DU_kj*s/n - e_k*(cu_j + ce_j)/n + (1/n^2)*s*(2 ce_j)*e_k
+//   d/db_j [k] = cu_j*e_k/n + DU_kj*s/n - (1/n^2)*s*(2 ce_j)*e_k
+// J is 3x6 row-major.
+LSL_HD void jac_rpt2ln(const double pos[3], const double c[9], const double l[6], double J[18]) {
+  double da[3] = {pos[0] - l[0], pos[1] - l[1], pos[2] - l[2]};
+  double db[3] = {pos[0] - l[3], pos[1] - l[4], pos[2] - l[5]};
+  double u[3], e[3];
+  for (int k = 0; k < 3; ++k) {
+    u[k] = c[k * 3] * da[0] + c[k * 3 + 1] * da[1] + c[k * 3 + 2] * da[2];
+    e[k] = c[k * 3] * da[0] - c[k * 3] * db[0] + c[k * 3 + 1] * da[1] - c[k * 3 + 1] * db[1] + c[k * 3 + 2] * da[2] -
+           c[k * 3 + 2] * db[2];
+  }
+  double s = u[0] * e[0] + u[1] * e[1] + u[2] * e[2];
+  double n = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+  double inv_n2 = 1.0 / (n * n);
+  for (int j = 0; j < 3; ++j) {
+    double cu = c[j] * u[0] + c[3 + j] * u[1] + c[6 + j] * u[2];
+    double ce = c[j] * e[0] + c[3 + j] * e[1] + c[6 + j] * e[2];
+    double ce2 = c[j] * e[0] * 2.0 + c[3 + j] * e[1] * 2.0 + c[6 + j] * e[2] * 2.0;
+    for (int k = 0; k < 3; ++k) {
+      double ckj = c[k * 3 + j];
+      J[k * 6 + j] = ckj - (ckj * s) / n - (e[k] * (cu + ce)) / n + inv_n2 * s * ce2 * e[k];
+      J[k * 6 + 3 + j] = (cu * e[k]) / n + (ckj * s) / n - inv_n2 * s * ce2 * e[k];
+    }
+  }
+}
+
+// (v - pt)^T Cinv (v - pt): end-point residual of costFun_MLEstimateLine3d (utils.cpp:966-971),
+// Eigen evaluation order (row vector times matrix first).
+LSL_HD double mah_sq_pt(const double e[3], const double pt[3], const double C[9]) {
+  double v[3] = {e[0] - pt[0], e[1] - pt[1], e[2] - pt[2]};
+  double r0 = v[0] * C[0] + v[1] * C[3] + v[2] * C[6];
+  double r1 = v[0] * C[1] + v[1] * C[4] + v[2] * C[7];
+  double r2 = v[0] * C[2] + v[1] * C[5] + v[2] * C[8];
+  return r0 * v[0] + r1 * v[1] + r2 * v[2];
+}
+
 }  // namespace lslm

@@ -23,7 +23,7 @@
 
 #if defined(__CUDACC__)
 #define LSL_HD __host__ __device__ __forceinline__
-#define LSL_HDN __host__ __device__ __noinline__
+#define LSL_HDN static __host__ __device__ __noinline__
 #else
 #define LSL_HD static inline
 #define LSL_HDN static inline

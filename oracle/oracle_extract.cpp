@@ -513,7 +513,7 @@ int dlevmar_dif_restated(void (*func)(double*, double*, int, int, void*), double
   if (info) {
     info[0] = init_p_eL2; info[1] = p_eL2; info[2] = jacTe_inf; info[3] = Dp_L2;
     tmp = DBL_MIN;
-    for (int i = 0; i < m; ++i) { double dgi = (stop == 0 || true) ? diag[i] : 0; if (tmp < dgi) tmp = dgi; }
+    for (int i = 0; i < m; ++i) if (tmp < diag[i]) tmp = diag[i];
     info[4] = mu / tmp; info[5] = (double)k; info[6] = (double)stop; info[7] = (double)nfev;
     info[8] = (double)njap; info[9] = (double)nlss;
   }
@@ -534,42 +534,9 @@ static void mle_cost(double* p, double* error, int, int, void* adata) {
     if ((int)i == d->idx1 || (int)i == d->idx2) {
       const double* C = ((int)i == d->idx1) ? d->cov_inv1 : d->cov_inv2;
       const double* e = ((int)i == d->idx1) ? p : p + 3;
-      double v[3] = {e[0] - pts[i].pos[0], e[1] - pts[i].pos[1], e[2] - pts[i].pos[2]};
-      double r0 = v[0] * C[0] + v[1] * C[3] + v[2] * C[6];
-      double r1 = v[0] * C[1] + v[1] * C[4] + v[2] * C[7];
-      double r2 = v[0] * C[2] + v[1] * C[5] + v[2] * C[8];
-      error[i] = r0 * v[0] + r1 * v[1] + r2 * v[2];
+      error[i] = mah_sq_pt(e, pts[i].pos, C);
     } else {
       error[i] = mah_dist3d_pt_line(pts[i].pos, pts[i].DU, p, p + 3);
-    }
-  }
-}
-
-// jac_rpt2ln_mahvec_wrt_ln (utils.cpp:1086-1115), structured form of the generated expressions:
-// u = DU(x-a), e = DU(x-a) - DU(x-b), s = u.e, n = e.e, cu_j = DU(:,j).u, ce_j = DU(:,j).e
-//   d/da_j [k] = DU_kj - DU_kj*s/n - e_k*(cu_j + ce_j)/n + (1/n^2)*s*(2 ce_j)*e_k
-//   d/db_j [k] = cu_j*e_k/n + DU_kj*s/n - (1/n^2)*s*(2 ce_j)*e_k
-static void jac_line(const Pt3& pt, const double l[6], double J[18]) {
-  const double* c = pt.DU;
-  double da[3] = {pt.pos[0] - l[0], pt.pos[1] - l[1], pt.pos[2] - l[2]};
-  double db[3] = {pt.pos[0] - l[3], pt.pos[1] - l[4], pt.pos[2] - l[5]};
-  double u[3], e[3];
-  for (int k = 0; k < 3; ++k) {
-    u[k] = c[k * 3] * da[0] + c[k * 3 + 1] * da[1] + c[k * 3 + 2] * da[2];
-    e[k] = c[k * 3] * da[0] - c[k * 3] * db[0] + c[k * 3 + 1] * da[1] - c[k * 3 + 1] * db[1] + c[k * 3 + 2] * da[2] -
-           c[k * 3 + 2] * db[2];
-  }
-  double s = u[0] * e[0] + u[1] * e[1] + u[2] * e[2];
-  double n = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
-  double inv_n2 = 1.0 / (n * n);
-  for (int j = 0; j < 3; ++j) {
-    double cu = c[j] * u[0] + c[3 + j] * u[1] + c[6 + j] * u[2];
-    double ce = c[j] * e[0] + c[3 + j] * e[1] + c[6 + j] * e[2];
-    double ce2 = c[j] * e[0] * 2.0 + c[3 + j] * e[1] * 2.0 + c[6 + j] * e[2] * 2.0;
-    for (int k = 0; k < 3; ++k) {
-      double ckj = c[k * 3 + j];
-      J[k * 6 + j] = ckj - (ckj * s) / n - (e[k] * (cu + ce)) / n + inv_n2 * s * ce2 * e[k];
-      J[k * 6 + 3 + j] = (cu * e[k]) / n + (ckj * s) / n - inv_n2 * s * ce2 * e[k];
     }
   }
 }
@@ -607,7 +574,7 @@ static int MLEstimateLine3d(const std::vector<Pt3>& pts, Line& out, const double
     for (int k = 0; k < 18; ++k) J[k] = 0;
     if ((int)i == idx_end1) { for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) J[r * 6 + c] = -pts[i].DU[r * 3 + c]; }
     else if ((int)i == idx_end2) { for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) J[r * 6 + 3 + c] = -pts[i].DU[r * 3 + c]; }
-    else jac_line(pts[i], para, J);
+    else jac_rpt2ln(pts[i].pos, pts[i].DU, para, J);
     for (int r = 0; r < 3; ++r)
       for (int a = 0; a < 6; ++a)
         for (int b = 0; b < 6; ++b) H[a * 6 + b] += J[r * 6 + a] * J[r * 6 + b];

@@ -1,0 +1,60 @@
+"""GPU parity, image stages + LSD: bit-exact against the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _stage_check(api, oracle, imgs, deps, K, max_batch):
+    n, H, W = deps.shape
+    ctx = api.Context(max_batch=max_batch, max_w=W, max_h=H)
+    frames = ctx.extract_batch(imgs, deps, K, seeds=np.arange(1, n + 1))
+    sw, sh = int(np.floor(W * 0.8)), int(np.floor(H * 0.8))
+    # frame 0 intermediates
+    g = oracle.gray(imgs[0])
+    segs, dbg = oracle.lsd(g, debug=True)
+    assert np.array_equal(ctx.debug_read(0, np.uint8, W * H).reshape(H, W), g)
+    assert np.array_equal(ctx.debug_read(1, np.float64, sw * sh).reshape(sh, sw), dbg["scaled"])
+    assert np.array_equal(ctx.debug_read(3, np.float64, sw * sh).reshape(sh, sw), dbg["modgrad"])
+    assert np.array_equal(ctx.debug_read(2, np.float64, sw * sh).reshape(sh, sw), dbg["angles"])
+    assert np.array_equal(ctx.debug_read(4, np.int32, sw * sh), dbg["seeds"])
+    gx, gy = oracle.sobel5(g)
+    assert np.array_equal(ctx.debug_read(5, np.int16, W * H).reshape(H, W).astype(np.float64), gx)
+    assert np.array_equal(ctx.debug_read(6, np.int16, W * H).reshape(H, W).astype(np.float64), gy)
+    # every frame: LSD segment endpoints bit-exact
+    for i in range(n):
+        ref = oracle.lsd(oracle.gray(imgs[i]))
+        got = frames[i].segments()
+        assert got.shape == ref.shape, (i, got.shape, ref.shape)
+        assert np.array_equal(got, ref), i
+    ctx.close()
+
+
+def test_stages_and_segments_vga(api, oracle, stream4):
+    imgs, deps, poses, K = stream4
+    _stage_check(api, oracle, imgs, deps, K, 4)
+
+
+def test_stages_and_segments_small(api, oracle, small_frames):
+    imgs, deps, poses, K = small_frames
+    _stage_check(api, oracle, imgs, deps, K, 2)
+
+
+def test_gray_input_and_noise_image(api, oracle):
+    """channels == 1 input; a noise image (no segments) and a step edge image."""
+    rng = np.random.default_rng(7)
+    H, W = 120, 160
+    noise = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    step = np.full((H, W), 40, np.uint8)
+    step[:, W // 2:] = 200
+    step[H // 3: 2 * H // 3, :] //= 2
+    imgs = np.stack([noise, step])
+    deps = np.ones((2, H, W), np.float32)
+    ctx = api.Context(max_batch=2, max_w=W, max_h=H)
+    frames = ctx.extract_batch(imgs, deps, np.array([[100., 0, 80], [0, 100, 60], [0, 0, 1]]))
+    for i in range(2):
+        ref = oracle.lsd(imgs[i])
+        got = frames[i].segments()
+        assert got.shape == ref.shape
+        assert np.array_equal(got, ref)
+    ctx.close()
