@@ -1,6 +1,863 @@
-// k_lines.cu — per-line stages (under construction: first GPU run validates K1-K4 only)
+// k_lines.cu — per-line stages of Node::detect3DLines (src/line/lineslam.cpp:213-349) for a batch
+// of frames (sm_100a):
+//   K5+K6 line3d_ransac_kernel   length filter, depth sampling along the segment, back-projection,
+//                                per-point covariance (compPt3dCov, utils.cpp:690-722) and the 3D-line
+//                                RANSAC extract3dline_mahdist (utils.cpp:343-427). One CTA per frame:
+//                                the reference consumes ONE rand() stream in line order, so lines are
+//                                visited in order and the parallelism is inside a line (hypotheses x
+//                                points) and across the frames of the batch.
+//   K7    line_msld_kernel       FrameLine::getGradient (lineslam.cpp:527-537) + computeMSLD
+//                                (utils.cpp:1544-1610), one CTA per kept line.
+//   K7b   msld_randfill_kernel   the rand() fill of descriptors without a valid sample (utils.cpp:1576-1580),
+//                                in line order, continuing the frame's stream.
+//   K8    line_mle_kernel        MLEstimateLine3d: dlevmar_dif m=6 (lm_core.c:438-847) + MleLine3dCov
+//                                (utils.cpp:1138-1159), one warp per kept line.
+// Floating-point sums follow the reference's order of operations (compiled with --fmad=false).
 #include "lsl_internal.h"
+#include "shared/lsl_linalg.h"
+#include "shared/lsl_math.h"
+#include "shared/lsl_rand.h"
+#include <float.h>
+
+using namespace lslm;
+
+#define FULL 0xffffffffu
+#define RANSAC_CH 8  // hypotheses evaluated per round
+
+struct LineParams {
+  double len2d_thres, sample_interval, collin_ratio, len3d_thres, mah_thres, support_ratio, depth_scaling;
+  double sigma_impt, c1, c2, c3, dt, fx, msld_step;
+  double Kinv[9];
+  int sample_min, sample_max, ransac_iters, ncells, mle_iters, msld_s;
+  int W, H;
+};
+
+__device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ double norm3(const double* a) { return sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); }
+
+// First-occurrence arg-min / arg-max of v over the set bits of mask[4] (point index order), with the
+// reference's initial values 100 / -100 (utils.cpp:587-600, 404-417). v(i) is evaluated by the caller's
+// functor. All 32 lanes of the warp participate; result uniform.
+template <class F>
+__device__ __forceinline__ void warp_argminmax(const uint32_t* mask, F v, int* imin, int* imax) {
+  const int lane = threadIdx.x & 31;
+  double lmin = 100.0, lmax = -100.0;
+  int kmin = 1 << 30, kmax = 1 << 30;
+  int first = 1 << 30;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    if ((mask[w] >> lane) & 1u) {
+      int i = w * 32 + lane;
+      if (first == (1 << 30)) first = i;
+      double x = v(i);
+      if (x < lmin) { lmin = x; kmin = i; }
+      if (x > lmax) { lmax = x; kmax = i; }
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    double t = __shfl_xor_sync(FULL, lmin, o);
+    int k = __shfl_xor_sync(FULL, kmin, o);
+    if (t < lmin || (t == lmin && k < kmin)) { lmin = t; kmin = k; }
+    t = __shfl_xor_sync(FULL, lmax, o);
+    k = __shfl_xor_sync(FULL, kmax, o);
+    if (t > lmax || (t == lmax && k < kmax)) { lmax = t; kmax = k; }
+    int f2 = __shfl_xor_sync(FULL, first, o);
+    if (f2 < first) first = f2;
+  }
+  *imin = (kmin == (1 << 30)) ? first : kmin;  // nothing below 100: index 0 of the list
+  *imax = (kmax == (1 << 30)) ? first : kmax;
+}
+
+// projectPt3d2Ln3d (utils.cpp:496-504) with a mid point and a direction
+__device__ __forceinline__ void project_pt(const double* P, const double* mid, const double* drct, double* out) {
+  double B[3] = {mid[0] + drct[0], mid[1] + drct[1], mid[2] + drct[2]};
+  double AB[3] = {B[0] - mid[0], B[1] - mid[1], B[2] - mid[2]};
+  double AP[3] = {P[0] - mid[0], P[1] - mid[1], P[2] - mid[2]};
+  double s = dot3(AB, AP) / dot3(AB, AB);
+  for (int k = 0; k < 3; ++k) out[k] = mid[k] + s * AB[k];
+}
+
+// verify3dLine (utils.cpp:570-624) on warp 0; mask = inlier set, A/B = the two sampled points
+__device__ bool verify3dLine(const double* s_pos, const uint32_t* mask, const double* A, const double* B, int nCells,
+                             double ratio) {
+  const int lane = threadIdx.x & 31;
+  double BA[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]};
+  int i1, i2;
+  warp_argminmax(mask, [&](int i) {
+    double d[3] = {s_pos[3 * i] - A[0], s_pos[3 * i + 1] - A[1], s_pos[3 * i + 2] - A[2]};
+    return dot3(d, BA);
+  }, &i1, &i2);
+  double mid[3] = {(A[0] + B[0]) * 0.5, (A[1] + B[1]) * 0.5, (A[2] + B[2]) * 0.5};
+  double C[3], D[3];
+  project_pt(s_pos + 3 * i1, mid, BA, C);
+  project_pt(s_pos + 3 * i2, mid, BA, D);
+  double DC[3] = {D[0] - C[0], D[1] - C[1], D[2] - C[2]};
+  double cd = norm3(DC);
+  if (cd < 1e-10) return false;
+  uint32_t cells = 0;
+#pragma unroll
+  for (int w = 0; w < 4; ++w)
+    if ((mask[w] >> lane) & 1u) {
+      int i = w * 32 + lane;
+      double XC[3] = {s_pos[3 * i] - C[0], s_pos[3 * i + 1] - C[1], s_pos[3 * i + 2] - C[2]};
+      double lambda = fabs(dot3(XC, DC) / cd / cd);
+      int c = (lambda >= 1) ? nCells - 1 : (int)floor(lambda * 10);
+      cells |= 1u << (c & 31);
+    }
+  for (int o = 16; o; o >>= 1) cells |= __shfl_xor_sync(FULL, cells, o);
+  double sum = 0;
+  for (int i = 0; i < nCells; ++i)
+    if ((cells >> i) & 1u) sum = sum + 1;
+  return sum / nCells > ratio;
+}
+
+// computeLine3d_svd (utils.cpp:471-493) over the set bits of mask, sums in index order. Warp 0, uniform result.
+__device__ void line3d_pca(const double* s_pos, const uint32_t* mask, int cnt, double* mean, double* drct) {
+  const int lane = threadIdx.x & 31;
+  // lanes 0..2: mean component; ordered accumulation
+  double acc = 0.0;
+  if (lane < 3) {
+    for (int w = 0; w < 4; ++w) {
+      uint32_t m = mask[w];
+      while (m) {
+        int b = __ffs(m) - 1;
+        m &= m - 1;
+        acc = acc + s_pos[3 * (w * 32 + b) + lane];
+      }
+    }
+    acc = acc * (1.0 / cnt);
+  }
+  mean[0] = __shfl_sync(FULL, acc, 0); mean[1] = __shfl_sync(FULL, acc, 1); mean[2] = __shfl_sync(FULL, acc, 2);
+  double s = 0.0;
+  if (lane < 9) {
+    int a = lane / 3, b2 = lane % 3;
+    for (int w = 0; w < 4; ++w) {
+      uint32_t m = mask[w];
+      while (m) {
+        int b = __ffs(m) - 1;
+        m &= m - 1;
+        const double* p = s_pos + 3 * (w * 32 + b);
+        s += (p[a] - mean[a]) * (p[b2] - mean[b2]);
+      }
+    }
+  }
+  double S[9], wv[3], V[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) S[k] = __shfl_sync(FULL, s, k);
+  jacobi_sym<3>(S, wv, V);
+  drct[0] = V[0]; drct[1] = V[3]; drct[2] = V[6];
+}
+
+__global__ void __launch_bounds__(128) line3d_ransac_kernel(LslWork w, LineParams P, const float* __restrict__ depth_all) {
+  __shared__ double s_pos[LSL_MAX_SMP * 3];
+  __shared__ double s_DU[LSL_MAX_SMP * 9];
+  __shared__ int s_idx[LSL_MAX_SMP];
+  __shared__ int s_hA[RANSAC_CH], s_hB[RANSAC_CH], s_hcnt[RANSAC_CH];
+  __shared__ uint32_t s_hmask[RANSAC_CH][4];
+  __shared__ uint32_t s_best[4];
+  __shared__ int s_wcnt[4];
+  __shared__ int s_flag[4];  // 0: done, 1: accepted
+  __shared__ GRand s_rng, s_snap;
+
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int W = P.W, H = P.H;
+  const float* depth = depth_all + (size_t)f * W * H;
+  const double* segs = w.segs + (size_t)f * LSL_MAX_SEGS * 5;
+  const int nsegs = min(w.nsegs[f], LSL_MAX_SEGS);
+  lsl_line_rec* lines = w.lines + (size_t)f * LSL_MAX_LINES;
+  int32_t* seg_of_line = w.keep_cand + (size_t)f * LSL_MAX_LINES;
+  int32_t* npts_out = w.npts + (size_t)f * LSL_MAX_LINES;
+  double* pts_out = w.pts + (size_t)f * LSL_MAX_LINES * LSL_MAX_SMP * 3;
+  int32_t* inl_out = w.inl_idx + (size_t)f * LSL_MAX_LINES * LSL_MAX_SMP;
+
+  if (tid == 0) grand_seed(&s_rng, w.seeds_rng[f]);
+  int nkept = 0;
+  __syncthreads();
+
+  for (int sidx = 0; sidx < nsegs; ++sidx) {
+    const double px = segs[sidx * 5 + 0], py = segs[sidx * 5 + 1], qx = segs[sidx * 5 + 2], qy = segs[sidx * 5 + 3];
+    const double ddx = px - qx, ddy = py - qy;
+    const double len = sqrt(ddx * ddx + ddy * ddy);
+    if (!(len > P.len2d_thres)) continue;  // lineslam.cpp:213-221 (uniform)
+    double numSmp = len / P.sample_interval;
+    if (numSmp < (double)P.sample_min) numSmp = (double)P.sample_min;  // std::max then std::min
+    if (numSmp > (double)P.sample_max) numSmp = (double)P.sample_max;
+    // ---- sampling + back-projection (lineslam.cpp:252-288), thread j = sample j
+    bool ok = false;
+    double pos[3] = {0, 0, 0};
+    if ((double)tid <= numSmp) {
+      const int j = tid;
+      double ptx = px * (1 - j / numSmp) + qx * (j / numSmp);
+      double pty = py * (1 - j / numSmp) + qy * (j / numSmp);
+      if (!(ptx < 0 || pty < 0 || ptx >= W || pty >= H)) {
+        int row, col;
+        if ((floor(ptx) == ptx) && (floor(pty) == pty)) {
+          col = max((int)(ptx - 1), 0);
+          row = max((int)(pty - 1), 0);
+        } else { col = (int)ptx; row = (int)pty; }
+        float dv = __ldg(depth + (size_t)row * W + col);
+        double depval = (double)dv;
+        if (!(depval < 1e-10 || isnan(dv))) {
+          double zval = depval / P.depth_scaling;
+          if (zval > 0) {
+            double x0 = P.Kinv[0] * ptx + P.Kinv[1] * pty + P.Kinv[2] * 1.0;
+            double x1 = P.Kinv[3] * ptx + P.Kinv[4] * pty + P.Kinv[5] * 1.0;
+            double x2 = P.Kinv[6] * ptx + P.Kinv[7] * pty + P.Kinv[8] * 1.0;
+            double inv = 1.0 / x2;
+            x0 = x0 * inv; x1 = x1 * inv;
+            pos[0] = x0 * zval; pos[1] = x1 * zval; pos[2] = zval;
+            ok = true;
+          }
+        }
+      }
+    }
+    unsigned bm = __ballot_sync(FULL, ok);
+    if (lane == 0) s_wcnt[warp] = __popc(bm);
+    __syncthreads();
+    int base = 0;
+    for (int k = 0; k < warp; ++k) base += s_wcnt[k];
+    const int n = s_wcnt[0] + s_wcnt[1] + s_wcnt[2] + s_wcnt[3];
+    double thr_n = numSmp * P.collin_ratio;
+    if (thr_n < 10.0) thr_n = 10.0;
+    if ((double)n < thr_n) { __syncthreads(); continue; }  // lineslam.cpp:289 (uniform)
+    if (ok) {
+      int k = base + __popc(bm & ((1u << lane) - 1u));
+      double cov[9], DU[9], Ws[3];
+      pt3d_cov(pos, P.fx, P.sigma_impt, P.c1, P.c2, P.c3, P.dt, cov);
+      cov_to_DU(cov, DU, Ws);
+      s_pos[3 * k] = pos[0]; s_pos[3 * k + 1] = pos[1]; s_pos[3 * k + 2] = pos[2];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) s_DU[9 * k + q] = DU[q];
+    }
+    if (tid < n) s_idx[tid] = tid;
+    if (tid < 4) s_best[tid] = 0;
+    __syncthreads();
+
+    // ---- RANSAC (utils.cpp:343-398)
+    const int maxIter = min(P.ransac_iters, (int)(n * (n - 1) * 0.5));
+    int best_cnt = 0, bestA = -1, bestB = -1;  // maintained uniformly by warp 0
+    bool done = false;
+    for (int it0 = 0; it0 < maxIter && !done; it0 += RANSAC_CH) {
+      const int nch = min(RANSAC_CH, maxIter - it0);
+      if (tid == 0) {
+        s_snap = s_rng;
+        for (int h = 0; h < nch; ++h) {
+          int left = n;
+          for (int k = 0; k < 2; ++k) {  // random_unique(begin, end, 2), utils.h:49-60
+            int r = grand_next(&s_rng) % left;
+            int t = s_idx[k]; s_idx[k] = s_idx[k + r]; s_idx[k + r] = t;
+            --left;
+          }
+          s_hA[h] = s_idx[0]; s_hB[h] = s_idx[1];
+        }
+      }
+      __syncthreads();
+      for (int h = warp; h < nch; h += 4) {
+        const double* A = s_pos + 3 * s_hA[h];
+        const double* B = s_pos + 3 * s_hB[h];
+        double BA[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]};
+        bool degenerate = norm3(BA) < 1e-10;
+        int cnt = 0;
+#pragma unroll
+        for (int wd = 0; wd < 4; ++wd) {
+          int i = wd * 32 + lane;
+          bool in = false;
+          if (i < n && !degenerate) in = mah_dist3d_pt_line(s_pos + 3 * i, s_DU + 9 * i, A, B) < P.mah_thres;
+          unsigned m = __ballot_sync(FULL, in);
+          if (lane == 0) s_hmask[h][wd] = m;
+          cnt += __popc(m);
+        }
+        if (lane == 0) s_hcnt[h] = degenerate ? -1 : cnt;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        int hexit = -1;
+        for (int h = 0; h < nch; ++h) {
+          int c = s_hcnt[h];
+          if (c < 0) continue;
+          if (c > best_cnt) {
+            if (verify3dLine(s_pos, s_hmask[h], s_pos + 3 * s_hA[h], s_pos + 3 * s_hB[h], P.ncells, P.support_ratio)) {
+              best_cnt = c; bestA = s_hA[h]; bestB = s_hB[h];
+              if (lane < 4) s_best[lane] = s_hmask[h][lane];
+              __syncwarp();
+            }
+          }
+          if ((double)best_cnt > n * 0.9) { hexit = h; break; }
+        }
+        if (hexit >= 0) {
+          done = true;
+          if (lane == 0 && hexit != nch - 1) {  // give back the draws of the hypotheses never visited
+            s_rng = s_snap;
+            for (int k = 0; k < 2 * (hexit + 1); ++k) grand_next(&s_rng);
+          }
+        }
+        if (lane == 0) s_flag[0] = done ? 1 : 0;
+      }
+      __syncthreads();
+      done = s_flag[0] != 0;
+    }
+
+    // ---- refit loop, end points, acceptance (utils.cpp:399-427, lineslam.cpp:302-307): warp 0
+    if (warp == 0) {
+      bool accept = false;
+      double A3[3] = {0, 0, 0}, B3[3] = {0, 0, 0};
+      if (best_cnt >= 2) {
+        double m[3], d[3];
+        for (int k = 0; k < 3; ++k) {
+          m[k] = (s_pos[3 * bestA + k] + s_pos[3 * bestB + k]) * 0.5;
+          d[k] = s_pos[3 * bestB + k] - s_pos[3 * bestA + k];
+        }
+        uint32_t cur[4] = {s_best[0], s_best[1], s_best[2], s_best[3]};
+        while (true) {
+          double tm[3], td[3], q2[3];
+          line3d_pca(s_pos, cur, best_cnt, tm, td);
+          for (int k = 0; k < 3; ++k) q2[k] = tm[k] + td[k];
+          uint32_t nm[4];
+          int cnt = 0;
+#pragma unroll
+          for (int wd = 0; wd < 4; ++wd) {
+            int i = wd * 32 + lane;
+            bool in = false;
+            if (i < n) in = mah_dist3d_pt_line(s_pos + 3 * i, s_DU + 9 * i, tm, q2) < P.mah_thres;
+            nm[wd] = __ballot_sync(FULL, in);
+            cnt += __popc(nm[wd]);
+          }
+          if (cnt > best_cnt) {
+            best_cnt = cnt;
+            for (int k = 0; k < 4; ++k) cur[k] = nm[k];
+            for (int k = 0; k < 3; ++k) { m[k] = tm[k]; d[k] = td[k]; }
+          } else break;
+        }
+        int e1, e2;
+        warp_argminmax(cur, [&](int i) {
+          double pm[3] = {s_pos[3 * i] - m[0], s_pos[3 * i + 1] - m[1], s_pos[3 * i + 2] - m[2]};
+          return dot3(pm, d);
+        }, &e1, &e2);
+        for (int k = 0; k < 3; ++k) { A3[k] = s_pos[3 * e1 + k]; B3[k] = s_pos[3 * e2 + k]; }
+        if (lane < 4) s_best[lane] = cur[lane];
+        double dAB[3] = {A3[0] - B3[0], A3[1] - B3[1], A3[2] - B3[2]};
+        accept = ((double)best_cnt / numSmp > P.collin_ratio) && (norm3(dAB) > P.len3d_thres);
+      }
+      if (accept && nkept < LSL_MAX_LINES && lane == 0) {
+        lsl_line_rec* L = lines + nkept;
+        L->p[0] = px; L->p[1] = py; L->q[0] = qx; L->q[1] = qy;
+        for (int k = 0; k < 3; ++k) { L->A[k] = A3[k]; L->B[k] = B3[k]; }
+        L->lid = nkept; L->haveDepth = 1;
+        // complineEq2d (lineslam.h:139-150)
+        double l0 = py * 1 - 1 * qy, l1 = 1 * qx - px * 1, l2 = px * qy - py * qx;
+        double inv = 1. / sqrt(l0 * l0 + l1 * l1);
+        L->lineEq2d[0] = l0 * inv; L->lineEq2d[1] = l1 * inv; L->lineEq2d[2] = l2 * inv;
+        seg_of_line[nkept] = sidx;
+        npts_out[nkept] = best_cnt;
+      }
+      if (lane == 0) s_flag[1] = accept ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_flag[1]) {
+      if (nkept < LSL_MAX_LINES && tid < n) {
+        int wd = tid >> 5, b = tid & 31;
+        uint32_t m = s_best[wd];
+        if ((m >> b) & 1u) {
+          int k = __popc(m & ((1u << b) - 1u));
+          for (int q = 0; q < wd; ++q) k += __popc(s_best[q]);
+          double* o = pts_out + ((size_t)nkept * LSL_MAX_SMP + k) * 3;
+          o[0] = s_pos[3 * tid]; o[1] = s_pos[3 * tid + 1]; o[2] = s_pos[3 * tid + 2];
+          inl_out[(size_t)nkept * LSL_MAX_SMP + k] = tid;
+        }
+      }
+      ++nkept;  // counts past the table size so the host can report the overflow
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    w.nlines[f] = nkept;
+    int32_t* st = w.rng_state + (size_t)f * 36;
+    for (int k = 0; k < 31; ++k) st[k] = s_rng.r[k];
+    st[31] = s_rng.f; st[32] = s_rng.b;
+  }
+}
+
+// ------------------------------------------------------------------ MSLD ----
+// cv::norm of a CV_64F vector (see oracle_extract.cpp:cvnorm for the summation order)
+__device__ double cvnorm(const double* v, int len) {
+  double result = 0;
+  int i = 0;
+  for (; i <= len - 4; i += 4) {
+    double v0 = v[i], v1 = v[i + 1];
+    result += v0 * v0 + v1 * v1;
+    v0 = v[i + 2]; v1 = v[i + 3];
+    result += v0 * v0 + v1 * v1;
+  }
+  for (; i < len; i++) result += v[i] * v[i];
+  return sqrt(result);
+}
+
+#define MSLD_CHUNK 32
+__global__ void __launch_bounds__(128) line_msld_kernel(LslWork w, LineParams P, int32_t* __restrict__ msld_fail) {
+  __shared__ double s_g[MSLD_CHUNK][36];
+  __shared__ uint8_t s_ok[MSLD_CHUNK];
+  __shared__ long long s_sum[2];
+  __shared__ double s_ms[72];
+  const int f = blockIdx.y, tid = threadIdx.x;
+  const int nl = min(w.nlines[f], LSL_MAX_LINES);
+  const int W = P.W, H = P.H;
+  for (int li = blockIdx.x; li < nl; li += gridDim.x) {
+  __syncthreads();
+  lsl_line_rec* L = w.lines + (size_t)f * LSL_MAX_LINES + li;
+  const int16_t* GX = w.gx + (size_t)f * W * H;
+  const int16_t* GY = w.gy + (size_t)f * W * H;
+  const double px = L->p[0], py = L->p[1], qx = L->q[0], qy = L->q[1];
+  // ---- getGradient: integer sums over the 8-connected Bresenham line (cv::LineIterator)
+  if (tid < 2) s_sum[tid] = 0;
+  __syncthreads();
+  {
+    int x1 = (int)nearbyint(px), y1 = (int)nearbyint(py), x2 = (int)nearbyint(qx), y2 = (int)nearbyint(qy);
+    long long sx = 0, sy = 0;
+    if ((unsigned)x1 < (unsigned)W && (unsigned)x2 < (unsigned)W && (unsigned)y1 < (unsigned)H && (unsigned)y2 < (unsigned)H) {
+      int dx = x2 - x1, dy = y2 - y1;
+      int stx = dx < 0 ? -1 : 1, sty = dy < 0 ? -1 : 1;
+      dx = dx < 0 ? -dx : dx; dy = dy < 0 ? -dy : dy;
+      bool steep = dy > dx;
+      int dmaj = steep ? dy : dx, dmin = steep ? dx : dy;
+      // pixel i: i steps along the major axis and m_i = floor((2 dmin i + dmaj - 1) / (2 dmaj)) along the
+      // minor axis (closed form of the error recurrence err += -2dmin + (2dmaj & mask))
+      for (int i = tid; i <= dmaj; i += blockDim.x) {
+        int m = (i == 0 || dmaj == 0) ? 0 : (int)((2LL * dmin * i + dmaj - 1) / (2LL * dmaj));
+        int x = steep ? x1 + stx * m : x1 + stx * i;
+        int y = steep ? y1 + sty * i : y1 + sty * m;
+        sx += GX[(size_t)y * W + x];
+        sy += GY[(size_t)y * W + x];
+      }
+    }
+    for (int o = 16; o; o >>= 1) { sx += __shfl_xor_sync(FULL, sx, o); sy += __shfl_xor_sync(FULL, sy, o); }
+    if ((tid & 31) == 0) { atomicAdd((unsigned long long*)&s_sum[0], (unsigned long long)sx); atomicAdd((unsigned long long*)&s_sum[1], (unsigned long long)sy); }
+  }
+  __syncthreads();
+  const double xSum = (double)s_sum[0], ySum = (double)s_sum[1];
+  const double glen = sqrt(xSum * xSum + ySum * ySum);
+  const double rx = xSum / glen, ry = ySum / glen;
+  if (tid == 0) { L->r[0] = rx; L->r[1] = ry; }
+  // ---- computeMSLD
+  const int s = P.msld_s;
+  const double sd = (double)s;
+  const double ddx = px - qx, ddy = py - qy;
+  const double len = sqrt(ddx * ddx + ddy * ddy);
+  const double step = P.msld_step;
+  const double gauss[9] = {0.24142, 0.30046, 0.35127, 0.38579, 0.39804, 0.38579, 0.35127, 0.30046, 0.24142};
+  double sum = 0, sum2 = 0;  // threads 0..35: one descriptor dimension each
+  int nvalid = 0;
+  for (int i0 = 0; i0 * step < len; i0 += MSLD_CHUNK) {
+    if (tid < MSLD_CHUNK) s_ok[tid] = 1;
+    __syncthreads();
+    for (int it = tid; it < MSLD_CHUNK * 9; it += blockDim.x) {
+      int ii = it / 9, jj = it - ii * 9;
+      int i = i0 + ii;
+      if (!(i * step < len)) continue;
+      double fr = i * step / len;
+      double ptx = px + (qx - px) * fr, pty = py + (qy - py) * fr;
+      int js = (jj - 4) * s;
+      double cx = ptx + js * rx, cy = pty + js * ry;
+      // computeSubPSR (utils.cpp:1510-1542)
+      double tl_x = floor(cx - sd / 2), tl_y = floor(cy - sd / 2);
+      if (tl_x < 0 || tl_y < 0 || tl_x + sd + 1 > W || tl_y + sd + 1 > H) { s_ok[ii] = 0; continue; }
+      double v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+      // (a NaN polarity passes the test above like in the reference; its loops then run zero times)
+      if (tl_x == tl_x && tl_y == tl_y)
+      for (int y = (int)tl_y; y < tl_y + sd; ++y)
+        for (int x = (int)tl_x; x < tl_x + sd; ++x) {
+          double gxv = (double)GX[(size_t)y * W + x], gyv = (double)GY[(size_t)y * W + x];
+          double tmp1 = gxv * rx + gyv * ry;
+          double tmp2 = gxv * (-ry) + gyv * rx;
+          if (tmp1 >= 0) v1 = v1 + tmp1; else v2 = v2 - tmp1;
+          if (tmp2 >= 0) v3 = v3 + tmp2; else v4 = v4 - tmp2;
+        }
+      s_g[ii][jj * 4 + 0] = v1; s_g[ii][jj * 4 + 1] = v2; s_g[ii][jj * 4 + 2] = v3; s_g[ii][jj * 4 + 3] = v4;
+    }
+    __syncthreads();
+    if (tid < 36) {
+      for (int ii = 0; ii < MSLD_CHUNK; ++ii) {
+        int i = i0 + ii;
+        if (!(i * step < len)) break;
+        if (!s_ok[ii]) continue;
+        double g = s_g[ii][tid] * gauss[tid / 4];
+        sum += g;
+        sum2 += g * g;
+        ++nvalid;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid < 36) {
+    if (nvalid > 0) {
+      double mean = sum / (double)(size_t)nvalid;
+      double sdv = sqrt(sum2 / (double)(size_t)nvalid - mean * mean);
+      s_ms[tid] = mean; s_ms[tid + 36] = sdv;
+    }
+    if (tid == 0) msld_fail[(size_t)f * LSL_MAX_LINES + li] = nvalid > 0 ? 0 : 1;
+  }
+  __syncthreads();
+  if (tid == 0 && nvalid > 0) {
+    double a = 1. / cvnorm(s_ms, 36), b = 1. / cvnorm(s_ms + 36, 36);
+    for (int i = 0; i < 36; ++i) { s_ms[i] = s_ms[i] * a; s_ms[i + 36] = s_ms[i + 36] * b; }
+    for (int i = 0; i < 72; ++i)
+      if (s_ms[i] > 0.4) s_ms[i] = 0.4;
+    double c = 1. / cvnorm(s_ms, 72);
+    for (int i = 0; i < 72; ++i) L->des[i] = s_ms[i] * c;
+  }
+  }
+}
+
+__global__ void msld_randfill_kernel(LslWork w, const int32_t* __restrict__ msld_fail, int nframes) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nframes) return;
+  const int nl = min(w.nlines[f], LSL_MAX_LINES);
+  const int32_t* fl = msld_fail + (size_t)f * LSL_MAX_LINES;
+  bool any = false;
+  for (int i = 0; i < nl; ++i) any |= fl[i] != 0;
+  if (!any) return;
+  GRand g;
+  int32_t* st = w.rng_state + (size_t)f * 36;
+  for (int k = 0; k < 31; ++k) g.r[k] = st[k];
+  g.f = st[31]; g.b = st[32];
+  for (int i = 0; i < nl; ++i)
+    if (fl[i]) {
+      lsl_line_rec* L = w.lines + (size_t)f * LSL_MAX_LINES + i;
+      for (int k = 0; k < 72; ++k) L->des[k] = (double)grand_next(&g);
+    }
+  for (int k = 0; k < 31; ++k) st[k] = g.r[k];
+  st[31] = g.f; st[32] = g.b;
+}
+
+// ------------------------------------------------------------------- MLE ----
+struct MleSmem {
+  double pos[LSL_MAX_SMP * 3];
+  double DU[LSL_MAX_SMP * 9];
+  double hx[LSL_MAX_SMP], e[LSL_MAX_SMP], wrk[LSL_MAX_SMP], wrk2[LSL_MAX_SMP];
+  double jac[LSL_MAX_SMP * 6];
+  double JtJ[36], Jte[6];
+  double cinv1[9], cinv2[9];
+  double Jt[32 * 18];
+};
+
+// costFun_MLEstimateLine3d (utils.cpp:954-978): lanes stride over the points
+__device__ __forceinline__ void mle_cost(const MleSmem& S, int n, int idx1, int idx2, const double* p, double* out) {
+  const int lane = threadIdx.x & 31;
+  for (int i = lane; i < n; i += 32) {
+    double r;
+    if (i == idx1) r = mah_sq_pt(p, S.pos + 3 * i, S.cinv1);
+    else if (i == idx2) r = mah_sq_pt(p + 3, S.pos + 3 * i, S.cinv2);
+    else r = mah_dist3d_pt_line(S.pos + 3 * i, S.DU + 9 * i, p, p + 3);
+    out[i] = r;
+  }
+  __syncwarp();
+}
+
+// LEVMAR_L2NRMXMY with x = 0 (misc_core.c:721-809): e = 0 - y, four interleaved accumulators walking
+// downwards in blocks of 8, remainder upwards. Every lane evaluates the same sequence (uniform result).
+__device__ double l2nrm_neg(double* e, const double* y, int n) {
+  const int lane = threadIdx.x & 31;
+  for (int i = lane; i < n; i += 32) e[i] = 0.0 - y[i];
+  __syncwarp();
+  double sum0 = 0.0, sum1 = 0.0, sum2 = 0.0, sum3 = 0.0;
+  int blockn = (n >> 3) << 3;
+  for (int i = blockn - 1; i > 0; i -= 8) {
+    sum0 += e[i] * e[i]; sum1 += e[i - 1] * e[i - 1]; sum2 += e[i - 2] * e[i - 2]; sum3 += e[i - 3] * e[i - 3];
+    sum0 += e[i - 4] * e[i - 4]; sum1 += e[i - 5] * e[i - 5]; sum2 += e[i - 6] * e[i - 6]; sum3 += e[i - 7] * e[i - 7];
+  }
+  int i = blockn;
+  if (i < n) {
+    switch (n - i) {
+      case 7: sum0 += e[i] * e[i]; ++i;
+      case 6: sum1 += e[i] * e[i]; ++i;
+      case 5: sum2 += e[i] * e[i]; ++i;
+      case 4: sum3 += e[i] * e[i]; ++i;
+      case 3: sum0 += e[i] * e[i]; ++i;
+      case 2: sum1 += e[i] * e[i]; ++i;
+      case 1: sum2 += e[i] * e[i];
+    }
+  }
+  return sum0 + sum1 + sum2 + sum3;
+}
+
+// AX_EQ_B_LU for m = 6 (Axb_core.c:1140-1277), executed identically by every lane
+__device__ int ax_eq_b_lu6(const double* A, const double* B, double* x) {
+  const int m = 6;
+  double a[36], work[6];
+  int idx[6];
+  int maxi = -1;
+  for (int i = 0; i < 36; ++i) a[i] = A[i];
+  for (int i = 0; i < m; ++i) x[i] = B[i];
+  for (int i = 0; i < m; ++i) {
+    double max = 0.0, tmp;
+    for (int j = 0; j < m; ++j)
+      if ((tmp = fabs(a[i * m + j])) > max) max = tmp;
+    if (max == 0.0) return 0;
+    work[i] = 1.0 / max;
+  }
+  for (int j = 0; j < m; ++j) {
+    for (int i = 0; i < j; ++i) {
+      double sum = a[i * m + j];
+      for (int k = 0; k < i; ++k) sum -= a[i * m + k] * a[k * m + j];
+      a[i * m + j] = sum;
+    }
+    double max = 0.0, tmp;
+    for (int i = j; i < m; ++i) {
+      double sum = a[i * m + j];
+      for (int k = 0; k < j; ++k) sum -= a[i * m + k] * a[k * m + j];
+      a[i * m + j] = sum;
+      if ((tmp = work[i] * fabs(sum)) >= max) { max = tmp; maxi = i; }
+    }
+    if (j != maxi) {
+      for (int k = 0; k < m; ++k) { double t = a[maxi * m + k]; a[maxi * m + k] = a[j * m + k]; a[j * m + k] = t; }
+      work[maxi] = work[j];
+    }
+    idx[j] = maxi;
+    if (a[j * m + j] == 0.0) a[j * m + j] = DBL_EPSILON;
+    if (j != m - 1) {
+      double tmp2 = 1.0 / (a[j * m + j]);
+      for (int i = j + 1; i < m; ++i) a[i * m + j] *= tmp2;
+    }
+  }
+  int k = 0;
+  for (int i = 0; i < m; ++i) {
+    int j = idx[i];
+    double sum = x[j];
+    x[j] = x[i];
+    if (k != 0)
+      for (j = k - 1; j < i; ++j) sum -= a[i * m + j] * x[j];
+    else if (sum != 0.0) k = i + 1;
+    x[i] = sum;
+  }
+  for (int i = m - 1; i >= 0; --i) {
+    double sum = x[i];
+    for (int j = i + 1; j < m; ++j) sum -= a[i * m + j] * x[j];
+    x[i] = sum / a[i * m + i];
+  }
+  return 1;
+}
+
+__global__ void __launch_bounds__(32) line_mle_kernel(LslWork w, LineParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MleSmem& S = *reinterpret_cast<MleSmem*>(smem_raw);
+  const int f = blockIdx.y, lane = threadIdx.x;
+  const int nl = min(w.nlines[f], LSL_MAX_LINES);
+  for (int li = blockIdx.x; li < nl; li += gridDim.x) {
+  __syncwarp();
+  lsl_line_rec* L = w.lines + (size_t)f * LSL_MAX_LINES + li;
+  const int n = w.npts[(size_t)f * LSL_MAX_LINES + li];
+  const double* gp = w.pts + ((size_t)f * LSL_MAX_LINES + li) * LSL_MAX_SMP * 3;
+  const int m = 6;
+  // points + their covariance factors (recomputed: same functions as the RANSAC stage)
+  for (int i = lane; i < n; i += 32) {
+    double pos[3] = {gp[3 * i], gp[3 * i + 1], gp[3 * i + 2]}, cov[9], DU[9], Ws[3];
+    pt3d_cov(pos, P.fx, P.sigma_impt, P.c1, P.c2, P.c3, P.dt, cov);
+    cov_to_DU(cov, DU, Ws);
+    for (int k = 0; k < 3; ++k) S.pos[3 * i + k] = pos[k];
+    for (int k = 0; k < 9; ++k) S.DU[9 * i + k] = DU[k];
+  }
+  __syncwarp();
+  // end points: extreme inliers along A0 - B0, ordered by index (utils.cpp:985-999)
+  double A0[3] = {L->A[0], L->A[1], L->A[2]}, B0[3] = {L->B[0], L->B[1], L->B[2]};
+  double AB[3] = {A0[0] - B0[0], A0[1] - B0[1], A0[2] - B0[2]};
+  uint32_t all[4];
+  for (int k = 0; k < 4; ++k) { int rem = n - 32 * k; all[k] = rem >= 32 ? FULL : (rem > 0 ? ((1u << rem) - 1u) : 0u); }
+  int idx1, idx2;
+  warp_argminmax(all, [&](int i) {
+    double d[3] = {S.pos[3 * i] - A0[0], S.pos[3 * i + 1] - A0[1], S.pos[3 * i + 2] - A0[2]};
+    return dot3(d, AB);
+  }, &idx1, &idx2);
+  if (idx1 > idx2) { int t = idx1; idx1 = idx2; idx2 = t; }
+  if (lane == 0) {
+    double cov[9];
+    pt3d_cov(S.pos + 3 * idx1, P.fx, P.sigma_impt, P.c1, P.c2, P.c3, P.dt, cov);
+    inv3(cov, S.cinv1);
+    pt3d_cov(S.pos + 3 * idx2, P.fx, P.sigma_impt, P.c1, P.c2, P.c3, P.dt, cov);
+    inv3(cov, S.cinv2);
+  }
+  __syncwarp();
+  double p[6], pDp[6], Dp[6], diag[6], jacTe[6];
+  for (int k = 0; k < 3; ++k) { p[k] = S.pos[3 * idx1 + k]; p[3 + k] = S.pos[3 * idx2 + k]; }
+
+  // ---- dlevmar_dif (lm_core.c:438-847); opts = {1e-3, 1e-10, 1e-20, 1e-20, 1e-6} (utils.cpp:1002-1008)
+  const double tau = 1E-03, eps1 = 1E-10, eps2 = 1E-20, eps2_sq = 1E-20 * 1E-20, eps3 = 1E-20, delta = 1E-06;
+  const int itmax = P.mle_iters;
+  double mu = 0, jacTe_inf = 0, p_L2 = 0, tmp, p_eL2, pDp_eL2, Dp_L2 = DBL_MAX, dF, dL;
+  int nu = 20, nu2, stop = 0, K = 10, updjac = 0, updp = 1, newjac = 0, k = 0;
+  int lm_ret = -1;
+  if (n >= m) {
+  mle_cost(S, n, idx1, idx2, p, S.hx);
+  p_eL2 = l2nrm_neg(S.e, S.hx, n);
+  if (!isfinite(p_eL2)) stop = 7;
+  for (k = 0; k < itmax && !stop; ++k) {
+    if (p_eL2 <= eps3) { stop = 6; break; }
+    if ((updp && nu > 16) || updjac == K) {
+      for (int j = 0; j < m; ++j) {  // LEVMAR_FDIF_FORW_JAC_APPROX (misc_core.c:137-172)
+        double d = 1E-04 * p[j];
+        d = fabs(d);
+        if (d < delta) d = delta;
+        double t = p[j];
+        p[j] += d;
+        mle_cost(S, n, idx1, idx2, p, S.wrk);
+        p[j] = t;
+        d = 1.0 / d;
+        for (int i = lane; i < n; i += 32) S.jac[i * m + j] = (S.wrk[i] - S.hx[i]) * d;
+      }
+      __syncwarp();
+      nu = 2; updjac = 0; updp = 0; newjac = 1;
+    }
+    if (newjac) {
+      newjac = 0;
+      // J^T J (lower triangle) and J^T e, each accumulator summed for l = n-1 .. 0 (lm_core.c:618-639)
+      if (lane < 27) {
+        double acc = 0.0;
+        if (lane < 21) {
+          int i = 0, r = lane;
+          while (r > i) { r -= i + 1; ++i; }  // lane -> (i, j), j <= i
+          int j = r;
+          for (int l = n; l-- > 0;) acc += S.jac[l * m + j] * S.jac[l * m + i];
+          S.JtJ[i * m + j] = acc; S.JtJ[j * m + i] = acc;
+        } else {
+          int i = lane - 21;
+          for (int l = n; l-- > 0;) acc += S.jac[l * m + i] * S.e[l];
+          S.Jte[i] = acc;
+        }
+      }
+      __syncwarp();
+      p_L2 = jacTe_inf = 0.0;
+      for (int i = 0; i < m; ++i) {
+        jacTe[i] = S.Jte[i];
+        if (jacTe_inf < (tmp = fabs(jacTe[i]))) jacTe_inf = tmp;
+        diag[i] = S.JtJ[i * m + i];
+        p_L2 += p[i] * p[i];
+      }
+    }
+    if (jacTe_inf <= eps1) { Dp_L2 = 0.0; stop = 1; break; }
+    if (k == 0) {
+      tmp = DBL_MIN;
+      for (int i = 0; i < m; ++i)
+        if (diag[i] > tmp) tmp = diag[i];
+      mu = tau * tmp;
+    }
+    {
+      double Aug[36];
+      for (int i = 0; i < 36; ++i) Aug[i] = S.JtJ[i];
+      for (int i = 0; i < m; ++i) Aug[i * m + i] = diag[i] + mu;
+      int issolved = ax_eq_b_lu6(Aug, jacTe, Dp);
+      if (issolved) {
+        Dp_L2 = 0.0;
+        for (int i = 0; i < m; ++i) { pDp[i] = p[i] + (tmp = Dp[i]); Dp_L2 += tmp * tmp; }
+        if (Dp_L2 <= eps2_sq * p_L2) { stop = 2; break; }
+        if (Dp_L2 >= (p_L2 + eps2) / (1E-12 * 1E-12)) { stop = 4; break; }
+        mle_cost(S, n, idx1, idx2, pDp, S.wrk);
+        pDp_eL2 = l2nrm_neg(S.wrk2, S.wrk, n);
+        if (!isfinite(pDp_eL2)) { stop = 7; break; }
+        dF = p_eL2 - pDp_eL2;
+        if (updp || dF > 0) {  // Broyden rank-one update of the Jacobian
+          for (int i = lane; i < n; i += 32) {
+            tmp = 0.0;
+            for (int l = 0; l < m; ++l) tmp += S.jac[i * m + l] * Dp[l];
+            tmp = (S.wrk[i] - S.hx[i] - tmp) / Dp_L2;
+            for (int j = 0; j < m; ++j) S.jac[i * m + j] += tmp * Dp[j];
+          }
+          __syncwarp();
+          ++updjac;
+          newjac = 1;
+        }
+        dL = 0.0;
+        for (int i = 0; i < m; ++i) dL += Dp[i] * (mu * Dp[i] + jacTe[i]);
+        if (dL > 0.0 && dF > 0.0) {
+          tmp = (2.0 * dF / dL - 1.0);
+          tmp = 1.0 - tmp * tmp * tmp;
+          mu = mu * ((tmp >= 0.3333333334) ? tmp : 0.3333333334);
+          nu = 2;
+          for (int i = 0; i < m; ++i) p[i] = pDp[i];
+          for (int i = lane; i < n; i += 32) { S.e[i] = S.wrk2[i]; S.hx[i] = S.wrk[i]; }
+          __syncwarp();
+          p_eL2 = pDp_eL2;
+          updp = 1;
+          continue;
+        }
+      }
+    }
+    mu *= nu;
+    nu2 = nu << 1;
+    if (nu2 <= nu) { stop = 5; break; }
+    nu = nu2;
+  }
+  if (k >= itmax) stop = 3;
+  lm_ret = (stop != 4 && stop != 7) ? k : -1;
+  }
+  // ---- MleLine3dCov (utils.cpp:1138-1159): H = sum_i J_i^T J_i in point / row order, cov = H^-1
+  {
+    double acc = 0.0;
+    int ha = 0, hb = 0;
+    if (lane < 21) { int i = 0, r = lane; while (r > i) { r -= i + 1; ++i; } ha = i; hb = r; }
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      int i = i0 + lane;
+      if (i < n) {
+        double J[18];
+        for (int q = 0; q < 18; ++q) J[q] = 0;
+        if (i == idx1) { for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) J[r * 6 + c] = -S.DU[9 * i + r * 3 + c]; }
+        else if (i == idx2) { for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) J[r * 6 + 3 + c] = -S.DU[9 * i + r * 3 + c]; }
+        else jac_rpt2ln(S.pos + 3 * i, S.DU + 9 * i, p, J);
+        for (int q = 0; q < 18; ++q) S.Jt[lane * 18 + q] = J[q];
+      }
+      __syncwarp();
+      if (lane < 21) {
+        int cnt = min(32, n - i0);
+        for (int q = 0; q < cnt; ++q)
+          for (int r = 0; r < 3; ++r) acc += S.Jt[q * 18 + r * 6 + ha] * S.Jt[q * 18 + r * 6 + hb];
+      }
+      __syncwarp();
+    }
+    if (lane < 21) { S.JtJ[ha * 6 + hb] = acc; S.JtJ[hb * 6 + ha] = acc; }
+    __syncwarp();
+    if (lane == 0) {
+      double Hm[36], cov[36];
+      for (int q = 0; q < 36; ++q) Hm[q] = S.JtJ[q];
+      inv_lu<6>(Hm, cov);
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) { L->covA[r * 3 + c] = cov[r * 6 + c]; L->covB[r * 3 + c] = cov[(r + 3) * 6 + 3 + c]; }
+      for (int q = 0; q < 3; ++q) { L->A[q] = p[q]; L->B[q] = p[3 + q]; }
+      w.lm_iters[(size_t)f * LSL_MAX_LINES + li] = lm_ret;
+    }
+    __syncwarp();
+    __threadfence_block();
+    if (lane < 2) {  // rndA / rndB: RandomPoint3d(pos, cov) (lineslam.h:59-81)
+      double cv[9], DU[9], Ws[3];
+      const double* src = lane ? L->covB : L->covA;
+      for (int q = 0; q < 9; ++q) cv[q] = src[q];
+      cov_to_DU(cv, DU, Ws);
+      double* dDU = lane ? L->DU_B : L->DU_A;
+      double* dW = lane ? L->Wsqrt_B : L->Wsqrt_A;
+      for (int q = 0; q < 9; ++q) dDU[q] = DU[q];
+      for (int q = 0; q < 3; ++q) dW[q] = Ws[q];
+    }
+  }
+  }
+}
+
 int lsl_launch_lines(lsl_ctx* ctx, int n, const float* d_depth, const double K[9], double dt) {
-  LSL_CUDA(cudaMemsetAsync(ctx->wk.nlines, 0, sizeof(int32_t) * n, ctx->stream));
+  const lsl_params& P = ctx->P;
+  const LslDims& d = ctx->dims;
+  LslWork& w = ctx->wk;
+  cudaStream_t st = ctx->stream;
+  LineParams LP;
+  LP.len2d_thres = P.line_2d_len_thres; LP.sample_interval = P.line_sample_interval; LP.collin_ratio = P.collin_pts_ratio;
+  LP.len3d_thres = P.line_3d_len_thres_m; LP.mah_thres = P.pt2line_mahdist_extractline;
+  LP.support_ratio = P.ratio_support_pts_on_line; LP.depth_scaling = P.depth_scaling;
+  LP.sigma_impt = P.stdev_sample_pt_imgline; LP.c1 = P.depth_stdev_coeff_c1; LP.c2 = P.depth_stdev_coeff_c2;
+  LP.c3 = P.depth_stdev_coeff_c3; LP.dt = dt; LP.fx = K[0]; LP.msld_step = P.msld_sample_interval;
+  inv3(K, LP.Kinv);  // Eigen 3x3 inverse of the global K (lineslam.cpp:241)
+  LP.sample_min = P.line_sample_min_num; LP.sample_max = P.line_sample_max_num; LP.ransac_iters = P.ransac_iters_extract_line;
+  LP.ncells = P.num_cells_lineseg_range; LP.mle_iters = P.line3d_mle_iter_num; LP.msld_s = d.msld_s;
+  LP.W = d.W; LP.H = d.H;
+  line3d_ransac_kernel<<<n, 128, 0, st>>>(w, LP, d_depth);
+  dim3 gl(256, n);
+  line_msld_kernel<<<gl, 128, 0, st>>>(w, LP, w.msld_fail);
+  msld_randfill_kernel<<<(n + 63) / 64, 64, 0, st>>>(w, w.msld_fail, n);
+  line_mle_kernel<<<gl, 32, sizeof(MleSmem), st>>>(w, LP);
+  ctx->stats.kernel_launches += 4;
+  LSL_CUDA(cudaGetLastError());
   return LSL_OK;
 }

@@ -66,6 +66,7 @@ static int carve(lsl_ctx* ctx, bool measure, size_t* total) {
   CARVE(seeds_rng, uint32_t, B);
   CARVE(rng_state, int32_t, (size_t)B * 36);
   CARVE(lm_iters, int32_t, (size_t)B * LSL_MAX_LINES);
+  CARVE(msld_fail, int32_t, (size_t)B * LSL_MAX_LINES);
   // tap tables
   if (!measure) ctx->taps.kx = (double*)(base + off); off += align_up(sizeof(double) * sw * 8);
   if (!measure) ctx->taps.xc = (int*)(base + off); off += align_up(sizeof(int) * sw);
@@ -91,7 +92,8 @@ extern "C" int lsl_ctx_create(lsl_ctx** out, const lsl_params* params, int cuda_
   memset(&ctx->stats, 0, sizeof(ctx->stats));
   memset(&ctx->dims, 0, sizeof(ctx->dims));
   ctx->ms_total = ctx->ms_rg = 0.f;
-  if (ctx->P.lsd_n_bins > 4096 || ctx->P.line_sample_max_num + 1 > LSL_MAX_SMP) { delete ctx; return LSL_ERR_ARG; }
+  if (ctx->P.lsd_n_bins > 4096 || ctx->P.line_sample_max_num + 1 > LSL_MAX_SMP || ctx->P.num_cells_lineseg_range > 32 ||
+      ctx->P.num_cells_lineseg_range < 10) { delete ctx; return LSL_ERR_ARG; }
   cudaError_t e = cudaSetDevice(cuda_device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);

@@ -58,6 +58,7 @@ struct LslWork {
   uint32_t* seeds_rng; // [B]
   int32_t* rng_state;  // [B][36] glibc TYPE_3 state carried from the RANSAC stage to the MSLD stage
   int32_t* lm_iters;   // [B][LSL_MAX_LINES]
+  int32_t* msld_fail;  // [B][LSL_MAX_LINES] 1 = descriptor has no valid sample (filled from rand())
 };
 
 struct lsl_frame {
