@@ -116,6 +116,11 @@ int lsl_match_pair_batch(lsl_ctx* ctx, int npairs, const lsl_frame* const* queri
                          const int32_t* id_query, const int32_t* id_train, const uint32_t* seeds,
                          lsl_pose_rec* out);
 
+/* Match lists of pair `pair` of the last lsl_match_pair_batch call: what = 0 all line matches
+ * (Node::lineMatching output), 1 refined inliers (output_line_inlier_matches), 2 inliers of the best
+ * RANSAC hypothesis (max_line_inlier_set, motion.cpp:714-721). */
+int lsl_pair_matches(lsl_ctx* ctx, int pair, int what, lsl_match* out, int cap, int* n);
+
 /* Graph-insert-time exchange: all ranks contribute nlocal records and receive
  * nranks*nlocal. nccl_comm is an ncclComm_t created by the host; NCCL is resolved with dlopen. */
 int lsl_allgather_poses(lsl_ctx* ctx, void* nccl_comm, int nranks, const lsl_pose_rec* local_recs, int nlocal,
@@ -134,6 +139,9 @@ int lsl_last_timing(const lsl_ctx* ctx, float* ms_total, float* ms_region_grow);
  * what: 0 gray u8[H*W], 1 scaled f64[sh*sw], 2 angles f64, 3 modgrad f64, 4 seeds i32 (x|y<<16),
  *       5 gx i16[H*W], 6 gy i16[H*W]. Returns the number of elements copied (or <0). */
 int64_t lsl_debug_read(lsl_ctx* ctx, int what, void* dst, int64_t cap_bytes);
+/* Per-line intermediates of a frame for parity tests: 3D-RANSAC inlier counts [n], inlier sample
+ * indices [n][101], LSD segment index of each kept line [n], levmar iteration counts [n]. */
+int lsl_frame_debug(const lsl_frame* f, int32_t* npts, int32_t* inl_idx, int32_t* seg_of_line, int32_t* lm_iters);
 
 #ifdef __cplusplus
 }

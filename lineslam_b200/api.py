@@ -156,15 +156,24 @@ class Context:
         return rec[0].copy(), inl[:n1.value].copy(), rinl[:n2.value].copy()
 
     def match_pair_batch(self, queries, trains, id_query, id_train, seeds):
+        """Node::matchNodePair for a batch of independent pairs (graph_manager.cpp:555). Returns POSE_DTYPE[n]."""
         n = len(queries)
-        q = (C.c_void_p * n)(*[f._h.value if isinstance(f._h, C.c_void_p) else f._h for f in queries])
-        t = (C.c_void_p * n)(*[f._h.value if isinstance(f._h, C.c_void_p) else f._h for f in trains])
+        q = (C.c_void_p * n)(*[f._h.value for f in queries])
+        t = (C.c_void_p * n)(*[f._h.value for f in trains])
         iq = np.ascontiguousarray(id_query, np.int32)
         it = np.ascontiguousarray(id_train, np.int32)
         sd = np.ascontiguousarray(seeds, np.uint32)
         out = np.zeros(n, POSE_DTYPE)
         _check(lib().lsl_match_pair_batch(self._h, n, q, t, ptr(iq), ptr(it), ptr(sd), ptr(out)), self._h)
         return out
+
+    def pair_matches(self, pair: int, what: int):
+        """Lists of the last match_pair_batch call: what 0 = all matches, 1 = refined inliers, 2 = RANSAC inliers."""
+        k = C.c_int(0)
+        lib().lsl_pair_matches(self._h, pair, what, None, 0, C.byref(k))
+        out = np.zeros(max(k.value, 1), MATCH_DTYPE)
+        _check(lib().lsl_pair_matches(self._h, pair, what, ptr(out), len(out), C.byref(k)), self._h)
+        return out[:k.value].copy()
 
     # ---- introspection --------------------------------------------------------------------
     def stats(self) -> Stats:

@@ -1,1 +1,740 @@
+// k_pair.cu — pair registration on the device, one CTA per (query, train) pair (sm_100a):
+//   K9  match_lines_kernel  Node::lineMatching (src/node.cpp:1619-1694): gated 72-D descriptor distance
+//                           matrix (f64, cv::norm summation order), mutual first-minimum + 0.7 ratio test.
+//   K10 pose_kernel         getTransform_PtsLines_ransac, line matches (src/line/motion.cpp:605-849):
+//                           500 minimal solves (getTransform_Line_svd / computeRelativeMotion_svd,
+//                           motion.cpp:315-365, 581-603), scoring of every hypothesis against every match
+//                           (float transform, f64 Mahalanobis, motion.cpp:688-699), first-best selection,
+//                           then the iterated refinement with the native g2o-style LM
+//                           (getTransformFromHybridMatchesG2O, src/transformation_estimation.cpp:218-461;
+//                           EdgeSE3LineEndpts::computeError, src/line/edge_se3_lineendpts.cpp:146-189).
+// Pairs are independent (GraphManager::nodeComparisons maps over them, src/graph_manager.cpp:555), so a
+// batch of pairs is a grid of CTAs. Sums that feed decisions run in the reference's order.
 #include "lsl_internal.h"
+#include "shared/lsl_linalg.h"
+#include "shared/lsl_math.h"
+#include "shared/lsl_rand.h"
+#include <float.h>
+
+using namespace lslm;
+
+#define FULL 0xffffffffu
+#define POSE_THREADS 512
+#define MD_STRIDE 72  // doubles of gathered data per match
+
+// ------------------------------------------------------------ lineMatching ----
+__device__ __forceinline__ double cvnorm_diff72(const double* a, const double* b) {
+  double result = 0;
+  for (int i = 0; i < 72; i += 4) {
+    double v0 = a[i] - b[i], v1 = a[i + 1] - b[i + 1];
+    result += v0 * v0 + v1 * v1;
+    v0 = a[i + 2] - b[i + 2]; v1 = a[i + 3] - b[i + 3];
+    result += v0 * v0 + v1 * v1;
+  }
+  return sqrt(result);
+}
+__device__ __forceinline__ double pt_to_line_dist2d(const double* p, const double* l) {  // utils.cpp:1250-1264
+  double a = l[0], b = l[1], c = l[2], x = p[0], y = p[1];
+  return fabs((a * x + b * y + c)) / sqrt(a * a + b * b);
+}
+__device__ __forceinline__ double norm2d(double x, double y) { return sqrt(x * x + y * y); }
+__device__ __forceinline__ double project2d(const double* X, const double* A, const double* B) {  // utils.cpp:1612-1618
+  double BX[2] = {X[0] - B[0], X[1] - B[1]}, BA[2] = {A[0] - B[0], A[1] - B[1]};
+  double n = norm2d(BA[0], BA[1]);
+  return (BX[0] * BA[0] + BX[1] * BA[1]) / n / n;
+}
+__device__ double lineSegmentOverlap(const lsl_line_rec& a, const lsl_line_rec& b) {  // utils.cpp:1620-1638
+  double la = norm2d(a.p[0] - a.q[0], a.p[1] - a.q[1]), lb = norm2d(b.p[0] - b.q[0], b.p[1] - b.q[1]);
+  if (la < lb) {
+    double lp = project2d(a.p, b.p, b.q), lq = project2d(a.q, b.p, b.q);
+    if ((lp < 0 && lq < 0) || (lp > 1 && lq > 1)) return -1;
+    return fabs(lp - lq) * lb;
+  } else {
+    double lp = project2d(b.p, a.p, a.q), lq = project2d(b.q, a.p, a.q);
+    if ((lp < 0 && lq < 0) || (lp > 1 && lq > 1)) return -1;
+    return fabs(lp - lq) * la;
+  }
+}
+
+// first-minimum (cv::minMaxLoc) of D[base + k*stride], k < n, over the warp; returns value, *arg = index
+__device__ __forceinline__ double warp_first_min(const double* D, size_t stride, int n, int* arg) {
+  const int lane = threadIdx.x & 31;
+  double best = 1e300;
+  int bi = 1 << 30;
+  for (int k = lane; k < n; k += 32) {
+    double v = D[(size_t)k * stride];
+    if (v < best) { best = v; bi = k; }
+  }
+  for (int o = 16; o; o >>= 1) {
+    double t = __shfl_xor_sync(FULL, best, o);
+    int k = __shfl_xor_sync(FULL, bi, o);
+    if (t < best || (t == best && k < bi)) { best = t; bi = k; }
+  }
+  *arg = bi;
+  return best;
+}
+// min over k != skip, starting from 100 (node.cpp:1670-1679)
+__device__ __forceinline__ double warp_min_except(const double* D, size_t stride, int n, int skip) {
+  const int lane = threadIdx.x & 31;
+  double best = 100;
+  for (int k = lane; k < n; k += 32) {
+    if (k == skip) continue;
+    double v = D[(size_t)k * stride];
+    if (best > v) best = v;
+  }
+  for (int o = 16; o; o >>= 1) {
+    double t = __shfl_xor_sync(FULL, best, o);
+    if (best > t) best = t;
+  }
+  return best;
+}
+
+__global__ void __launch_bounds__(256) match_lines_kernel(const LslPairDesc* __restrict__ pairs, double* __restrict__ Dall,
+                                                          lsl_match* __restrict__ matches_all, int32_t* __restrict__ nmatch,
+                                                          double cosT) {
+  __shared__ int s_warp_cnt[8];
+  __shared__ int s_base;
+  const LslPairDesc pd = pairs[blockIdx.x];
+  const int n1 = pd.nq, n2 = pd.nt, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  lsl_match* out = matches_all + pd.m_off;
+  if (n1 == 0 || n2 == 0) { if (tid == 0) nmatch[blockIdx.x] = 0; return; }
+  double* D = Dall + pd.d_off;
+  double lineDistThresh, descDiffThresh, lineOverlapThresh;
+  const double ratio = 0.7;
+  if (pd.adjacent) { lineDistThresh = 45; descDiffThresh = 0.85; lineOverlapThresh = 0; }
+  else { lineDistThresh = 80; descDiffThresh = 0.7; lineOverlapThresh = -1; }
+  for (int e = tid; e < n1 * n2; e += blockDim.x) {
+    int i = e / n2, j = e - i * n2;
+    const lsl_line_rec& a = pd.q[i];
+    const lsl_line_rec& b = pd.t[j];
+    double v = 100.0;
+    if (a.r[0] * b.r[0] + a.r[1] * b.r[1] > cosT) {
+      double dd = 0.25 * pt_to_line_dist2d(a.p, b.lineEq2d) + 0.25 * pt_to_line_dist2d(a.q, b.lineEq2d) +
+                  0.25 * pt_to_line_dist2d(b.p, a.lineEq2d) + 0.25 * pt_to_line_dist2d(b.q, a.lineEq2d);
+      if (dd < lineDistThresh && lineSegmentOverlap(a, b) > lineOverlapThresh) v = cvnorm_diff72(a.des, b.des);
+    }
+    D[e] = v;
+  }
+  __syncthreads();
+  if (tid == 0) s_base = 0;
+  // rows in chunks of 8 (one per warp); matches are appended in row order
+  for (int i0 = 0; i0 < n1; i0 += 8) {
+    int i = i0 + warp;
+    bool hit = false;
+    int minX = 0;
+    double minVal = 0;
+    if (i < n1) {
+      minVal = warp_first_min(D + (size_t)i * n2, 1, n2, &minX);
+      if (minVal < descDiffThresh) {
+        int minY;
+        warp_first_min(D + minX, n2, n1, &minY);
+        if (i == minY) {
+          double rowmin2 = warp_min_except(D + (size_t)i * n2, 1, n2, minX);
+          double colmin2 = warp_min_except(D + minX, n2, n1, minY);
+          if (rowmin2 * ratio > minVal && colmin2 * ratio > minVal) hit = pd.q[i].haveDepth && pd.t[minX].haveDepth;
+        }
+      }
+    }
+    if (lane == 0) s_warp_cnt[warp] = hit ? 1 : 0;
+    __syncthreads();
+    if (hit && lane == 0) {
+      int pos = s_base;
+      for (int k = 0; k < warp; ++k) pos += s_warp_cnt[k];
+      if (pos < pd.cap_m) { out[pos].queryIdx = i; out[pos].trainIdx = minX; out[pos].distance = (float)minVal; }
+    }
+    __syncthreads();
+    if (tid == 0) { int c = 0; for (int k = 0; k < 8; ++k) c += s_warp_cnt[k]; s_base += c; }
+    __syncthreads();
+  }
+  if (tid == 0) nmatch[blockIdx.x] = s_base;
+}
+
+// ------------------------------------------------------- minimal solver ----
+struct Iso { double R[9], t[3]; };
+
+__device__ __forceinline__ void cross3(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ void q2r(const double* q, double* R) {  // utils.cpp:1659-1694
+  double a = q[0], b = q[1], c = q[2], d = q[3];
+  double nm = sqrt(a * a + b * b + c * c + d * d);
+  a = a / nm; b = b / nm; c = c / nm; d = d / nm;
+  R[0] = a * a + b * b - c * c - d * d; R[1] = 2 * b * c - 2 * a * d; R[2] = 2 * b * d + 2 * a * c;
+  R[3] = 2 * b * c + 2 * a * d; R[4] = a * a - b * b + c * c - d * d; R[5] = 2 * c * d - 2 * a * b;
+  R[6] = 2 * b * d - 2 * a * c; R[7] = 2 * c * d + 2 * a * b; R[8] = a * a - b * b - c * c + d * d;
+}
+__device__ __forceinline__ void skew(const double* v, double* m) {  // vec2SkewMat, utils.cpp:1649
+  m[0] = 0; m[1] = -v[2]; m[2] = v[1]; m[3] = v[2]; m[4] = 0; m[5] = -v[0]; m[6] = -v[1]; m[7] = v[0]; m[8] = 0;
+}
+// computeRelativeMotion_svd (motion.cpp:315-365) for exactly three line pairs; a = query, b = train.
+// md[k] points at the gathered data of sampled match k: qA(3) qB(3) tA(3) tB(3).
+__device__ void relmotion_svd3(const double* const md[3], double* R, double* t) {
+  double au[9], ad[9], bu[9], bd[9];
+  for (int i = 0; i < 3; ++i)
+    for (int s = 0; s < 2; ++s) {
+      const double* A = md[i] + (s ? 6 : 0);
+      const double* B = A + 3;
+      double* u = s ? bu + 3 * i : au + 3 * i;
+      double* d = s ? bd + 3 * i : ad + 3 * i;
+      double l[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]};
+      double m[3] = {(A[0] + B[0]) * 0.5, (A[1] + B[1]) * 0.5, (A[2] + B[2]) * 0.5};
+      double inv = 1 / sqrt(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]);
+      u[0] = l[0] * inv; u[1] = l[1] * inv; u[2] = l[2] * inv;
+      cross3(u, m, d);
+    }
+  double A[16];
+  for (int i = 0; i < 16; ++i) A[i] = 0;
+  for (int i = 0; i < 3; ++i) {
+    double Ai[16];
+    for (int k = 0; k < 16; ++k) Ai[k] = 0;
+    double dm[3] = {au[3 * i] - bu[3 * i], au[3 * i + 1] - bu[3 * i + 1], au[3 * i + 2] - bu[3 * i + 2]};
+    double dp[3] = {au[3 * i] + bu[3 * i], au[3 * i + 1] + bu[3 * i + 1], au[3 * i + 2] + bu[3 * i + 2]};
+    double dn[3] = {bu[3 * i] - au[3 * i], bu[3 * i + 1] - au[3 * i + 1], bu[3 * i + 2] - au[3 * i + 2]};
+    Ai[1] = dm[0]; Ai[2] = dm[1]; Ai[3] = dm[2];
+    Ai[4] = dn[0]; Ai[8] = dn[1]; Ai[12] = dn[2];
+    double S[9]; skew(dp, S);
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Ai[(r + 1) * 4 + c + 1] = S[r * 3 + c];
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) {
+        double s = 0;
+        for (int k = 0; k < 4; ++k) s += Ai[k * 4 + r] * Ai[k * 4 + c];
+        A[r * 4 + c] = A[r * 4 + c] + s;
+      }
+  }
+  double w[4], V[16];
+  jacobi_sym<4>(A, w, V);
+  double q[4] = {V[3], V[7], V[11], V[15]};
+  q2r(q, R);
+  double uu[9], udr[3] = {0, 0, 0};
+  for (int i = 0; i < 9; ++i) uu[i] = 0;
+  for (int i = 0; i < 3; ++i) {
+    double S[9]; skew(bu + 3 * i, S);
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        double s = 0;
+        for (int k = 0; k < 3; ++k) s += S[r * 3 + k] * S[c * 3 + k];
+        uu[r * 3 + c] = uu[r * 3 + c] + s;
+      }
+    double Rad[3], v[3];
+    for (int r = 0; r < 3; ++r) Rad[r] = R[r * 3] * ad[3 * i] + R[r * 3 + 1] * ad[3 * i + 1] + R[r * 3 + 2] * ad[3 * i + 2];
+    for (int r = 0; r < 3; ++r) v[r] = bd[3 * i + r] - Rad[r];
+    for (int r = 0; r < 3; ++r) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += S[k * 3 + r] * v[k];
+      udr[r] = udr[r] + s;
+    }
+  }
+  double ui[9];
+  inv3(uu, ui);
+  for (int r = 0; r < 3; ++r) t[r] = ui[r * 3] * udr[0] + ui[r * 3 + 1] * udr[1] + ui[r * 3 + 2] * udr[2];
+}
+
+// Eigen Matrix4f * Vector4f: per row (((a0 x) + a1 y) + a2 z) + a3 w in float; tf = 12 floats
+__device__ __forceinline__ void tf_apply_f(const float* tf, const float* v, double* out) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    float acc = __fmul_rn(tf[r * 4 + 0], v[0]);
+    acc = __fadd_rn(__fmul_rn(tf[r * 4 + 1], v[1]), acc);
+    acc = __fadd_rn(__fmul_rn(tf[r * 4 + 2], v[2]), acc);
+    acc = __fadd_rn(__fmul_rn(tf[r * 4 + 3], 1.0f), acc);
+    out[r] = (double)acc;
+  }
+}
+// both Mahalanobis distances of match data md under tf (motion.cpp:688-693)
+__device__ __forceinline__ void score_match(const double* md, const float* tf, double* da, double* db) {
+  float qa[3] = {(float)md[0], (float)md[1], (float)md[2]}, qb[3] = {(float)md[3], (float)md[4], (float)md[5]};
+  double qA[3], qB[3];
+  tf_apply_f(tf, qa, qA);
+  tf_apply_f(tf, qb, qB);
+  *da = mah_dist3d_pt_line(md + 6, md + 12, qA, qB);
+  *db = mah_dist3d_pt_line(md + 9, md + 21, qA, qB);
+}
+
+// ------------------------------------------------- g2o-style refinement ----
+__device__ __forceinline__ void iso_mul(const Iso& a, const Iso& b, Iso& c) {
+  for (int r = 0; r < 3; ++r) {
+    for (int k = 0; k < 3; ++k) c.R[r * 3 + k] = a.R[r * 3] * b.R[k] + a.R[r * 3 + 1] * b.R[3 + k] + a.R[r * 3 + 2] * b.R[6 + k];
+    c.t[r] = a.R[r * 3] * b.t[0] + a.R[r * 3 + 1] * b.t[1] + a.R[r * 3 + 2] * b.t[2] + a.t[r];
+  }
+}
+__device__ __forceinline__ void iso_inv(const Iso& a, Iso& c) {
+  for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) c.R[r * 3 + k] = a.R[k * 3 + r];
+  for (int r = 0; r < 3; ++r) c.t[r] = -(c.R[r * 3] * a.t[0] + c.R[r * 3 + 1] * a.t[1] + c.R[r * 3 + 2] * a.t[2]);
+}
+__device__ void iso_oplus(const Iso& est, const double* u, Iso& out) {  // VertexSE3::oplusImpl / fromVectorMQT
+  double w2 = 1. - (u[3] * u[3] + u[4] * u[4] + u[5] * u[5]);
+  double q[4] = {w2 > 0 ? sqrt(w2) : 0.0, u[3], u[4], u[5]};
+  Iso inc;
+  q2r(q, inc.R);
+  inc.t[0] = u[0]; inc.t[1] = u[1]; inc.t[2] = u[2];
+  iso_mul(est, inc, out);
+}
+// EdgeSE3LineEndpts::computeError (edge_se3_lineendpts.cpp:146-189); w2n = pose^-1
+__device__ void edge_error(const Iso& w2n, const double* L, const double* meas, const double* AffA, const double* AffB, double* e) {
+  double ptA[3], ptB[3];
+  for (int r = 0; r < 3; ++r) {
+    ptA[r] = w2n.R[r * 3] * L[0] + w2n.R[r * 3 + 1] * L[1] + w2n.R[r * 3 + 2] * L[2] + w2n.t[r];
+    ptB[r] = w2n.R[r * 3] * L[3] + w2n.R[r * 3 + 1] * L[4] + w2n.R[r * 3 + 2] * L[5] + w2n.t[r];
+  }
+  for (int h = 0; h < 2; ++h) {
+    const double* Af = h ? AffB : AffA;
+    const double* mp = meas + 3 * h;
+    double dA[3] = {ptA[0] - mp[0], ptA[1] - mp[1], ptA[2] - mp[2]}, dB[3] = {ptB[0] - mp[0], ptB[1] - mp[1], ptB[2] - mp[2]};
+    double Ap[3], Bp[3], BA[3];
+    for (int r = 0; r < 3; ++r) {
+      Ap[r] = Af[r * 3] * dA[0] + Af[r * 3 + 1] * dA[1] + Af[r * 3 + 2] * dA[2];
+      Bp[r] = Af[r * 3] * dB[0] + Af[r * 3 + 1] * dB[1] + Af[r * 3 + 2] * dB[2];
+    }
+    for (int r = 0; r < 3; ++r) BA[r] = Bp[r] - Ap[r];
+    double tt = -(Ap[0] * BA[0] + Ap[1] * BA[1] + Ap[2] * BA[2]) / (BA[0] * BA[0] + BA[1] * BA[1] + BA[2] * BA[2]);
+    for (int r = 0; r < 3; ++r) e[3 * h + r] = Ap[r] + tt * BA[r];
+  }
+}
+__device__ void affn(const double* cov, double* Af) {  // endpt_AffnMat = D^-1/2 U^T (transformation_estimation.cpp:349-372)
+  double A[9], w[3], V[9];
+  for (int i = 0; i < 9; ++i) A[i] = cov[i];
+  jacobi_sym<3>(A, w, V);
+  for (int i = 0; i < 3; ++i) {
+    double d = sqrt(1 / w[i]);
+    for (int j = 0; j < 3; ++j) Af[i * 3 + j] = d * V[j * 3 + i];
+  }
+}
+__device__ __forceinline__ void huber(double e2, double delta, double* rho) {  // g2o RobustKernelHuber::robustify
+  double dsqr = delta * delta;
+  if (e2 <= dsqr) { rho[0] = e2; rho[1] = 1.; rho[2] = 0.; }
+  else { double sqrte = sqrt(e2); rho[0] = 2 * sqrte * delta - dsqr; rho[1] = delta / sqrte; rho[2] = -0.5 * rho[1] / e2; }
+}
+
+struct PoseParams {
+  double thr, line_weight_g2o, huber_delta;
+  int robust, max_iter, min_matches, min_loopclose, line_weight;
+};
+
+// Per-match scratch of the LM (doubles), laid out [field][match] blocks inside the pair's slice
+struct LmView {
+  double *L, *Lnew, *Hll, *Hpl, *bl, *HllInv, *contrib, *dl, *terms, *chi;  // 6,6,36,36,6,36,42,6,6,2 per match
+  int32_t* sel;   // [n] index into the pair's match list
+  int32_t* okf;   // [n]
+};
+
+// chi2 of all edges (SparseOptimizer::activeRobustChi2), terms in edge order: per match side 0 (newer) then 1 (older)
+__device__ void chi2_terms(const LmView& V, const double* md_all, int n, const Iso& w2n, const Iso& ident, const double* Lv,
+                           const PoseParams& PP) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double* md = md_all + (size_t)V.sel[i] * MD_STRIDE;
+    for (int side = 0; side < 2; ++side) {
+      double e[6];
+      edge_error(side ? w2n : ident, Lv + 6 * i, side ? md + 6 : md, side ? md + 54 : md + 36, side ? md + 63 : md + 45, e);
+      double c2 = 0;
+      for (int k = 0; k < 6; ++k) c2 += e[k] * PP.line_weight_g2o * e[k];
+      if (PP.robust) { double rho[3]; huber(c2, PP.huber_delta, rho); c2 = rho[0]; }
+      V.chi[2 * i + side] = c2;
+    }
+  }
+}
+
+// getTransformFromHybridMatchesG2O restated (see oracle/oracle_pair.cpp:refine_pose_lines for the derivation):
+// pose vertex + one free 6-vector per line match, numeric central-difference Jacobians, Huber, g2o's LM
+// damping policy, landmark blocks eliminated exactly. Whole CTA; tf (12 floats, shared memory) in/out.
+__device__ void refine_pose(const LmView& V, const double* md_all, int n, float* tf, int iterations, const PoseParams& PP,
+                            double* s_red /* >= 64 doubles shared */, double* s_S /* 48 doubles shared */) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  if (n == 0) return;
+  Iso tfd, cam1, ident;
+  for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) tfd.R[r * 3 + c] = (double)tf[r * 4 + c]; tfd.t[r] = (double)tf[r * 4 + 3]; }
+  iso_inv(tfd, cam1);
+  for (int i = 0; i < 9; ++i) ident.R[i] = (i % 4 == 0) ? 1 : 0;
+  ident.t[0] = ident.t[1] = ident.t[2] = 0;
+  for (int i = tid; i < n; i += nthr) {
+    const double* md = md_all + (size_t)V.sel[i] * MD_STRIDE;
+    for (int k = 0; k < 6; ++k) V.L[6 * i + k] = md[k];
+  }
+  __syncthreads();
+  const double w = PP.line_weight_g2o;
+  double lambda = 0, ni = 2;
+  const double tau = 1e-5, lowS = 1. / 3., upS = 2. / 3.;
+  const double del = 1e-9, scalar = 1 / (2 * del);
+  for (int it = 0; it < iterations; ++it) {
+    Iso w2n;
+    iso_inv(cam1, w2n);
+    chi2_terms(V, md_all, n, w2n, ident, V.L, PP);
+    // ---- build the normal equations: per match blocks
+    for (int i = tid; i < n; i += nthr) {
+      const double* md = md_all + (size_t)V.sel[i] * MD_STRIDE;
+      double* hll = V.Hll + 36 * i; double* hpl = V.Hpl + 36 * i; double* b = V.bl + 6 * i; double* cp = V.contrib + 42 * i;
+      for (int k = 0; k < 36; ++k) { hll[k] = 0; hpl[k] = 0; }
+      for (int k = 0; k < 6; ++k) b[k] = 0;
+      const double* Li = V.L + 6 * i;
+      for (int side = 0; side < 2; ++side) {
+        const double* meas = side ? md + 6 : md;
+        const double* A1 = side ? md + 54 : md + 36;
+        const double* A2 = A1 + 9;
+        double e[6], Jl[36], Jp[36];
+        for (int d = 0; d < 6; ++d) {
+          double Lp[6], e1[6], e2[6];
+          for (int k = 0; k < 6; ++k) Lp[k] = Li[k];
+          Lp[d] = Li[d] + del;
+          edge_error(side ? w2n : ident, Lp, meas, A1, A2, e1);
+          Lp[d] = Li[d] + (-del);
+          edge_error(side ? w2n : ident, Lp, meas, A1, A2, e2);
+          for (int k = 0; k < 6; ++k) Jl[k * 6 + d] = scalar * (e1[k] - e2[k]);
+        }
+        if (side) {
+          for (int d = 0; d < 6; ++d) {
+            double u[6] = {0, 0, 0, 0, 0, 0}, e1[6], e2[6];
+            Iso c, ci;
+            u[d] = del; iso_oplus(cam1, u, c); iso_inv(c, ci); edge_error(ci, Li, meas, A1, A2, e1);
+            u[d] = -del; iso_oplus(cam1, u, c); iso_inv(c, ci); edge_error(ci, Li, meas, A1, A2, e2);
+            for (int k = 0; k < 6; ++k) Jp[k * 6 + d] = scalar * (e1[k] - e2[k]);
+          }
+        }
+        edge_error(side ? w2n : ident, Li, meas, A1, A2, e);
+        double c2 = 0; for (int k = 0; k < 6; ++k) c2 += e[k] * w * e[k];
+        double wgt = w;
+        if (PP.robust) { double rho[3]; huber(c2, PP.huber_delta, rho); wgt = rho[1] * w; }
+        for (int a = 0; a < 6; ++a) {
+          double s = 0; for (int k = 0; k < 6; ++k) s += Jl[k * 6 + a] * (wgt * e[k]);
+          b[a] -= s;
+          for (int c = 0; c < 6; ++c) { double h = 0; for (int k = 0; k < 6; ++k) h += Jl[k * 6 + a] * wgt * Jl[k * 6 + c]; hll[a * 6 + c] += h; }
+        }
+        if (side) {
+          for (int a = 0; a < 6; ++a) {
+            double s = 0; for (int k = 0; k < 6; ++k) s += Jp[k * 6 + a] * (wgt * e[k]);
+            cp[36 + a] = s;
+            for (int c = 0; c < 6; ++c) {
+              double h = 0, g = 0;
+              for (int k = 0; k < 6; ++k) { h += Jp[k * 6 + a] * wgt * Jp[k * 6 + c]; g += Jp[k * 6 + a] * wgt * Jl[k * 6 + c]; }
+              cp[a * 6 + c] = h;
+              hpl[a * 6 + c] += g;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ordered sums over the matches: Hpp (36), bp (6) by threads 0..41; chi2 by thread 64
+    if (tid < 36) { double s = 0; for (int i = 0; i < n; ++i) s += V.contrib[42 * i + tid]; s_S[tid] = s; }
+    else if (tid < 42) { double s = 0; for (int i = 0; i < n; ++i) s -= V.contrib[42 * i + tid]; s_S[tid] = s; }
+    else if (tid == 64) { double c = 0; for (int i = 0; i < 2 * n; ++i) c += V.chi[i]; s_red[0] = c; }
+    __syncthreads();
+    double Hpp[36], bp[6];
+    for (int k = 0; k < 36; ++k) Hpp[k] = s_S[k];
+    for (int k = 0; k < 6; ++k) bp[k] = s_S[36 + k];
+    double currentChi = s_red[0];
+    __syncthreads();
+    if (it == 0) {  // computeLambdaInit: tau * max |diagonal entry|
+      double md_ = 0;
+      for (int i = tid; i < n; i += nthr)
+        for (int a = 0; a < 6; ++a) md_ = fmax(fabs(V.Hll[36 * i + a * 6 + a]), md_);
+      for (int o = 16; o; o >>= 1) md_ = fmax(md_, __shfl_xor_sync(FULL, md_, o));
+      if ((tid & 31) == 0) s_red[1 + (tid >> 5)] = md_;
+      __syncthreads();
+      double maxDiag = 0;
+      for (int a = 0; a < 6; ++a) maxDiag = fmax(fabs(Hpp[a * 6 + a]), maxDiag);
+      for (int k = 0; k < nthr / 32; ++k) maxDiag = fmax(maxDiag, s_red[1 + k]);
+      __syncthreads();
+      lambda = tau * maxDiag;
+      ni = 2;
+    }
+    double rho = 0;
+    int qmax = 0;
+    do {
+      for (int i = tid; i < n; i += nthr) {
+        double M[36], hi[36];
+        for (int k = 0; k < 36; ++k) M[k] = V.Hll[36 * i + k];
+        for (int a = 0; a < 6; ++a) M[a * 6 + a] += lambda;
+        V.okf[i] = inv_lu<6>(M, hi);
+        const double* hpl = V.Hpl + 36 * i;
+        double* cp = V.contrib + 42 * i;
+        double T[36];
+        for (int a = 0; a < 6; ++a) for (int c = 0; c < 6; ++c) { double s = 0; for (int k = 0; k < 6; ++k) s += hpl[a * 6 + k] * hi[k * 6 + c]; T[a * 6 + c] = s; }
+        for (int a = 0; a < 6; ++a) {
+          double s = 0; for (int k = 0; k < 6; ++k) s += T[a * 6 + k] * V.bl[6 * i + k];
+          cp[36 + a] = s;
+          for (int c = 0; c < 6; ++c) { double h = 0; for (int k = 0; k < 6; ++k) h += T[a * 6 + k] * hpl[c * 6 + k]; cp[a * 6 + c] = h; }
+        }
+        for (int k = 0; k < 36; ++k) V.HllInv[36 * i + k] = hi[k];
+      }
+      __syncthreads();
+      if (tid < 42) {
+        double s = tid < 36 ? Hpp[tid] : bp[tid - 36];
+        if (tid < 36 && (tid / 6 == tid % 6)) s += lambda;
+        for (int i = 0; i < n; ++i) s -= V.contrib[42 * i + tid];
+        s_S[tid] = s;
+      } else if (tid == 64) {
+        int ok = 1;
+        for (int i = 0; i < n; ++i) ok &= V.okf[i];
+        s_red[2] = (double)ok;
+      }
+      __syncthreads();
+      double S[36], Si[36], rhs[6], dp[6];
+      for (int k = 0; k < 36; ++k) S[k] = s_S[k];
+      for (int k = 0; k < 6; ++k) rhs[k] = s_S[36 + k];
+      bool ok = s_red[2] != 0.0;
+      if (!inv_lu<6>(S, Si)) ok = false;
+      for (int a = 0; a < 6; ++a) { double s = 0; for (int k = 0; k < 6; ++k) s += Si[a * 6 + k] * rhs[k]; dp[a] = s; }
+      double scale = 0;
+      for (int a = 0; a < 6; ++a) scale += dp[a] * (lambda * dp[a] + bp[a]);
+      for (int i = tid; i < n; i += nthr) {
+        const double* hi = V.HllInv + 36 * i; const double* hpl = V.Hpl + 36 * i;
+        double r[6];
+        for (int a = 0; a < 6; ++a) { double s = 0; for (int k = 0; k < 6; ++k) s += hpl[k * 6 + a] * dp[k]; r[a] = V.bl[6 * i + a] - s; }
+        for (int a = 0; a < 6; ++a) {
+          double s = 0; for (int k = 0; k < 6; ++k) s += hi[a * 6 + k] * r[k];
+          V.dl[6 * i + a] = s;
+          V.terms[6 * i + a] = s * (lambda * s + V.bl[6 * i + a]);
+          V.Lnew[6 * i + a] = V.L[6 * i + a] + s;
+        }
+      }
+      Iso camNew, w2nNew;
+      iso_oplus(cam1, dp, camNew);
+      iso_inv(camNew, w2nNew);
+      __syncthreads();
+      chi2_terms(V, md_all, n, w2nNew, ident, V.Lnew, PP);
+      __syncthreads();
+      if (tid == 0) { double sc = scale; for (int i = 0; i < 6 * n; ++i) sc += V.terms[i]; s_red[3] = sc; }
+      else if (tid == 64) { double c = 0; for (int i = 0; i < 2 * n; ++i) c += V.chi[i]; s_red[4] = c; }
+      __syncthreads();
+      scale = s_red[3];
+      double tempChi = s_red[4];
+      __syncthreads();
+      if (!ok) tempChi = DBL_MAX;
+      rho = (currentChi - tempChi);
+      scale += 1e-3;
+      rho /= scale;
+      if (rho > 0 && isfinite(tempChi)) {
+        double alpha = 1. - (2 * rho - 1) * (2 * rho - 1) * (2 * rho - 1);
+        alpha = fmin(alpha, upS);
+        double scaleFactor = fmax(lowS, alpha);
+        lambda *= scaleFactor;
+        ni = 2;
+        currentChi = tempChi;
+        cam1 = camNew;
+        for (int i = tid; i < 6 * n; i += nthr) V.L[i] = V.Lnew[i];
+        __syncthreads();
+      } else {
+        lambda *= ni;
+        ni *= 2;
+      }
+      qmax++;
+    } while (rho < 0 && qmax < 10);
+    if (qmax == 10 || rho == 0) break;
+  }
+  Iso out;
+  iso_inv(cam1, out);
+  __syncthreads();
+  if (tid == 0) {
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) tf[r * 4 + c] = (float)out.R[r * 3 + c]; tf[r * 4 + 3] = (float)out.t[r]; }
+  }
+  __syncthreads();
+}
+
+// score all matches under tf; ordered inlier list -> sel; returns count; *sse_out (double or float accumulation)
+__device__ int score_all(const double* md_all, int nm, const float* tf, double thr, double* da_s, double* db_s, int32_t* sel,
+                         bool float_sse, double* sse_out, int* s_i /* 2 ints shared */, double* s_d /* 1 double shared */) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < nm; i += blockDim.x) {
+    double da, db;
+    score_match(md_all + (size_t)i * MD_STRIDE, tf, &da, &db);
+    da_s[i] = da; db_s[i] = db;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int c = 0;
+    float sf = 0; double sd = 0;
+    for (int i = 0; i < nm; ++i) {
+      double da = da_s[i], db = db_s[i];
+      if (da < thr && db < thr) {
+        sel[c++] = i;
+        if (float_sse) sf += da * da + db * db; else sd += da * da + db * db;
+      }
+    }
+    s_i[0] = c;
+    s_d[0] = float_sse ? (double)sf : sd;
+  }
+  __syncthreads();
+  int c = s_i[0];
+  *sse_out = s_d[0];
+  __syncthreads();
+  return c;
+}
+
+__global__ void __launch_bounds__(POSE_THREADS) pose_kernel(const LslPairDesc* __restrict__ pairs, const lsl_match* __restrict__ matches_all,
+                                                            const int32_t* __restrict__ nmatch, LslPairScratch sc, PoseParams PP,
+                                                            lsl_pose_rec* __restrict__ out) {
+  __shared__ float s_tf[16];
+  __shared__ double s_red[64];
+  __shared__ double s_S[48];
+  __shared__ int s_i[4];
+  __shared__ double s_d[2];
+  __shared__ GRand s_rng;
+  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = POSE_THREADS / 32;
+  const LslPairDesc pd = pairs[pair];
+  const int nm = min(nmatch[pair], pd.cap_m);
+  const lsl_match* ms = matches_all + pd.m_off;
+  lsl_pose_rec* rec = out + pair;
+  // per-pair slices of the scratch
+  double* md_all = sc.md + pd.m_off * MD_STRIDE;
+  double* da_s = sc.dab + pd.m_off * 2;
+  double* db_s = da_s + pd.cap_m;
+  int32_t* sel_r = sc.sel + pd.m_off * 3;      // RANSAC inlier set
+  int32_t* sel_f = sel_r + pd.cap_m;            // refined inlier set
+  int32_t* sel_t = sel_f + pd.cap_m;            // trial set
+  float* tfs = sc.tfs + (size_t)pair * sc.max_iter * 12;
+  int32_t* cnts = sc.cnts + (size_t)pair * sc.max_iter;
+  uint16_t* trip = sc.trip + (size_t)pair * sc.max_iter * 3;
+  LmView V;
+  {
+    double* lm = sc.lm + pd.m_off * 182;
+    const size_t c = pd.cap_m;
+    V.L = lm; V.Lnew = V.L + 6 * c; V.Hll = V.Lnew + 6 * c; V.Hpl = V.Hll + 36 * c; V.bl = V.Hpl + 36 * c;
+    V.HllInv = V.bl + 6 * c; V.contrib = V.HllInv + 36 * c; V.dl = V.contrib + 42 * c; V.terms = V.dl + 6 * c; V.chi = V.terms + 6 * c;
+    V.okf = sc.okf + pd.m_off;
+    V.sel = sel_r;
+  }
+  if (tid == 0) {
+    rec->id_train = pd.id_t; rec->id_query = pd.id_q; rec->found = 0; rec->n_line_matches = nm;
+    rec->n_ransac_inliers = 0; rec->n_inliers = 0; rec->rmse = 1e9f; rec->best_iter = -1;
+    for (int i = 0; i < 16; ++i) rec->tf[i] = (i % 5 == 0) ? 1.f : 0.f;
+    for (int i = 0; i < 8; ++i) rec->pad[i] = 0;
+    sc.n_inl[pair] = 0; sc.n_rinl[pair] = 0;
+  }
+  const int nPt = 0, nLn = nm, line_weight = PP.line_weight;
+  int min_inlier_nmb = PP.min_matches;
+  if (nPt + nLn * line_weight < min_inlier_nmb) return;  // motion.cpp:621-624 (uniform)
+  if (min_inlier_nmb > 0.7 * (nPt + nLn * line_weight)) min_inlier_nmb = (int)(0.7 * (nPt + nLn * line_weight));
+  if (abs(pd.id_t - pd.id_q) > 50) min_inlier_nmb = PP.min_loopclose;
+  const int maxIter = PP.max_iter;
+  // ---- gather: qA qB tA tB | t.DU_A t.DU_B | affn(q.covA) affn(q.covB) affn(t.covA) affn(t.covB)
+  for (int i = tid; i < nm; i += blockDim.x) {
+    const lsl_line_rec& q = pd.q[ms[i].queryIdx];
+    const lsl_line_rec& t = pd.t[ms[i].trainIdx];
+    double* md = md_all + (size_t)i * MD_STRIDE;
+    for (int k = 0; k < 3; ++k) { md[k] = q.A[k]; md[3 + k] = q.B[k]; md[6 + k] = t.A[k]; md[9 + k] = t.B[k]; }
+    for (int k = 0; k < 9; ++k) { md[12 + k] = t.DU_A[k]; md[21 + k] = t.DU_B[k]; }
+    affn(q.covA, md + 36); affn(q.covB, md + 45); affn(t.covA, md + 54); affn(t.covB, md + 63);
+  }
+  // ---- the 500 sample triples: one rand() stream, cumulative shuffle (motion.cpp:635-658)
+  if (tid == 0) {
+    grand_seed(&s_rng, pd.seed);
+    int32_t* idx = sel_t;  // borrowed as the `indexes` vector
+    for (int i = 0; i < nm; ++i) idx[i] = i;
+    for (int it = 0; it < maxIter; ++it) {
+      int left = nm;
+      for (int k = 0; k < 3; ++k) {
+        int r = grand_next(&s_rng) % left;
+        int t = idx[k]; idx[k] = idx[k + r]; idx[k + r] = t;
+        --left;
+      }
+      trip[3 * it] = (uint16_t)idx[0]; trip[3 * it + 1] = (uint16_t)idx[1]; trip[3 * it + 2] = (uint16_t)idx[2];
+    }
+  }
+  __syncthreads();
+  // ---- minimal solutions (getTransform_Line_svd, motion.cpp:581-603)
+  for (int h = tid; h < maxIter; h += blockDim.x) {
+    const double* mdp[3] = {md_all + (size_t)trip[3 * h] * MD_STRIDE, md_all + (size_t)trip[3 * h + 1] * MD_STRIDE,
+                            md_all + (size_t)trip[3 * h + 2] * MD_STRIDE};
+    double R[9], t[3];
+    relmotion_svd3(mdp, R, t);
+    float* tf = tfs + (size_t)h * 12;
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) tf[r * 4 + c] = (float)R[r * 3 + c]; tf[r * 4 + 3] = (float)t[r]; }
+  }
+  __syncthreads();
+  // ---- scoring: warp per hypothesis, lanes over matches
+  for (int h = warp; h < maxIter; h += nwarp) {
+    const float* tfh = tfs + (size_t)h * 12;
+    float tf[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) tf[k] = tfh[k];
+    int c = 0;
+    for (int i0 = 0; i0 < nm; i0 += 32) {
+      int i = i0 + lane;
+      bool in = false;
+      if (i < nm) {
+        double da, db;
+        score_match(md_all + (size_t)i * MD_STRIDE, tf, &da, &db);
+        in = da < PP.thr && db < PP.thr;
+      }
+      c += __popc(__ballot_sync(FULL, in));
+    }
+    if (lane == 0) cnts[h] = c;
+  }
+  __syncthreads();
+  // ---- first best (strict >, motion.cpp:714-720)
+  if (warp == 0) {
+    int best = 0, bh = 1 << 30;
+    for (int h = lane; h < maxIter; h += 32) {
+      int c = line_weight * cnts[h];
+      if (c > best) { best = c; bh = h; }
+    }
+    for (int o = 16; o; o >>= 1) {
+      int b2 = __shfl_xor_sync(FULL, best, o), h2 = __shfl_xor_sync(FULL, bh, o);
+      if (b2 > best || (b2 == best && h2 < bh)) { best = b2; bh = h2; }
+    }
+    if (lane == 0) { s_i[2] = best > 0 ? bh : -1; }
+  }
+  __syncthreads();
+  const int bh = s_i[2];
+  if (bh < 0) return;
+  if (tid < 12) s_tf[tid] = tfs[(size_t)bh * 12 + tid];
+  if (tid >= 12 && tid < 16) s_tf[tid] = tid == 15 ? 1.f : 0.f;
+  __syncthreads();
+  double sse;
+  const int best_cnt = score_all(md_all, nm, s_tf, PP.thr, da_s, db_s, sel_r, true, &sse, s_i, s_d);
+  if (tid == 0) rec->best_iter = bh;
+  if (best_cnt < 3) return;  // motion.cpp:722-725
+  if (tid == 0) {
+    rec->n_ransac_inliers = best_cnt;
+    sc.n_rinl[pair] = best_cnt;
+    float* tr = sc.tf_ransac + (size_t)pair * 16;
+    for (int i = 0; i < 16; ++i) tr[i] = s_tf[i];
+  }
+  const float sum_squared_error = (float)sse;
+  // ---- refinement (motion.cpp:726-839)
+  V.sel = sel_r;
+  refine_pose(V, md_all, best_cnt, s_tf, 25, PP, s_red, s_S);
+  double refined_rmse = sqrt(sum_squared_error / (double)best_cnt);
+  int refined_cnt = 0;
+  for (int it = 0; it < 20; ++it) {
+    double tmp_sse;
+    int c = score_all(md_all, nm, s_tf, PP.thr, da_s, db_s, sel_t, false, &tmp_sse, s_i, s_d);
+    if (c * line_weight > refined_cnt * line_weight) {
+      for (int i = tid; i < c; i += blockDim.x) sel_f[i] = sel_t[i];
+      refined_cnt = c;
+      refined_rmse = sqrt(tmp_sse / (double)c);
+      __syncthreads();
+      V.sel = sel_f;
+      refine_pose(V, md_all, refined_cnt, s_tf, 20, PP, s_red, s_S);
+    } else break;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    rec->n_inliers = refined_cnt;
+    rec->rmse = (float)refined_rmse;
+    for (int i = 0; i < 12; ++i) rec->tf[i] = s_tf[i];
+    rec->found = (line_weight * refined_cnt) >= min_inlier_nmb ? 1 : 0;
+    sc.n_inl[pair] = refined_cnt;
+  }
+}
+
+// ------------------------------------------------------------- launchers ----
+int lsl_launch_match(lsl_ctx* ctx, int npairs) {
+  const double PI_T = 3.14159265;  // lineslam.h:38
+  double cosT = lsl_cos(30 * PI_T / 180);
+  match_lines_kernel<<<npairs, 256, 0, ctx->stream>>>(ctx->pw.d_pairs, ctx->pw.D, ctx->pw.matches, ctx->pw.nmatch, cosT);
+  ctx->stats.kernel_launches += 1;
+  LSL_CUDA(cudaGetLastError());
+  return LSL_OK;
+}
+
+int lsl_launch_pose(lsl_ctx* ctx, int npairs) {
+  const lsl_params& P = ctx->P;
+  PoseParams PP;
+  PP.thr = P.max_mah_dist_for_inliers; PP.line_weight_g2o = P.g2o_line_error_weight; PP.huber_delta = P.g2o_BA_kernel_delta;
+  PP.robust = P.g2o_BA_use_kernel; PP.max_iter = P.ransac_iters_line_motion; PP.min_matches = P.min_feature_matches;
+  PP.min_loopclose = P.min_matches_loopclose; PP.line_weight = P.line_match_number_weight;
+  pose_kernel<<<npairs, POSE_THREADS, 0, ctx->stream>>>(ctx->pw.d_pairs, ctx->pw.matches, ctx->pw.nmatch, ctx->pw.sc, PP, ctx->pw.recs);
+  ctx->stats.kernel_launches += 1;
+  LSL_CUDA(cudaGetLastError());
+  return LSL_OK;
+}

@@ -87,7 +87,10 @@ extern "C" int lsl_ctx_create(lsl_ctx** out, const lsl_params* params, int cuda_
   if (!ctx) return LSL_ERR_ARG;
   if (params) ctx->P = *params; else lsl_params_default_impl(&ctx->P);
   ctx->device = cuda_device; ctx->max_batch = max_batch; ctx->max_w = max_w; ctx->max_h = max_h;
-  ctx->wk_block = nullptr; ctx->pair_block = nullptr; ctx->pair_bytes = 0; ctx->pair_cap = 0;
+  ctx->wk_block = nullptr;
+  memset(&ctx->pw.sc, 0, sizeof(ctx->pw.sc));
+  ctx->pw.d_pairs = nullptr; ctx->pw.D = nullptr; ctx->pw.matches = nullptr; ctx->pw.nmatch = nullptr; ctx->pw.recs = nullptr;
+  ctx->pw.cap_pairs = ctx->pw.cap_m = ctx->pw.cap_d = 0;
   ctx->h_pin = nullptr; ctx->h_pin_bytes = 0;
   memset(&ctx->stats, 0, sizeof(ctx->stats));
   memset(&ctx->dims, 0, sizeof(ctx->dims));
@@ -110,12 +113,22 @@ extern "C" int lsl_ctx_create(lsl_ctx** out, const lsl_params* params, int cuda_
   return LSL_OK;
 }
 
+static void free_pair_ws(lsl_ctx* ctx) {
+  LslPairWork& p = ctx->pw;
+  void* ptrs[] = {p.d_pairs, p.D, p.matches, p.nmatch, p.recs, p.sc.md, p.sc.dab, p.sc.sel, p.sc.lm, p.sc.okf, p.sc.tfs,
+                  p.sc.cnts, p.sc.trip, p.sc.n_inl, p.sc.n_rinl, p.sc.tf_ransac};
+  for (void* q : ptrs) if (q) cudaFree(q);
+  memset(&p.sc, 0, sizeof(p.sc));
+  p.d_pairs = nullptr; p.D = nullptr; p.matches = nullptr; p.nmatch = nullptr; p.recs = nullptr;
+  p.cap_pairs = p.cap_m = p.cap_d = 0;
+}
+
 extern "C" void lsl_ctx_destroy(lsl_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->wk_block) cudaFree(ctx->wk_block);
-  if (ctx->pair_block) cudaFree(ctx->pair_block);
+  free_pair_ws(ctx);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);
   cudaStreamDestroy(ctx->stream);
@@ -266,6 +279,174 @@ extern "C" void lsl_frame_free(lsl_frame* f) {
   if (f->d_lines) { cudaSetDevice(f->ctx->device); cudaFree(f->d_lines); }
   delete f;
 }
+// ------------------------------------------------------------- pair registration ----
+template <class T>
+static cudaError_t regrow(T** p, size_t count) {
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  return cudaMalloc((void**)p, sizeof(T) * (count ? count : 1));
+}
+// Sizes the pair workspace for npairs pairs with tot_m match slots and tot_d distance-matrix entries.
+static int ensure_pair_ws(lsl_ctx* ctx, size_t npairs, size_t tot_m, size_t tot_d) {
+  LslPairWork& p = ctx->pw;
+  const int max_iter = ctx->P.ransac_iters_line_motion;
+  if (max_iter < 1 || max_iter > 65535) { ctx->err = "ransac_iters_line_motion out of range"; return LSL_ERR_ARG; }
+  if (npairs > p.cap_pairs || p.sc.max_iter != max_iter) {
+    size_t c = npairs + npairs / 2;
+    LSL_CUDA(regrow(&p.d_pairs, c)); LSL_CUDA(regrow(&p.nmatch, c)); LSL_CUDA(regrow(&p.recs, c));
+    LSL_CUDA(regrow(&p.sc.tfs, c * max_iter * 12)); LSL_CUDA(regrow(&p.sc.cnts, c * max_iter));
+    LSL_CUDA(regrow(&p.sc.trip, c * max_iter * 3)); LSL_CUDA(regrow(&p.sc.n_inl, c)); LSL_CUDA(regrow(&p.sc.n_rinl, c));
+    LSL_CUDA(regrow(&p.sc.tf_ransac, c * 16));
+    p.cap_pairs = c; p.sc.max_iter = max_iter;
+  }
+  if (tot_m > p.cap_m) {
+    size_t c = tot_m + tot_m / 2;
+    LSL_CUDA(regrow(&p.matches, c)); LSL_CUDA(regrow(&p.sc.md, c * 72)); LSL_CUDA(regrow(&p.sc.dab, c * 2));
+    LSL_CUDA(regrow(&p.sc.sel, c * 3)); LSL_CUDA(regrow(&p.sc.lm, c * 182)); LSL_CUDA(regrow(&p.sc.okf, c));
+    p.cap_m = c;
+  }
+  if (tot_d > p.cap_d) {
+    size_t c = tot_d + tot_d / 2;
+    LSL_CUDA(regrow(&p.D, c));
+    p.cap_d = c;
+  }
+  return LSL_OK;
+}
+
+// Fills the descriptors of a batch (host + device). cap_override >= 0 forces the match capacity (pose-only calls).
+static int setup_pairs(lsl_ctx* ctx, int npairs, const lsl_frame* const* queries, const lsl_frame* const* trains,
+                       const int32_t* id_query, const int32_t* id_train, const uint32_t* seeds, const int* adjacent,
+                       int cap_override) {
+  LslPairWork& p = ctx->pw;
+  p.h_pairs.resize(npairs);
+  size_t m_off = 0, d_off = 0;
+  for (int i = 0; i < npairs; ++i) {
+    const lsl_frame* q = queries[i];
+    const lsl_frame* t = trains[i];
+    if (!q || !t) return LSL_ERR_ARG;
+    LslPairDesc& d = p.h_pairs[i];
+    d.q = q->d_lines; d.t = t->d_lines; d.nq = q->nlines; d.nt = t->nlines;
+    d.id_q = id_query ? id_query[i] : 1; d.id_t = id_train ? id_train[i] : 0;
+    d.seed = seeds ? seeds[i] : 1u;
+    d.adjacent = adjacent ? adjacent[i] : (abs(d.id_q - d.id_t) <= ctx->P.adjacent_linematch_window);  // node.cpp:1505-1507
+    d.cap_m = cap_override >= 0 ? cap_override : (d.nq < d.nt ? d.nq : d.nt);
+    d.d_off = d_off; d.m_off = m_off; d.pad_ = 0;
+    m_off += (size_t)(d.cap_m > 0 ? d.cap_m : 1);
+    d_off += (size_t)d.nq * d.nt;
+  }
+  int rc = ensure_pair_ws(ctx, npairs, m_off, d_off);
+  if (rc) return rc;
+  LSL_CUDA(cudaMemcpyAsync(p.d_pairs, p.h_pairs.data(), sizeof(LslPairDesc) * npairs, cudaMemcpyHostToDevice, ctx->stream));
+  return LSL_OK;
+}
+
+static int fetch_counts(lsl_ctx* ctx, int npairs) {
+  LslPairWork& p = ctx->pw;
+  p.h_nmatch.resize(npairs); p.h_ninl.resize(npairs); p.h_nrinl.resize(npairs);
+  LSL_CUDA(cudaMemcpyAsync(p.h_nmatch.data(), p.nmatch, 4 * npairs, cudaMemcpyDeviceToHost, ctx->stream));
+  LSL_CUDA(cudaMemcpyAsync(p.h_ninl.data(), p.sc.n_inl, 4 * npairs, cudaMemcpyDeviceToHost, ctx->stream));
+  LSL_CUDA(cudaMemcpyAsync(p.h_nrinl.data(), p.sc.n_rinl, 4 * npairs, cudaMemcpyDeviceToHost, ctx->stream));
+  return LSL_OK;
+}
+
+extern "C" int lsl_match_lines(lsl_ctx* ctx, const lsl_frame* query, const lsl_frame* train, int adjacent, lsl_match* out,
+                               int cap, int* n) {
+  if (!ctx || !query || !train || !n) return LSL_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int adj = adjacent ? 1 : 0;
+  int rc = setup_pairs(ctx, 1, &query, &train, nullptr, nullptr, nullptr, &adj, -1);
+  if (rc) return rc;
+  if ((rc = lsl_launch_match(ctx, 1))) return rc;
+  int32_t nm = 0;
+  LSL_CUDA(cudaMemcpyAsync(&nm, ctx->pw.nmatch, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  LSL_CUDA(cudaStreamSynchronize(ctx->stream));
+  *n = nm;
+  ctx->stats.pairs += 1; ctx->stats.matches += nm;
+  if (nm > cap || (nm && !out)) return LSL_ERR_CAPACITY;
+  if (nm) {
+    LSL_CUDA(cudaMemcpy(out, ctx->pw.matches, sizeof(lsl_match) * nm, cudaMemcpyDeviceToHost));
+    ctx->stats.d2h_bytes += sizeof(lsl_match) * nm;
+  }
+  return LSL_OK;
+}
+
+// copies the index list `sel` (indices into the pair's match list) back as matches
+static int fetch_sel(lsl_ctx* ctx, const LslPairDesc& d, int which, int count, const std::vector<lsl_match>& all, lsl_match* out) {
+  if (!count) return LSL_OK;
+  std::vector<int32_t> idx(count);
+  LSL_CUDA(cudaMemcpy(idx.data(), ctx->pw.sc.sel + d.m_off * 3 + (size_t)which * d.cap_m, 4 * count, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < count; ++i) out[i] = all[idx[i]];
+  ctx->stats.d2h_bytes += 4 * count;
+  return LSL_OK;
+}
+
+extern "C" int lsl_pose_ransac(lsl_ctx* ctx, const lsl_frame* train, const lsl_frame* query, int id_train, int id_query,
+                               const lsl_match* pt_matches, int npt, const lsl_match* ln_matches, int nln, uint32_t seed,
+                               lsl_pose_rec* rec, lsl_match* inliers_out, int cap, int* n_inl, lsl_match* ransac_inliers_out,
+                               int cap2, int* n_rinl) {
+  if (!ctx || !train || !query || !rec || nln < 0 || (nln && !ln_matches)) return LSL_ERR_ARG;
+  if (npt != 0) { ctx->err = "point matches are not part of this build (line-only path)"; return LSL_ERR_ARG; }
+  if (nln > LSL_MAX_MATCH) return LSL_ERR_CAPACITY;
+  for (int i = 0; i < nln; ++i)
+    if (ln_matches[i].queryIdx < 0 || ln_matches[i].queryIdx >= query->nlines || ln_matches[i].trainIdx < 0 ||
+        ln_matches[i].trainIdx >= train->nlines) return LSL_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc = setup_pairs(ctx, 1, &query, &train, &id_query, &id_train, &seed, nullptr, nln);
+  if (rc) return rc;
+  int32_t nm = nln;
+  LSL_CUDA(cudaMemcpyAsync(ctx->pw.nmatch, &nm, 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (nln) LSL_CUDA(cudaMemcpyAsync(ctx->pw.matches, ln_matches, sizeof(lsl_match) * nln, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->stats.h2d_bytes += sizeof(lsl_match) * nln;
+  if ((rc = lsl_launch_pose(ctx, 1))) return rc;
+  if ((rc = fetch_counts(ctx, 1))) return rc;
+  LSL_CUDA(cudaMemcpyAsync(rec, ctx->pw.recs, sizeof(lsl_pose_rec), cudaMemcpyDeviceToHost, ctx->stream));
+  LSL_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->stats.pairs += 1; ctx->stats.d2h_bytes += sizeof(lsl_pose_rec);
+  std::vector<lsl_match> all(ln_matches, ln_matches + nln);
+  int ni = ctx->pw.h_ninl[0], nr = ctx->pw.h_nrinl[0];
+  if (n_inl) *n_inl = ni;
+  if (n_rinl) *n_rinl = nr;
+  if (inliers_out) { if (ni > cap) return LSL_ERR_CAPACITY; if ((rc = fetch_sel(ctx, ctx->pw.h_pairs[0], 1, ni, all, inliers_out))) return rc; }
+  if (ransac_inliers_out) { if (nr > cap2) return LSL_ERR_CAPACITY; if ((rc = fetch_sel(ctx, ctx->pw.h_pairs[0], 0, nr, all, ransac_inliers_out))) return rc; }
+  return LSL_OK;
+}
+
+extern "C" int lsl_match_pair_batch(lsl_ctx* ctx, int npairs, const lsl_frame* const* queries, const lsl_frame* const* trains,
+                                    const int32_t* id_query, const int32_t* id_train, const uint32_t* seeds, lsl_pose_rec* out) {
+  if (!ctx || npairs < 1 || !queries || !trains || !out) return LSL_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc = setup_pairs(ctx, npairs, queries, trains, id_query, id_train, seeds, nullptr, -1);
+  if (rc) return rc;
+  cudaEventRecord(ctx->ev0, ctx->stream);
+  if ((rc = lsl_launch_match(ctx, npairs))) return rc;
+  if ((rc = lsl_launch_pose(ctx, npairs))) return rc;
+  cudaEventRecord(ctx->ev3, ctx->stream);
+  if ((rc = fetch_counts(ctx, npairs))) return rc;
+  LSL_CUDA(cudaMemcpyAsync(out, ctx->pw.recs, sizeof(lsl_pose_rec) * npairs, cudaMemcpyDeviceToHost, ctx->stream));
+  LSL_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaEventElapsedTime(&ctx->ms_total, ctx->ev0, ctx->ev3);
+  ctx->stats.pairs += npairs; ctx->stats.d2h_bytes += (sizeof(lsl_pose_rec) + 12) * npairs;
+  for (int i = 0; i < npairs; ++i) ctx->stats.matches += ctx->pw.h_nmatch[i];
+  return LSL_OK;
+}
+
+// Match lists of pair `pair` of the last lsl_match_pair_batch call: what = 0 all line matches,
+// 1 refined inliers (output_line_inlier_matches), 2 inliers of the best RANSAC hypothesis.
+extern "C" int lsl_pair_matches(lsl_ctx* ctx, int pair, int what, lsl_match* out, int cap, int* n) {
+  if (!ctx || !n || pair < 0 || pair >= (int)ctx->pw.h_nmatch.size() || what < 0 || what > 2) return LSL_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  const LslPairDesc& d = ctx->pw.h_pairs[pair];
+  int nm = ctx->pw.h_nmatch[pair];
+  int cnt = what == 0 ? nm : (what == 1 ? ctx->pw.h_ninl[pair] : ctx->pw.h_nrinl[pair]);
+  *n = cnt;
+  if (cnt > cap || (cnt && !out)) return LSL_ERR_CAPACITY;
+  if (!cnt) return LSL_OK;
+  std::vector<lsl_match> all(nm);
+  LSL_CUDA(cudaMemcpy(all.data(), ctx->pw.matches + d.m_off, sizeof(lsl_match) * nm, cudaMemcpyDeviceToHost));
+  if (what == 0) { memcpy(out, all.data(), sizeof(lsl_match) * nm); return LSL_OK; }
+  return fetch_sel(ctx, d, what == 1 ? 1 : 0, cnt, all, out);
+}
+
 // parity-test read-back of per-line intermediates (inlier sample indices of the 3D-line RANSAC etc.)
 extern "C" int lsl_frame_debug(const lsl_frame* f, int32_t* npts, int32_t* inl_idx, int32_t* seg_of_line, int32_t* lm_iters) {
   if (!f) return LSL_ERR_ARG;

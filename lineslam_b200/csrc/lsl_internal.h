@@ -61,6 +61,44 @@ struct LslWork {
   int32_t* msld_fail;  // [B][LSL_MAX_LINES] 1 = descriptor has no valid sample (filled from rand())
 };
 
+// ---- pair registration workspace (k_pair.cu) ----
+struct LslPairDesc {
+  const lsl_line_rec* q;  // query (newer) frame lines, device
+  const lsl_line_rec* t;  // train (older) frame lines, device
+  int nq, nt, id_q, id_t;
+  uint32_t seed;
+  int adjacent;
+  size_t d_off;  // offset of this pair's nq x nt distance matrix in LslPairWork::D (doubles)
+  size_t m_off;  // offset of this pair's match-sized slices (in matches)
+  int cap_m;     // min(nq, nt): upper bound of the match count
+  int pad_;
+};
+struct LslPairScratch {
+  double* md;        // [M][72]  gathered per-match data
+  double* dab;       // [M][2]   Mahalanobis distances of the last scoring pass
+  int32_t* sel;      // [M][3]   RANSAC / refined / trial inlier index lists
+  double* lm;        // [M][182] per-match blocks of the LM refinement
+  int32_t* okf;      // [M]
+  float* tfs;        // [pairs][max_iter][12] hypotheses
+  int32_t* cnts;     // [pairs][max_iter]     inlier counts
+  uint16_t* trip;    // [pairs][max_iter][3]  sampled match triples
+  int32_t* n_inl;    // [pairs]
+  int32_t* n_rinl;   // [pairs]
+  float* tf_ransac;  // [pairs][16]
+  int max_iter;
+};
+struct LslPairWork {
+  LslPairDesc* d_pairs;
+  double* D;
+  lsl_match* matches;  // [M]
+  int32_t* nmatch;     // [pairs]
+  lsl_pose_rec* recs;  // [pairs]
+  LslPairScratch sc;
+  size_t cap_pairs, cap_m, cap_d;
+  std::vector<LslPairDesc> h_pairs;   // descriptors of the last batch (host copy)
+  std::vector<int32_t> h_nmatch, h_ninl, h_nrinl;
+};
+
 struct lsl_frame {
   lsl_ctx* ctx;
   int nlines, nsegs;
@@ -79,8 +117,7 @@ struct lsl_ctx {
   LslTaps taps;
   LslWork wk;
   void* wk_block; size_t wk_bytes;
-  // pair workspace
-  void* pair_block; size_t pair_bytes; int pair_cap;
+  LslPairWork pw;
   uint8_t* h_pin; size_t h_pin_bytes;   // pinned staging
   std::string err;
   lsl_stats stats;
@@ -101,3 +138,5 @@ int lsl_launch_image(lsl_ctx* ctx, int n, const uint8_t* d_img, int channels);
 int lsl_launch_lsd(lsl_ctx* ctx, int n);
 int lsl_launch_lines(lsl_ctx* ctx, int n, const float* d_depth, const double K[9], double dt);
 int lsl_prepare_taps(lsl_ctx* ctx);
+int lsl_launch_match(lsl_ctx* ctx, int npairs);
+int lsl_launch_pose(lsl_ctx* ctx, int npairs);
