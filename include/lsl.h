@@ -71,6 +71,11 @@ const char* lsl_last_error(const lsl_ctx* ctx);
 /* max_batch frames / pairs can be in flight per call; scratch is sized at creation. */
 int lsl_ctx_create(lsl_ctx** out, const lsl_params* params, int cuda_device, int max_batch, int max_w, int max_h);
 void lsl_ctx_destroy(lsl_ctx* ctx);
+/* Run every call of this context on the caller's cudaStream_t (NULL restores the context's own stream). */
+int lsl_ctx_set_stream(lsl_ctx* ctx, void* cuda_stream);
+/* Debug mode keeps the LSD rows and per-line intermediates of extracted frames on the host
+ * (lsl_frame_segments, lsl_frame_debug); off by default: the product path moves 8 bytes per frame. */
+int lsl_ctx_set_debug(lsl_ctx* ctx, int on);
 
 /* Node::detect3DLines (src/node.h:286-287, src/line/lineslam.cpp:200-357) for one frame.
  * img: u8, channels = 1 (gray, as detect3DLines receives it) or 3 (interleaved, memory-order
@@ -90,7 +95,8 @@ int lsl_extract_batch_dev(lsl_ctx* ctx, int n, const uint8_t* d_imgs, int channe
 
 int lsl_frame_num_lines(const lsl_frame* f);
 int lsl_frame_lines(const lsl_frame* f, lsl_line_rec* dst, int cap, int* n);
-/* LSD output (ntuple_list of lsd(), external/lsd/lsd.h): n x 5 doubles x1,y1,x2,y2,width */
+/* LSD output (ntuple_list of lsd(), external/lsd/lsd.h): n x 5 doubles x1,y1,x2,y2,width.
+ * Only frames extracted in debug mode keep the rows; otherwise *n is set and LSL_ERR_ARG returned. */
 int lsl_frame_segments(const lsl_frame* f, double* dst, int cap, int* n);
 /* Builds a frame from caller-supplied records (e.g. features cached by the host). */
 int lsl_frame_from_lines(lsl_ctx* ctx, const lsl_line_rec* recs, int n, lsl_frame** out);
@@ -125,6 +131,12 @@ int lsl_pair_matches(lsl_ctx* ctx, int pair, int what, lsl_match* out, int cap, 
  * nranks*nlocal. nccl_comm is an ncclComm_t created by the host; NCCL is resolved with dlopen. */
 int lsl_allgather_poses(lsl_ctx* ctx, void* nccl_comm, int nranks, const lsl_pose_rec* local_recs, int nlocal,
                         lsl_pose_rec* all_recs);
+/* Communicator owned by the library (the reference has no communication layer; this is the plumbing the
+ * sharded deployment needs): rank 0 calls lsl_comm_unique_id (128-byte ncclUniqueId), the host ships it
+ * to the other ranks by any means, every rank calls lsl_comm_init; lsl_allgather_poses(ctx, NULL, 0, ...)
+ * then uses it. */
+int lsl_comm_unique_id(void* id128);
+int lsl_comm_init(lsl_ctx* ctx, const void* id128, int nranks, int rank);
 
 /* Stage counters of the last call (segments, lines, matches, LM iterations, kernel launches). */
 typedef struct lsl_stats {
@@ -134,6 +146,10 @@ int lsl_get_stats(const lsl_ctx* ctx, lsl_stats* out);
 /* Device-time of the region-growing kernel of the last extract call in ms (CUDA events on the
  * context stream), and of the whole last call. */
 int lsl_last_timing(const lsl_ctx* ctx, float* ms_total, float* ms_region_grow);
+/* Device time (ms, CUDA events on the context stream) of every kernel launched by the last extract call
+ * and the last pair call; lsl_kernel_name(i) names entry i. */
+int lsl_kernel_times(const lsl_ctx* ctx, float* ms, int cap, int* n);
+const char* lsl_kernel_name(int i);
 
 /* Stage-wise read-back for parity tests (frame 0 of the last extract call):
  * what: 0 gray u8[H*W], 1 scaled f64[sh*sw], 2 angles f64, 3 modgrad f64, 4 seeds i32 (x|y<<16),

@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -47,6 +48,8 @@ def lib():
         L.lsl_frame_free.argtypes = [C.c_void_p]
         L.lsl_frame_free.restype = None
         L.lsl_frame_num_lines.argtypes = [C.c_void_p]
+        L.lsl_kernel_name.restype = C.c_char_p
+        L.lsl_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -87,16 +90,42 @@ class Context:
     """Owns the device workspace (lsl_ctx). max_batch frames can be extracted per call."""
 
     def __init__(self, params: Params | None = None, device: int = 0, max_batch: int = 1, max_w: int = 640,
-                 max_h: int = 480):
+                 max_h: int = 480, debug: bool = False):
         self.params = params if params is not None else default_params()
         self._h = C.c_void_p()
+        self._frames = weakref.WeakSet()
         _check(lib().lsl_ctx_create(C.byref(self._h), C.byref(self.params), device, max_batch, max_w, max_h))
         self.max_batch = max_batch
+        if debug:
+            _check(lib().lsl_ctx_set_debug(self._h, 1))
 
     def close(self):
         if self._h:
+            for f in list(self._frames):
+                f.free()
             lib().lsl_ctx_destroy(self._h)
             self._h = C.c_void_p()
+
+    def set_stream(self, cuda_stream: int | None):
+        """Run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); None restores ours."""
+        _check(lib().lsl_ctx_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None), self._h)
+
+    # ---- pose exchange (one process per GPU; the id travels over the host's plumbing) ----
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(lib().lsl_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, uid: bytes, nranks: int, rank: int):
+        _check(lib().lsl_comm_init(self._h, C.c_char_p(uid), nranks, rank), self._h)
+        self.nranks, self.rank = nranks, rank
+
+    def allgather_poses(self, local_recs):
+        loc = np.ascontiguousarray(local_recs, POSE_DTYPE)
+        out = np.zeros(len(loc) * self.nranks, POSE_DTYPE)
+        _check(lib().lsl_allgather_poses(self._h, None, 0, ptr(loc), len(loc), ptr(out)), self._h)
+        return out
 
     def __del__(self):
         try:
@@ -181,6 +210,13 @@ class Context:
         _check(lib().lsl_get_stats(self._h, C.byref(s)))
         return s
 
+    def kernel_times(self) -> dict:
+        """Device ms per kernel of the last extract call and the last pair call."""
+        ms = (C.c_float * 32)()
+        n = C.c_int(0)
+        _check(lib().lsl_kernel_times(self._h, ms, 32, C.byref(n)))
+        return {lib().lsl_kernel_name(i).decode(): float(ms[i]) for i in range(n.value)}
+
     def last_timing(self):
         a, b = C.c_float(0), C.c_float(0)
         _check(lib().lsl_last_timing(self._h, C.byref(a), C.byref(b)))
@@ -198,6 +234,7 @@ class Frame:
     def __init__(self, ctx: Context, handle):
         self.ctx = ctx
         self._h = handle if isinstance(handle, C.c_void_p) else C.c_void_p(handle)
+        ctx._frames.add(self)
 
     @property
     def num_lines(self) -> int:
@@ -211,6 +248,7 @@ class Frame:
         return out[:k.value].copy()
 
     def segments(self) -> np.ndarray:
+        """LSD rows (only for frames of a debug=True context)."""
         k = C.c_int(0)
         lib().lsl_frame_segments(self._h, None, 0, C.byref(k))
         out = np.zeros((max(k.value, 1), 5))

@@ -220,20 +220,31 @@ int lsl_launch_image(lsl_ctx* ctx, int n, const uint8_t* d_img, int channels) {
   size_t npix = (size_t)d.W * d.H;
   if (channels == 3) {
     long n4 = (long)(npix * n / 4);
+    LSL_KSTART(ctx, LSL_K_GRAY);
     gray_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(d_img, w.gray, n4);
+    LSL_KSTOP(ctx, LSL_K_GRAY);
   } else {
     LSL_CUDA(cudaMemcpyAsync(w.gray, d_img, npix * n, cudaMemcpyDeviceToDevice, st));
   }
   dim3 bx(128), gxp((d.sw + 127) / 128, d.H, n), gyp((d.sw + 127) / 128, d.sh, n);
+  LSL_KSTART(ctx, LSL_K_XPASS);
   xpass_kernel<<<gxp, bx, 0, st>>>(w.gray, w.aux, ctx->taps.kx, ctx->taps.xc, d.W, d.H, d.sw, ctx->taps.h, ctx->taps.n);
+  LSL_KSTOP(ctx, LSL_K_XPASS);
+  LSL_KSTART(ctx, LSL_K_YPASS);
   ypass_kernel<<<gyp, bx, 0, st>>>(w.aux, w.scaled, ctx->taps.ky, ctx->taps.yc, d.H, d.sw, d.sh, ctx->taps.h, ctx->taps.n);
+  LSL_KSTOP(ctx, LSL_K_YPASS);
   double prec = LSL_PI * P.lsd_ang_th / 180.0;
   double rho = P.lsd_quant / lsl_sin(prec);
+  LSL_KSTART(ctx, LSL_K_LLANGLE);
   ll_angle_kernel<<<gyp, bx, 0, st>>>(w.scaled, w.angles, w.modgrad, w.cs, w.binT, d.sw, d.sh, rho, P.lsd_n_bins, P.lsd_max_grad);
+  LSL_KSTOP(ctx, LSL_K_LLANGLE);
+  LSL_KSTART(ctx, LSL_K_SEEDS);
   seed_list_kernel<<<n, 256, P.lsd_n_bins * sizeof(int), st>>>(w.binT, w.seeds, w.nseeds, d.sw, d.sh, P.lsd_n_bins);
+  LSL_KSTOP(ctx, LSL_K_SEEDS);
   dim3 bs(32, 16), gs((d.W + 31) / 32, (d.H + 15) / 16, n);
+  LSL_KSTART(ctx, LSL_K_SOBEL);
   sobel5_kernel<<<gs, bs, 0, st>>>(w.gray, w.gx, w.gy, d.W, d.H);
-  ctx->stats.kernel_launches += 6;
+  LSL_KSTOP(ctx, LSL_K_SOBEL);
   LSL_CUDA(cudaGetLastError());
   return LSL_OK;
 }

@@ -852,12 +852,37 @@ int lsl_launch_lines(lsl_ctx* ctx, int n, const float* d_depth, const double K[9
   LP.sample_min = P.line_sample_min_num; LP.sample_max = P.line_sample_max_num; LP.ransac_iters = P.ransac_iters_extract_line;
   LP.ncells = P.num_cells_lineseg_range; LP.mle_iters = P.line3d_mle_iter_num; LP.msld_s = d.msld_s;
   LP.W = d.W; LP.H = d.H;
+  LSL_KSTART(ctx, LSL_K_RANSAC3D);
   line3d_ransac_kernel<<<n, 128, 0, st>>>(w, LP, d_depth);
+  LSL_KSTOP(ctx, LSL_K_RANSAC3D);
   dim3 gl(256, n);
+  LSL_KSTART(ctx, LSL_K_MSLD);
   line_msld_kernel<<<gl, 128, 0, st>>>(w, LP, w.msld_fail);
+  LSL_KSTOP(ctx, LSL_K_MSLD);
+  LSL_KSTART(ctx, LSL_K_RANDFILL);
   msld_randfill_kernel<<<(n + 63) / 64, 64, 0, st>>>(w, w.msld_fail, n);
+  LSL_KSTOP(ctx, LSL_K_RANDFILL);
+  LSL_KSTART(ctx, LSL_K_MLE);
   line_mle_kernel<<<gl, 32, sizeof(MleSmem), st>>>(w, LP);
-  ctx->stats.kernel_launches += 4;
+  LSL_KSTOP(ctx, LSL_K_MLE);
+  LSL_CUDA(cudaGetLastError());
+  return LSL_OK;
+}
+
+// Packs the kept line records of every frame of the batch into one dense block (offsets in ctx->d_goff).
+__global__ void gather_lines_kernel(LslWork w, const int32_t* __restrict__ goff, lsl_line_rec* __restrict__ dst) {
+  const int f = blockIdx.y;
+  const int nl = min(w.nlines[f], LSL_MAX_LINES);
+  const int nwords = nl * (int)(sizeof(lsl_line_rec) / 16);
+  const uint4* src = reinterpret_cast<const uint4*>(w.lines + (size_t)f * LSL_MAX_LINES);
+  uint4* out = reinterpret_cast<uint4*>(dst + goff[f]);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += gridDim.x * blockDim.x) out[i] = src[i];
+}
+int lsl_launch_gather(lsl_ctx* ctx, int n, lsl_line_rec* dst) {
+  dim3 g(8, n);
+  LSL_KSTART(ctx, LSL_K_GATHER);
+  gather_lines_kernel<<<g, 256, 0, ctx->stream>>>(ctx->wk, ctx->d_goff, dst);
+  LSL_KSTOP(ctx, LSL_K_GATHER);
   LSL_CUDA(cudaGetLastError());
   return LSL_OK;
 }

@@ -531,11 +531,10 @@ int lsl_launch_lsd(lsl_ctx* ctx, int n) {
   double p = P.lsd_ang_th / 180.0;
   double logNT = 5.0 * (lsl_log10((double)d.sw) + lsl_log10((double)d.sh)) / 2.0;
   int min_reg_size = (int)(-logNT / lsl_log10(p));
-  cudaEventRecord(ctx->ev1, ctx->stream);
+  LSL_KSTART(ctx, LSL_K_REGION);
   lsd_region_kernel<<<n, 32, 0, ctx->stream>>>(w, d.sw, d.sh, P.lsd_ang_th, P.lsd_density_th, P.lsd_eps, P.lsd_scale,
                                                 logNT, min_reg_size);
-  cudaEventRecord(ctx->ev2, ctx->stream);
-  ctx->stats.kernel_launches += 1;
+  LSL_KSTOP(ctx, LSL_K_REGION);
   LSL_CUDA(cudaGetLastError());
   return LSL_OK;
 }

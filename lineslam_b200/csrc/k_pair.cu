@@ -721,8 +721,9 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_kernel(const LslPairDesc* _
 int lsl_launch_match(lsl_ctx* ctx, int npairs) {
   const double PI_T = 3.14159265;  // lineslam.h:38
   double cosT = lsl_cos(30 * PI_T / 180);
+  LSL_KSTART(ctx, LSL_K_MATCH);
   match_lines_kernel<<<npairs, 256, 0, ctx->stream>>>(ctx->pw.d_pairs, ctx->pw.D, ctx->pw.matches, ctx->pw.nmatch, cosT);
-  ctx->stats.kernel_launches += 1;
+  LSL_KSTOP(ctx, LSL_K_MATCH);
   LSL_CUDA(cudaGetLastError());
   return LSL_OK;
 }
@@ -733,8 +734,9 @@ int lsl_launch_pose(lsl_ctx* ctx, int npairs) {
   PP.thr = P.max_mah_dist_for_inliers; PP.line_weight_g2o = P.g2o_line_error_weight; PP.huber_delta = P.g2o_BA_kernel_delta;
   PP.robust = P.g2o_BA_use_kernel; PP.max_iter = P.ransac_iters_line_motion; PP.min_matches = P.min_feature_matches;
   PP.min_loopclose = P.min_matches_loopclose; PP.line_weight = P.line_match_number_weight;
+  LSL_KSTART(ctx, LSL_K_POSE);
   pose_kernel<<<npairs, POSE_THREADS, 0, ctx->stream>>>(ctx->pw.d_pairs, ctx->pw.matches, ctx->pw.nmatch, ctx->pw.sc, PP, ctx->pw.recs);
-  ctx->stats.kernel_launches += 1;
+  LSL_KSTOP(ctx, LSL_K_POSE);
   LSL_CUDA(cudaGetLastError());
   return LSL_OK;
 }

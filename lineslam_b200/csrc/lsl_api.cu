@@ -1,8 +1,9 @@
-// lsl_api.cu — C ABI of liblsl_b200 (include/lsl.h): contexts, frames, batched extraction.
-// There is no CPU fallback anywhere in this library: without a CUDA device every entry point
-// that computes returns LSL_ERR_NO_DEVICE.
+// lsl_api.cu — C ABI of liblsl_b200 (include/lsl.h): contexts, frames, batched extraction, pair
+// registration and the pose exchange. There is no CPU fallback anywhere in this library: without a
+// CUDA device every entry point that computes returns LSL_ERR_NO_DEVICE.
 #include "lsl_internal.h"
 #include "shared/lsl_params_default.h"
+#include <dlfcn.h>
 #include <string.h>
 #include <stdlib.h>
 #include <new>
@@ -21,6 +22,12 @@ extern "C" const char* lsl_strerror(int s) {
   }
 }
 extern "C" const char* lsl_last_error(const lsl_ctx* ctx) { return ctx ? ctx->err.c_str() : ""; }
+
+static const char* const kKernelNames[LSL_K_COUNT] = {
+    "gray_kernel", "xpass_kernel", "ypass_kernel", "ll_angle_kernel", "seed_list_kernel", "sobel5_kernel",
+    "lsd_region_kernel", "line3d_ransac_kernel", "line_msld_kernel", "msld_randfill_kernel", "line_mle_kernel",
+    "gather_lines_kernel", "match_lines_kernel", "pose_kernel"};
+extern "C" const char* lsl_kernel_name(int i) { return (i >= 0 && i < LSL_K_COUNT) ? kKernelNames[i] : ""; }
 
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -67,14 +74,25 @@ static int carve(lsl_ctx* ctx, bool measure, size_t* total) {
   CARVE(rng_state, int32_t, (size_t)B * 36);
   CARVE(lm_iters, int32_t, (size_t)B * LSL_MAX_LINES);
   CARVE(msld_fail, int32_t, (size_t)B * LSL_MAX_LINES);
-  // tap tables
+  // tap tables, gather offsets
   if (!measure) ctx->taps.kx = (double*)(base + off); off += align_up(sizeof(double) * sw * 8);
   if (!measure) ctx->taps.xc = (int*)(base + off); off += align_up(sizeof(int) * sw);
   if (!measure) ctx->taps.ky = (double*)(base + off); off += align_up(sizeof(double) * sh * 8);
   if (!measure) ctx->taps.yc = (int*)(base + off); off += align_up(sizeof(int) * sh);
+  if (!measure) ctx->d_goff = (int32_t*)(base + off); off += align_up(sizeof(int32_t) * B);
 #undef CARVE
   *total = off;
   return LSL_OK;
+}
+
+static void free_pair_ws(lsl_ctx* ctx) {
+  LslPairWork& p = ctx->pw;
+  void* ptrs[] = {p.d_pairs, p.D, p.matches, p.nmatch, p.recs, p.sc.md, p.sc.dab, p.sc.sel, p.sc.lm, p.sc.okf, p.sc.tfs,
+                  p.sc.cnts, p.sc.trip, p.sc.n_inl, p.sc.n_rinl, p.sc.tf_ransac};
+  for (void* q : ptrs) if (q) cudaFree(q);
+  memset(&p.sc, 0, sizeof(p.sc));
+  p.d_pairs = nullptr; p.D = nullptr; p.matches = nullptr; p.nmatch = nullptr; p.recs = nullptr;
+  p.cap_pairs = p.cap_m = p.cap_d = 0;
 }
 
 extern "C" int lsl_ctx_create(lsl_ctx** out, const lsl_params* params, int cuda_device, int max_batch, int max_w, int max_h) {
@@ -94,15 +112,29 @@ extern "C" int lsl_ctx_create(lsl_ctx** out, const lsl_params* params, int cuda_
   ctx->h_pin = nullptr; ctx->h_pin_bytes = 0;
   memset(&ctx->stats, 0, sizeof(ctx->stats));
   memset(&ctx->dims, 0, sizeof(ctx->dims));
+  memset(ctx->kran, 0, sizeof(ctx->kran));
+  memset(ctx->kms, 0, sizeof(ctx->kms));
   ctx->ms_total = ctx->ms_rg = 0.f;
+  ctx->debug = 0;
+  ctx->nccl_lib = nullptr; ctx->nccl_comm = nullptr; ctx->nccl_rank = 0; ctx->nccl_nranks = 1; ctx->nccl_own = false;
   if (ctx->P.lsd_n_bins > 4096 || ctx->P.line_sample_max_num + 1 > LSL_MAX_SMP || ctx->P.num_cells_lineseg_range > 32 ||
       ctx->P.num_cells_lineseg_range < 10) { delete ctx; return LSL_ERR_ARG; }
   cudaError_t e = cudaSetDevice(cuda_device);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+  ctx->stream = ctx->own_stream;
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
-  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
-  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev2);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev3);
+  for (int k = 0; k < LSL_K_COUNT && e == cudaSuccess; ++k) {
+    e = cudaEventCreate(&ctx->kev[k][0]);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->kev[k][1]);
+  }
+  if (e == cudaSuccess) {  // keep freed line blocks in the stream-ordered pool instead of returning them to the OS
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, cuda_device) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
   size_t total = 0;
   carve(ctx, true, &total);
   ctx->wk_bytes = total;
@@ -113,26 +145,33 @@ extern "C" int lsl_ctx_create(lsl_ctx** out, const lsl_params* params, int cuda_
   return LSL_OK;
 }
 
-static void free_pair_ws(lsl_ctx* ctx) {
-  LslPairWork& p = ctx->pw;
-  void* ptrs[] = {p.d_pairs, p.D, p.matches, p.nmatch, p.recs, p.sc.md, p.sc.dab, p.sc.sel, p.sc.lm, p.sc.okf, p.sc.tfs,
-                  p.sc.cnts, p.sc.trip, p.sc.n_inl, p.sc.n_rinl, p.sc.tf_ransac};
-  for (void* q : ptrs) if (q) cudaFree(q);
-  memset(&p.sc, 0, sizeof(p.sc));
-  p.d_pairs = nullptr; p.D = nullptr; p.matches = nullptr; p.nmatch = nullptr; p.recs = nullptr;
-  p.cap_pairs = p.cap_m = p.cap_d = 0;
-}
+static void nccl_teardown(lsl_ctx* ctx);
 
 extern "C" void lsl_ctx_destroy(lsl_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  nccl_teardown(ctx);
   if (ctx->wk_block) cudaFree(ctx->wk_block);
   free_pair_ws(ctx);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
-  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);
-  cudaStreamDestroy(ctx->stream);
+  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev3);
+  for (int k = 0; k < LSL_K_COUNT; ++k) { cudaEventDestroy(ctx->kev[k][0]); cudaEventDestroy(ctx->kev[k][1]); }
+  cudaStreamDestroy(ctx->own_stream);
   delete ctx;
+}
+
+extern "C" int lsl_ctx_set_stream(lsl_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return LSL_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return LSL_OK;
+}
+extern "C" int lsl_ctx_set_debug(lsl_ctx* ctx, int on) {
+  if (!ctx) return LSL_ERR_ARG;
+  ctx->debug = on ? 1 : 0;
+  return LSL_OK;
 }
 
 static int set_dims(lsl_ctx* ctx, int W, int H) {
@@ -155,6 +194,14 @@ static int ensure_pinned(lsl_ctx* ctx, size_t bytes) {
   return LSL_OK;
 }
 
+static void clear_ktimes(lsl_ctx* ctx, int from, int to) {
+  for (int k = from; k < to; ++k) { ctx->kran[k] = false; ctx->kms[k] = 0.f; }
+}
+static void collect_ktimes(lsl_ctx* ctx, int from, int to) {
+  for (int k = from; k < to; ++k)
+    if (ctx->kran[k]) cudaEventElapsedTime(&ctx->kms[k], ctx->kev[k][0], ctx->kev[k][1]);
+}
+
 // Runs all extraction kernels for n frames whose inputs are on the device, then builds the handles.
 static int extract_device(lsl_ctx* ctx, int n, const uint8_t* d_imgs, int channels, const float* d_depths, int W, int H,
                           const double K[9], double dt, const uint32_t* seeds, lsl_frame** out) {
@@ -165,46 +212,61 @@ static int extract_device(lsl_ctx* ctx, int n, const uint8_t* d_imgs, int channe
   std::vector<uint32_t> sd(n);
   for (int i = 0; i < n; ++i) sd[i] = seeds ? seeds[i] : 1u;
   LSL_CUDA(cudaMemcpyAsync(w.seeds_rng, sd.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+  clear_ktimes(ctx, 0, LSL_K_MATCH);
   cudaEventRecord(ctx->ev0, st);
   if ((rc = lsl_launch_image(ctx, n, d_imgs, channels))) return rc;
   if ((rc = lsl_launch_lsd(ctx, n))) return rc;
   if ((rc = lsl_launch_lines(ctx, n, d_depths, K, dt))) return rc;
-  cudaEventRecord(ctx->ev3, st);
-  // ---- results back: counts, then the records actually produced
-  std::vector<int32_t> nsegs(n), nlines(n);
+  // ---- counts back (8 bytes per frame), then one dense block for the records of the whole batch
+  std::vector<int32_t> nsegs(n), nlines(n), goff(n);
   LSL_CUDA(cudaMemcpyAsync(nsegs.data(), w.nsegs, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
   LSL_CUDA(cudaMemcpyAsync(nlines.data(), w.nlines, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
   LSL_CUDA(cudaStreamSynchronize(st));
   ctx->stats.d2h_bytes += 8 * n;
+  size_t tot = 0;
   for (int f = 0; f < n; ++f) {
     if (nsegs[f] > LSL_MAX_SEGS || nlines[f] > LSL_MAX_LINES) { ctx->err = "per-frame segment/line table overflow"; return LSL_ERR_CAPACITY; }
+    goff[f] = (int32_t)tot;
+    tot += nlines[f];
+  }
+  LslLineBlock* blk = nullptr;
+  if (tot) {
+    blk = new (std::nothrow) LslLineBlock();
+    if (!blk) return LSL_ERR_ARG;
+    blk->refs = 0; blk->d = nullptr;
+    LSL_CUDA(cudaMallocAsync((void**)&blk->d, sizeof(lsl_line_rec) * tot, st));
+    LSL_CUDA(cudaMemcpyAsync(ctx->d_goff, goff.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    if ((rc = lsl_launch_gather(ctx, n, blk->d))) return rc;
+  }
+  cudaEventRecord(ctx->ev3, st);
+  for (int f = 0; f < n; ++f) {
     lsl_frame* fr = new (std::nothrow) lsl_frame();
     if (!fr) return LSL_ERR_ARG;
-    fr->ctx = ctx; fr->nlines = nlines[f]; fr->nsegs = nsegs[f]; fr->d_lines = nullptr;
-    fr->lines.resize(fr->nlines); fr->segs.resize((size_t)fr->nsegs * 5);
-    fr->dbg_npts.resize(fr->nlines); fr->dbg_inl.resize((size_t)fr->nlines * LSL_MAX_SMP);
-    fr->dbg_seg.resize(fr->nlines); fr->dbg_lm.resize(fr->nlines);
-    if (fr->nsegs)
-      LSL_CUDA(cudaMemcpyAsync(fr->segs.data(), w.segs + (size_t)f * LSL_MAX_SEGS * 5, sizeof(double) * 5 * fr->nsegs, cudaMemcpyDeviceToHost, st));
-    if (fr->nlines) {
-      size_t lb = sizeof(lsl_line_rec) * fr->nlines;
-      LSL_CUDA(cudaMalloc((void**)&fr->d_lines, lb));
-      LSL_CUDA(cudaMemcpyAsync(fr->d_lines, w.lines + (size_t)f * LSL_MAX_LINES, lb, cudaMemcpyDeviceToDevice, st));
-      LSL_CUDA(cudaMemcpyAsync(fr->lines.data(), w.lines + (size_t)f * LSL_MAX_LINES, lb, cudaMemcpyDeviceToHost, st));
-      LSL_CUDA(cudaMemcpyAsync(fr->dbg_npts.data(), w.npts + (size_t)f * LSL_MAX_LINES, 4 * fr->nlines, cudaMemcpyDeviceToHost, st));
-      LSL_CUDA(cudaMemcpyAsync(fr->dbg_inl.data(), w.inl_idx + (size_t)f * LSL_MAX_LINES * LSL_MAX_SMP, 4 * (size_t)fr->nlines * LSL_MAX_SMP, cudaMemcpyDeviceToHost, st));
-      LSL_CUDA(cudaMemcpyAsync(fr->dbg_seg.data(), w.keep_cand + (size_t)f * LSL_MAX_LINES, 4 * fr->nlines, cudaMemcpyDeviceToHost, st));
-      LSL_CUDA(cudaMemcpyAsync(fr->dbg_lm.data(), w.lm_iters + (size_t)f * LSL_MAX_LINES, 4 * fr->nlines, cudaMemcpyDeviceToHost, st));
-      ctx->stats.d2h_bytes += lb;
+    fr->ctx = ctx; fr->nlines = nlines[f]; fr->nsegs = nsegs[f]; fr->d_lines = nullptr; fr->blk = nullptr;
+    fr->have_host = false; fr->have_dbg = false;
+    if (fr->nlines) { fr->blk = blk; blk->refs += 1; fr->d_lines = blk->d + goff[f]; }
+    if (ctx->debug) {
+      fr->have_dbg = true;
+      fr->segs.resize((size_t)fr->nsegs * 5);
+      fr->dbg_npts.resize(fr->nlines); fr->dbg_inl.resize((size_t)fr->nlines * LSL_MAX_SMP);
+      fr->dbg_seg.resize(fr->nlines); fr->dbg_lm.resize(fr->nlines);
+      if (fr->nsegs)
+        LSL_CUDA(cudaMemcpyAsync(fr->segs.data(), w.segs + (size_t)f * LSL_MAX_SEGS * 5, sizeof(double) * 5 * fr->nsegs, cudaMemcpyDeviceToHost, st));
+      if (fr->nlines) {
+        LSL_CUDA(cudaMemcpyAsync(fr->dbg_npts.data(), w.npts + (size_t)f * LSL_MAX_LINES, 4 * fr->nlines, cudaMemcpyDeviceToHost, st));
+        LSL_CUDA(cudaMemcpyAsync(fr->dbg_inl.data(), w.inl_idx + (size_t)f * LSL_MAX_LINES * LSL_MAX_SMP, 4 * (size_t)fr->nlines * LSL_MAX_SMP, cudaMemcpyDeviceToHost, st));
+        LSL_CUDA(cudaMemcpyAsync(fr->dbg_seg.data(), w.keep_cand + (size_t)f * LSL_MAX_LINES, 4 * fr->nlines, cudaMemcpyDeviceToHost, st));
+        LSL_CUDA(cudaMemcpyAsync(fr->dbg_lm.data(), w.lm_iters + (size_t)f * LSL_MAX_LINES, 4 * fr->nlines, cudaMemcpyDeviceToHost, st));
+      }
     }
-    ctx->stats.d2h_bytes += sizeof(double) * 5 * fr->nsegs;
     ctx->stats.segments += fr->nsegs; ctx->stats.lines3d += fr->nlines;
     out[f] = fr;
   }
   LSL_CUDA(cudaStreamSynchronize(st));
   ctx->stats.frames += n;
   cudaEventElapsedTime(&ctx->ms_total, ctx->ev0, ctx->ev3);
-  cudaEventElapsedTime(&ctx->ms_rg, ctx->ev1, ctx->ev2);
+  collect_ktimes(ctx, 0, LSL_K_MATCH);
+  ctx->ms_rg = ctx->kms[LSL_K_REGION];
   return LSL_OK;
 }
 
@@ -216,6 +278,12 @@ extern "C" int lsl_extract_batch_dev(lsl_ctx* ctx, int n, const uint8_t* d_imgs,
   return extract_device(ctx, n, d_imgs, channels, d_depths, W, H, K, dt, seeds, out);
 }
 
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 extern "C" int lsl_extract_batch(lsl_ctx* ctx, int n, const uint8_t* const* imgs, int channels, const float* const* depths,
                                  int W, int H, const double K[9], double dt, const uint32_t* seeds, lsl_frame** out) {
   if (!ctx || !imgs || !depths || !K || !out || n < 1 || (channels != 1 && channels != 3)) return LSL_ERR_ARG;
@@ -224,16 +292,33 @@ extern "C" int lsl_extract_batch(lsl_ctx* ctx, int n, const uint8_t* const* imgs
   int rc = set_dims(ctx, W, H);
   if (rc) return rc;
   const size_t ib = (size_t)W * H * channels, db = (size_t)W * H * sizeof(float);
-  // stage through pinned memory so the copies are truly asynchronous (inputs may be pageable)
-  if ((rc = ensure_pinned(ctx, (ib + db) * n))) return rc;
-  uint8_t* hp = ctx->h_pin;
-  for (int i = 0; i < n; ++i) {
+  for (int i = 0; i < n; ++i)
     if (!imgs[i] || !depths[i]) return LSL_ERR_ARG;
-    memcpy(hp + ib * i, imgs[i], ib);
-    memcpy(hp + ib * n + db * i, depths[i], db);
+  // page-locked caller buffers are copied straight from where they are; pageable ones are staged through
+  // the context's pinned buffer so the copies stay asynchronous
+  bool pinned = is_pinned(imgs[0]) && is_pinned(depths[0]);
+  if (pinned) {
+    bool contiguous = true;
+    for (int i = 1; i < n; ++i) contiguous &= (imgs[i] == imgs[0] + ib * i) && ((const uint8_t*)depths[i] == (const uint8_t*)depths[0] + db * i);
+    if (contiguous) {
+      LSL_CUDA(cudaMemcpyAsync(ctx->wk.img, imgs[0], ib * n, cudaMemcpyHostToDevice, ctx->stream));
+      LSL_CUDA(cudaMemcpyAsync(ctx->wk.depth, depths[0], db * n, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+      for (int i = 0; i < n; ++i) {
+        LSL_CUDA(cudaMemcpyAsync(ctx->wk.img + ib * i, imgs[i], ib, cudaMemcpyHostToDevice, ctx->stream));
+        LSL_CUDA(cudaMemcpyAsync((uint8_t*)ctx->wk.depth + db * i, depths[i], db, cudaMemcpyHostToDevice, ctx->stream));
+      }
+    }
+  } else {
+    if ((rc = ensure_pinned(ctx, (ib + db) * n))) return rc;
+    uint8_t* hp = ctx->h_pin;
+    for (int i = 0; i < n; ++i) {
+      memcpy(hp + ib * i, imgs[i], ib);
+      memcpy(hp + ib * n + db * i, depths[i], db);
+    }
+    LSL_CUDA(cudaMemcpyAsync(ctx->wk.img, hp, ib * n, cudaMemcpyHostToDevice, ctx->stream));
+    LSL_CUDA(cudaMemcpyAsync(ctx->wk.depth, hp + ib * n, db * n, cudaMemcpyHostToDevice, ctx->stream));
   }
-  LSL_CUDA(cudaMemcpyAsync(ctx->wk.img, hp, ib * n, cudaMemcpyHostToDevice, ctx->stream));
-  LSL_CUDA(cudaMemcpyAsync(ctx->wk.depth, hp + ib * n, db * n, cudaMemcpyHostToDevice, ctx->stream));
   ctx->stats.h2d_bytes += (ib + db) * n;
   return extract_device(ctx, n, ctx->wk.img, channels, ctx->wk.depth, W, H, K, dt, seeds, out);
 }
@@ -244,16 +329,28 @@ extern "C" int lsl_extract(lsl_ctx* ctx, const uint8_t* img, int channels, const
 }
 
 extern "C" int lsl_frame_num_lines(const lsl_frame* f) { return f ? f->nlines : LSL_ERR_ARG; }
-extern "C" int lsl_frame_lines(const lsl_frame* f, lsl_line_rec* dst, int cap, int* n) {
+extern "C" int lsl_frame_lines(const lsl_frame* fc, lsl_line_rec* dst, int cap, int* n) {
+  lsl_frame* f = const_cast<lsl_frame*>(fc);
   if (!f || !n) return LSL_ERR_ARG;
   *n = f->nlines;
   if (cap < f->nlines || (!dst && f->nlines)) return LSL_ERR_CAPACITY;
-  if (f->nlines) memcpy(dst, f->lines.data(), sizeof(lsl_line_rec) * f->nlines);
+  if (!f->nlines) return LSL_OK;
+  if (!f->have_host) {  // host mirror on first use
+    lsl_ctx* ctx = f->ctx;
+    cudaSetDevice(ctx->device);
+    f->lines.resize(f->nlines);
+    LSL_CUDA(cudaMemcpyAsync(f->lines.data(), f->d_lines, sizeof(lsl_line_rec) * f->nlines, cudaMemcpyDeviceToHost, ctx->stream));
+    LSL_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += sizeof(lsl_line_rec) * f->nlines;
+    f->have_host = true;
+  }
+  memcpy(dst, f->lines.data(), sizeof(lsl_line_rec) * f->nlines);
   return LSL_OK;
 }
 extern "C" int lsl_frame_segments(const lsl_frame* f, double* dst, int cap, int* n) {
   if (!f || !n) return LSL_ERR_ARG;
   *n = f->nsegs;
+  if (!f->have_dbg) return f->nsegs ? LSL_ERR_ARG : LSL_OK;  // LSD rows are only kept in debug mode
   if (cap < f->nsegs || (!dst && f->nsegs)) return LSL_ERR_CAPACITY;
   if (f->nsegs) memcpy(dst, f->segs.data(), sizeof(double) * 5 * f->nsegs);
   return LSL_OK;
@@ -263,7 +360,8 @@ extern "C" int lsl_frame_from_lines(lsl_ctx* ctx, const lsl_line_rec* recs, int 
   cudaSetDevice(ctx->device);
   lsl_frame* fr = new (std::nothrow) lsl_frame();
   if (!fr) return LSL_ERR_ARG;
-  fr->ctx = ctx; fr->nlines = n; fr->nsegs = 0; fr->d_lines = nullptr;
+  fr->ctx = ctx; fr->nlines = n; fr->nsegs = 0; fr->d_lines = nullptr; fr->blk = nullptr;
+  fr->have_dbg = false; fr->have_host = true;
   fr->lines.assign(recs, recs + n);
   if (n) {
     LSL_CUDA(cudaMalloc((void**)&fr->d_lines, sizeof(lsl_line_rec) * n));
@@ -276,9 +374,24 @@ extern "C" int lsl_frame_from_lines(lsl_ctx* ctx, const lsl_line_rec* recs, int 
 }
 extern "C" void lsl_frame_free(lsl_frame* f) {
   if (!f) return;
-  if (f->d_lines) { cudaSetDevice(f->ctx->device); cudaFree(f->d_lines); }
+  if (f->d_lines) {
+    cudaSetDevice(f->ctx->device);
+    if (f->blk) {
+      if (--f->blk->refs == 0) { cudaFreeAsync(f->blk->d, f->ctx->stream); delete f->blk; }
+    } else cudaFree(f->d_lines);
+  }
   delete f;
 }
+// parity-test read-back of per-line intermediates (inlier sample indices of the 3D-line RANSAC etc.)
+extern "C" int lsl_frame_debug(const lsl_frame* f, int32_t* npts, int32_t* inl_idx, int32_t* seg_of_line, int32_t* lm_iters) {
+  if (!f || !f->have_dbg) return LSL_ERR_ARG;
+  if (npts) memcpy(npts, f->dbg_npts.data(), 4 * f->dbg_npts.size());
+  if (inl_idx) memcpy(inl_idx, f->dbg_inl.data(), 4 * f->dbg_inl.size());
+  if (seg_of_line) memcpy(seg_of_line, f->dbg_seg.data(), 4 * f->dbg_seg.size());
+  if (lm_iters) memcpy(lm_iters, f->dbg_lm.data(), 4 * f->dbg_lm.size());
+  return LSL_OK;
+}
+
 // ------------------------------------------------------------- pair registration ----
 template <class T>
 static cudaError_t regrow(T** p, size_t count) {
@@ -293,6 +406,7 @@ static int ensure_pair_ws(lsl_ctx* ctx, size_t npairs, size_t tot_m, size_t tot_
   if (max_iter < 1 || max_iter > 65535) { ctx->err = "ransac_iters_line_motion out of range"; return LSL_ERR_ARG; }
   if (npairs > p.cap_pairs || p.sc.max_iter != max_iter) {
     size_t c = npairs + npairs / 2;
+    LSL_CUDA(cudaStreamSynchronize(ctx->stream));
     LSL_CUDA(regrow(&p.d_pairs, c)); LSL_CUDA(regrow(&p.nmatch, c)); LSL_CUDA(regrow(&p.recs, c));
     LSL_CUDA(regrow(&p.sc.tfs, c * max_iter * 12)); LSL_CUDA(regrow(&p.sc.cnts, c * max_iter));
     LSL_CUDA(regrow(&p.sc.trip, c * max_iter * 3)); LSL_CUDA(regrow(&p.sc.n_inl, c)); LSL_CUDA(regrow(&p.sc.n_rinl, c));
@@ -301,12 +415,14 @@ static int ensure_pair_ws(lsl_ctx* ctx, size_t npairs, size_t tot_m, size_t tot_
   }
   if (tot_m > p.cap_m) {
     size_t c = tot_m + tot_m / 2;
+    LSL_CUDA(cudaStreamSynchronize(ctx->stream));
     LSL_CUDA(regrow(&p.matches, c)); LSL_CUDA(regrow(&p.sc.md, c * 72)); LSL_CUDA(regrow(&p.sc.dab, c * 2));
     LSL_CUDA(regrow(&p.sc.sel, c * 3)); LSL_CUDA(regrow(&p.sc.lm, c * 182)); LSL_CUDA(regrow(&p.sc.okf, c));
     p.cap_m = c;
   }
   if (tot_d > p.cap_d) {
     size_t c = tot_d + tot_d / 2;
+    LSL_CUDA(cudaStreamSynchronize(ctx->stream));
     LSL_CUDA(regrow(&p.D, c));
     p.cap_d = c;
   }
@@ -356,15 +472,18 @@ extern "C" int lsl_match_lines(lsl_ctx* ctx, const lsl_frame* query, const lsl_f
   int adj = adjacent ? 1 : 0;
   int rc = setup_pairs(ctx, 1, &query, &train, nullptr, nullptr, nullptr, &adj, -1);
   if (rc) return rc;
+  clear_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
   if ((rc = lsl_launch_match(ctx, 1))) return rc;
   int32_t nm = 0;
   LSL_CUDA(cudaMemcpyAsync(&nm, ctx->pw.nmatch, 4, cudaMemcpyDeviceToHost, ctx->stream));
   LSL_CUDA(cudaStreamSynchronize(ctx->stream));
+  collect_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
   *n = nm;
   ctx->stats.pairs += 1; ctx->stats.matches += nm;
   if (nm > cap || (nm && !out)) return LSL_ERR_CAPACITY;
   if (nm) {
-    LSL_CUDA(cudaMemcpy(out, ctx->pw.matches, sizeof(lsl_match) * nm, cudaMemcpyDeviceToHost));
+    LSL_CUDA(cudaMemcpyAsync(out, ctx->pw.matches, sizeof(lsl_match) * nm, cudaMemcpyDeviceToHost, ctx->stream));
+    LSL_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->stats.d2h_bytes += sizeof(lsl_match) * nm;
   }
   return LSL_OK;
@@ -374,7 +493,8 @@ extern "C" int lsl_match_lines(lsl_ctx* ctx, const lsl_frame* query, const lsl_f
 static int fetch_sel(lsl_ctx* ctx, const LslPairDesc& d, int which, int count, const std::vector<lsl_match>& all, lsl_match* out) {
   if (!count) return LSL_OK;
   std::vector<int32_t> idx(count);
-  LSL_CUDA(cudaMemcpy(idx.data(), ctx->pw.sc.sel + d.m_off * 3 + (size_t)which * d.cap_m, 4 * count, cudaMemcpyDeviceToHost));
+  LSL_CUDA(cudaMemcpyAsync(idx.data(), ctx->pw.sc.sel + d.m_off * 3 + (size_t)which * d.cap_m, 4 * count, cudaMemcpyDeviceToHost, ctx->stream));
+  LSL_CUDA(cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < count; ++i) out[i] = all[idx[i]];
   ctx->stats.d2h_bytes += 4 * count;
   return LSL_OK;
@@ -384,6 +504,7 @@ extern "C" int lsl_pose_ransac(lsl_ctx* ctx, const lsl_frame* train, const lsl_f
                                const lsl_match* pt_matches, int npt, const lsl_match* ln_matches, int nln, uint32_t seed,
                                lsl_pose_rec* rec, lsl_match* inliers_out, int cap, int* n_inl, lsl_match* ransac_inliers_out,
                                int cap2, int* n_rinl) {
+  (void)pt_matches;
   if (!ctx || !train || !query || !rec || nln < 0 || (nln && !ln_matches)) return LSL_ERR_ARG;
   if (npt != 0) { ctx->err = "point matches are not part of this build (line-only path)"; return LSL_ERR_ARG; }
   if (nln > LSL_MAX_MATCH) return LSL_ERR_CAPACITY;
@@ -397,10 +518,13 @@ extern "C" int lsl_pose_ransac(lsl_ctx* ctx, const lsl_frame* train, const lsl_f
   LSL_CUDA(cudaMemcpyAsync(ctx->pw.nmatch, &nm, 4, cudaMemcpyHostToDevice, ctx->stream));
   if (nln) LSL_CUDA(cudaMemcpyAsync(ctx->pw.matches, ln_matches, sizeof(lsl_match) * nln, cudaMemcpyHostToDevice, ctx->stream));
   ctx->stats.h2d_bytes += sizeof(lsl_match) * nln;
+  clear_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
   if ((rc = lsl_launch_pose(ctx, 1))) return rc;
   if ((rc = fetch_counts(ctx, 1))) return rc;
   LSL_CUDA(cudaMemcpyAsync(rec, ctx->pw.recs, sizeof(lsl_pose_rec), cudaMemcpyDeviceToHost, ctx->stream));
   LSL_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->pw.h_nmatch[0] = nln;
+  collect_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
   ctx->stats.pairs += 1; ctx->stats.d2h_bytes += sizeof(lsl_pose_rec);
   std::vector<lsl_match> all(ln_matches, ln_matches + nln);
   int ni = ctx->pw.h_ninl[0], nr = ctx->pw.h_nrinl[0];
@@ -417,6 +541,7 @@ extern "C" int lsl_match_pair_batch(lsl_ctx* ctx, int npairs, const lsl_frame* c
   cudaSetDevice(ctx->device);
   int rc = setup_pairs(ctx, npairs, queries, trains, id_query, id_train, seeds, nullptr, -1);
   if (rc) return rc;
+  clear_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
   cudaEventRecord(ctx->ev0, ctx->stream);
   if ((rc = lsl_launch_match(ctx, npairs))) return rc;
   if ((rc = lsl_launch_pose(ctx, npairs))) return rc;
@@ -425,13 +550,12 @@ extern "C" int lsl_match_pair_batch(lsl_ctx* ctx, int npairs, const lsl_frame* c
   LSL_CUDA(cudaMemcpyAsync(out, ctx->pw.recs, sizeof(lsl_pose_rec) * npairs, cudaMemcpyDeviceToHost, ctx->stream));
   LSL_CUDA(cudaStreamSynchronize(ctx->stream));
   cudaEventElapsedTime(&ctx->ms_total, ctx->ev0, ctx->ev3);
+  collect_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
   ctx->stats.pairs += npairs; ctx->stats.d2h_bytes += (sizeof(lsl_pose_rec) + 12) * npairs;
   for (int i = 0; i < npairs; ++i) ctx->stats.matches += ctx->pw.h_nmatch[i];
   return LSL_OK;
 }
 
-// Match lists of pair `pair` of the last lsl_match_pair_batch call: what = 0 all line matches,
-// 1 refined inliers (output_line_inlier_matches), 2 inliers of the best RANSAC hypothesis.
 extern "C" int lsl_pair_matches(lsl_ctx* ctx, int pair, int what, lsl_match* out, int cap, int* n) {
   if (!ctx || !n || pair < 0 || pair >= (int)ctx->pw.h_nmatch.size() || what < 0 || what > 2) return LSL_ERR_ARG;
   cudaSetDevice(ctx->device);
@@ -442,21 +566,96 @@ extern "C" int lsl_pair_matches(lsl_ctx* ctx, int pair, int what, lsl_match* out
   if (cnt > cap || (cnt && !out)) return LSL_ERR_CAPACITY;
   if (!cnt) return LSL_OK;
   std::vector<lsl_match> all(nm);
-  LSL_CUDA(cudaMemcpy(all.data(), ctx->pw.matches + d.m_off, sizeof(lsl_match) * nm, cudaMemcpyDeviceToHost));
+  LSL_CUDA(cudaMemcpyAsync(all.data(), ctx->pw.matches + d.m_off, sizeof(lsl_match) * nm, cudaMemcpyDeviceToHost, ctx->stream));
+  LSL_CUDA(cudaStreamSynchronize(ctx->stream));
   if (what == 0) { memcpy(out, all.data(), sizeof(lsl_match) * nm); return LSL_OK; }
   return fetch_sel(ctx, d, what == 1 ? 1 : 0, cnt, all, out);
 }
 
-// parity-test read-back of per-line intermediates (inlier sample indices of the 3D-line RANSAC etc.)
-extern "C" int lsl_frame_debug(const lsl_frame* f, int32_t* npts, int32_t* inl_idx, int32_t* seg_of_line, int32_t* lm_iters) {
-  if (!f) return LSL_ERR_ARG;
-  if (npts) memcpy(npts, f->dbg_npts.data(), 4 * f->dbg_npts.size());
-  if (inl_idx) memcpy(inl_idx, f->dbg_inl.data(), 4 * f->dbg_inl.size());
-  if (seg_of_line) memcpy(seg_of_line, f->dbg_seg.data(), 4 * f->dbg_seg.size());
-  if (lm_iters) memcpy(lm_iters, f->dbg_lm.data(), 4 * f->dbg_lm.size());
+// ------------------------------------------------------------------ pose exchange (NCCL) ----
+// NCCL is resolved at run time (dlopen) so the library has no link-time dependency on it; the only
+// collective of the path is the all-gather of fixed-size pose records at graph-insert time.
+struct lsl_nccl_uid { char internal[128]; };  // ncclUniqueId
+typedef int (*nccl_get_uid_fn)(lsl_nccl_uid*);
+typedef int (*nccl_init_rank_fn)(void**, int, lsl_nccl_uid, int);
+typedef int (*nccl_allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef int (*nccl_destroy_fn)(void*);
+typedef const char* (*nccl_errstr_fn)(int);
+
+static void* nccl_open(lsl_ctx* ctx) {
+  if (ctx && ctx->nccl_lib) return ctx->nccl_lib;
+  const char* env = getenv("LSL_NCCL_LIB");
+  void* h = nullptr;
+  if (env && *env) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (ctx) ctx->nccl_lib = h;
+  return h;
+}
+extern "C" int lsl_comm_unique_id(void* id128) {
+  if (!id128) return LSL_ERR_ARG;
+  void* h = nccl_open(nullptr);
+  if (!h) return LSL_ERR_NCCL;
+  nccl_get_uid_fn f = (nccl_get_uid_fn)dlsym(h, "ncclGetUniqueId");
+  if (!f || f((lsl_nccl_uid*)id128) != 0) return LSL_ERR_NCCL;
+  return LSL_OK;
+}
+extern "C" int lsl_comm_init(lsl_ctx* ctx, const void* id128, int nranks, int rank) {
+  if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return LSL_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  void* h = nccl_open(ctx);
+  if (!h) { ctx->err = "libnccl not found (set LSL_NCCL_LIB)"; return LSL_ERR_NCCL; }
+  nccl_init_rank_fn f = (nccl_init_rank_fn)dlsym(h, "ncclCommInitRank");
+  if (!f) return LSL_ERR_NCCL;
+  lsl_nccl_uid uid;
+  memcpy(&uid, id128, 128);
+  void* comm = nullptr;
+  int rc = f(&comm, nranks, uid, rank);
+  if (rc != 0) {
+    nccl_errstr_fn es = (nccl_errstr_fn)dlsym(h, "ncclGetErrorString");
+    ctx->err = std::string("ncclCommInitRank: ") + (es ? es(rc) : "error");
+    return LSL_ERR_NCCL;
+  }
+  ctx->nccl_comm = comm; ctx->nccl_rank = rank; ctx->nccl_nranks = nranks; ctx->nccl_own = true;
+  return LSL_OK;
+}
+static void nccl_teardown(lsl_ctx* ctx) {
+  if (ctx->nccl_comm && ctx->nccl_own && ctx->nccl_lib) {
+    nccl_destroy_fn f = (nccl_destroy_fn)dlsym(ctx->nccl_lib, "ncclCommDestroy");
+    if (f) f(ctx->nccl_comm);
+  }
+  ctx->nccl_comm = nullptr;
+}
+extern "C" int lsl_allgather_poses(lsl_ctx* ctx, void* nccl_comm, int nranks, const lsl_pose_rec* local_recs, int nlocal,
+                                   lsl_pose_rec* all_recs) {
+  if (!ctx || !local_recs || !all_recs || nlocal < 1) return LSL_ERR_ARG;
+  void* comm = nccl_comm ? nccl_comm : ctx->nccl_comm;
+  if (!nccl_comm) nranks = ctx->nccl_nranks;
+  if (!comm || nranks < 1) { ctx->err = "no communicator: call lsl_comm_init or pass an ncclComm_t"; return LSL_ERR_NCCL; }
+  cudaSetDevice(ctx->device);
+  void* h = nccl_open(ctx);
+  if (!h) return LSL_ERR_NCCL;
+  nccl_allgather_fn ag = (nccl_allgather_fn)dlsym(h, "ncclAllGather");
+  if (!ag) return LSL_ERR_NCCL;
+  const size_t lb = sizeof(lsl_pose_rec) * (size_t)nlocal;
+  uint8_t* d = nullptr;
+  LSL_CUDA(cudaMallocAsync((void**)&d, lb * (size_t)(nranks + 1), ctx->stream));
+  LSL_CUDA(cudaMemcpyAsync(d, local_recs, lb, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = ag(d, d + lb, lb, /* ncclChar */ 0, comm, ctx->stream);
+  if (rc != 0) {
+    nccl_errstr_fn es = (nccl_errstr_fn)dlsym(h, "ncclGetErrorString");
+    ctx->err = std::string("ncclAllGather: ") + (es ? es(rc) : "error");
+    cudaFreeAsync(d, ctx->stream);
+    return LSL_ERR_NCCL;
+  }
+  LSL_CUDA(cudaMemcpyAsync(all_recs, d + lb, lb * (size_t)nranks, cudaMemcpyDeviceToHost, ctx->stream));
+  LSL_CUDA(cudaFreeAsync(d, ctx->stream));
+  LSL_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->stats.h2d_bytes += lb; ctx->stats.d2h_bytes += lb * nranks;
   return LSL_OK;
 }
 
+// ------------------------------------------------------------------ introspection ----
 extern "C" int lsl_get_stats(const lsl_ctx* ctx, lsl_stats* out) {
   if (!ctx || !out) return LSL_ERR_ARG;
   *out = ctx->stats;
@@ -466,6 +665,13 @@ extern "C" int lsl_last_timing(const lsl_ctx* ctx, float* ms_total, float* ms_rg
   if (!ctx) return LSL_ERR_ARG;
   if (ms_total) *ms_total = ctx->ms_total;
   if (ms_rg) *ms_rg = ctx->ms_rg;
+  return LSL_OK;
+}
+extern "C" int lsl_kernel_times(const lsl_ctx* ctx, float* ms, int cap, int* n) {
+  if (!ctx || !n) return LSL_ERR_ARG;
+  *n = LSL_K_COUNT;
+  if (cap < LSL_K_COUNT || !ms) return LSL_ERR_CAPACITY;
+  for (int k = 0; k < LSL_K_COUNT; ++k) ms[k] = ctx->kran[k] ? ctx->kms[k] : 0.f;
   return LSL_OK;
 }
 

@@ -99,20 +99,44 @@ struct LslPairWork {
   std::vector<int32_t> h_nmatch, h_ninl, h_nrinl;
 };
 
+// Kernel ids for the per-kernel device timers (CUDA events on the context stream)
+enum LslKernelId {
+  LSL_K_GRAY = 0, LSL_K_XPASS, LSL_K_YPASS, LSL_K_LLANGLE, LSL_K_SEEDS, LSL_K_SOBEL, LSL_K_REGION, LSL_K_RANSAC3D,
+  LSL_K_MSLD, LSL_K_RANDFILL, LSL_K_MLE, LSL_K_GATHER, LSL_K_MATCH, LSL_K_POSE, LSL_K_COUNT
+};
+
+// Line records of all frames of one extract call live in ONE device allocation (stream-ordered pool);
+// frames reference-count it.
+struct LslLineBlock {
+  lsl_line_rec* d;
+  int refs;
+};
+
 struct lsl_frame {
   lsl_ctx* ctx;
   int nlines, nsegs;
-  lsl_line_rec* d_lines;            // device copy (owned)
-  std::vector<lsl_line_rec> lines;  // host mirror
-  std::vector<double> segs;         // host mirror of LSD output (5 per row)
+  lsl_line_rec* d_lines;            // device records (inside blk, or own allocation when blk == nullptr)
+  LslLineBlock* blk;
+  std::vector<lsl_line_rec> lines;  // host mirror, filled on first lsl_frame_lines call
+  bool have_host;
+  // debug mode only (lsl_ctx_set_debug): LSD output and per-line intermediates
+  std::vector<double> segs;
   std::vector<int32_t> dbg_npts, dbg_inl, dbg_seg, dbg_lm;
+  bool have_dbg;
 };
 
 struct lsl_ctx {
   lsl_params P;
   int device, max_batch, max_w, max_h;
-  cudaStream_t stream;
-  cudaEvent_t ev0, ev1, ev2, ev3;
+  cudaStream_t stream;       // stream every call of this context runs on
+  cudaStream_t own_stream;   // created with the context; `stream` may be replaced by lsl_ctx_set_stream
+  cudaEvent_t ev0, ev3;      // whole-call bracket
+  cudaEvent_t kev[LSL_K_COUNT][2];
+  bool kran[LSL_K_COUNT];
+  float kms[LSL_K_COUNT];
+  int debug;
+  int32_t* d_goff;           // [max_batch] gather offsets
+  void* nccl_lib; void* nccl_comm; int nccl_rank, nccl_nranks; bool nccl_own;
   LslDims dims;   // dims the workspace / taps were last prepared for
   LslTaps taps;
   LslWork wk;
@@ -123,6 +147,10 @@ struct lsl_ctx {
   lsl_stats stats;
   float ms_total, ms_rg;
 };
+
+// device-time bracket of one kernel launch
+#define LSL_KSTART(ctx, id) do { cudaEventRecord((ctx)->kev[id][0], (ctx)->stream); } while (0)
+#define LSL_KSTOP(ctx, id) do { cudaEventRecord((ctx)->kev[id][1], (ctx)->stream); (ctx)->kran[id] = true; (ctx)->stats.kernel_launches += 1; } while (0)
 
 #define LSL_CUDA(call)                                                                  \
   do {                                                                                  \
@@ -138,5 +166,6 @@ int lsl_launch_image(lsl_ctx* ctx, int n, const uint8_t* d_img, int channels);
 int lsl_launch_lsd(lsl_ctx* ctx, int n);
 int lsl_launch_lines(lsl_ctx* ctx, int n, const float* d_depth, const double K[9], double dt);
 int lsl_prepare_taps(lsl_ctx* ctx);
+int lsl_launch_gather(lsl_ctx* ctx, int n, lsl_line_rec* dst);
 int lsl_launch_match(lsl_ctx* ctx, int npairs);
 int lsl_launch_pose(lsl_ctx* ctx, int npairs);

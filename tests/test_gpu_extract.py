@@ -33,7 +33,7 @@ def _compare(got, ref, dbg_got, dbg_ref, tag):
 
 def test_detect3DLines_vga_batch(api, oracle, stream4):
     imgs, deps, poses, K = stream4
-    ctx = api.Context(max_batch=4, max_w=640, max_h=480)
+    ctx = api.Context(max_batch=4, max_w=640, max_h=480, debug=True)
     seeds = [1, 2, 3, 4]
     frames = ctx.extract_batch(imgs, deps, K, seeds=seeds)
     for i in range(4):
@@ -44,7 +44,7 @@ def test_detect3DLines_vga_batch(api, oracle, stream4):
 
 def test_detect3DLines_small_and_single(api, oracle, small_frames):
     imgs, deps, poses, K = small_frames
-    ctx = api.Context(max_batch=1, max_w=320, max_h=240)
+    ctx = api.Context(max_batch=1, max_w=320, max_h=240, debug=True)
     for i in range(2):
         node = api.Node(ctx, imgs[i], deps[i], K, node_id=i, seed=7 + i)
         ref, dref = oracle.detect3DLines(imgs[i], deps[i], K, seed=7 + i, debug=True)
@@ -59,7 +59,7 @@ def test_detect3DLines_holes_and_no_depth(api, oracle, stream4):
     d1 = deps[0].copy()
     d1[rng.random(d1.shape) < 0.4] = np.nan
     d2 = np.zeros_like(deps[0])
-    ctx = api.Context(max_batch=2, max_w=640, max_h=480)
+    ctx = api.Context(max_batch=2, max_w=640, max_h=480, debug=True)
     frames = ctx.extract_batch(np.stack([imgs[0], imgs[0]]), np.stack([d1, d2]), K, seeds=[5, 6])
     ref, dref = oracle.detect3DLines(imgs[0], d1, K, seed=5, debug=True)
     _compare(frames[0].lines(), ref, frames[0].debug(), dref, "holes")
@@ -73,7 +73,7 @@ def test_asynch_dt_and_launch_params(api, oracle, stream4):
     imgs, deps, poses, K = stream4
     p = api.default_params()
     p.lsd_ang_th = 40.0
-    ctx = api.Context(params=p, max_batch=1, max_w=640, max_h=480)
+    ctx = api.Context(params=p, max_batch=1, max_w=640, max_h=480, debug=True)
     fr = ctx.extract_batch(imgs[:1], deps[:1], K, seeds=[3], dt=0.02)[0]
     ref, dref = oracle.detect3DLines(imgs[0], deps[0], K, seed=3, params=p, dt=0.02, debug=True)
     _compare(fr.lines(), ref, fr.debug(), dref, "dt")

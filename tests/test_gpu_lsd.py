@@ -7,7 +7,7 @@ pytestmark = pytest.mark.gpu
 
 def _stage_check(api, oracle, imgs, deps, K, max_batch):
     n, H, W = deps.shape
-    ctx = api.Context(max_batch=max_batch, max_w=W, max_h=H)
+    ctx = api.Context(max_batch=max_batch, max_w=W, max_h=H, debug=True)
     frames = ctx.extract_batch(imgs, deps, K, seeds=np.arange(1, n + 1))
     sw, sh = int(np.floor(W * 0.8)), int(np.floor(H * 0.8))
     # frame 0 intermediates
@@ -50,7 +50,7 @@ def test_gray_input_and_noise_image(api, oracle):
     step[H // 3: 2 * H // 3, :] //= 2
     imgs = np.stack([noise, step])
     deps = np.ones((2, H, W), np.float32)
-    ctx = api.Context(max_batch=2, max_w=W, max_h=H)
+    ctx = api.Context(max_batch=2, max_w=W, max_h=H, debug=True)
     frames = ctx.extract_batch(imgs, deps, np.array([[100., 0, 80], [0, 100, 60], [0, 0, 1]]))
     for i in range(2):
         ref = oracle.lsd(imgs[i])

@@ -25,7 +25,7 @@ def _pose_close(tf_a, tf_b):
 @pytest.fixture(scope="module")
 def extracted(api, oracle, stream4):
     imgs, deps, poses, K = stream4
-    ctx = api.Context(max_batch=4, max_w=640, max_h=480)
+    ctx = api.Context(max_batch=4, max_w=640, max_h=480, debug=True)
     frames = ctx.extract_batch(imgs, deps, K, seeds=[1, 2, 3, 4])
     lines = [f.lines() for f in frames]
     yield ctx, frames, lines, poses
