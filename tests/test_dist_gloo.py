@@ -1,0 +1,69 @@
+"""world_size-2 gloo test of the host-side sharding: pairs / stream batches are dealt to ranks,
+every rank registers its own units, pose records are all-gathered; the union equals the unsharded result."""
+import os
+import socket
+
+import numpy as np
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _fake_register(pair_ids):
+    """Deterministic stand-in for the device call: the record depends only on the pair id."""
+    from lineslam_b200.records import POSE_DTYPE
+    recs = np.zeros(len(pair_ids), POSE_DTYPE)
+    for k, i in enumerate(pair_ids):
+        recs[k]["id_train"], recs[k]["id_query"], recs[k]["found"] = i, i + 1, i % 3 != 0
+        recs[k]["tf"] = np.arange(16, dtype=np.float32) + i
+        recs[k]["rmse"] = 0.5 * i
+    return recs
+
+
+def _worker(rank, world, port, n_pairs, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lineslam_b200 import shard
+    lo, hi, per = shard.shard_pairs(n_pairs, world, rank)
+    local = shard.pad_records(_fake_register(list(range(lo, hi))), per)
+    allr = shard.drop_padding(shard.allgather_pose_records(local))
+    ranges = shard.shard_stream(100, world, rank, 16)
+    q.put((rank, allr.tobytes(), ranges))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_pairs_allgather_equals_unsharded():
+    from lineslam_b200.records import POSE_DTYPE
+    world, n_pairs = 2, 37
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    port = _free_port()
+    ps = [ctxm.Process(target=_worker, args=(r, world, port, n_pairs, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = _fake_register(list(range(n_pairs)))
+    cover = []
+    for rank, blob, ranges in res:
+        got = np.frombuffer(blob, POSE_DTYPE)
+        assert got.tobytes() == full.tobytes()      # every rank sees all records, in pair order
+        cover += ranges
+    cover.sort()
+    assert cover[0][0] == 0 and cover[-1][1] == 100 and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+
+
+def test_shard_helpers_edge_cases():
+    from lineslam_b200 import shard
+    assert shard.shard_pairs(0, 4, 2) == (0, 0, 0)
+    assert shard.shard_pairs(5, 8, 7) == (5, 5, 1)
+    assert [shard.shard_pairs(256, 8, r)[:2] for r in (0, 7)] == [(0, 32), (224, 256)]
+    assert shard.shard_stream(10, 3, 1, 4) == [(4, 8)]
+    assert len(shard.pad_records(np.zeros(0, shard.POSE_DTYPE), 3)) == 3

@@ -58,3 +58,16 @@ def test_gray_input_and_noise_image(api, oracle):
         assert got.shape == ref.shape
         assert np.array_equal(got, ref)
     ctx.close()
+
+
+def test_cuda_segments_equal_upstream_golden(api, stream4):
+    """The device LSD output equals the committed output of the UNMODIFIED upstream lsd.c (tests/golden)."""
+    import os
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    imgs, deps, poses, K = stream4
+    ctx = api.Context(max_batch=2, max_w=640, max_h=480, debug=True)
+    frames = ctx.extract_batch(imgs[:2], deps[:2], K)
+    for i in range(2):
+        gold = np.load(os.path.join(gold_dir, f"lsd_upstream_scene2000_f{i}.npy"))
+        assert np.array_equal(frames[i].segments(), gold)
+    ctx.close()

@@ -1,0 +1,121 @@
+"""Pins the oracle (the CPU restatement every parity test leans on) to the reference's own code:
+  * LSD: oracle.lsd == UNMODIFIED upstream lsd.c (+ glibc libm) segment lists, on synthetic frames, on the
+    committed golden vectors produced by that same upstream build, and on the reference's bundled images
+    (chairs.pgm, the TUM frame) when /root/reference is mounted.
+  * levmar: the restated dlevmar_dif == the reference's dlevmar_dif (built-in LU) on known-answer problems of
+    external/levmar-2.6/lmdemo.c, bit for bit.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from refimpl import LMFUNC, have_ref, levmar_ref, lsd_ref
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+needs_ref = pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+
+
+@needs_ref
+def test_lsd_oracle_equals_upstream_on_synthetic(oracle, stream4, small_frames):
+    for imgs in (stream4[0][:2], small_frames[0]):
+        for img in imgs:
+            g = oracle.gray(img)
+            for ang in (22.5, 40.0):
+                p = oracle.default_params()
+                p.lsd_ang_th = ang
+                a, b = oracle.lsd(g, p), lsd_ref(g, ang)
+                assert a.shape == b.shape and np.array_equal(a, b), ang
+
+
+def test_lsd_oracle_equals_golden(oracle, stream4):
+    """golden/lsd_upstream_*.npy were written by tests/golden/make_golden.py from the upstream lsd.c build."""
+    for i in range(2):
+        gold = np.load(os.path.join(GOLD, f"lsd_upstream_scene2000_f{i}.npy"))
+        assert np.array_equal(oracle.lsd(oracle.gray(stream4[0][i])), gold)
+
+
+@needs_ref
+@pytest.mark.skipif(not os.path.isdir("/root/reference/external/lsd/lsd-1.5"), reason="reference tree not mounted")
+def test_lsd_oracle_equals_upstream_on_reference_images(oracle):
+    import cv2
+    d = "/root/reference/external/lsd/lsd-1.5"
+    chairs = cv2.imread(os.path.join(d, "chairs.pgm"), cv2.IMREAD_GRAYSCALE)
+    tum = cv2.imread(os.path.join(d, "1305031453.359684.png"), cv2.IMREAD_COLOR)
+    assert chairs is not None and tum is not None
+    a, b = oracle.lsd(chairs), lsd_ref(chairs)
+    assert len(b) == 725                      # the strict-IEEE count the survey measured for upstream LSD 1.5
+    # Same 725 segments. glibc's libm is < 1 ulp but not correctly rounded, the shared math is: one row of 725
+    # differs in the last bits (measured: 1 row, 2 ulp). Bound it instead of hiding it.
+    assert a.shape == b.shape
+    ulp = np.abs(a.view(np.int64) - b.view(np.int64))
+    assert ulp.max() <= 4 and (ulp.max(axis=1) > 0).sum() <= 3, (ulp.max(), (ulp.max(axis=1) > 0).sum())
+    g = oracle.gray(tum)
+    a, b = oracle.lsd(g), lsd_ref(g)
+    assert len(b) > 300 and np.array_equal(a, b)
+
+
+def _problems():
+    def rosenbrock(p, hx, m, n, _):
+        for i in range(n):
+            hx[i] = (1.0 - p[0]) ** 2 + 105.0 * (p[1] - p[0] * p[0]) ** 2
+    def powell(p, hx, m, n, _):
+        hx[0] = p[0]
+        hx[1] = 10.0 * p[0] / (p[0] + 0.1) + 2 * p[1] * p[1]
+    def wood(p, hx, m, n, _):
+        hx[0] = 10.0 * (p[1] - p[0] * p[0]); hx[1] = 1.0 - p[0]
+        hx[2] = np.sqrt(90.0) * (p[3] - p[2] * p[2]); hx[3] = 1.0 - p[2]
+        hx[4] = np.sqrt(10.0) * (p[1] + p[3] - 2.0); hx[5] = (p[1] - p[3]) / np.sqrt(10.0)
+    def helval(p, hx, m, n, _):
+        M_PI = 3.14159265358979323846
+        if p[0] < 0.0: theta = np.arctan(p[1] / p[0]) / (2.0 * M_PI) + 0.5
+        elif 0.0 < p[0]: theta = np.arctan(p[1] / p[0]) / (2.0 * M_PI)
+        else: theta = 0.25 if p[1] >= 0 else -0.25
+        hx[0] = 10.0 * (p[2] - 10.0 * theta); hx[1] = 10.0 * (np.sqrt(p[0] * p[0] + p[1] * p[1]) - 1.0); hx[2] = p[2]
+    return [("rosenbrock", rosenbrock, [-1.2, 1.0], [0.0, 0.0], [1.0, 1.0]),
+            ("powell", powell, [3.0, 1.0], [0.0, 0.0], [0.0, 0.0]),
+            ("wood", wood, [-3.0, -1.0, -3.0, -1.0], [0.0] * 6, [1.0, 1.0, 1.0, 1.0]),
+            ("helical valley", helval, [-1.0, 0.0, 0.0], [0.0] * 3, [1.0, 0.0, 0.0])]
+
+
+@needs_ref
+def test_levmar_restatement_equals_reference(oracle):
+    L = oracle.lib()
+    opts = [1e-3, 1e-15, 1e-15, 1e-20, 1e-6]
+    for name, f, p0, x, pstar in _problems():
+        cb = LMFUNC(f)
+        ret_r, p_r, info_r = levmar_ref(cb, p0, x, 1000, opts)
+        p = np.array(p0, np.float64); xx = np.array(x, np.float64); info = np.zeros(10); o = np.array(opts)
+        ret_o = L.orc_dlevmar_dif(cb, p.ctypes.data_as(C.c_void_p), xx.ctypes.data_as(C.c_void_p), len(p), len(xx), 1000,
+                                  o.ctypes.data_as(C.c_void_p), info.ctypes.data_as(C.c_void_p))
+        assert ret_o == ret_r, name
+        assert np.array_equal(p, p_r), (name, p, p_r)
+        assert np.array_equal(info, info_r), name
+        assert info[1] < info[0]
+        if name != "rosenbrock":   # (slow valley: not at the minimum after 1000 iterations, identically on both sides)
+            assert np.allclose(p, pstar, atol=2e-3), (name, p)   # the minima lmdemo.c lists
+
+
+@needs_ref
+def test_levmar_restatement_on_line_mle_shape(oracle):
+    """m = 6, n = 60 residuals of the same form as costFun_MLEstimateLine3d (point-to-line distances)."""
+    rng = np.random.default_rng(3)
+    n = 60
+    t = np.linspace(0, 1, n)
+    A, B = np.array([0.1, -0.2, 1.5]), np.array([0.6, 0.3, 2.2])
+    pts = A + t[:, None] * (B - A) + rng.normal(0, 0.004, (n, 3))
+    def cost(p, hx, m, nn, _):
+        a = np.array([p[0], p[1], p[2]]); b = np.array([p[3], p[4], p[5]])
+        d = b - a
+        for i in range(nn):
+            hx[i] = np.linalg.norm(np.cross(pts[i] - a, pts[i] - b)) / np.linalg.norm(d)
+    cb = LMFUNC(cost)
+    p0 = list(pts[0]) + list(pts[-1])
+    opts = [1e-3, 1e-10, 1e-20, 1e-20, 1e-6]
+    ret_r, p_r, info_r = levmar_ref(cb, p0, [0.0] * n, 100, opts)
+    L = oracle.lib()
+    p = np.array(p0); xx = np.zeros(n); info = np.zeros(10); o = np.array(opts)
+    ret_o = L.orc_dlevmar_dif(cb, p.ctypes.data_as(C.c_void_p), xx.ctypes.data_as(C.c_void_p), 6, n, 100,
+                              o.ctypes.data_as(C.c_void_p), info.ctypes.data_as(C.c_void_p))
+    assert ret_o == ret_r and np.array_equal(p, p_r) and np.array_equal(info, info_r)
