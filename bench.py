@@ -49,21 +49,35 @@ def make_unique_frames(u: int, rank: int):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons every 200 ms while the timed region runs (B200_PROFILING.md). NVML in-process
+    (one init before the region): spawning nvidia-smi per sample stalls the CUDA driver for ~0.3 s a call."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
 
     def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nv is not None:
+                    sm = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                    try:
+                        mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    self.rows.append((float(sm), float(self.max), int(mask)))
             except Exception:
                 pass
             self._halt.wait(0.2)
@@ -71,12 +85,10 @@ class ClockSampler(threading.Thread):
     def stop(self):
         self._halt.set()
         self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 7 and r[3 + i].lower() == "active"})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({n for r in self.rows for n, bit in self.REASONS if r[2] & bit})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.rows[0][1] if self.rows else None,
+                "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self.nv is not None else "unavailable"}
 
 
 # ------------------------------------------------------------------------------------------ CPU arm ----

@@ -536,8 +536,7 @@ struct MleSmem {
   double jac[LSL_MAX_SMP * 6];
   double JtJ[36], Jte[6];
   double cinv1[9], cinv2[9];
-  double Jt[32 * 18];
-};
+};  // the 32 x 18 tile of MleLine3dCov reuses `jac` once the LM has finished
 
 // costFun_MLEstimateLine3d (utils.cpp:954-978): lanes stride over the points
 __device__ __forceinline__ void mle_cost(const MleSmem& S, int n, int idx1, int idx2, const double* p, double* out) {
@@ -579,64 +578,89 @@ __device__ double l2nrm_neg(double* e, const double* y, int n) {
   return sum0 + sum1 + sum2 + sum3;
 }
 
-// AX_EQ_B_LU for m = 6 (Axb_core.c:1140-1277), executed identically by every lane
-__device__ int ax_eq_b_lu6(const double* A, const double* B, double* x) {
-  const int m = 6;
-  double a[36], work[6];
+// AX_EQ_B_LU for m = 6 (Axb_core.c:1140-1277), executed identically by every lane. Fully unrolled with
+// static indices so the 6x6 system lives in registers (row swaps and the permuted forward substitution are
+// compare-and-select over the unrolled rows); the operation order per element is the reference's.
+// The system is (JtJ with diag + mu on the diagonal) x = B.
+__device__ __forceinline__ int ax_eq_b_lu6(const double* __restrict__ JtJ, const double* diag, double mu, const double* B,
+                                           double* x) {
+  double a[6][6], work[6];
   int idx[6];
   int maxi = -1;
-  for (int i = 0; i < 36; ++i) a[i] = A[i];
-  for (int i = 0; i < m; ++i) x[i] = B[i];
-  for (int i = 0; i < m; ++i) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) a[i][j] = (i == j) ? diag[i] + mu : JtJ[i * 6 + j];
+    x[i] = B[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
     double max = 0.0, tmp;
-    for (int j = 0; j < m; ++j)
-      if ((tmp = fabs(a[i * m + j])) > max) max = tmp;
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+      if ((tmp = fabs(a[i][j])) > max) max = tmp;
     if (max == 0.0) return 0;
     work[i] = 1.0 / max;
   }
-  for (int j = 0; j < m; ++j) {
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+#pragma unroll
     for (int i = 0; i < j; ++i) {
-      double sum = a[i * m + j];
-      for (int k = 0; k < i; ++k) sum -= a[i * m + k] * a[k * m + j];
-      a[i * m + j] = sum;
+      double sum = a[i][j];
+#pragma unroll
+      for (int k = 0; k < i; ++k) sum -= a[i][k] * a[k][j];
+      a[i][j] = sum;
     }
     double max = 0.0, tmp;
-    for (int i = j; i < m; ++i) {
-      double sum = a[i * m + j];
-      for (int k = 0; k < j; ++k) sum -= a[i * m + k] * a[k * m + j];
-      a[i * m + j] = sum;
+#pragma unroll
+    for (int i = j; i < 6; ++i) {
+      double sum = a[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) sum -= a[i][k] * a[k][j];
+      a[i][j] = sum;
       if ((tmp = work[i] * fabs(sum)) >= max) { max = tmp; maxi = i; }
     }
-    if (j != maxi) {
-      for (int k = 0; k < m; ++k) { double t = a[maxi * m + k]; a[maxi * m + k] = a[j * m + k]; a[j * m + k] = t; }
-      work[maxi] = work[j];
-    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+      if (r != j && r == maxi) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { double t = a[r][k]; a[r][k] = a[j][k]; a[j][k] = t; }
+        work[r] = work[j];
+      }
     idx[j] = maxi;
-    if (a[j * m + j] == 0.0) a[j * m + j] = DBL_EPSILON;
-    if (j != m - 1) {
-      double tmp2 = 1.0 / (a[j * m + j]);
-      for (int i = j + 1; i < m; ++i) a[i * m + j] *= tmp2;
+    if (a[j][j] == 0.0) a[j][j] = DBL_EPSILON;
+    if (j != 5) {
+      double tmp2 = 1.0 / (a[j][j]);
+#pragma unroll
+      for (int i = j + 1; i < 6; ++i) a[i][j] *= tmp2;
     }
   }
   int k = 0;
-  for (int i = 0; i < m; ++i) {
-    int j = idx[i];
-    double sum = x[j];
-    x[j] = x[i];
-    if (k != 0)
-      for (j = k - 1; j < i; ++j) sum -= a[i * m + j] * x[j];
-    else if (sum != 0.0) k = i + 1;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int jj = idx[i];
+    double sum = x[i];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+      if (r == jj) { sum = x[r]; x[r] = x[i]; }
+    if (k != 0) {
+#pragma unroll
+      for (int j2 = 0; j2 < i; ++j2)
+        if (j2 >= k - 1) sum -= a[i][j2] * x[j2];
+    } else if (sum != 0.0) k = i + 1;
     x[i] = sum;
   }
-  for (int i = m - 1; i >= 0; --i) {
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
     double sum = x[i];
-    for (int j = i + 1; j < m; ++j) sum -= a[i * m + j] * x[j];
-    x[i] = sum / a[i * m + i];
+#pragma unroll
+    for (int j = i + 1; j < 6; ++j) sum -= a[i][j] * x[j];
+    x[i] = sum / a[i][i];
   }
   return 1;
 }
 
-__global__ void __launch_bounds__(32) line_mle_kernel(LslWork w, LineParams P) {
+__global__ void __launch_bounds__(32, 12) line_mle_kernel(LslWork w, LineParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MleSmem& S = *reinterpret_cast<MleSmem*>(smem_raw);
   const int f = blockIdx.y, lane = threadIdx.x;
@@ -739,10 +763,7 @@ __global__ void __launch_bounds__(32) line_mle_kernel(LslWork w, LineParams P) {
       mu = tau * tmp;
     }
     {
-      double Aug[36];
-      for (int i = 0; i < 36; ++i) Aug[i] = S.JtJ[i];
-      for (int i = 0; i < m; ++i) Aug[i * m + i] = diag[i] + mu;
-      int issolved = ax_eq_b_lu6(Aug, jacTe, Dp);
+      int issolved = ax_eq_b_lu6(S.JtJ, diag, mu, jacTe, Dp);
       if (issolved) {
         Dp_L2 = 0.0;
         for (int i = 0; i < m; ++i) { pDp[i] = p[i] + (tmp = Dp[i]); Dp_L2 += tmp * tmp; }
@@ -791,6 +812,8 @@ __global__ void __launch_bounds__(32) line_mle_kernel(LslWork w, LineParams P) {
   {
     double acc = 0.0;
     int ha = 0, hb = 0;
+    double* Jt = S.jac;  // 32 x 18 doubles <= 101 x 6
+    __syncwarp();
     if (lane < 21) { int i = 0, r = lane; while (r > i) { r -= i + 1; ++i; } ha = i; hb = r; }
     for (int i0 = 0; i0 < n; i0 += 32) {
       int i = i0 + lane;
@@ -800,13 +823,13 @@ __global__ void __launch_bounds__(32) line_mle_kernel(LslWork w, LineParams P) {
         if (i == idx1) { for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) J[r * 6 + c] = -S.DU[9 * i + r * 3 + c]; }
         else if (i == idx2) { for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) J[r * 6 + 3 + c] = -S.DU[9 * i + r * 3 + c]; }
         else jac_rpt2ln(S.pos + 3 * i, S.DU + 9 * i, p, J);
-        for (int q = 0; q < 18; ++q) S.Jt[lane * 18 + q] = J[q];
+        for (int q = 0; q < 18; ++q) Jt[lane * 18 + q] = J[q];
       }
       __syncwarp();
       if (lane < 21) {
         int cnt = min(32, n - i0);
         for (int q = 0; q < cnt; ++q)
-          for (int r = 0; r < 3; ++r) acc += S.Jt[q * 18 + r * 6 + ha] * S.Jt[q * 18 + r * 6 + hb];
+          for (int r = 0; r < 3; ++r) acc += Jt[q * 18 + r * 6 + ha] * Jt[q * 18 + r * 6 + hb];
       }
       __syncwarp();
     }

@@ -311,33 +311,103 @@ struct PoseParams {
 };
 
 // Per-match scratch of the LM (doubles), laid out [field][match] blocks inside the pair's slice
+#define LM_STRIDE 306
 struct LmView {
   double *L, *Lnew, *Hll, *Hpl, *bl, *HllInv, *contrib, *dl, *terms, *chi;  // 6,6,36,36,6,36,42,6,6,2 per match
+  double *J;      // 124 per match: Jl(newer) 36 | Jl(older) 36 | Jp 36 | e(newer) 6 | e(older) 6 | wgt 2 | pad 2
   int32_t* sel;   // [n] index into the pair's match list
   int32_t* okf;   // [n]
 };
 
-// chi2 of all edges (SparseOptimizer::activeRobustChi2), terms in edge order: per match side 0 (newer) then 1 (older)
+// ordered sum s = init (+|-) v[0] (+|-) v[stride] ... (n terms): the adds form one dependent chain in the
+// reference's order; the loads are issued 16 at a time ahead of it.
+template <bool SUB>
+__device__ __forceinline__ double chain_sum(double init, const double* __restrict__ v, int stride, int n) {
+  double s = init;
+  int i = 0;
+  for (; i + 16 <= n; i += 16) {
+    double t[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) t[k] = v[(size_t)(i + k) * stride];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s = SUB ? s - t[k] : s + t[k];
+  }
+  for (; i < n; ++i) s = SUB ? s - v[(size_t)i * stride] : s + v[(size_t)i * stride];
+  return s;
+}
+
+// chi2 of all edges (SparseOptimizer::activeRobustChi2), terms in edge order: per match side 0 (newer) then 1
+// (older); one thread per (match, side)
 __device__ void chi2_terms(const LmView& V, const double* md_all, int n, const Iso& w2n, const Iso& ident, const double* Lv,
                            const PoseParams& PP) {
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int t = threadIdx.x; t < 2 * n; t += blockDim.x) {
+    const int i = t >> 1, side = t & 1;
     const double* md = md_all + (size_t)V.sel[i] * MD_STRIDE;
-    for (int side = 0; side < 2; ++side) {
-      double e[6];
-      edge_error(side ? w2n : ident, Lv + 6 * i, side ? md + 6 : md, side ? md + 54 : md + 36, side ? md + 63 : md + 45, e);
-      double c2 = 0;
-      for (int k = 0; k < 6; ++k) c2 += e[k] * PP.line_weight_g2o * e[k];
-      if (PP.robust) { double rho[3]; huber(c2, PP.huber_delta, rho); c2 = rho[0]; }
-      V.chi[2 * i + side] = c2;
-    }
+    double e[6];
+    edge_error(side ? w2n : ident, Lv + 6 * i, side ? md + 6 : md, side ? md + 54 : md + 36, side ? md + 63 : md + 45, e);
+    double c2 = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) c2 += e[k] * PP.line_weight_g2o * e[k];
+    if (PP.robust) { double rho[3]; huber(c2, PP.huber_delta, rho); c2 = rho[0]; }
+    V.chi[t] = c2;
   }
+}
+
+// Column c of inv_lu<6> (shared/lsl_linalg.h: Gauss-Jordan LU with partial pivoting, cv::Mat::inv analogue):
+// the columns of the inverse evolve independently, so six threads each run the elimination on a register
+// copy of A and keep one column. Row swaps are compare-and-select over the unrolled rows (static indices).
+// M = H (row-major, stride 6) with lambda added to the diagonal. Returns 0 if singular.
+__device__ __forceinline__ int inv6_column(const double* __restrict__ H, double lambda, int c, double* Rc) {
+  double A[6][6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) A[i][j] = H[i * 6 + j];
+    A[i][i] += lambda;
+    Rc[i] = (i == c) ? 1.0 : 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    int k = i;
+    double best = fabs(A[i][i]);
+#pragma unroll
+    for (int j = i + 1; j < 6; ++j)
+      if (fabs(A[j][i]) > best) { best = fabs(A[j][i]); k = j; }
+    if (best < 2.2250738585072014e-308) return 0;
+#pragma unroll
+    for (int r = i + 1; r < 6; ++r)
+      if (r == k) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { double t = A[i][j]; A[i][j] = A[r][j]; A[r][j] = t; }
+        double t = Rc[i]; Rc[i] = Rc[r]; Rc[r] = t;
+      }
+    double d = -1.0 / A[i][i];
+#pragma unroll
+    for (int j = i + 1; j < 6; ++j) {
+      double alpha = A[j][i] * d;
+#pragma unroll
+      for (int q = i + 1; q < 6; ++q) A[j][q] += alpha * A[i][q];
+      Rc[j] += alpha * Rc[i];
+    }
+    A[i][i] = -d;
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double s = Rc[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) s -= A[i][k] * Rc[k];
+    Rc[i] = s * A[i][i];
+  }
+  return 1;
 }
 
 // getTransformFromHybridMatchesG2O restated (see oracle/oracle_pair.cpp:refine_pose_lines for the derivation):
 // pose vertex + one free 6-vector per line match, numeric central-difference Jacobians, Huber, g2o's LM
-// damping policy, landmark blocks eliminated exactly. Whole CTA; tf (12 floats, shared memory) in/out.
+// damping policy, landmark blocks eliminated exactly. Whole CTA, six threads per match (one per Jacobian
+// column / block row); sums over the matches run as ordered chains on dedicated threads.
+// tf (12 floats, shared memory) in/out.
 __device__ void refine_pose(const LmView& V, const double* md_all, int n, float* tf, int iterations, const PoseParams& PP,
-                            double* s_red /* >= 64 doubles shared */, double* s_S /* 48 doubles shared */) {
+                            double* s_red /* >= 64 doubles shared */, double* s_S /* 96 doubles shared */) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   if (n == 0) return;
   Iso tfd, cam1, ident;
@@ -345,9 +415,9 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
   iso_inv(tfd, cam1);
   for (int i = 0; i < 9; ++i) ident.R[i] = (i % 4 == 0) ? 1 : 0;
   ident.t[0] = ident.t[1] = ident.t[2] = 0;
-  for (int i = tid; i < n; i += nthr) {
-    const double* md = md_all + (size_t)V.sel[i] * MD_STRIDE;
-    for (int k = 0; k < 6; ++k) V.L[6 * i + k] = md[k];
+  for (int t = tid; t < 6 * n; t += nthr) {
+    const int i = t / 6, k = t - 6 * i;
+    V.L[t] = md_all[(size_t)V.sel[i] * MD_STRIDE + k];
   }
   __syncthreads();
   const double w = PP.line_weight_g2o;
@@ -358,78 +428,123 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
     Iso w2n;
     iso_inv(cam1, w2n);
     chi2_terms(V, md_all, n, w2n, ident, V.L, PP);
-    // ---- build the normal equations: per match blocks
-    for (int i = tid; i < n; i += nthr) {
+    // ---- numeric Jacobian columns: thread (match i, column d)
+    for (int t = tid; t < 6 * n; t += nthr) {
+      const int i = t / 6, d = t - 6 * i;
       const double* md = md_all + (size_t)V.sel[i] * MD_STRIDE;
-      double* hll = V.Hll + 36 * i; double* hpl = V.Hpl + 36 * i; double* b = V.bl + 6 * i; double* cp = V.contrib + 42 * i;
-      for (int k = 0; k < 36; ++k) { hll[k] = 0; hpl[k] = 0; }
-      for (int k = 0; k < 6; ++k) b[k] = 0;
       const double* Li = V.L + 6 * i;
+      double* Jm = V.J + (size_t)124 * i;
+      double Lp[6], e1[6], e2[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) Lp[k] = Li[k];
+      const double lplus = Li[d] + del, lminus = Li[d] + (-del);
+#pragma unroll
       for (int side = 0; side < 2; ++side) {
         const double* meas = side ? md + 6 : md;
         const double* A1 = side ? md + 54 : md + 36;
         const double* A2 = A1 + 9;
-        double e[6], Jl[36], Jp[36];
-        for (int d = 0; d < 6; ++d) {
-          double Lp[6], e1[6], e2[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) if (k == d) Lp[k] = lplus;
+        edge_error(side ? w2n : ident, Lp, meas, A1, A2, e1);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) if (k == d) Lp[k] = lminus;
+        edge_error(side ? w2n : ident, Lp, meas, A1, A2, e2);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) Jm[side * 36 + k * 6 + d] = scalar * (e1[k] - e2[k]);
+        if (side) {
+#pragma unroll
           for (int k = 0; k < 6; ++k) Lp[k] = Li[k];
-          Lp[d] = Li[d] + del;
-          edge_error(side ? w2n : ident, Lp, meas, A1, A2, e1);
-          Lp[d] = Li[d] + (-del);
-          edge_error(side ? w2n : ident, Lp, meas, A1, A2, e2);
-          for (int k = 0; k < 6; ++k) Jl[k * 6 + d] = scalar * (e1[k] - e2[k]);
+          double u[6] = {0, 0, 0, 0, 0, 0};
+          Iso c, ci;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) if (k == d) u[k] = del;
+          iso_oplus(cam1, u, c); iso_inv(c, ci); edge_error(ci, Lp, meas, A1, A2, e1);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) if (k == d) u[k] = -del;
+          iso_oplus(cam1, u, c); iso_inv(c, ci); edge_error(ci, Lp, meas, A1, A2, e2);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) Jm[72 + k * 6 + d] = scalar * (e1[k] - e2[k]);
         }
-        if (side) {
-          for (int d = 0; d < 6; ++d) {
-            double u[6] = {0, 0, 0, 0, 0, 0}, e1[6], e2[6];
-            Iso c, ci;
-            u[d] = del; iso_oplus(cam1, u, c); iso_inv(c, ci); edge_error(ci, Li, meas, A1, A2, e1);
-            u[d] = -del; iso_oplus(cam1, u, c); iso_inv(c, ci); edge_error(ci, Li, meas, A1, A2, e2);
-            for (int k = 0; k < 6; ++k) Jp[k * 6 + d] = scalar * (e1[k] - e2[k]);
-          }
-        }
-        edge_error(side ? w2n : ident, Li, meas, A1, A2, e);
-        double c2 = 0; for (int k = 0; k < 6; ++k) c2 += e[k] * w * e[k];
-        double wgt = w;
-        if (PP.robust) { double rho[3]; huber(c2, PP.huber_delta, rho); wgt = rho[1] * w; }
-        for (int a = 0; a < 6; ++a) {
-          double s = 0; for (int k = 0; k < 6; ++k) s += Jl[k * 6 + a] * (wgt * e[k]);
-          b[a] -= s;
-          for (int c = 0; c < 6; ++c) { double h = 0; for (int k = 0; k < 6; ++k) h += Jl[k * 6 + a] * wgt * Jl[k * 6 + c]; hll[a * 6 + c] += h; }
-        }
-        if (side) {
-          for (int a = 0; a < 6; ++a) {
-            double s = 0; for (int k = 0; k < 6; ++k) s += Jp[k * 6 + a] * (wgt * e[k]);
-            cp[36 + a] = s;
-            for (int c = 0; c < 6; ++c) {
-              double h = 0, g = 0;
-              for (int k = 0; k < 6; ++k) { h += Jp[k * 6 + a] * wgt * Jp[k * 6 + c]; g += Jp[k * 6 + a] * wgt * Jl[k * 6 + c]; }
-              cp[a * 6 + c] = h;
-              hpl[a * 6 + c] += g;
-            }
-          }
+        if (d == side) {  // residual and robust weight of this edge (threads d = 0 / 1 of the group)
+#pragma unroll
+          for (int k = 0; k < 6; ++k) Lp[k] = Li[k];
+          double e[6];
+          edge_error(side ? w2n : ident, Lp, meas, A1, A2, e);
+          double c2 = 0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) c2 += e[k] * w * e[k];
+          double wgt = w;
+          if (PP.robust) { double rho[3]; huber(c2, PP.huber_delta, rho); wgt = rho[1] * w; }
+#pragma unroll
+          for (int k = 0; k < 6; ++k) Jm[108 + 6 * side + k] = e[k];
+          Jm[120 + side] = wgt;
         }
       }
     }
     __syncthreads();
-    // ordered sums over the matches: Hpp (36), bp (6) by threads 0..41; chi2 by thread 64
-    if (tid < 36) { double s = 0; for (int i = 0; i < n; ++i) s += V.contrib[42 * i + tid]; s_S[tid] = s; }
-    else if (tid < 42) { double s = 0; for (int i = 0; i < n; ++i) s -= V.contrib[42 * i + tid]; s_S[tid] = s; }
-    else if (tid == 64) { double c = 0; for (int i = 0; i < 2 * n; ++i) c += V.chi[i]; s_red[0] = c; }
+    // ---- block rows: thread (match i, row a)
+    for (int t = tid; t < 6 * n; t += nthr) {
+      const int i = t / 6, a = t - 6 * i;
+      const double* Jm = V.J + (size_t)124 * i;
+      double* hll = V.Hll + 36 * i; double* hpl = V.Hpl + 36 * i; double* cp = V.contrib + 42 * i;
+      double b = 0, hrow[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        const double* Jl = Jm + 36 * side;
+        const double* e = Jm + 108 + 6 * side;
+        const double wgt = Jm[120 + side];
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s += Jl[k * 6 + a] * (wgt * e[k]);
+        b -= s;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          double h = 0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) h += Jl[k * 6 + a] * wgt * Jl[k * 6 + c];
+          hrow[c] += h;
+        }
+        if (side) {
+          const double* Jp = Jm + 72;
+          double sp = 0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) sp += Jp[k * 6 + a] * (wgt * e[k]);
+          cp[36 + a] = sp;
+#pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            double h = 0, g = 0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { h += Jp[k * 6 + a] * wgt * Jp[k * 6 + c]; g += Jp[k * 6 + a] * wgt * Jl[k * 6 + c]; }
+            cp[a * 6 + c] = h;
+            hpl[a * 6 + c] = 0.0 + g;
+          }
+        }
+      }
+      V.bl[6 * i + a] = b;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) hll[a * 6 + c] = hrow[c];
+    }
+    __syncthreads();
+    // ordered sums over the matches: Hpp (36), bp (6) on threads 0..41; chi2 on thread 64
+    if (tid < 36) s_S[tid] = chain_sum<false>(0.0, V.contrib + tid, 42, n);
+    else if (tid < 42) s_S[tid] = chain_sum<true>(0.0, V.contrib + tid, 42, n);
+    else if (tid == 64) s_red[0] = chain_sum<false>(0.0, V.chi, 1, 2 * n);
     __syncthreads();
     double Hpp[36], bp[6];
+#pragma unroll
     for (int k = 0; k < 36; ++k) Hpp[k] = s_S[k];
+#pragma unroll
     for (int k = 0; k < 6; ++k) bp[k] = s_S[36 + k];
     double currentChi = s_red[0];
     __syncthreads();
     if (it == 0) {  // computeLambdaInit: tau * max |diagonal entry|
       double md_ = 0;
-      for (int i = tid; i < n; i += nthr)
-        for (int a = 0; a < 6; ++a) md_ = fmax(fabs(V.Hll[36 * i + a * 6 + a]), md_);
+      for (int t = tid; t < 6 * n; t += nthr) { const int i = t / 6, a = t - 6 * i; md_ = fmax(fabs(V.Hll[36 * i + a * 6 + a]), md_); }
       for (int o = 16; o; o >>= 1) md_ = fmax(md_, __shfl_xor_sync(FULL, md_, o));
       if ((tid & 31) == 0) s_red[1 + (tid >> 5)] = md_;
       __syncthreads();
       double maxDiag = 0;
+#pragma unroll
       for (int a = 0; a < 6; ++a) maxDiag = fmax(fabs(Hpp[a * 6 + a]), maxDiag);
       for (int k = 0; k < nthr / 32; ++k) maxDiag = fmax(maxDiag, s_red[1 + k]);
       __syncthreads();
@@ -439,61 +554,96 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
     double rho = 0;
     int qmax = 0;
     do {
-      for (int i = tid; i < n; i += nthr) {
-        double M[36], hi[36];
-        for (int k = 0; k < 36; ++k) M[k] = V.Hll[36 * i + k];
-        for (int a = 0; a < 6; ++a) M[a * 6 + a] += lambda;
-        V.okf[i] = inv_lu<6>(M, hi);
-        const double* hpl = V.Hpl + 36 * i;
+      // (Hll + lambda I)^-1, one column per thread
+      for (int t = tid; t < 6 * n; t += nthr) {
+        const int i = t / 6, c = t - 6 * i;
+        double Rc[6];
+        int ok = inv6_column(V.Hll + 36 * i, lambda, c, Rc);
+        if (c == 0) V.okf[i] = ok;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) V.HllInv[36 * i + k * 6 + c] = Rc[k];
+      }
+      __syncthreads();
+      // Schur terms: thread (match i, row a)
+      for (int t = tid; t < 6 * n; t += nthr) {
+        const int i = t / 6, a = t - 6 * i;
+        const double* hi = V.HllInv + 36 * i; const double* hpl = V.Hpl + 36 * i;
         double* cp = V.contrib + 42 * i;
-        double T[36];
-        for (int a = 0; a < 6; ++a) for (int c = 0; c < 6; ++c) { double s = 0; for (int k = 0; k < 6; ++k) s += hpl[a * 6 + k] * hi[k * 6 + c]; T[a * 6 + c] = s; }
-        for (int a = 0; a < 6; ++a) {
-          double s = 0; for (int k = 0; k < 6; ++k) s += T[a * 6 + k] * V.bl[6 * i + k];
-          cp[36 + a] = s;
-          for (int c = 0; c < 6; ++c) { double h = 0; for (int k = 0; k < 6; ++k) h += T[a * 6 + k] * hpl[c * 6 + k]; cp[a * 6 + c] = h; }
+        double T[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          double s = 0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) s += hpl[a * 6 + k] * hi[k * 6 + c];
+          T[c] = s;
         }
-        for (int k = 0; k < 36; ++k) V.HllInv[36 * i + k] = hi[k];
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s += T[k] * V.bl[6 * i + k];
+        cp[36 + a] = s;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          double h = 0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) h += T[k] * hpl[c * 6 + k];
+          cp[a * 6 + c] = h;
+        }
       }
       __syncthreads();
       if (tid < 42) {
-        double s = tid < 36 ? Hpp[tid] : bp[tid - 36];
-        if (tid < 36 && (tid / 6 == tid % 6)) s += lambda;
-        for (int i = 0; i < n; ++i) s -= V.contrib[42 * i + tid];
-        s_S[tid] = s;
+        double s0 = tid < 36 ? Hpp[tid] : bp[tid - 36];
+        if (tid < 36 && (tid / 6 == tid % 6)) s0 += lambda;
+        s_S[tid] = chain_sum<true>(s0, V.contrib + tid, 42, n);
       } else if (tid == 64) {
         int ok = 1;
         for (int i = 0; i < n; ++i) ok &= V.okf[i];
         s_red[2] = (double)ok;
       }
       __syncthreads();
-      double S[36], Si[36], rhs[6], dp[6];
-      for (int k = 0; k < 36; ++k) S[k] = s_S[k];
-      for (int k = 0; k < 6; ++k) rhs[k] = s_S[36 + k];
-      bool ok = s_red[2] != 0.0;
-      if (!inv_lu<6>(S, Si)) ok = false;
-      for (int a = 0; a < 6; ++a) { double s = 0; for (int k = 0; k < 6; ++k) s += Si[a * 6 + k] * rhs[k]; dp[a] = s; }
+      // 6x6 pose system: threads 0..5 invert S column-wise, then dp
+      if (tid < 6) {
+        double Rc[6];
+        int ok = inv6_column(s_S, 0.0, tid, Rc);
+        if (tid == 0 && !ok) s_red[2] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s_S[48 + k * 6 + tid] = Rc[k];
+      }
+      __syncthreads();
+      double dp[6];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s += s_S[48 + a * 6 + k] * s_S[36 + k];
+        dp[a] = s;
+      }
+      const bool ok = s_red[2] != 0.0;
       double scale = 0;
+#pragma unroll
       for (int a = 0; a < 6; ++a) scale += dp[a] * (lambda * dp[a] + bp[a]);
-      for (int i = tid; i < n; i += nthr) {
+      for (int t = tid; t < 6 * n; t += nthr) {
+        const int i = t / 6, a = t - 6 * i;
         const double* hi = V.HllInv + 36 * i; const double* hpl = V.Hpl + 36 * i;
-        double r[6];
-        for (int a = 0; a < 6; ++a) { double s = 0; for (int k = 0; k < 6; ++k) s += hpl[k * 6 + a] * dp[k]; r[a] = V.bl[6 * i + a] - s; }
-        for (int a = 0; a < 6; ++a) {
-          double s = 0; for (int k = 0; k < 6; ++k) s += hi[a * 6 + k] * r[k];
-          V.dl[6 * i + a] = s;
-          V.terms[6 * i + a] = s * (lambda * s + V.bl[6 * i + a]);
-          V.Lnew[6 * i + a] = V.L[6 * i + a] + s;
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          double q = 0;
+#pragma unroll
+          for (int m = 0; m < 6; ++m) q += hpl[m * 6 + k] * dp[m];
+          s += hi[a * 6 + k] * (V.bl[6 * i + k] - q);
         }
+        V.dl[t] = s;
+        V.terms[t] = s * (lambda * s + V.bl[t]);
+        V.Lnew[t] = V.L[t] + s;
       }
       Iso camNew, w2nNew;
       iso_oplus(cam1, dp, camNew);
       iso_inv(camNew, w2nNew);
       __syncthreads();
       chi2_terms(V, md_all, n, w2nNew, ident, V.Lnew, PP);
+      if (tid == nthr - 1) s_red[3] = chain_sum<false>(scale, V.terms, 1, 6 * n);   // overlaps the chi2 terms of the other warps
       __syncthreads();
-      if (tid == 0) { double sc = scale; for (int i = 0; i < 6 * n; ++i) sc += V.terms[i]; s_red[3] = sc; }
-      else if (tid == 64) { double c = 0; for (int i = 0; i < 2 * n; ++i) c += V.chi[i]; s_red[4] = c; }
+      if (tid == 64) s_red[4] = chain_sum<false>(0.0, V.chi, 1, 2 * n);
       __syncthreads();
       scale = s_red[3];
       double tempChi = s_red[4];
@@ -564,10 +714,11 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_kernel(const LslPairDesc* _
                                                             lsl_pose_rec* __restrict__ out) {
   __shared__ float s_tf[16];
   __shared__ double s_red[64];
-  __shared__ double s_S[48];
+  __shared__ double s_S[96];
   __shared__ int s_i[4];
   __shared__ double s_d[2];
   __shared__ GRand s_rng;
+  __shared__ uint16_t s_idx[LSL_MAX_MATCH];
   const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = POSE_THREADS / 32;
   const LslPairDesc pd = pairs[pair];
   const int nm = min(nmatch[pair], pd.cap_m);
@@ -585,10 +736,11 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_kernel(const LslPairDesc* _
   uint16_t* trip = sc.trip + (size_t)pair * sc.max_iter * 3;
   LmView V;
   {
-    double* lm = sc.lm + pd.m_off * 182;
+    double* lm = sc.lm + pd.m_off * LM_STRIDE;
     const size_t c = pd.cap_m;
     V.L = lm; V.Lnew = V.L + 6 * c; V.Hll = V.Lnew + 6 * c; V.Hpl = V.Hll + 36 * c; V.bl = V.Hpl + 36 * c;
     V.HllInv = V.bl + 6 * c; V.contrib = V.HllInv + 36 * c; V.dl = V.contrib + 42 * c; V.terms = V.dl + 6 * c; V.chi = V.terms + 6 * c;
+    V.J = V.chi + 2 * c;
     V.okf = sc.okf + pd.m_off;
     V.sel = sel_r;
   }
@@ -617,13 +769,13 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_kernel(const LslPairDesc* _
   // ---- the 500 sample triples: one rand() stream, cumulative shuffle (motion.cpp:635-658)
   if (tid == 0) {
     grand_seed(&s_rng, pd.seed);
-    int32_t* idx = sel_t;  // borrowed as the `indexes` vector
-    for (int i = 0; i < nm; ++i) idx[i] = i;
+    uint16_t* idx = s_idx;  // the `indexes` vector
+    for (int i = 0; i < nm; ++i) idx[i] = (uint16_t)i;
     for (int it = 0; it < maxIter; ++it) {
       int left = nm;
       for (int k = 0; k < 3; ++k) {
         int r = grand_next(&s_rng) % left;
-        int t = idx[k]; idx[k] = idx[k + r]; idx[k + r] = t;
+        uint16_t t = idx[k]; idx[k] = idx[k + r]; idx[k + r] = t;
         --left;
       }
       trip[3 * it] = (uint16_t)idx[0]; trip[3 * it + 1] = (uint16_t)idx[1]; trip[3 * it + 2] = (uint16_t)idx[2];

@@ -417,7 +417,7 @@ static int ensure_pair_ws(lsl_ctx* ctx, size_t npairs, size_t tot_m, size_t tot_
     size_t c = tot_m + tot_m / 2;
     LSL_CUDA(cudaStreamSynchronize(ctx->stream));
     LSL_CUDA(regrow(&p.matches, c)); LSL_CUDA(regrow(&p.sc.md, c * 72)); LSL_CUDA(regrow(&p.sc.dab, c * 2));
-    LSL_CUDA(regrow(&p.sc.sel, c * 3)); LSL_CUDA(regrow(&p.sc.lm, c * 182)); LSL_CUDA(regrow(&p.sc.okf, c));
+    LSL_CUDA(regrow(&p.sc.sel, c * 3)); LSL_CUDA(regrow(&p.sc.lm, c * 306)); LSL_CUDA(regrow(&p.sc.okf, c));
     p.cap_m = c;
   }
   if (tot_d > p.cap_d) {

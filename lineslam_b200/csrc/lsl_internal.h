@@ -77,7 +77,7 @@ struct LslPairScratch {
   double* md;        // [M][72]  gathered per-match data
   double* dab;       // [M][2]   Mahalanobis distances of the last scoring pass
   int32_t* sel;      // [M][3]   RANSAC / refined / trial inlier index lists
-  double* lm;        // [M][182] per-match blocks of the LM refinement
+  double* lm;        // [M][306] per-match blocks of the LM refinement (k_pair.cu:LM_STRIDE)
   int32_t* okf;      // [M]
   float* tfs;        // [pairs][max_iter][12] hypotheses
   int32_t* cnts;     // [pairs][max_iter]     inlier counts
