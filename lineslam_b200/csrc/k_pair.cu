@@ -19,7 +19,9 @@
 using namespace lslm;
 
 #define FULL 0xffffffffu
-#define POSE_THREADS 512
+#ifndef POSE_THREADS
+#define POSE_THREADS 256
+#endif
 #define MD_STRIDE 72  // doubles of gathered data per match
 
 // ------------------------------------------------------------ lineMatching ----
