@@ -529,138 +529,153 @@ __global__ void msld_randfill_kernel(LslWork w, const int32_t* __restrict__ msld
 }
 
 // ------------------------------------------------------------------- MLE ----
+// One warp per line. Lane `lane` owns the points i = lane + 32 q (q < 4): their positions, residuals hx / wrk
+// live in registers; the covariance factors DU, the Jacobian and the two residual-difference vectors that other
+// lanes must read (J^T e, the ordered norms) live in shared memory.
 struct MleSmem {
   double pos[LSL_MAX_SMP * 3];
   double DU[LSL_MAX_SMP * 9];
-  double hx[LSL_MAX_SMP], e[LSL_MAX_SMP], wrk[LSL_MAX_SMP], wrk2[LSL_MAX_SMP];
+  double eA[LSL_MAX_SMP], eB[LSL_MAX_SMP];  // e of the current estimate / of the trial point (roles swap on accept)
   double jac[LSL_MAX_SMP * 6];
   double JtJ[36], Jte[6];
   double cinv1[9], cinv2[9];
 };  // the 32 x 18 tile of MleLine3dCov reuses `jac` once the LM has finished
 
-// costFun_MLEstimateLine3d (utils.cpp:954-978): lanes stride over the points
-__device__ __forceinline__ void mle_cost(const MleSmem& S, int n, int idx1, int idx2, const double* p, double* out) {
+// costFun_MLEstimateLine3d (utils.cpp:954-978) for the points a lane owns. Deliberately NOT inlined and not
+// unrolled: the LM loop is instruction-fetch bound when its body outgrows the instruction cache (ncu: 50 % of
+// the stall samples were `no_instructions` with three inlined, four-way unrolled copies).
+__device__ __noinline__ void mle_cost(const MleSmem& S, int n, int idx1, int idx2, const double* p, double* r) {
   const int lane = threadIdx.x & 31;
-  for (int i = lane; i < n; i += 32) {
-    double r;
-    if (i == idx1) r = mah_sq_pt(p, S.pos + 3 * i, S.cinv1);
-    else if (i == idx2) r = mah_sq_pt(p + 3, S.pos + 3 * i, S.cinv2);
-    else r = mah_dist3d_pt_line(S.pos + 3 * i, S.DU + 9 * i, p, p + 3);
-    out[i] = r;
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) {
+    const int i = lane + 32 * q;
+    if (32 * q >= n) break;               // uniform
+    const int ic = i < n ? i : n - 1;     // lanes past the end recompute the last point (discarded)
+    double v = mah_dist3d_pt_line(S.pos + 3 * ic, S.DU + 9 * ic, p, p + 3);
+    if (i == idx1) v = mah_sq_pt(p, S.pos + 3 * ic, S.cinv1);
+    else if (i == idx2) v = mah_sq_pt(p + 3, S.pos + 3 * ic, S.cinv2);
+    r[q] = v;
   }
-  __syncwarp();
 }
 
-// LEVMAR_L2NRMXMY with x = 0 (misc_core.c:721-809): e = 0 - y, four interleaved accumulators walking
-// downwards in blocks of 8, remainder upwards. Every lane evaluates the same sequence (uniform result).
-__device__ double l2nrm_neg(double* e, const double* y, int n) {
+// LEVMAR_L2NRMXMY with x = 0 (misc_core.c:721-809): e = 0 - y, four accumulators walking downwards in blocks
+// of 8 and the remainder upwards. Accumulator a sees the indices congruent to 3 - a (mod 4) below
+// blockn = 8 floor(n / 8) in descending order, then its share of the remainder; lanes 0..3 run one accumulator
+// each and the four partial sums are added left to right.
+__device__ __noinline__ double l2nrm_neg(double* E, const double* y, int n) {
   const int lane = threadIdx.x & 31;
-  for (int i = lane; i < n; i += 32) e[i] = 0.0 - y[i];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { const int i = lane + 32 * q; if (i < n) E[i] = 0.0 - y[q]; }
   __syncwarp();
-  double sum0 = 0.0, sum1 = 0.0, sum2 = 0.0, sum3 = 0.0;
-  int blockn = (n >> 3) << 3;
-  for (int i = blockn - 1; i > 0; i -= 8) {
-    sum0 += e[i] * e[i]; sum1 += e[i - 1] * e[i - 1]; sum2 += e[i - 2] * e[i - 2]; sum3 += e[i - 3] * e[i - 3];
-    sum0 += e[i - 4] * e[i - 4]; sum1 += e[i - 5] * e[i - 5]; sum2 += e[i - 6] * e[i - 6]; sum3 += e[i - 7] * e[i - 7];
+  const int a = lane & 3;
+  const int blockn = (n >> 3) << 3;
+  double s = 0.0;
+  int i = blockn - 1 - a;
+  for (; i >= 12; i -= 16) {
+    double t0 = E[i], t1 = E[i - 4], t2 = E[i - 8], t3 = E[i - 12];
+    s += t0 * t0; s += t1 * t1; s += t2 * t2; s += t3 * t3;
   }
-  int i = blockn;
-  if (i < n) {
-    switch (n - i) {
-      case 7: sum0 += e[i] * e[i]; ++i;
-      case 6: sum1 += e[i] * e[i]; ++i;
-      case 5: sum2 += e[i] * e[i]; ++i;
-      case 4: sum3 += e[i] * e[i]; ++i;
-      case 3: sum0 += e[i] * e[i]; ++i;
-      case 2: sum1 += e[i] * e[i]; ++i;
-      case 1: sum2 += e[i] * e[i];
-    }
+  for (; i >= 0; i -= 4) { double t0 = E[i]; s += t0 * t0; }
+  const int rem = n - blockn;
+  for (int t = 0; t < rem; ++t) {
+    const int c = rem - t;                                    // switch case label of element blockn + t
+    const int acc = (c == 7 || c == 3) ? 0 : ((c == 6 || c == 2) ? 1 : ((c == 5 || c == 1) ? 2 : 3));
+    if (acc == a) { double t0 = E[blockn + t]; s += t0 * t0; }
   }
-  return sum0 + sum1 + sum2 + sum3;
+  const double s0 = __shfl_sync(FULL, s, 0), s1 = __shfl_sync(FULL, s, 1), s2 = __shfl_sync(FULL, s, 2), s3 = __shfl_sync(FULL, s, 3);
+  return s0 + s1 + s2 + s3;
 }
 
-// AX_EQ_B_LU for m = 6 (Axb_core.c:1140-1277), executed identically by every lane. Fully unrolled with
-// static indices so the 6x6 system lives in registers (row swaps and the permuted forward substitution are
-// compare-and-select over the unrolled rows); the operation order per element is the reference's.
-// The system is (JtJ with diag + mu on the diagonal) x = B.
-__device__ __forceinline__ int ax_eq_b_lu6(const double* __restrict__ JtJ, const double* diag, double mu, const double* B,
-                                           double* x) {
-  double a[6][6], work[6];
+// AX_EQ_B_LU for m = 6 (Axb_core.c:1140-1277) with the six rows on lanes 0..5 (Crout by columns, implicit
+// scaling, partial pivoting); every element sees the reference's operation order (k ascending), the lane
+// only decides where it is computed. Row swaps are lane-to-lane exchanges. The system is
+// (JtJ + mu on the diagonal) x = Jte; on return every lane holds the full solution x[6].
+__device__ __noinline__ int ax_eq_b_lu6(const MleSmem& S, double mu, double* x) {
+  const int lane = threadIdx.x & 31;
+  const int row = lane < 6 ? lane : 5;   // lanes >= 6 shadow row 5 (results unused)
+  double a[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) a[j] = S.JtJ[row * 6 + j];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) if (j == row) a[j] = a[j] + mu;
+  double xr = S.Jte[row];
+  double mx = 0.0, tmp;
+#pragma unroll
+  for (int j = 0; j < 6; ++j)
+    if ((tmp = fabs(a[j])) > mx) mx = tmp;
+  if (__ballot_sync(FULL, mx == 0.0) & 0x3fu) return 0;
+  double work = 1.0 / mx;
   int idx[6];
   int maxi = -1;
 #pragma unroll
-  for (int i = 0; i < 6; ++i) {
-#pragma unroll
-    for (int j = 0; j < 6; ++j) a[i][j] = (i == j) ? diag[i] + mu : JtJ[i * 6 + j];
-    x[i] = B[i];
-  }
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    double max = 0.0, tmp;
-#pragma unroll
-    for (int j = 0; j < 6; ++j)
-      if ((tmp = fabs(a[i][j])) > max) max = tmp;
-    if (max == 0.0) return 0;
-    work[i] = 1.0 / max;
-  }
-#pragma unroll
   for (int j = 0; j < 6; ++j) {
+    double sum = a[j];
 #pragma unroll
-    for (int i = 0; i < j; ++i) {
-      double sum = a[i][j];
-#pragma unroll
-      for (int k = 0; k < i; ++k) sum -= a[i][k] * a[k][j];
-      a[i][j] = sum;
+    for (int k = 0; k < j; ++k) {           // a[i][j] -= a[i][k] * a[k][j], k < min(i, j); row k is final at step k
+      const double v = __shfl_sync(FULL, sum, k);
+      if (lane > k) sum -= a[k] * v;
     }
-    double max = 0.0, tmp;
+    a[j] = sum;
+    // pivot: last row i >= j with the largest work[i] * |sum| (the reference's `>=` scan), NaNs never win
+    tmp = work * fabs(sum);
+    double bv = (lane >= j && lane < 6 && tmp == tmp) ? tmp : -1.0;
+    int bi = lane;
 #pragma unroll
-    for (int i = j; i < 6; ++i) {
-      double sum = a[i][j];
-#pragma unroll
-      for (int k = 0; k < j; ++k) sum -= a[i][k] * a[k][j];
-      a[i][j] = sum;
-      if ((tmp = work[i] * fabs(sum)) >= max) { max = tmp; maxi = i; }
+    for (int o = 1; o < 8; o <<= 1) {
+      const double ov = __shfl_xor_sync(FULL, bv, o);
+      const int oi = __shfl_xor_sync(FULL, bi, o);
+      if (ov > bv || (ov == bv && oi > bi)) { bv = ov; bi = oi; }
     }
+    bv = __shfl_sync(FULL, bv, 0); bi = __shfl_sync(FULL, bi, 0);
+    if (bv >= 0.0) maxi = bi;
+    if (j != maxi) {                         // uniform
+      const int partner = lane == j ? maxi : (lane == maxi ? j : lane);
 #pragma unroll
-    for (int r = 0; r < 6; ++r)
-      if (r != j && r == maxi) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) { double t = a[r][k]; a[r][k] = a[j][k]; a[j][k] = t; }
-        work[r] = work[j];
-      }
+      for (int c = 0; c < 6; ++c) a[c] = __shfl_sync(FULL, a[c], partner);
+      const double wj = __shfl_sync(FULL, work, j);
+      if (lane == maxi) work = wj;
+    }
     idx[j] = maxi;
-    if (a[j][j] == 0.0) a[j][j] = DBL_EPSILON;
+    if (lane == j && a[j] == 0.0) a[j] = DBL_EPSILON;
     if (j != 5) {
-      double tmp2 = 1.0 / (a[j][j]);
-#pragma unroll
-      for (int i = j + 1; i < 6; ++i) a[i][j] *= tmp2;
+      const double piv = __shfl_sync(FULL, a[j], j);
+      const double tmp2 = 1.0 / piv;
+      if (lane > j) a[j] *= tmp2;
     }
   }
+  // forward substitution with the row permutation
   int k = 0;
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     const int jj = idx[i];
-    double sum = x[i];
-#pragma unroll
-    for (int r = 0; r < 6; ++r)
-      if (r == jj) { sum = x[r]; x[r] = x[i]; }
+    const double xi = __shfl_sync(FULL, xr, i);
+    double sum = __shfl_sync(FULL, xr, jj);   // sum = x[jj]; x[jj] = x[i]
+    if (lane == jj) xr = xi;
     if (k != 0) {
 #pragma unroll
-      for (int j2 = 0; j2 < i; ++j2)
-        if (j2 >= k - 1) sum -= a[i][j2] * x[j2];
+      for (int j2 = 0; j2 < i; ++j2) {
+        const double xv = __shfl_sync(FULL, xr, j2);
+        if (j2 >= k - 1) sum -= a[j2] * xv;   // meaningful on lane i (its row)
+      }
     } else if (sum != 0.0) k = i + 1;
-    x[i] = sum;
+    if (lane == i) xr = sum;
   }
 #pragma unroll
   for (int i = 5; i >= 0; --i) {
-    double sum = x[i];
+    double sum = xr;
 #pragma unroll
-    for (int j = i + 1; j < 6; ++j) sum -= a[i][j] * x[j];
-    x[i] = sum / a[i][i];
+    for (int j = i + 1; j < 6; ++j) {
+      const double xv = __shfl_sync(FULL, xr, j);
+      sum -= a[j] * xv;
+    }
+    if (lane == i) xr = sum / a[i];
   }
+#pragma unroll
+  for (int r = 0; r < 6; ++r) x[r] = __shfl_sync(FULL, xr, r);
   return 1;
 }
 
-__global__ void __launch_bounds__(32, 12) line_mle_kernel(LslWork w, LineParams P) {
+__global__ void __launch_bounds__(32, 13) line_mle_kernel(LslWork w, LineParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MleSmem& S = *reinterpret_cast<MleSmem*>(smem_raw);
   const int f = blockIdx.y, lane = threadIdx.x;
@@ -672,6 +687,7 @@ __global__ void __launch_bounds__(32, 12) line_mle_kernel(LslWork w, LineParams 
   const double* gp = w.pts + ((size_t)f * LSL_MAX_LINES + li) * LSL_MAX_SMP * 3;
   const int m = 6;
   // points + their covariance factors (recomputed: same functions as the RANSAC stage)
+#pragma unroll 1
   for (int i = lane; i < n; i += 32) {
     double pos[3] = {gp[3 * i], gp[3 * i + 1], gp[3 * i + 2]}, cov[9], DU[9], Ws[3];
     pt3d_cov(pos, P.fx, P.sigma_impt, P.c1, P.c2, P.c3, P.dt, cov);
@@ -687,20 +703,21 @@ __global__ void __launch_bounds__(32, 12) line_mle_kernel(LslWork w, LineParams 
   for (int k = 0; k < 4; ++k) { int rem = n - 32 * k; all[k] = rem >= 32 ? FULL : (rem > 0 ? ((1u << rem) - 1u) : 0u); }
   int idx1, idx2;
   warp_argminmax(all, [&](int i) {
-    double d[3] = {S.pos[3 * i] - A0[0], S.pos[3 * i + 1] - A0[1], S.pos[3 * i + 2] - A0[2]};
+    double d[3] = {gp[3 * i] - A0[0], gp[3 * i + 1] - A0[1], gp[3 * i + 2] - A0[2]};
     return dot3(d, AB);
   }, &idx1, &idx2);
   if (idx1 > idx2) { int t = idx1; idx1 = idx2; idx2 = t; }
   if (lane == 0) {
-    double cov[9];
-    pt3d_cov(S.pos + 3 * idx1, P.fx, P.sigma_impt, P.c1, P.c2, P.c3, P.dt, cov);
+    double cov[9], pp[3] = {gp[3 * idx1], gp[3 * idx1 + 1], gp[3 * idx1 + 2]};
+    pt3d_cov(pp, P.fx, P.sigma_impt, P.c1, P.c2, P.c3, P.dt, cov);
     inv3(cov, S.cinv1);
-    pt3d_cov(S.pos + 3 * idx2, P.fx, P.sigma_impt, P.c1, P.c2, P.c3, P.dt, cov);
+    double pq[3] = {gp[3 * idx2], gp[3 * idx2 + 1], gp[3 * idx2 + 2]};
+    pt3d_cov(pq, P.fx, P.sigma_impt, P.c1, P.c2, P.c3, P.dt, cov);
     inv3(cov, S.cinv2);
   }
   __syncwarp();
-  double p[6], pDp[6], Dp[6], diag[6], jacTe[6];
-  for (int k = 0; k < 3; ++k) { p[k] = S.pos[3 * idx1 + k]; p[3 + k] = S.pos[3 * idx2 + k]; }
+  double p[6], pDp[6], Dp[6];
+  for (int k = 0; k < 3; ++k) { p[k] = gp[3 * idx1 + k]; p[3 + k] = gp[3 * idx2 + k]; }
 
   // ---- dlevmar_dif (lm_core.c:438-847); opts = {1e-3, 1e-10, 1e-20, 1e-20, 1e-6} (utils.cpp:1002-1008)
   const double tau = 1E-03, eps1 = 1E-10, eps2 = 1E-20, eps2_sq = 1E-20 * 1E-20, eps3 = 1E-20, delta = 1E-06;
@@ -708,92 +725,125 @@ __global__ void __launch_bounds__(32, 12) line_mle_kernel(LslWork w, LineParams 
   double mu = 0, jacTe_inf = 0, p_L2 = 0, tmp, p_eL2, pDp_eL2, Dp_L2 = DBL_MAX, dF, dL;
   int nu = 20, nu2, stop = 0, K = 10, updjac = 0, updp = 1, newjac = 0, k = 0;
   int lm_ret = -1;
+  double hx[4], wrk[4];
+  double* Ecur = S.eA;   // e = x - hx of the current estimate
+  double* Enew = S.eB;   // of the trial point
   if (n >= m) {
-  mle_cost(S, n, idx1, idx2, p, S.hx);
-  p_eL2 = l2nrm_neg(S.e, S.hx, n);
+  mle_cost(S, n, idx1, idx2, p, hx);
+  p_eL2 = l2nrm_neg(Ecur, hx, n);
   if (!isfinite(p_eL2)) stop = 7;
   for (k = 0; k < itmax && !stop; ++k) {
     if (p_eL2 <= eps3) { stop = 6; break; }
     if ((updp && nu > 16) || updjac == K) {
+#pragma unroll 1
       for (int j = 0; j < m; ++j) {  // LEVMAR_FDIF_FORW_JAC_APPROX (misc_core.c:137-172)
-        double d = 1E-04 * p[j];
+        double pj = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) if (c == j) pj = p[c];
+        double d = 1E-04 * pj;
         d = fabs(d);
         if (d < delta) d = delta;
-        double t = p[j];
-        p[j] += d;
-        mle_cost(S, n, idx1, idx2, p, S.wrk);
-        p[j] = t;
+        double pp[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) pp[c] = (c == j) ? p[c] + d : p[c];
+        mle_cost(S, n, idx1, idx2, pp, wrk);
         d = 1.0 / d;
-        for (int i = lane; i < n; i += 32) S.jac[i * m + j] = (S.wrk[i] - S.hx[i]) * d;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const int i = lane + 32 * q; if (i < n) S.jac[i * m + j] = (wrk[q] - hx[q]) * d; }
       }
       __syncwarp();
       nu = 2; updjac = 0; updp = 0; newjac = 1;
     }
     if (newjac) {
       newjac = 0;
-      // J^T J (lower triangle) and J^T e, each accumulator summed for l = n-1 .. 0 (lm_core.c:618-639)
+      // J^T J (lower triangle) and J^T e, each accumulator summed for l = n-1 .. 0 (lm_core.c:618-639);
+      // four products are formed ahead of the dependent adds
       if (lane < 27) {
         double acc = 0.0;
+        const double* ja; const double* jb; int sb;
         if (lane < 21) {
           int i = 0, r = lane;
           while (r > i) { r -= i + 1; ++i; }  // lane -> (i, j), j <= i
-          int j = r;
-          for (int l = n; l-- > 0;) acc += S.jac[l * m + j] * S.jac[l * m + i];
-          S.JtJ[i * m + j] = acc; S.JtJ[j * m + i] = acc;
-        } else {
-          int i = lane - 21;
-          for (int l = n; l-- > 0;) acc += S.jac[l * m + i] * S.e[l];
-          S.Jte[i] = acc;
+          ja = S.jac + r; jb = S.jac + i; sb = m;
+        } else { ja = S.jac + (lane - 21); jb = Ecur; sb = 1; }
+        int l = n - 1;
+        for (; l >= 3; l -= 4) {
+          double t0 = ja[l * m] * jb[l * sb], t1 = ja[(l - 1) * m] * jb[(l - 1) * sb], t2 = ja[(l - 2) * m] * jb[(l - 2) * sb],
+                 t3 = ja[(l - 3) * m] * jb[(l - 3) * sb];
+          acc += t0; acc += t1; acc += t2; acc += t3;
         }
+        for (; l >= 0; --l) acc += ja[l * m] * jb[l * sb];
+        if (lane < 21) {
+          int i = 0, r = lane;
+          while (r > i) { r -= i + 1; ++i; }
+          S.JtJ[i * m + r] = acc; S.JtJ[r * m + i] = acc;
+        } else S.Jte[lane - 21] = acc;
       }
       __syncwarp();
       p_L2 = jacTe_inf = 0.0;
+#pragma unroll
       for (int i = 0; i < m; ++i) {
-        jacTe[i] = S.Jte[i];
-        if (jacTe_inf < (tmp = fabs(jacTe[i]))) jacTe_inf = tmp;
-        diag[i] = S.JtJ[i * m + i];
+        if (jacTe_inf < (tmp = fabs(S.Jte[i]))) jacTe_inf = tmp;
         p_L2 += p[i] * p[i];
       }
     }
     if (jacTe_inf <= eps1) { Dp_L2 = 0.0; stop = 1; break; }
     if (k == 0) {
       tmp = DBL_MIN;
+#pragma unroll
       for (int i = 0; i < m; ++i)
-        if (diag[i] > tmp) tmp = diag[i];
+        if (S.JtJ[i * m + i] > tmp) tmp = S.JtJ[i * m + i];
       mu = tau * tmp;
     }
     {
-      int issolved = ax_eq_b_lu6(S.JtJ, diag, mu, jacTe, Dp);
+      int issolved = ax_eq_b_lu6(S, mu, Dp);
       if (issolved) {
         Dp_L2 = 0.0;
+#pragma unroll
         for (int i = 0; i < m; ++i) { pDp[i] = p[i] + (tmp = Dp[i]); Dp_L2 += tmp * tmp; }
         if (Dp_L2 <= eps2_sq * p_L2) { stop = 2; break; }
         if (Dp_L2 >= (p_L2 + eps2) / (1E-12 * 1E-12)) { stop = 4; break; }
-        mle_cost(S, n, idx1, idx2, pDp, S.wrk);
-        pDp_eL2 = l2nrm_neg(S.wrk2, S.wrk, n);
+        mle_cost(S, n, idx1, idx2, pDp, wrk);
+        pDp_eL2 = l2nrm_neg(Enew, wrk, n);
         if (!isfinite(pDp_eL2)) { stop = 7; break; }
         dF = p_eL2 - pDp_eL2;
-        if (updp || dF > 0) {  // Broyden rank-one update of the Jacobian
-          for (int i = lane; i < n; i += 32) {
-            tmp = 0.0;
-            for (int l = 0; l < m; ++l) tmp += S.jac[i * m + l] * Dp[l];
-            tmp = (S.wrk[i] - S.hx[i] - tmp) / Dp_L2;
-            for (int j = 0; j < m; ++j) S.jac[i * m + j] += tmp * Dp[j];
+        if (updp || dF > 0) {  // Broyden rank-one update of the Jacobian (own rows; the divisions overlap)
+          double tq[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int i = lane + 32 * q;
+            const int ic = i < n ? i : n - 1;
+            double t = 0.0;
+#pragma unroll
+            for (int l = 0; l < m; ++l) t += S.jac[ic * m + l] * Dp[l];
+            tq[q] = (wrk[q] - hx[q] - t) / Dp_L2;
+          }
+          __syncwarp();   // lanes past the end read the last row: all reads before any write
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int i = lane + 32 * q;
+            if (i < n) {
+#pragma unroll
+              for (int j = 0; j < m; ++j) S.jac[i * m + j] += tq[q] * Dp[j];
+            }
           }
           __syncwarp();
           ++updjac;
           newjac = 1;
         }
         dL = 0.0;
-        for (int i = 0; i < m; ++i) dL += Dp[i] * (mu * Dp[i] + jacTe[i]);
+#pragma unroll
+        for (int i = 0; i < m; ++i) dL += Dp[i] * (mu * Dp[i] + S.Jte[i]);
         if (dL > 0.0 && dF > 0.0) {
           tmp = (2.0 * dF / dL - 1.0);
           tmp = 1.0 - tmp * tmp * tmp;
           mu = mu * ((tmp >= 0.3333333334) ? tmp : 0.3333333334);
           nu = 2;
+#pragma unroll
           for (int i = 0; i < m; ++i) p[i] = pDp[i];
-          for (int i = lane; i < n; i += 32) { S.e[i] = S.wrk2[i]; S.hx[i] = S.wrk[i]; }
-          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) hx[q] = wrk[q];
+          { double* t = Ecur; Ecur = Enew; Enew = t; }
           p_eL2 = pDp_eL2;
           updp = 1;
           continue;
@@ -815,14 +865,18 @@ __global__ void __launch_bounds__(32, 12) line_mle_kernel(LslWork w, LineParams 
     double* Jt = S.jac;  // 32 x 18 doubles <= 101 x 6
     __syncwarp();
     if (lane < 21) { int i = 0, r = lane; while (r > i) { r -= i + 1; ++i; } ha = i; hb = r; }
-    for (int i0 = 0; i0 < n; i0 += 32) {
-      int i = i0 + lane;
+#pragma unroll 1
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const int i0 = 32 * q4;
+      if (i0 >= n) break;
+      const int i = i0 + lane;
       if (i < n) {
         double J[18];
         for (int q = 0; q < 18; ++q) J[q] = 0;
+        double pq[3] = {gp[3 * i], gp[3 * i + 1], gp[3 * i + 2]};
         if (i == idx1) { for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) J[r * 6 + c] = -S.DU[9 * i + r * 3 + c]; }
         else if (i == idx2) { for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) J[r * 6 + 3 + c] = -S.DU[9 * i + r * 3 + c]; }
-        else jac_rpt2ln(S.pos + 3 * i, S.DU + 9 * i, p, J);
+        else jac_rpt2ln(pq, S.DU + 9 * i, p, J);
         for (int q = 0; q < 18; ++q) Jt[lane * 18 + q] = J[q];
       }
       __syncwarp();
