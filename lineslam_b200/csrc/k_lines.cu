@@ -586,10 +586,23 @@ __device__ __noinline__ double l2nrm_neg(double* E, const double* y, int n) {
   return s0 + s1 + s2 + s3;
 }
 
+// a[k] / a[k] = v for a run-time k without local memory (k is warp-uniform)
+__device__ __forceinline__ double sel6(const double* a, int k) {
+  double v = a[0];
+#pragma unroll
+  for (int c = 1; c < 6; ++c) if (k == c) v = a[c];
+  return v;
+}
+__device__ __forceinline__ void put6(double* a, int k, double v) {
+#pragma unroll
+  for (int c = 0; c < 6; ++c) if (k == c) a[c] = v;
+}
+
 // AX_EQ_B_LU for m = 6 (Axb_core.c:1140-1277) with the six rows on lanes 0..5 (Crout by columns, implicit
 // scaling, partial pivoting); every element sees the reference's operation order (k ascending), the lane
-// only decides where it is computed. Row swaps are lane-to-lane exchanges. The system is
-// (JtJ + mu on the diagonal) x = Jte; on return every lane holds the full solution x[6].
+// only decides where it is computed. Row swaps are lane-to-lane exchanges. The column / row loops are kept
+// rolled (run-time column index through sel6 / put6) so the solver stays small in the instruction cache.
+// The system is (JtJ + mu on the diagonal) x = Jte; on return every lane holds the full solution x[6].
 __device__ __noinline__ int ax_eq_b_lu6(const MleSmem& S, double mu, double* x) {
   const int lane = threadIdx.x & 31;
   const int row = lane < 6 ? lane : 5;   // lanes >= 6 shadow row 5 (results unused)
@@ -605,17 +618,19 @@ __device__ __noinline__ int ax_eq_b_lu6(const MleSmem& S, double mu, double* x) 
     if ((tmp = fabs(a[j])) > mx) mx = tmp;
   if (__ballot_sync(FULL, mx == 0.0) & 0x3fu) return 0;
   double work = 1.0 / mx;
-  int idx[6];
+  int idxp = 0;   // idx[j] packed, 3 bits each
   int maxi = -1;
-#pragma unroll
+#pragma unroll 1
   for (int j = 0; j < 6; ++j) {
-    double sum = a[j];
+    double sum = sel6(a, j);
 #pragma unroll
-    for (int k = 0; k < j; ++k) {           // a[i][j] -= a[i][k] * a[k][j], k < min(i, j); row k is final at step k
-      const double v = __shfl_sync(FULL, sum, k);
-      if (lane > k) sum -= a[k] * v;
+    for (int k = 0; k < 5; ++k) {           // a[i][j] -= a[i][k] * a[k][j], k < min(i, j); row k is final at step k
+      if (k < j) {
+        const double v = __shfl_sync(FULL, sum, k);
+        if (lane > k) sum -= a[k] * v;
+      }
     }
-    a[j] = sum;
+    put6(a, j, sum);
     // pivot: last row i >= j with the largest work[i] * |sum| (the reference's `>=` scan), NaNs never win
     tmp = work * fabs(sum);
     double bv = (lane >= j && lane < 6 && tmp == tmp) ? tmp : -1.0;
@@ -635,40 +650,45 @@ __device__ __noinline__ int ax_eq_b_lu6(const MleSmem& S, double mu, double* x) 
       const double wj = __shfl_sync(FULL, work, j);
       if (lane == maxi) work = wj;
     }
-    idx[j] = maxi;
-    if (lane == j && a[j] == 0.0) a[j] = DBL_EPSILON;
+    idxp |= (maxi & 7) << (3 * j);
+    double ajj = sel6(a, j);
+    if (lane == j && ajj == 0.0) { ajj = DBL_EPSILON; put6(a, j, ajj); }
     if (j != 5) {
-      const double piv = __shfl_sync(FULL, a[j], j);
+      const double piv = __shfl_sync(FULL, ajj, j);
       const double tmp2 = 1.0 / piv;
-      if (lane > j) a[j] *= tmp2;
+      if (lane > j) put6(a, j, ajj * tmp2);
     }
   }
   // forward substitution with the row permutation
   int k = 0;
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < 6; ++i) {
-    const int jj = idx[i];
+    const int jj = (idxp >> (3 * i)) & 7;
     const double xi = __shfl_sync(FULL, xr, i);
     double sum = __shfl_sync(FULL, xr, jj);   // sum = x[jj]; x[jj] = x[i]
     if (lane == jj) xr = xi;
     if (k != 0) {
 #pragma unroll
-      for (int j2 = 0; j2 < i; ++j2) {
-        const double xv = __shfl_sync(FULL, xr, j2);
-        if (j2 >= k - 1) sum -= a[j2] * xv;   // meaningful on lane i (its row)
+      for (int j2 = 0; j2 < 5; ++j2) {
+        if (j2 < i) {
+          const double xv = __shfl_sync(FULL, xr, j2);
+          if (j2 >= k - 1) sum -= a[j2] * xv;   // meaningful on lane i (its row)
+        }
       }
     } else if (sum != 0.0) k = i + 1;
     if (lane == i) xr = sum;
   }
-#pragma unroll
+#pragma unroll 1
   for (int i = 5; i >= 0; --i) {
     double sum = xr;
 #pragma unroll
-    for (int j = i + 1; j < 6; ++j) {
-      const double xv = __shfl_sync(FULL, xr, j);
-      sum -= a[j] * xv;
+    for (int j = 1; j < 6; ++j) {
+      if (j > i) {
+        const double xv = __shfl_sync(FULL, xr, j);
+        sum -= a[j] * xv;
+      }
     }
-    if (lane == i) xr = sum / a[i];
+    if (lane == i) xr = sum / sel6(a, i);
   }
 #pragma unroll
   for (int r = 0; r < 6; ++r) x[r] = __shfl_sync(FULL, xr, r);
@@ -807,25 +827,17 @@ __global__ void __launch_bounds__(32, 13) line_mle_kernel(LslWork w, LineParams 
         pDp_eL2 = l2nrm_neg(Enew, wrk, n);
         if (!isfinite(pDp_eL2)) { stop = 7; break; }
         dF = p_eL2 - pDp_eL2;
-        if (updp || dF > 0) {  // Broyden rank-one update of the Jacobian (own rows; the divisions overlap)
-          double tq[4];
-#pragma unroll
+        if (updp || dF > 0) {  // Broyden rank-one update of the Jacobian (own rows)
+#pragma unroll 1
           for (int q = 0; q < 4; ++q) {
             const int i = lane + 32 * q;
-            const int ic = i < n ? i : n - 1;
+            if (i >= n) break;
             double t = 0.0;
 #pragma unroll
-            for (int l = 0; l < m; ++l) t += S.jac[ic * m + l] * Dp[l];
-            tq[q] = (wrk[q] - hx[q] - t) / Dp_L2;
-          }
-          __syncwarp();   // lanes past the end read the last row: all reads before any write
+            for (int l = 0; l < m; ++l) t += S.jac[i * m + l] * Dp[l];
+            t = (wrk[q] - hx[q] - t) / Dp_L2;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int i = lane + 32 * q;
-            if (i < n) {
-#pragma unroll
-              for (int j = 0; j < m; ++j) S.jac[i * m + j] += tq[q] * Dp[j];
-            }
+            for (int j = 0; j < m; ++j) S.jac[i * m + j] += t * Dp[j];
           }
           __syncwarp();
           ++updjac;
