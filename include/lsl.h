@@ -35,6 +35,7 @@ typedef struct lsl_params {
   double depth_stdev_coeff_c1, depth_stdev_coeff_c2, depth_stdev_coeff_c3, depth_scaling;
   double max_mah_dist_for_inliers, g2o_line_error_weight, g2o_BA_kernel_delta;
   double pt2line3d_dist_relmotion, line3d_angle_relmotion;
+  double sigma_depth, nn_distance_ratio;   /* point features: src/parameter_server.cpp:45,146 */
   int32_t lsd_n_bins, line_sample_max_num, line_sample_min_num, line3d_mle_iter_num;
   int32_t ransac_iters_extract_line, num_cells_lineseg_range;
   int32_t ransac_iters_line_motion, adjacent_linematch_window, line_match_number_weight;

@@ -17,4 +17,5 @@ static inline void lsl_params_default_impl(lsl_params* p) {
   p->min_feature_matches = 20; p->min_matches_loopclose = 20;
   p->max_mah_dist_for_inliers = 3.0; p->g2o_line_error_weight = 1.0; p->g2o_BA_kernel_delta = 10.0;
   p->g2o_BA_use_kernel = 1; p->pt2line3d_dist_relmotion = 0.05; p->line3d_angle_relmotion = 10.0;
+  p->sigma_depth = 0.01; p->nn_distance_ratio = 0.5;
 }

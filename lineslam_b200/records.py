@@ -10,7 +10,7 @@ class Params(C.Structure):
         "pt2line_mahdist_extractline ratio_support_pts_on_line stdev_sample_pt_imgline "
         "depth_stdev_coeff_c1 depth_stdev_coeff_c2 depth_stdev_coeff_c3 depth_scaling "
         "max_mah_dist_for_inliers g2o_line_error_weight g2o_BA_kernel_delta "
-        "pt2line3d_dist_relmotion line3d_angle_relmotion").split()] + [(n, C.c_int32) for n in (
+        "pt2line3d_dist_relmotion line3d_angle_relmotion sigma_depth nn_distance_ratio").split()] + [(n, C.c_int32) for n in (
         "lsd_n_bins line_sample_max_num line_sample_min_num line3d_mle_iter_num "
         "ransac_iters_extract_line num_cells_lineseg_range "
         "ransac_iters_line_motion adjacent_linematch_window line_match_number_weight "

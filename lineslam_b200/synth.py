@@ -174,3 +174,48 @@ def make_stream(n: int, scene_seed: int = 2000, W: int = 640, H: int = 480, traj
         img, d, R, p = make_frame(scene, start + k * stride, scene_seed, W, H, traj)
         imgs[k] = img; deps[k] = d; poses.append((R, p))
     return imgs, deps, poses
+
+
+# ------------------------------------------------------------------ point features (cfg 3) ----
+def make_landmarks(scene_seed: int, n: int = 6000, dim: int = 128):
+    """World landmarks on the room walls with a RootSIFT-shaped base descriptor each (non-negative, unit L2).
+    Stand-in for SIFT keypoints (point features are an INPUT of the hot path, SURVEY.md §2 #16)."""
+    rng = np.random.default_rng(scene_seed * 7919 + 13)
+    wall = rng.integers(0, 6, n)
+    P = rng.uniform(0, 1, (n, 3)) * ROOM
+    ax, side = wall // 2, wall % 2
+    P[np.arange(n), ax] = ROOM[ax] * side
+    base = np.abs(rng.normal(0, 1, (n, dim))).astype(np.float32) ** 2
+    base = np.sqrt(base / base.sum(1, keepdims=True)).astype(np.float32)
+    return P, base
+
+
+def make_points(scene_seed: int, frame_index: int, depth: np.ndarray, R_wc: np.ndarray, t_wc: np.ndarray, K: np.ndarray,
+                max_keypoints: int = 600, dim: int = 128, desc_noise: float = 0.01, outlier_frac: float = 0.1):
+    """Point features of one frame: (xyz1 float32 [n,4] camera coordinates with the frame's noisy depth, NaN z where the
+    depth map has a hole; desc float32 [n,dim] RootSIFT-like rows; landmark ids). Deterministic in (scene_seed, frame)."""
+    P, base = make_landmarks(scene_seed, dim=dim)
+    H, W = depth.shape
+    Pc = (P - t_wc) @ R_wc          # x_c = R^T (x_w - t)
+    z = Pc[:, 2]
+    ok = z > 0.3
+    u = K[0, 0] * Pc[:, 0] / np.where(ok, z, 1) + K[0, 2]
+    v = K[1, 1] * Pc[:, 1] / np.where(ok, z, 1) + K[1, 2]
+    ok &= (u >= 2) & (u <= W - 3) & (v >= 2) & (v <= H - 3)
+    idx = np.nonzero(ok)[0]
+    ui, vi = np.rint(u[idx]).astype(int), np.rint(v[idx]).astype(int)
+    d = depth[vi, ui].astype(np.float64)
+    vis = ~np.isfinite(d) | (np.abs(d - z[idx]) < 0.05)     # occluded by a cuboid -> not a feature
+    idx, ui, vi, d = idx[vis], ui[vis], vi[vis], d[vis]
+    idx, ui, vi, d = idx[:max_keypoints], ui[:max_keypoints], vi[:max_keypoints], d[:max_keypoints]
+    rng = np.random.default_rng(scene_seed * 1000003 + 7 * frame_index + 1)
+    xyz1 = np.ones((len(idx), 4), np.float32)
+    xyz1[:, 0] = ((u[idx] - K[0, 2]) / K[0, 0] * d).astype(np.float32)
+    xyz1[:, 1] = ((v[idx] - K[1, 2]) / K[1, 1] * d).astype(np.float32)
+    xyz1[:, 2] = d.astype(np.float32)
+    desc = base[idx] + rng.normal(0, desc_noise, (len(idx), dim)).astype(np.float32)
+    out = rng.random(len(idx)) < outlier_frac               # features whose descriptor matches nothing
+    desc[out] = np.abs(rng.normal(0, 1, (int(out.sum()), dim))).astype(np.float32)
+    desc = np.abs(desc)
+    desc = np.sqrt(desc / desc.sum(1, keepdims=True)).astype(np.float32)
+    return np.ascontiguousarray(xyz1), np.ascontiguousarray(desc), idx

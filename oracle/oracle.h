@@ -37,6 +37,8 @@ struct Params {
   double max_mah_dist_for_inliers = 3.0, g2o_line_error_weight = 1.0, g2o_BA_kernel_delta = 10.0;
   int g2o_BA_use_kernel = 1;
   double pt2line3d_dist_relmotion = 0.05, line3d_angle_relmotion = 10.0;
+  // point features (src/parameter_server.cpp:45,146)
+  double sigma_depth = 0.01, nn_distance_ratio = 0.5;
 };
 
 // glibc TYPE_3 rand() restated; stdlib/random_r.c semantics.
@@ -91,7 +93,19 @@ struct Match { int32_t queryIdx, trainIdx; float distance; };
 void lineMatching(const std::vector<Line>& f1, const std::vector<Line>& f2, bool adjacent,
                   std::vector<Match>& matches, int omp_threads = 1);
 
+// Point features of a frame as the pair stage sees them (inputs):
+// feature_locations_3d_ (Eigen::Vector4f, w = 1, z may be NaN) and feature_descriptors_ (CV_32F rows).
+struct Points { int n = 0, dim = 0; const float* xyz1 = nullptr; const float* desc = nullptr; };
+
+// Node::featureMatching, BRUTEFORCE branch (src/node.cpp:606-641): BFMatcher L2 knnMatch k = 2, ratio test,
+// unique trainIdx, distance = ratio + rand()/(1000 RAND_MAX); one rand() per accepted match.
+void featureMatching(const Points& query, const Points& train, double nn_ratio, GlibcRand& rng, std::vector<Match>& out);
+// squareroot_descriptor_space (src/node.cpp:1823-1837), in place
+void rootsift(float* desc, int n, int dim);
+
 struct PoseResult {
+  std::vector<Match> pt_inliers;          // output_point_inlier_matches
+  std::vector<Match> pt_ransac_inliers;   // max_point_inlier_set of the best hypothesis
   bool found = false;
   float tf[16];       // row-major Matrix4f, query -> train
   float rmse = 1e9f;
@@ -105,6 +119,18 @@ struct PoseResult {
 void getTransform_Lines_ransac(const std::vector<Line>& train, const std::vector<Line>& query,
                                int id_train, int id_query, const std::vector<Match>& ln_matches,
                                uint32_t seed, const Params& P, PoseResult& out);
+
+// getTransform_PtsLines_ransac (src/line/motion.cpp:605-849) with point and line matches; fx = K(0,0) (the
+// focal length compPt3dCov uses for the point-edge information, transformation_estimation.cpp:243-262).
+// The rand() stream continues from `rng` (featureMatching draws first in matchNodePair).
+void getTransform_PtsLines_ransac(const std::vector<Line>& train, const std::vector<Line>& query,
+                                  const Points& train_pts, const Points& query_pts, int id_train, int id_query,
+                                  const std::vector<Match>& pt_matches, const std::vector<Match>& ln_matches,
+                                  GlibcRand& rng, double fx, double asynch_dt, const Params& P, PoseResult& out);
+// getTransformFromHybridMatchesG2O (src/transformation_estimation.cpp:218-461) restated natively
+void refine_pose_hybrid(const std::vector<Line>& train, const std::vector<Line>& query, const Points& train_pts,
+                        const Points& query_pts, const std::vector<Match>& pt_ms, const std::vector<Match>& ln_ms,
+                        float tf[16], int iterations, double fx, double asynch_dt, const Params& P);
 
 // sub-pieces exposed for unit tests
 void sobel5(const uint8_t* gray, int W, int H, std::vector<double>& gx, std::vector<double>& gy);

@@ -7,6 +7,7 @@
 #include <omp.h>
 #include "../lineslam_b200/csrc/shared/lsl_math.h"
 #include "../lineslam_b200/csrc/shared/lsl_params_default.h"
+#include "../lineslam_b200/csrc/shared/lsl_points.h"
 
 static orc::Params toP(const lsl_params* p) {
   orc::Params P;
@@ -32,6 +33,7 @@ static orc::Params toP(const lsl_params* p) {
   P.max_mah_dist_for_inliers = p->max_mah_dist_for_inliers; P.g2o_line_error_weight = p->g2o_line_error_weight;
   P.g2o_BA_kernel_delta = p->g2o_BA_kernel_delta; P.g2o_BA_use_kernel = p->g2o_BA_use_kernel;
   P.pt2line3d_dist_relmotion = p->pt2line3d_dist_relmotion; P.line3d_angle_relmotion = p->line3d_angle_relmotion;
+  P.sigma_depth = p->sigma_depth; P.nn_distance_ratio = p->nn_distance_ratio;
   return P;
 }
 static_assert(sizeof(orc::Line) == sizeof(lsl_line_rec), "record layouts must agree");
@@ -145,6 +147,70 @@ int orc_pose_ransac(const lsl_line_rec* train, int ntrain, const lsl_line_rec* q
   for (int i = 0; i < (int)r.ransac_inliers.size() && i < cap2; ++i) memcpy(&rinl[i], &r.ransac_inliers[i], sizeof(lsl_match));
   return 0;
 }
+
+// Node::featureMatching (BRUTEFORCE). Returns the number of matches; *draws = rand() calls consumed.
+int orc_featureMatching(const float* qdesc, int nq, const float* tdesc, int nt, int dim, double nn_ratio, uint32_t seed,
+                        lsl_match* out, int cap) {
+  orc::Points q, t;
+  q.n = nq; q.dim = dim; q.desc = qdesc; t.n = nt; t.dim = dim; t.desc = tdesc;
+  orc::GlibcRand rng; rng.seed(seed);
+  std::vector<orc::Match> m;
+  orc::featureMatching(q, t, nn_ratio, rng, m);
+  for (int i = 0; i < (int)m.size() && i < cap; ++i) memcpy(&out[i], &m[i], sizeof(lsl_match));
+  return (int)m.size();
+}
+void orc_rootsift(float* desc, int n, int dim) { orc::rootsift(desc, n, dim); }
+
+// getTransform_PtsLines_ransac with point + line matches. skip_draws: rand() calls already consumed from the
+// seed's stream (the featureMatching jitter of the same matchNodePair call). pad[0] = #point matches,
+// pad[1] = #point inliers of the best hypothesis, pad[2] = #refined point inliers.
+int orc_pose_ransac_hybrid(const lsl_line_rec* train, int ntrain, const lsl_line_rec* query, int nquery,
+                           const float* train_xyz1, int ntp, const float* query_xyz1, int nqp, int id_train, int id_query,
+                           const lsl_match* pms, int npm, const lsl_match* ms, int nm, uint32_t seed, int skip_draws,
+                           double fx, double dt, const lsl_params* p, lsl_pose_rec* rec, lsl_match* inl, int* n_inl,
+                           lsl_match* rinl, int* n_rinl, lsl_match* pinl, int* n_pinl, lsl_match* prinl, int* n_prinl,
+                           float* tf_ransac) {
+  orc::Params P = toP(p);
+  std::vector<orc::Line> t(ntrain), q(nquery);
+  if (ntrain) memcpy(t.data(), train, sizeof(lsl_line_rec) * ntrain);
+  if (nquery) memcpy(q.data(), query, sizeof(lsl_line_rec) * nquery);
+  std::vector<orc::Match> m(nm), pm(npm);
+  if (nm) memcpy(m.data(), ms, sizeof(lsl_match) * nm);
+  if (npm) memcpy(pm.data(), pms, sizeof(lsl_match) * npm);
+  orc::Points tp, qp;
+  tp.n = ntp; tp.xyz1 = train_xyz1; qp.n = nqp; qp.xyz1 = query_xyz1;
+  orc::GlibcRand rng; rng.seed(seed);
+  for (int i = 0; i < skip_draws; ++i) rng.next();
+  orc::PoseResult r;
+  orc::getTransform_PtsLines_ransac(t, q, tp, qp, id_train, id_query, pm, m, rng, fx, dt, P, r);
+  memset(rec, 0, sizeof(*rec));
+  rec->id_train = id_train; rec->id_query = id_query; rec->found = r.found ? 1 : 0;
+  rec->n_line_matches = nm; rec->n_ransac_inliers = (int)r.ransac_inliers.size(); rec->n_inliers = (int)r.inliers.size();
+  rec->rmse = r.rmse; rec->best_iter = r.best_iter;
+  rec->pad[0] = npm; rec->pad[1] = (int)r.pt_ransac_inliers.size(); rec->pad[2] = (int)r.pt_inliers.size();
+  memcpy(rec->tf, r.tf, 64);
+  if (tf_ransac) memcpy(tf_ransac, r.tf_ransac, 64);
+  *n_inl = (int)r.inliers.size(); *n_rinl = (int)r.ransac_inliers.size();
+  *n_pinl = (int)r.pt_inliers.size(); *n_prinl = (int)r.pt_ransac_inliers.size();
+  for (size_t i = 0; i < r.inliers.size(); ++i) memcpy(&inl[i], &r.inliers[i], sizeof(lsl_match));
+  for (size_t i = 0; i < r.ransac_inliers.size(); ++i) memcpy(&rinl[i], &r.ransac_inliers[i], sizeof(lsl_match));
+  for (size_t i = 0; i < r.pt_inliers.size(); ++i) memcpy(&pinl[i], &r.pt_inliers[i], sizeof(lsl_match));
+  for (size_t i = 0; i < r.pt_ransac_inliers.size(); ++i) memcpy(&prinl[i], &r.pt_ransac_inliers[i], sizeof(lsl_match));
+  return 0;
+}
+
+// point math probes (tests/test_oracle_points.py)
+double orc_error_function2(const float* x1, const float* x2, const float* tf, double sigma_depth) {
+  double tfd[16];
+  for (int i = 0; i < 16; ++i) tfd[i] = (double)tf[i];
+  return lslm::error_function2(x1, x2, tfd, sigma_depth);
+}
+void orc_kabsch(const float* from, const float* to, const float* w, int n, float* tf) {
+  lslm::Tfc t; lslm::tfc_reset(&t);
+  for (int i = 0; i < n; ++i) lslm::tfc_add(&t, from + 3 * i, to + 3 * i, w[i]);
+  lslm::tfc_get(&t, tf);
+}
+void orc_ldlt3_solve(const double* A, const double* b, double* x) { lslm::ldlt3_solve(A, b, x); }
 
 // levmar restatement probe: Rosenbrock-like known-answer problems are driven from tests through this.
 typedef void (*orc_lm_fn)(double*, double*, int, int, void*);

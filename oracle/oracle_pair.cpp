@@ -12,6 +12,7 @@
 #include <algorithm>
 #include "../lineslam_b200/csrc/shared/lsl_math.h"
 #include "../lineslam_b200/csrc/shared/lsl_linalg.h"
+#include "../lineslam_b200/csrc/shared/lsl_points.h"
 
 using namespace lslm;
 
@@ -272,10 +273,25 @@ static void huber(double e2, double delta, double rho[3]) {  // g2o RobustKernel
   else { double sqrte = sqrt(e2); rho[0] = 2 * sqrte * delta - dsqr; rho[1] = delta / sqrte; rho[2] = -0.5 * rho[1] / e2; }
 }
 
-void refine_pose_lines(const std::vector<Line>& train, const std::vector<Line>& query, const std::vector<Match>& ms,
-                       float tf[16], int iterations, const Params& P) {
-  int n = (int)ms.size();
-  if (n == 0) return;
+// Point edge EdgeSE3PointXYZ::computeError (src/line/edge_se3_ptxyz.cpp:84-90): e = w2n * X - measurement
+static void pt_edge_error(const Iso& w2n, const double X[3], const double meas[3], double e[3]) {
+  for (int r = 0; r < 3; ++r)
+    e[r] = (w2n.R[r * 3] * X[0] + w2n.R[r * 3 + 1] * X[1] + w2n.R[r * 3 + 2] * X[2] + w2n.t[r]) - meas[r];
+}
+// chi2 = e^T Omega e (Omega e first, Eigen 3x3 * vec3 order)
+static double pt_chi2(const double e[3], const double Om[9], double Oe[3]) {
+  for (int r = 0; r < 3; ++r) Oe[r] = (Om[r * 3] * e[0] + Om[r * 3 + 1] * e[1]) + Om[r * 3 + 2] * e[2];
+  return (e[0] * Oe[0] + e[1] * Oe[1]) + e[2] * Oe[2];
+}
+
+// Unknowns: cam1, one free 3-vector per point match (VertexPointXYZ, initialised with the newer frame's
+// point), one free 6-vector per line match. Edges in insertion order: per point match newer then older
+// (EdgeSE3PointXYZ, information = compPt3dCov(Vector3f)^-1), then per line match newer then older.
+void refine_pose_hybrid(const std::vector<Line>& train, const std::vector<Line>& query, const Points& train_pts,
+                        const Points& query_pts, const std::vector<Match>& pt_ms, const std::vector<Match>& ms,
+                        float tf[16], int iterations, double fx, double asynch_dt, const Params& P) {
+  int n = (int)ms.size(), np = (int)pt_ms.size();
+  if (n + np == 0) return;
   // tfinv = tf.inverse() (Matrix4f general inverse) -> cam1 = SE3Quat(Quaterniond(R), t). The rigid
   // inverse in double and a quaternion round trip are restated as: cam1 = [R^T, -R^T t] in double.
   Iso tfd, cam1;
@@ -291,11 +307,26 @@ void refine_pose_lines(const std::vector<Line>& train, const std::vector<Line>& 
     affn(q.covA, &AfN[18 * i]); affn(q.covB, &AfN[18 * i + 9]);
     affn(t.covA, &AfO[18 * i]); affn(t.covB, &AfO[18 * i + 9]);
   }
+  std::vector<double> X(3 * np), pmN(3 * np), pmO(3 * np), OmN(9 * np), OmO(9 * np);
+  for (int i = 0; i < np; ++i) {
+    const float* qn = query_pts.xyz1 + 4 * pt_ms[i].queryIdx;
+    const float* to = train_pts.xyz1 + 4 * pt_ms[i].trainIdx;
+    for (int k = 0; k < 3; ++k) { pmN[3 * i + k] = (double)qn[k]; pmO[3 * i + k] = (double)to[k]; X[3 * i + k] = (double)qn[k]; }
+    pt_info_f(qn, fx, P.stdev_sample_pt_imgline, P.depth_stdev_coeff_c1, P.depth_stdev_coeff_c2, P.depth_stdev_coeff_c3, asynch_dt, &OmN[9 * i]);
+    pt_info_f(to, fx, P.stdev_sample_pt_imgline, P.depth_stdev_coeff_c1, P.depth_stdev_coeff_c2, P.depth_stdev_coeff_c3, asynch_dt, &OmO[9 * i]);
+  }
   const double w = P.g2o_line_error_weight, hdelta = P.g2o_BA_kernel_delta;
   const bool robust = P.g2o_BA_use_kernel != 0;
-  auto chi2_all = [&](const Iso& c1, const std::vector<double>& Lv) {
+  auto chi2_all = [&](const Iso& c1, const std::vector<double>& Xv, const std::vector<double>& Lv) {
     Iso w2n; iso_inv(c1, w2n);
     double chi = 0;
+    for (int i = 0; i < np; ++i)
+      for (int side = 0; side < 2; ++side) {
+        double e[3], Oe[3];
+        pt_edge_error(side ? w2n : ident, &Xv[3 * i], side ? &pmO[3 * i] : &pmN[3 * i], e);
+        double c2 = pt_chi2(e, side ? &OmO[9 * i] : &OmN[9 * i], Oe);
+        if (robust) { double rho[3]; huber(c2, hdelta, rho); chi += rho[0]; } else chi += c2;
+      }
     for (int i = 0; i < n; ++i) {
       double e[6];
       for (int side = 0; side < 2; ++side) {
@@ -311,13 +342,68 @@ void refine_pose_lines(const std::vector<Line>& train, const std::vector<Line>& 
   const double tau = 1e-5, lowS = 1. / 3., upS = 2. / 3.;
   const double del = 1e-9, scalar = 1 / (2 * del);
   std::vector<double> Hll(36 * n), Hpl(36 * n), bl(6 * n), dl(6 * n), HllInv(36 * n);
+  std::vector<double> Hxx(9 * np), Hpx(18 * np), bx(3 * np), dx(3 * np), HxxInv(9 * np);
   for (int it = 0; it < iterations; ++it) {
-    double currentChi = chi2_all(cam1, L);
+    double currentChi = chi2_all(cam1, X, L);
     // ---- build system
     double Hpp[36], bp[6];
     for (int i = 0; i < 36; ++i) Hpp[i] = 0;
     for (int i = 0; i < 6; ++i) bp[i] = 0;
     Iso w2n; iso_inv(cam1, w2n);
+    for (int i = 0; i < np; ++i) {
+      double* hxx = &Hxx[9 * i]; double* hpx = &Hpx[18 * i]; double* b = &bx[3 * i];
+      for (int k = 0; k < 9; ++k) hxx[k] = 0;
+      for (int k = 0; k < 18; ++k) hpx[k] = 0;
+      for (int k = 0; k < 3; ++k) b[k] = 0;
+      for (int side = 0; side < 2; ++side) {
+        const double* meas = side ? &pmO[3 * i] : &pmN[3 * i];
+        const double* Om = side ? &OmO[9 * i] : &OmN[9 * i];
+        double e[3], Jl[9], Jp[18];
+        for (int d = 0; d < 3; ++d) {  // numeric Jacobian wrt the point vertex (additive)
+          double Xp[3], e1[3], e2[3];
+          for (int k = 0; k < 3; ++k) Xp[k] = X[3 * i + k];
+          Xp[d] = X[3 * i + d] + del;
+          pt_edge_error(side ? w2n : ident, Xp, meas, e1);
+          Xp[d] = X[3 * i + d] + (-del);
+          pt_edge_error(side ? w2n : ident, Xp, meas, e2);
+          for (int k = 0; k < 3; ++k) Jl[k * 3 + d] = scalar * (e1[k] - e2[k]);
+        }
+        if (side) {
+          for (int d = 0; d < 6; ++d) {
+            double u[6] = {0, 0, 0, 0, 0, 0}, e1[3], e2[3];
+            Iso c, ci;
+            u[d] = del; iso_oplus(cam1, u, c); iso_inv(c, ci); pt_edge_error(ci, &X[3 * i], meas, e1);
+            u[d] = -del; iso_oplus(cam1, u, c); iso_inv(c, ci); pt_edge_error(ci, &X[3 * i], meas, e2);
+            for (int k = 0; k < 3; ++k) Jp[k * 6 + d] = scalar * (e1[k] - e2[k]);
+          }
+        }
+        pt_edge_error(side ? w2n : ident, &X[3 * i], meas, e);
+        double Oe[3];
+        double c2 = pt_chi2(e, Om, Oe);
+        double r1 = 1.0;
+        if (robust) { double rho[3]; huber(c2, hdelta, rho); r1 = rho[1]; }
+        double WO[9], WOe[3];
+        for (int k = 0; k < 9; ++k) WO[k] = r1 * Om[k];
+        for (int k = 0; k < 3; ++k) WOe[k] = r1 * Oe[k];
+        double AtO[9];  // Jl^T * WO
+        for (int a = 0; a < 3; ++a) for (int k = 0; k < 3; ++k) { double s = 0; for (int j = 0; j < 3; ++j) s += Jl[j * 3 + a] * WO[j * 3 + k]; AtO[a * 3 + k] = s; }
+        for (int a = 0; a < 3; ++a) {
+          double s = 0; for (int k = 0; k < 3; ++k) s += Jl[k * 3 + a] * WOe[k];
+          b[a] -= s;
+          for (int c = 0; c < 3; ++c) { double h = 0; for (int k = 0; k < 3; ++k) h += AtO[a * 3 + k] * Jl[k * 3 + c]; hxx[a * 3 + c] += h; }
+        }
+        if (side) {
+          double PtO[18];  // Jp^T * WO (6x3)
+          for (int a = 0; a < 6; ++a) for (int k = 0; k < 3; ++k) { double s = 0; for (int j = 0; j < 3; ++j) s += Jp[j * 6 + a] * WO[j * 3 + k]; PtO[a * 3 + k] = s; }
+          for (int a = 0; a < 6; ++a) {
+            double s = 0; for (int k = 0; k < 3; ++k) s += Jp[k * 6 + a] * WOe[k];
+            bp[a] -= s;
+            for (int c = 0; c < 6; ++c) { double h = 0; for (int k = 0; k < 3; ++k) h += PtO[a * 3 + k] * Jp[k * 6 + c]; Hpp[a * 6 + c] += h; }
+            for (int c = 0; c < 3; ++c) { double g = 0; for (int k = 0; k < 3; ++k) g += PtO[a * 3 + k] * Jl[k * 3 + c]; hpx[a * 3 + c] += g; }
+          }
+        }
+      }
+    }
     for (int i = 0; i < n; ++i) {
       double* hll = &Hll[36 * i]; double* hpl = &Hpl[36 * i]; double* b = &bl[6 * i];
       for (int k = 0; k < 36; ++k) { hll[k] = 0; hpl[k] = 0; }
@@ -372,6 +458,7 @@ void refine_pose_lines(const std::vector<Line>& train, const std::vector<Line>& 
     if (it == 0) {  // computeLambdaInit: tau * max diagonal entry
       double maxDiag = 0;
       for (int a = 0; a < 6; ++a) maxDiag = std::max(fabs(Hpp[a * 6 + a]), maxDiag);
+      for (int i = 0; i < np; ++i) for (int a = 0; a < 3; ++a) maxDiag = std::max(fabs(Hxx[9 * i + a * 3 + a]), maxDiag);
       for (int i = 0; i < n; ++i) for (int a = 0; a < 6; ++a) maxDiag = std::max(fabs(Hll[36 * i + a * 6 + a]), maxDiag);
       lambda = tau * maxDiag;
       ni = 2;
@@ -379,11 +466,25 @@ void refine_pose_lines(const std::vector<Line>& train, const std::vector<Line>& 
     double rho = 0;
     int qmax = 0;
     do {
-      // solve (H + lambda I) x = b by eliminating the line blocks
+      // solve (H + lambda I) x = b by eliminating the landmark blocks (points, then lines)
       double S[36], rhs[6], dp[6];
       for (int k = 0; k < 36; ++k) S[k] = Hpp[k];
       for (int a = 0; a < 6; ++a) { S[a * 6 + a] += lambda; rhs[a] = bp[a]; }
       bool ok = true;
+      for (int i = 0; i < np; ++i) {
+        double M[9];
+        for (int k = 0; k < 9; ++k) M[k] = Hxx[9 * i + k];
+        for (int a = 0; a < 3; ++a) M[a * 3 + a] += lambda;
+        if (!inv_lu<3>(M, &HxxInv[9 * i])) ok = false;
+        const double* hi = &HxxInv[9 * i]; const double* hpx = &Hpx[18 * i];
+        double T[18];  // Hpx * Hxx^-1 (6x3)
+        for (int a = 0; a < 6; ++a) for (int c = 0; c < 3; ++c) { double s = 0; for (int k = 0; k < 3; ++k) s += hpx[a * 3 + k] * hi[k * 3 + c]; T[a * 3 + c] = s; }
+        for (int a = 0; a < 6; ++a) {
+          double s = 0; for (int k = 0; k < 3; ++k) s += T[a * 3 + k] * bx[3 * i + k];
+          rhs[a] -= s;
+          for (int c = 0; c < 6; ++c) { double h = 0; for (int k = 0; k < 3; ++k) h += T[a * 3 + k] * hpx[c * 3 + k]; S[a * 6 + c] -= h; }
+        }
+      }
       for (int i = 0; i < n; ++i) {
         double M[36];
         for (int k = 0; k < 36; ++k) M[k] = Hll[36 * i + k];
@@ -403,6 +504,13 @@ void refine_pose_lines(const std::vector<Line>& train, const std::vector<Line>& 
       for (int a = 0; a < 6; ++a) { double s = 0; for (int k = 0; k < 6; ++k) s += Si[a * 6 + k] * rhs[k]; dp[a] = s; }
       double scale = 0;
       for (int a = 0; a < 6; ++a) scale += dp[a] * (lambda * dp[a] + bp[a]);
+      for (int i = 0; i < np; ++i) {
+        const double* hi = &HxxInv[9 * i]; const double* hpx = &Hpx[18 * i];
+        double r[3];
+        for (int a = 0; a < 3; ++a) { double s = 0; for (int k = 0; k < 6; ++k) s += hpx[k * 3 + a] * dp[k]; r[a] = bx[3 * i + a] - s; }
+        for (int a = 0; a < 3; ++a) { double s = 0; for (int k = 0; k < 3; ++k) s += hi[a * 3 + k] * r[k]; dx[3 * i + a] = s; }
+        for (int a = 0; a < 3; ++a) scale += dx[3 * i + a] * (lambda * dx[3 * i + a] + bx[3 * i + a]);
+      }
       for (int i = 0; i < n; ++i) {
         const double* hi = &HllInv[36 * i]; const double* hpl = &Hpl[36 * i];
         double r[6];
@@ -411,9 +519,10 @@ void refine_pose_lines(const std::vector<Line>& train, const std::vector<Line>& 
         for (int a = 0; a < 6; ++a) scale += dl[6 * i + a] * (lambda * dl[6 * i + a] + bl[6 * i + a]);
       }
       Iso camNew; iso_oplus(cam1, dp, camNew);
-      std::vector<double> Lnew(L);
+      std::vector<double> Lnew(L), Xnew(X);
+      for (int k = 0; k < 3 * np; ++k) Xnew[k] += dx[k];
       for (int k = 0; k < 6 * n; ++k) Lnew[k] += dl[k];
-      double tempChi = chi2_all(camNew, Lnew);
+      double tempChi = chi2_all(camNew, Xnew, Lnew);
       if (!ok) tempChi = DBL_MAX;
       rho = (currentChi - tempChi);
       scale += 1e-3;
@@ -425,7 +534,7 @@ void refine_pose_lines(const std::vector<Line>& train, const std::vector<Line>& 
         lambda *= scaleFactor;
         ni = 2;
         currentChi = tempChi;
-        cam1 = camNew; L.swap(Lnew);
+        cam1 = camNew; L.swap(Lnew); X.swap(Xnew);
       } else {
         lambda *= ni;
         ni *= 2;
@@ -439,12 +548,116 @@ void refine_pose_lines(const std::vector<Line>& train, const std::vector<Line>& 
   tf[12] = 0; tf[13] = 0; tf[14] = 0; tf[15] = 1;
 }
 
-// ---------------------------------------------------- pose RANSAC (lines) ----
-void getTransform_Lines_ransac(const std::vector<Line>& train, const std::vector<Line>& query, int id_train, int id_query,
-                               const std::vector<Match>& all_ln, uint32_t seed, const Params& P, PoseResult& out) {
+void refine_pose_lines(const std::vector<Line>& train, const std::vector<Line>& query, const std::vector<Match>& ms,
+                       float tf[16], int iterations, const Params& P) {
+  Points none;
+  refine_pose_hybrid(train, query, none, none, std::vector<Match>(), ms, tf, iterations, 525.0, 0.0, P);
+}
+
+// ------------------------------------------------------- point matching ----
+void rootsift(float* desc, int n, int dim) {  // src/node.cpp:1823-1837
+  for (int r = 0; r < n; ++r) {
+    float* d = desc + (size_t)r * dim;
+    for (int c = 0; c < dim; ++c) d[c] = fabsf(d[c]);
+    // cv::reduce(CV_REDUCE_SUM, CV_32FC1) over a float row: sequential float accumulation
+    float sum = 0.f;
+    for (int c = 0; c < dim; ++c) sum += d[c];
+    if (sum == 0) continue;
+    for (int c = 0; c < dim; ++c) d[c] = sqrtf(d[c] / sum);
+  }
+}
+
+void featureMatching(const Points& q, const Points& t, double nn_ratio, GlibcRand& rng, std::vector<Match>& out) {
+  if (q.n == 0 || t.n < 2) return;  // knnMatch needs two neighbours (node.cpp:628-629 reads [i][1])
+  std::vector<char> used(t.n, 0);
+  for (int i = 0; i < q.n; ++i) {
+    // batchDistance K = 2: keeps the two smallest, earlier train index first on ties (strict <)
+    float d1 = FLT_MAX, d2 = FLT_MAX; int i1 = -1, i2 = -1;
+    for (int j = 0; j < t.n; ++j) {
+      float d = sqrtf(l2sqr_f(q.desc + (size_t)i * q.dim, t.desc + (size_t)j * t.dim, q.dim));
+      if (d < d1) { d2 = d1; i2 = i1; d1 = d; i1 = j; }
+      else if (d < d2) { d2 = d; i2 = j; }
+    }
+    (void)i2;
+    float dist_ratio_fac = d1 / d2;
+    if (dist_ratio_fac < nn_ratio) {
+      if (used[i1]) continue;
+      used[i1] = 1;
+      Match m; m.queryIdx = i; m.trainIdx = i1;
+      m.distance = (float)(dist_ratio_fac + (float)rng.next() / (1000.0 * 2147483647));
+      out.push_back(m);
+    }
+  }
+}
+
+// ------------------------------------------ pose RANSAC (points + lines) ----
+static void tf_to_double(const float tf[16], double tfd[16]) { for (int i = 0; i < 16; ++i) tfd[i] = (double)tf[i]; }
+
+struct ScoreH { std::vector<int> pt, ln; double sse; };
+static void score_hybrid(const std::vector<Line>& train, const std::vector<Line>& query, const Points& tp, const Points& qp,
+                         const std::vector<Match>& pm, const std::vector<Match>& lm, const float tf[16], double thr,
+                         double sigma_depth, ScoreH& sc, bool float_sse) {
+  sc.pt.clear(); sc.ln.clear();
+  float sse_f = 0; double sse_d = 0;
+  double tfd[16]; tf_to_double(tf, tfd);
+  for (size_t i = 0; i < pm.size(); ++i) {
+    double d2 = error_function2(qp.xyz1 + 4 * pm[i].queryIdx, tp.xyz1 + 4 * pm[i].trainIdx, tfd, sigma_depth);
+    if (d2 < thr * thr) { sc.pt.push_back((int)i); if (float_sse) sse_f += d2; else sse_d += d2; }
+  }
+  for (size_t i = 0; i < lm.size(); ++i) {
+    const Line& q = query[lm[i].queryIdx];
+    const Line& t = train[lm[i].trainIdx];
+    float qa[4] = {(float)q.A[0], (float)q.A[1], (float)q.A[2], 1.f}, qb[4] = {(float)q.B[0], (float)q.B[1], (float)q.B[2], 1.f};
+    double qA[3], qB[3];
+    tf_apply_f(tf, qa, qA);
+    tf_apply_f(tf, qb, qB);
+    double da = mah_dist3d_pt_line(t.A, t.DU_A, qA, qB);
+    double db = mah_dist3d_pt_line(t.B, t.DU_B, qA, qB);
+    if (da < thr && db < thr) {
+      sc.ln.push_back((int)i);
+      if (float_sse) sse_f += da * da + db * db; else sse_d += da * da + db * db;
+    }
+  }
+  sc.sse = float_sse ? (double)sse_f : sse_d;
+}
+
+// getTransform_Lns_Pts_pcl (motion.cpp:530-579)
+static bool transform_lns_pts_pcl(const std::vector<Line>& train, const std::vector<Line>& query, const Points& tp, const Points& qp,
+                                  const Match* pm, int npm, const Match* lm, int nlm, GlibcRand& rng, float tf[16]) {
+  if (npm < 1 || npm + nlm < 3) return false;
+  Tfc tfc; tfc_reset(&tfc);
+  for (int i = 0; i < nlm; ++i) {
+    int ptidx = rng.next() % npm;
+    const float* tpt = tp.xyz1 + 4 * pm[ptidx].trainIdx;
+    const float* qpt = qp.xyz1 + 4 * pm[ptidx].queryIdx;
+    double train_pt[3] = {(double)tpt[0], (double)tpt[1], (double)tpt[2]}, query_pt[3] = {(double)qpt[0], (double)qpt[1], (double)qpt[2]};
+    double train_prj[3], query_prj[3];
+    project_pt_ln(train_pt, train[lm[i].trainIdx].A, train[lm[i].trainIdx].B, train_prj);
+    project_pt_ln(query_pt, query[lm[i].queryIdx].A, query[lm[i].queryIdx].B, query_prj);
+    float from[3] = {(float)query_prj[0], (float)query_prj[1], (float)query_prj[2]}, to[3] = {(float)train_prj[0], (float)train_prj[1], (float)train_prj[2]};
+    if (from[2] != from[2] || to[2] != to[2]) continue;
+    float weight = 1 / (fabsf(to[2]) + fabsf(from[2]));
+    tfc_add(&tfc, from, to, weight);
+  }
+  for (int i = 0; i < npm; ++i) {
+    const float* from = qp.xyz1 + 4 * pm[i].queryIdx;
+    const float* to = tp.xyz1 + 4 * pm[i].trainIdx;
+    if (from[2] != from[2] || to[2] != to[2]) continue;
+    float weight = 1 / (fabsf(to[2]) + fabsf(from[2]));
+    tfc_add(&tfc, from, to, weight);
+  }
+  bool valid = tfc.n >= 3;
+  tfc_get(&tfc, tf);
+  return valid;
+}
+
+void getTransform_PtsLines_ransac(const std::vector<Line>& train, const std::vector<Line>& query, const Points& train_pts,
+                                  const Points& query_pts, int id_train, int id_query, const std::vector<Match>& all_pt,
+                                  const std::vector<Match>& all_ln, GlibcRand& rng, double fx, double asynch_dt,
+                                  const Params& P, PoseResult& out) {
   out = PoseResult();
   for (int i = 0; i < 16; ++i) out.tf[i] = out.tf_ransac[i] = (i % 5 == 0) ? 1.f : 0.f;
-  int nPt = 0, nLn = (int)all_ln.size();
+  int nPt = (int)all_pt.size(), nLn = (int)all_ln.size();
   int min_inlier_nmb = P.min_feature_matches, line_weight = P.line_match_number_weight;
   if (nPt + nLn * line_weight < min_inlier_nmb) { out.rmse = 1e9f; return; }
   if (min_inlier_nmb > 0.7 * (nPt + nLn * line_weight)) min_inlier_nmb = 0.7 * (nPt + nLn * line_weight);
@@ -453,9 +666,8 @@ void getTransform_Lines_ransac(const std::vector<Line>& train, const std::vector
   for (size_t i = 0; i < indexes.size(); ++i) indexes[i] = (int)i;
   int maxIter = P.ransac_iters_line_motion;
   double thr = P.max_mah_dist_for_inliers;
-  GlibcRand rng; rng.seed(seed);
   float sum_squared_error = 1e9f;
-  std::vector<int> best_inl;
+  std::vector<int> best_pt, best_ln;
   float tf_best[16];
   for (int i = 0; i < 16; ++i) tf_best[i] = 0;
   int iter = 0;
@@ -463,50 +675,70 @@ void getTransform_Lines_ransac(const std::vector<Line>& train, const std::vector
     ++iter;
     int left = (int)indexes.size();
     for (int k = 0; k < 3; ++k) { int r = rng.next() % left; std::swap(indexes[k], indexes[k + r]); --left; }
-    double qA[9], qB[9], tA[9], tB[9];
+    Match ptM[3], lnM[3]; int npm = 0, nlm = 0;
     for (int k = 0; k < 3; ++k) {
-      const Match& m = all_ln[indexes[k] - nPt];
-      for (int c = 0; c < 3; ++c) {
-        qA[3 * k + c] = query[m.queryIdx].A[c]; qB[3 * k + c] = query[m.queryIdx].B[c];
-        tA[3 * k + c] = train[m.trainIdx].A[c]; tB[3 * k + c] = train[m.trainIdx].B[c];
-      }
+      if (indexes[k] < nPt) ptM[npm++] = all_pt[indexes[k]];
+      else lnM[nlm++] = all_ln[indexes[k] - nPt];
     }
-    double R[9], t[3];
-    if (!relmotion_svd(qA, qB, tA, tB, 3, R, t)) continue;
     float tf[16];
-    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) tf[r * 4 + c] = (float)R[r * 3 + c]; tf[r * 4 + 3] = (float)t[r]; }
-    tf[12] = tf[13] = tf[14] = 0; tf[15] = 1;
-    Score sc;
-    score_lines(train, query, all_ln, tf, thr, sc, true);
-    if ((int)(line_weight * sc.inl.size()) > (int)(line_weight * best_inl.size())) {
-      best_inl = sc.inl;
+    bool valid;
+    if (nlm == 3) {
+      double qA[9], qB[9], tA[9], tB[9];
+      for (int k = 0; k < 3; ++k)
+        for (int c = 0; c < 3; ++c) {
+          qA[3 * k + c] = query[lnM[k].queryIdx].A[c]; qB[3 * k + c] = query[lnM[k].queryIdx].B[c];
+          tA[3 * k + c] = train[lnM[k].trainIdx].A[c]; tB[3 * k + c] = train[lnM[k].trainIdx].B[c];
+        }
+      double R[9], t[3];
+      valid = relmotion_svd(qA, qB, tA, tB, 3, R, t);
+      for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) tf[r * 4 + c] = (float)R[r * 3 + c]; tf[r * 4 + 3] = (float)t[r]; }
+      tf[12] = tf[13] = tf[14] = 0; tf[15] = 1;
+    } else {
+      valid = transform_lns_pts_pcl(train, query, train_pts, query_pts, ptM, npm, lnM, nlm, rng, tf);
+    }
+    if (!valid) continue;
+    ScoreH sc;
+    score_hybrid(train, query, train_pts, query_pts, all_pt, all_ln, tf, thr, P.sigma_depth, sc, true);
+    if ((int)(sc.pt.size() + line_weight * sc.ln.size()) > (int)(best_pt.size() + line_weight * best_ln.size())) {
+      best_pt = sc.pt; best_ln = sc.ln;
       memcpy(tf_best, tf, sizeof(tf));
       sum_squared_error = (float)sc.sse;
       out.best_iter = iter - 1;
     }
   }
-  if (best_inl.size() < 3) return;
-  for (int i : best_inl) out.ransac_inliers.push_back(all_ln[i]);
+  if (best_pt.size() + best_ln.size() < 3) return;
+  for (int i : best_pt) out.pt_ransac_inliers.push_back(all_pt[i]);
+  for (int i : best_ln) out.ransac_inliers.push_back(all_ln[i]);
   memcpy(out.tf_ransac, tf_best, sizeof(tf_best));
   float refined_tf[16];
   memcpy(refined_tf, tf_best, sizeof(tf_best));
-  refine_pose_lines(train, query, out.ransac_inliers, refined_tf, 25, P);
-  double refined_rmse = sqrt(sum_squared_error / (double)(best_inl.size()));
-  std::vector<Match> refined;
+  refine_pose_hybrid(train, query, train_pts, query_pts, out.pt_ransac_inliers, out.ransac_inliers, refined_tf, 25, fx, asynch_dt, P);
+  double refined_rmse = sqrt(sum_squared_error / (double)(best_pt.size() + best_ln.size()));
+  std::vector<Match> refined_pt, refined_ln;
   for (int it = 0; it < 20; ++it) {
-    Score sc;
-    score_lines(train, query, all_ln, refined_tf, thr, sc, false);
-    if (sc.inl.size() * P.line_match_number_weight > refined.size() * P.line_match_number_weight) {
-      refined.clear();
-      for (int i : sc.inl) refined.push_back(all_ln[i]);
-      refined_rmse = sqrt(sc.sse / (double)(sc.inl.size()));
-      refine_pose_lines(train, query, refined, refined_tf, 20, P);
+    ScoreH sc;
+    score_hybrid(train, query, train_pts, query_pts, all_pt, all_ln, refined_tf, thr, P.sigma_depth, sc, false);
+    if (sc.pt.size() + sc.ln.size() * P.line_match_number_weight > refined_pt.size() + refined_ln.size() * P.line_match_number_weight) {
+      refined_pt.clear(); refined_ln.clear();
+      for (int i : sc.pt) refined_pt.push_back(all_pt[i]);
+      for (int i : sc.ln) refined_ln.push_back(all_ln[i]);
+      refined_rmse = sqrt(sc.sse / (double)(sc.pt.size() + sc.ln.size()));
+      refine_pose_hybrid(train, query, train_pts, query_pts, refined_pt, refined_ln, refined_tf, 20, fx, asynch_dt, P);
     } else break;
   }
-  out.inliers = refined;
+  out.pt_inliers = refined_pt;
+  out.inliers = refined_ln;
   out.rmse = (float)refined_rmse;
   memcpy(out.tf, refined_tf, sizeof(refined_tf));
-  out.found = (int)(line_weight * refined.size()) >= min_inlier_nmb;
+  out.found = (int)(refined_pt.size() + line_weight * refined_ln.size()) >= min_inlier_nmb;
+}
+
+// getTransform_PtsLines_ransac with line-only input (nPt = 0)
+void getTransform_Lines_ransac(const std::vector<Line>& train, const std::vector<Line>& query, int id_train, int id_query,
+                               const std::vector<Match>& all_ln, uint32_t seed, const Params& P, PoseResult& out) {
+  Points none;
+  GlibcRand rng; rng.seed(seed);
+  getTransform_PtsLines_ransac(train, query, none, none, id_train, id_query, std::vector<Match>(), all_ln, rng, 525.0, 0.0, P, out);
 }
 
 }  // namespace orc

@@ -33,6 +33,7 @@ def lib():
         for n in "atan2 pow".split():
             f = getattr(L, "orc_m_" + n); f.restype = C.c_double; f.argtypes = [C.c_double, C.c_double]
         L.orc_stream_step.restype = C.c_double
+        L.orc_error_function2.restype = C.c_double
     return _LIB
 
 
@@ -137,3 +138,57 @@ def stream_step(img, depth, K, seed, prev_lines, params=None, omp_threads=1):
     sec = lib().orc_stream_step(ptr(img), ch, ptr(depth), W, H, ptr(Kc), C.c_uint32(seed), C.byref(p), ptr(prev),
                                 len(prev), ptr(cur), cap, C.byref(ncur), ptr(rec), omp_threads)
     return sec, cur[:ncur.value].copy(), rec[0].copy()
+
+
+def rootsift(desc):
+    d = np.ascontiguousarray(desc, np.float32).copy()
+    lib().orc_rootsift(ptr(d), d.shape[0], d.shape[1])
+    return d
+
+
+def featureMatching(qdesc, tdesc, nn_ratio=0.5, seed=1):
+    """Node::featureMatching, BRUTEFORCE branch; one rand() per returned match."""
+    q = np.ascontiguousarray(qdesc, np.float32); t = np.ascontiguousarray(tdesc, np.float32)
+    cap = max(len(q), 1)
+    out = np.zeros(cap, MATCH_DTYPE)
+    n = lib().orc_featureMatching(ptr(q), len(q), ptr(t), len(t), q.shape[1] if q.ndim == 2 else 0, C.c_double(nn_ratio),
+                                  C.c_uint32(seed), ptr(out), cap)
+    return out[:n].copy()
+
+
+def pose_ransac_hybrid(train, query, train_xyz1, query_xyz1, pt_matches, ln_matches, id_train=0, id_query=1, seed=1,
+                       skip_draws=0, fx=525.0, dt=0.0, params=None):
+    p = params or default_params()
+    train = np.ascontiguousarray(train, LINE_DTYPE); query = np.ascontiguousarray(query, LINE_DTYPE)
+    tx = np.ascontiguousarray(train_xyz1, np.float32).reshape(-1, 4); qx = np.ascontiguousarray(query_xyz1, np.float32).reshape(-1, 4)
+    pm = np.ascontiguousarray(pt_matches, MATCH_DTYPE); m = np.ascontiguousarray(ln_matches, MATCH_DTYPE)
+    rec = np.zeros(1, POSE_DTYPE)
+    inl = np.zeros(max(len(m), 1), MATCH_DTYPE); rinl = np.zeros(max(len(m), 1), MATCH_DTYPE)
+    pinl = np.zeros(max(len(pm), 1), MATCH_DTYPE); prinl = np.zeros(max(len(pm), 1), MATCH_DTYPE)
+    n = [C.c_int(0) for _ in range(4)]
+    tfr = np.zeros(16, np.float32)
+    lib().orc_pose_ransac_hybrid(ptr(train), len(train), ptr(query), len(query), ptr(tx), len(tx), ptr(qx), len(qx),
+                                 id_train, id_query, ptr(pm), len(pm), ptr(m), len(m), C.c_uint32(seed), skip_draws,
+                                 C.c_double(fx), C.c_double(dt), C.byref(p), ptr(rec), ptr(inl), C.byref(n[0]), ptr(rinl),
+                                 C.byref(n[1]), ptr(pinl), C.byref(n[2]), ptr(prinl), C.byref(n[3]), ptr(tfr))
+    return dict(rec=rec[0].copy(), ln_inliers=inl[:n[0].value].copy(), ln_ransac_inliers=rinl[:n[1].value].copy(),
+                pt_inliers=pinl[:n[2].value].copy(), pt_ransac_inliers=prinl[:n[3].value].copy(), tf_ransac=tfr.reshape(4, 4))
+
+
+def error_function2(x1, x2, tf, sigma_depth=0.01):
+    a = np.ascontiguousarray(x1, np.float32); b = np.ascontiguousarray(x2, np.float32)
+    t = np.ascontiguousarray(tf, np.float32).reshape(16)
+    return lib().orc_error_function2(ptr(a), ptr(b), ptr(t), C.c_double(sigma_depth))
+
+
+def kabsch(frm, to, w):
+    f = np.ascontiguousarray(frm, np.float32); t = np.ascontiguousarray(to, np.float32); ww = np.ascontiguousarray(w, np.float32)
+    tf = np.zeros(16, np.float32)
+    lib().orc_kabsch(ptr(f), ptr(t), ptr(ww), len(ww), ptr(tf))
+    return tf.reshape(4, 4)
+
+
+def ldlt3_solve(A, b):
+    A = np.ascontiguousarray(A, np.float64); b = np.ascontiguousarray(b, np.float64); x = np.zeros(3)
+    lib().orc_ldlt3_solve(ptr(A), ptr(b), ptr(x))
+    return x

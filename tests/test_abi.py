@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(api):
 def test_record_layouts():
     from lineslam_b200.records import LINE_DTYPE, MATCH_DTYPE, POSE_DTYPE, Params
     assert LINE_DTYPE.itemsize == 1040 and MATCH_DTYPE.itemsize == 12 and POSE_DTYPE.itemsize == 128
-    assert C.sizeof(Params) == 24 * 8 + 12 * 4
+    assert C.sizeof(Params) == 26 * 8 + 12 * 4
 
 
 def test_defaults_match_reference_parameter_server(api):
