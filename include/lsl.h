@@ -107,25 +107,41 @@ void lsl_frame_free(lsl_frame* f);
 int lsl_match_lines(lsl_ctx* ctx, const lsl_frame* query, const lsl_frame* train, int adjacent,
                     lsl_match* out, int cap, int* n);
 
-/* getTransform_PtsLines_ransac (src/line/utils.h:147-153, src/line/motion.cpp:605-849), line
- * matches only in this round (npt must be 0; point features are a "next" row).
- * inliers_out receives output_line_inlier_matches; ransac_inliers_out (optional) the
- * max_line_inlier_set of the best hypothesis. */
+/* Point features of a frame: Node::feature_locations_3d_ (Eigen::Vector4f rows x,y,z,1; z may be NaN) and
+ * Node::feature_descriptors_ (CV_32F rows, after squareroot_descriptor_space, src/node.cpp:304-310, 1823-1837).
+ * They are INPUTS of the path (the detectors are out of scope); copied to the device, n <= 2048. */
+int lsl_frame_set_points(lsl_ctx* ctx, lsl_frame* f, const float* xyz1, const float* desc, int n, int dim);
+int lsl_frame_num_points(const lsl_frame* f);
+/* fx = K(0,0) and Node::asynch_time_diff_sec_ used by the point-edge information matrices of the refinement
+ * (compPt3dCov, src/transformation_estimation.cpp:243-262). Every extract call sets them from its K / dt. */
+int lsl_ctx_set_camera(lsl_ctx* ctx, double fx, double asynch_dt_s);
+
+/* Node::featureMatching, matcher_type BRUTEFORCE (src/node.h:139, src/node.cpp:606-641): L2 k = 2 nearest
+ * neighbours, ratio < nn_distance_ratio, unique trainIdx, distance = ratio + rand()/(1000 RAND_MAX). */
+int lsl_match_points(lsl_ctx* ctx, const lsl_frame* query, const lsl_frame* train, uint32_t seed, lsl_match* out,
+                     int cap, int* n);
+
+/* getTransform_PtsLines_ransac (src/line/utils.h:147-153, src/line/motion.cpp:605-849) with point and/or line
+ * matches. inliers_out receives output_line_inlier_matches; ransac_inliers_out (optional) the
+ * max_line_inlier_set of the best hypothesis; the point lists are read with lsl_pair_matches(ctx, 0, 3..5).
+ * With point matches the rand() stream starts after npt draws (the featureMatching jitter of the same
+ * matchNodePair call). rec->pad[0..2] = #point matches, #point inliers of the best hypothesis, #refined. */
 int lsl_pose_ransac(lsl_ctx* ctx, const lsl_frame* train, const lsl_frame* query, int id_train, int id_query,
                     const lsl_match* pt_matches, int npt, const lsl_match* ln_matches, int nln, uint32_t seed,
                     lsl_pose_rec* rec, lsl_match* inliers_out, int cap, int* n_inl,
                     lsl_match* ransac_inliers_out, int cap2, int* n_rinl);
 
 /* Node::matchNodePair (src/node.h:107, src/node.cpp:1494-1545) for npairs independent pairs, the
- * unit GraphManager::nodeComparisons maps over (src/graph_manager.cpp:555): lineMatching +
- * pose RANSAC + refinement on the device, one 128-byte record per pair back. */
+ * unit GraphManager::nodeComparisons maps over (src/graph_manager.cpp:555): featureMatching (when both frames
+ * carry point features) + lineMatching + pose RANSAC + refinement on the device, one 128-byte record per pair back. */
 int lsl_match_pair_batch(lsl_ctx* ctx, int npairs, const lsl_frame* const* queries, const lsl_frame* const* trains,
                          const int32_t* id_query, const int32_t* id_train, const uint32_t* seeds,
                          lsl_pose_rec* out);
 
-/* Match lists of pair `pair` of the last lsl_match_pair_batch call: what = 0 all line matches
- * (Node::lineMatching output), 1 refined inliers (output_line_inlier_matches), 2 inliers of the best
- * RANSAC hypothesis (max_line_inlier_set, motion.cpp:714-721). */
+/* Match lists of pair `pair` of the last lsl_match_pair_batch / lsl_pose_ransac call: what = 0 all line
+ * matches (Node::lineMatching output), 1 refined inliers (output_line_inlier_matches), 2 inliers of the best
+ * RANSAC hypothesis (max_line_inlier_set, motion.cpp:714-721); 3, 4, 5 the same three lists for points
+ * (Node::featureMatching output, output_point_inlier_matches, max_point_inlier_set). */
 int lsl_pair_matches(lsl_ctx* ctx, int pair, int what, lsl_match* out, int cap, int* n);
 
 /* Graph-insert-time exchange: all ranks contribute nlocal records and receive

@@ -73,7 +73,9 @@ def _check(rc, ctx=None):
 
 @dataclass
 class MatchingResult:
-    """src/matching_result.h: the subset the line path fills."""
+    """src/matching_result.h: the subset the path fills."""
+    all_matches: np.ndarray = field(default_factory=lambda: np.zeros(0, MATCH_DTYPE))        # point matches
+    inlier_matches: np.ndarray = field(default_factory=lambda: np.zeros(0, MATCH_DTYPE))
     all_line_matches: np.ndarray = field(default_factory=lambda: np.zeros(0, MATCH_DTYPE))
     inlier_line_matches: np.ndarray = field(default_factory=lambda: np.zeros(0, MATCH_DTYPE))
     ransac_line_inliers: np.ndarray = field(default_factory=lambda: np.zeros(0, MATCH_DTYPE))
@@ -172,16 +174,29 @@ class Context:
         _check(lib().lsl_match_lines(self._h, query._h, train._h, int(adjacent), ptr(out), cap, C.byref(n)), self._h)
         return out[:n.value].copy()
 
-    def pose_ransac(self, train: "Frame", query: "Frame", ln_matches, id_train=0, id_query=1, seed=1):
-        m = np.ascontiguousarray(ln_matches, MATCH_DTYPE)
+    def match_points(self, query: "Frame", train: "Frame", seed: int = 1):
+        """Node::featureMatching (BRUTEFORCE) on the frames' point features."""
+        cap = max(query.num_points, 1)
+        out = np.zeros(cap, MATCH_DTYPE)
+        n = C.c_int(0)
+        _check(lib().lsl_match_points(self._h, query._h, train._h, C.c_uint32(seed), ptr(out), cap, C.byref(n)), self._h)
+        return out[:n.value].copy()
+
+    def set_camera(self, fx: float, dt: float = 0.0):
+        _check(lib().lsl_ctx_set_camera(self._h, C.c_double(fx), C.c_double(dt)), self._h)
+
+    def pose_ransac(self, train: "Frame", query: "Frame", ln_matches, id_train=0, id_query=1, seed=1, pt_matches=None):
+        """getTransform_PtsLines_ransac. Point inlier lists of a hybrid call: pair_matches(0, 4) / (0, 5)."""
+        m = np.ascontiguousarray(ln_matches if ln_matches is not None else np.zeros(0, MATCH_DTYPE), MATCH_DTYPE)
+        pm = np.ascontiguousarray(pt_matches if pt_matches is not None else np.zeros(0, MATCH_DTYPE), MATCH_DTYPE)
         rec = np.zeros(1, POSE_DTYPE)
         cap = max(len(m), 1)
         inl = np.zeros(cap, MATCH_DTYPE)
         rinl = np.zeros(cap, MATCH_DTYPE)
         n1, n2 = C.c_int(0), C.c_int(0)
-        _check(lib().lsl_pose_ransac(self._h, train._h, query._h, id_train, id_query, None, 0, ptr(m), len(m),
-                                     C.c_uint32(seed), ptr(rec), ptr(inl), cap, C.byref(n1), ptr(rinl), cap,
-                                     C.byref(n2)), self._h)
+        _check(lib().lsl_pose_ransac(self._h, train._h, query._h, id_train, id_query, ptr(pm) if len(pm) else None, len(pm),
+                                     ptr(m) if len(m) else None, len(m), C.c_uint32(seed), ptr(rec), ptr(inl), cap,
+                                     C.byref(n1), ptr(rinl), cap, C.byref(n2)), self._h)
         return rec[0].copy(), inl[:n1.value].copy(), rinl[:n2.value].copy()
 
     def match_pair_batch(self, queries, trains, id_query, id_train, seeds):
@@ -197,7 +212,8 @@ class Context:
         return out
 
     def pair_matches(self, pair: int, what: int):
-        """Lists of the last match_pair_batch call: what 0 = all matches, 1 = refined inliers, 2 = RANSAC inliers."""
+        """Lists of the last pair call: what 0 = all line matches, 1 = refined line inliers, 2 = line inliers of the
+        best RANSAC hypothesis; 3, 4, 5 = the same lists for point matches."""
         k = C.c_int(0)
         lib().lsl_pair_matches(self._h, pair, what, None, 0, C.byref(k))
         out = np.zeros(max(k.value, 1), MATCH_DTYPE)
@@ -240,6 +256,17 @@ class Frame:
     def num_lines(self) -> int:
         return _check(lib().lsl_frame_num_lines(self._h))
 
+    @property
+    def num_points(self) -> int:
+        return _check(lib().lsl_frame_num_points(self._h))
+
+    def set_points(self, xyz1, desc):
+        """feature_locations_3d_ (n,4) and feature_descriptors_ (n,dim) of the Node this frame belongs to."""
+        x = np.ascontiguousarray(xyz1, np.float32).reshape(-1, 4)
+        d = np.ascontiguousarray(desc, np.float32).reshape(len(x), -1) if len(x) else np.zeros((0, 1), np.float32)
+        _check(lib().lsl_frame_set_points(self.ctx._h, self._h, ptr(x), ptr(d), len(x), d.shape[1]), self.ctx._h)
+        return self
+
     def lines(self) -> np.ndarray:
         n = self.num_lines
         out = np.zeros(max(n, 1), LINE_DTYPE)
@@ -277,15 +304,19 @@ class Frame:
 
 
 class Node:
-    """One RGB-D frame (src/node.h). The constructor runs Node::detect3DLines on the device."""
+    """One RGB-D frame (src/node.h). The constructor runs Node::detect3DLines on the device; point features
+    (feature_locations_3d_, feature_descriptors_) are handed in by the caller like the detectors' output."""
 
-    def __init__(self, ctx: Context, visual, depth, K, node_id: int = 0, seed: int = 1, frame: Frame | None = None):
+    def __init__(self, ctx: Context, visual, depth, K, node_id: int = 0, seed: int = 1, frame: Frame | None = None,
+                 feature_locations_3d=None, feature_descriptors=None):
         self.ctx = ctx
         self.id_ = node_id
         self.seed = seed
         if frame is None:
             frame = ctx.extract_batch(np.asarray(visual)[None], np.asarray(depth)[None], K, [seed])[0]
         self.frame = frame
+        if feature_locations_3d is not None:
+            frame.set_points(feature_locations_3d, feature_descriptors)
 
     @property
     def lines(self) -> np.ndarray:
@@ -294,31 +325,34 @@ class Node:
     def lineMatching(self, other: "Node", adjacentFrame: bool) -> np.ndarray:
         return self.ctx.match_lines(self.frame, other.frame, adjacentFrame)
 
+    def featureMatching(self, other: "Node", seed: int | None = None) -> np.ndarray:
+        return self.ctx.match_points(self.frame, other.frame, seed if seed is not None else self.seed)
+
     def matchNodePair(self, older: "Node", seed: int | None = None) -> MatchingResult:
-        """src/node.cpp:1494-1545 (USE_LINES, line features only): lineMatching -> RANSAC -> edge."""
+        """src/node.cpp:1494-1545 (USE_LINES): featureMatching + lineMatching -> RANSAC -> edge, one device call."""
         P = self.ctx.params
         mr = MatchingResult()
-        adjacent = abs(self.id_ - older.id_) <= P.adjacent_linematch_window
-        mr.all_line_matches = self.lineMatching(older, adjacent)
-        if len(mr.all_line_matches) * P.line_match_number_weight < P.min_feature_matches:
+        sd = seed if seed is not None else self.seed
+        rec = self.ctx.match_pair_batch([self.frame], [older.frame], [self.id_], [older.id_], [sd])[0]
+        mr.all_line_matches = self.ctx.pair_matches(0, 0)
+        mr.all_matches = self.ctx.pair_matches(0, 3)
+        if len(mr.all_matches) + len(mr.all_line_matches) * P.line_match_number_weight < P.min_feature_matches:
             return mr
-        rec, inl, rinl = getTransform_PtsLines_ransac(older, self, None, mr.all_line_matches,
-                                                      seed if seed is not None else self.seed)
-        mr.inlier_line_matches, mr.ransac_line_inliers = inl, rinl
+        mr.inlier_line_matches, mr.ransac_line_inliers = self.ctx.pair_matches(0, 1), self.ctx.pair_matches(0, 2)
+        mr.inlier_matches = self.ctx.pair_matches(0, 4)
         mr.rmse = float(rec["rmse"])
         mr.found = bool(rec["found"])
         if mr.found:
             mr.final_trafo = rec["tf"].reshape(4, 4).copy()
             mr.ransac_trafo = mr.final_trafo
             mr.id1, mr.id2 = older.id_, self.id_
-            w = len(inl) * P.line_match_number_weight
+            w = len(mr.inlier_matches) + len(mr.inlier_line_matches) * P.line_match_number_weight
             mr.informationMatrix = np.eye(6) * (w / (mr.rmse * mr.rmse))
         return mr
 
 
 def getTransform_PtsLines_ransac(trainNode: Node, queryNode: Node, all_point_matches, all_line_matches, seed: int = 1):
-    """src/line/motion.cpp:605-849, line matches only (point features are a later row of the scope table)."""
-    if all_point_matches is not None and len(all_point_matches):
-        raise LslError("point matches are not supported by this build (line-only path)")
+    """src/line/motion.cpp:605-849: (record, output_line_inlier_matches, max_line_inlier_set); the point inlier
+    lists of a hybrid call are ctx.pair_matches(0, 4) and (0, 5)."""
     return trainNode.ctx.pose_ransac(trainNode.frame, queryNode.frame, all_line_matches, trainNode.id_,
-                                     queryNode.id_, seed)
+                                     queryNode.id_, seed, pt_matches=all_point_matches)

@@ -3,6 +3,7 @@
 // CUDA device every entry point that computes returns LSL_ERR_NO_DEVICE.
 #include "lsl_internal.h"
 #include "shared/lsl_params_default.h"
+#include "shared/lsl_rand.h"
 #include <dlfcn.h>
 #include <string.h>
 #include <stdlib.h>
@@ -26,7 +27,7 @@ extern "C" const char* lsl_last_error(const lsl_ctx* ctx) { return ctx ? ctx->er
 static const char* const kKernelNames[LSL_K_COUNT] = {
     "gray_kernel", "xpass_kernel", "ypass_kernel", "ll_angle_kernel", "seed_list_kernel", "sobel5_kernel",
     "lsd_region_kernel", "line3d_ransac_kernel", "line_msld_kernel", "msld_randfill_kernel", "line_mle_kernel",
-    "gather_lines_kernel", "match_lines_kernel", "pose_kernel"};
+    "gather_lines_kernel", "match_lines_kernel", "pose_kernel", "match_points_kernel", "pose_hybrid_kernel"};
 extern "C" const char* lsl_kernel_name(int i) { return (i >= 0 && i < LSL_K_COUNT) ? kKernelNames[i] : ""; }
 
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -93,6 +94,13 @@ static void free_pair_ws(lsl_ctx* ctx) {
   memset(&p.sc, 0, sizeof(p.sc));
   p.d_pairs = nullptr; p.D = nullptr; p.matches = nullptr; p.nmatch = nullptr; p.recs = nullptr;
   p.cap_pairs = p.cap_m = p.cap_d = 0;
+  LslHybWork& h = ctx->hw;
+  void* hp[] = {h.d_ppairs, h.knn, h.pmatches, h.npmatch, h.hs.pmd, h.hs.pd2, h.hs.psel, h.hs.plm, h.hs.pokf, h.hs.ptidx,
+                h.hs.rng, h.hs.n_pinl, h.hs.n_prinl};
+  for (void* q : hp) if (q) cudaFree(q);
+  memset(&h.hs, 0, sizeof(h.hs));
+  h.d_ppairs = nullptr; h.knn = nullptr; h.pmatches = nullptr; h.npmatch = nullptr;
+  h.cap_pairs = h.cap_pm = h.cap_knn = 0; h.max_iter = 0; h.last_hybrid = false;
 }
 
 extern "C" int lsl_ctx_create(lsl_ctx** out, const lsl_params* params, int cuda_device, int max_batch, int max_w, int max_h) {
@@ -109,6 +117,10 @@ extern "C" int lsl_ctx_create(lsl_ctx** out, const lsl_params* params, int cuda_
   memset(&ctx->pw.sc, 0, sizeof(ctx->pw.sc));
   ctx->pw.d_pairs = nullptr; ctx->pw.D = nullptr; ctx->pw.matches = nullptr; ctx->pw.nmatch = nullptr; ctx->pw.recs = nullptr;
   ctx->pw.cap_pairs = ctx->pw.cap_m = ctx->pw.cap_d = 0;
+  memset(&ctx->hw.hs, 0, sizeof(ctx->hw.hs));
+  ctx->hw.d_ppairs = nullptr; ctx->hw.knn = nullptr; ctx->hw.pmatches = nullptr; ctx->hw.npmatch = nullptr;
+  ctx->hw.cap_pairs = ctx->hw.cap_pm = ctx->hw.cap_knn = 0; ctx->hw.max_iter = 0; ctx->hw.last_hybrid = false;
+  ctx->cam_fx = 525.0; ctx->cam_dt = 0.0;   // K(0,0) of src/openni_listener.cpp:1256; replaced by the K of the last extract call
   ctx->h_pin = nullptr; ctx->h_pin_bytes = 0;
   memset(&ctx->stats, 0, sizeof(ctx->stats));
   memset(&ctx->dims, 0, sizeof(ctx->dims));
@@ -207,6 +219,7 @@ static int extract_device(lsl_ctx* ctx, int n, const uint8_t* d_imgs, int channe
                           const double K[9], double dt, const uint32_t* seeds, lsl_frame** out) {
   int rc = set_dims(ctx, W, H);
   if (rc) return rc;
+  ctx->cam_fx = K[0]; ctx->cam_dt = dt;   // the global K of src/node.cpp:200-206 (read again by the g2o set-up)
   LslWork& w = ctx->wk;
   cudaStream_t st = ctx->stream;
   std::vector<uint32_t> sd(n);
@@ -380,8 +393,35 @@ extern "C" void lsl_frame_free(lsl_frame* f) {
       if (--f->blk->refs == 0) { cudaFreeAsync(f->blk->d, f->ctx->stream); delete f->blk; }
     } else cudaFree(f->d_lines);
   }
+  if (f->d_xyz1) cudaFree(f->d_xyz1);
+  if (f->d_desc) cudaFree(f->d_desc);
   delete f;
 }
+// Point features of a frame (inputs of the hot path: Node::feature_locations_3d_ and feature_descriptors_,
+// src/node.h; SIFT/SURF rows after squareroot_descriptor_space). Copies to the device; replaces earlier points.
+extern "C" int lsl_frame_set_points(lsl_ctx* ctx, lsl_frame* f, const float* xyz1, const float* desc, int n, int dim) {
+  if (!ctx || !f || n < 0 || n > LSL_MAX_POINTS || (n && (!xyz1 || !desc)) || dim < 1 || dim > 512) return LSL_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (f->d_xyz1) { cudaFree(f->d_xyz1); f->d_xyz1 = nullptr; }
+  if (f->d_desc) { cudaFree(f->d_desc); f->d_desc = nullptr; }
+  f->npoints = n; f->pdim = dim;
+  if (n) {
+    LSL_CUDA(cudaMalloc((void**)&f->d_xyz1, sizeof(float) * 4 * n));
+    LSL_CUDA(cudaMalloc((void**)&f->d_desc, sizeof(float) * (size_t)dim * n));
+    LSL_CUDA(cudaMemcpyAsync(f->d_xyz1, xyz1, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+    LSL_CUDA(cudaMemcpyAsync(f->d_desc, desc, sizeof(float) * (size_t)dim * n, cudaMemcpyHostToDevice, ctx->stream));
+    LSL_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.h2d_bytes += sizeof(float) * (size_t)(4 + dim) * n;
+  }
+  return LSL_OK;
+}
+extern "C" int lsl_frame_num_points(const lsl_frame* f) { return f ? f->npoints : LSL_ERR_ARG; }
+extern "C" int lsl_ctx_set_camera(lsl_ctx* ctx, double fx, double asynch_dt_s) {
+  if (!ctx || !(fx > 0)) return LSL_ERR_ARG;
+  ctx->cam_fx = fx; ctx->cam_dt = asynch_dt_s;
+  return LSL_OK;
+}
+
 // parity-test read-back of per-line intermediates (inlier sample indices of the 3D-line RANSAC etc.)
 extern "C" int lsl_frame_debug(const lsl_frame* f, int32_t* npts, int32_t* inl_idx, int32_t* seg_of_line, int32_t* lm_iters) {
   if (!f || !f->have_dbg) return LSL_ERR_ARG;
@@ -456,6 +496,77 @@ static int setup_pairs(lsl_ctx* ctx, int npairs, const lsl_frame* const* queries
   return LSL_OK;
 }
 
+// Point side of a batch: descriptors of the pairs' point sets and the point-match-sized scratch.
+static int setup_ppairs(lsl_ctx* ctx, int npairs, const lsl_frame* const* queries, const lsl_frame* const* trains,
+                        int cap_override, int* max_nq, int* dim_out) {
+  LslHybWork& h = ctx->hw;
+  h.h_ppairs.resize(npairs);
+  size_t pm_off = 0, knn_off = 0;
+  int mq = 0, dim = 0;
+  for (int i = 0; i < npairs; ++i) {
+    const lsl_frame* q = queries[i];
+    const lsl_frame* t = trains[i];
+    LslPairPts& d = h.h_ppairs[i];
+    d.qx = q->d_xyz1; d.tx = t->d_xyz1; d.qd = q->d_desc; d.td = t->d_desc;
+    d.nqp = q->npoints; d.ntp = t->npoints;
+    if (d.nqp && d.ntp && q->pdim != t->pdim) { ctx->err = "descriptor dimensions of the two frames differ"; return LSL_ERR_ARG; }
+    d.dim = d.nqp ? q->pdim : t->pdim;
+    if (cap_override < 0 && d.nqp && d.ntp) { if (dim && d.dim != dim) { ctx->err = "mixed descriptor dimensions in one batch"; return LSL_ERR_ARG; } dim = d.dim; }
+    d.cap_pm = cap_override >= 0 ? cap_override : d.nqp;
+    d.pm_off = pm_off; d.knn_off = knn_off;
+    pm_off += (size_t)(d.cap_pm > 0 ? d.cap_pm : 1);
+    knn_off += (size_t)(d.nqp > 0 ? d.nqp : 1);
+    if (d.nqp > mq && d.ntp >= 2) mq = d.nqp;
+  }
+  const int max_iter = ctx->P.ransac_iters_line_motion;
+  if ((size_t)npairs > h.cap_pairs || h.max_iter != max_iter) {
+    size_t c = (size_t)npairs + npairs / 2;
+    LSL_CUDA(cudaStreamSynchronize(ctx->stream));
+    LSL_CUDA(regrow(&h.d_ppairs, c)); LSL_CUDA(regrow(&h.npmatch, c)); LSL_CUDA(regrow(&h.hs.ptidx, c * max_iter * 2));
+    LSL_CUDA(regrow(&h.hs.rng, c * 33)); LSL_CUDA(regrow(&h.hs.n_pinl, c)); LSL_CUDA(regrow(&h.hs.n_prinl, c));
+    h.cap_pairs = c; h.max_iter = max_iter;
+  }
+  if (pm_off > h.cap_pm) {
+    size_t c = pm_off + pm_off / 2;
+    LSL_CUDA(cudaStreamSynchronize(ctx->stream));
+    LSL_CUDA(regrow(&h.pmatches, c)); LSL_CUDA(regrow(&h.hs.pmd, c * 22)); LSL_CUDA(regrow(&h.hs.pd2, c));
+    LSL_CUDA(regrow(&h.hs.psel, c * 3)); LSL_CUDA(regrow(&h.hs.plm, c * 160)); LSL_CUDA(regrow(&h.hs.pokf, c));
+    h.cap_pm = c;
+  }
+  if (knn_off > h.cap_knn) {
+    size_t c = knn_off + knn_off / 2;
+    LSL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h.knn) cudaFree(h.knn);
+    h.knn = nullptr;
+    LSL_CUDA(cudaMalloc(&h.knn, 12 * c));
+    h.cap_knn = c;
+  }
+  LSL_CUDA(cudaMemcpyAsync(h.d_ppairs, h.h_ppairs.data(), sizeof(LslPairPts) * npairs, cudaMemcpyHostToDevice, ctx->stream));
+  if (max_nq) *max_nq = mq;
+  if (dim_out) *dim_out = dim ? dim : 1;
+  return LSL_OK;
+}
+// seeds the per-pair rand() state on the host (pose-only calls have no featureMatching pass before them)
+static int upload_fresh_rng(lsl_ctx* ctx, uint32_t seed, int skip) {
+  lslm::GRand g;
+  lslm::grand_seed(&g, seed);
+  for (int i = 0; i < skip; ++i) lslm::grand_next(&g);
+  int32_t st[33];
+  for (int k = 0; k < 31; ++k) st[k] = g.r[k];
+  st[31] = g.f; st[32] = g.b;
+  LSL_CUDA(cudaMemcpyAsync(ctx->hw.hs.rng, st, sizeof(st), cudaMemcpyHostToDevice, ctx->stream));
+  LSL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return LSL_OK;
+}
+static int fetch_counts_hyb(lsl_ctx* ctx, int npairs) {
+  LslHybWork& h = ctx->hw;
+  h.h_npmatch.resize(npairs); h.h_npinl.resize(npairs); h.h_nprinl.resize(npairs);
+  LSL_CUDA(cudaMemcpyAsync(h.h_npmatch.data(), h.npmatch, 4 * npairs, cudaMemcpyDeviceToHost, ctx->stream));
+  LSL_CUDA(cudaMemcpyAsync(h.h_npinl.data(), h.hs.n_pinl, 4 * npairs, cudaMemcpyDeviceToHost, ctx->stream));
+  LSL_CUDA(cudaMemcpyAsync(h.h_nprinl.data(), h.hs.n_prinl, 4 * npairs, cudaMemcpyDeviceToHost, ctx->stream));
+  return LSL_OK;
+}
+
 static int fetch_counts(lsl_ctx* ctx, int npairs) {
   LslPairWork& p = ctx->pw;
   p.h_nmatch.resize(npairs); p.h_ninl.resize(npairs); p.h_nrinl.resize(npairs);
@@ -500,30 +611,82 @@ static int fetch_sel(lsl_ctx* ctx, const LslPairDesc& d, int which, int count, c
   return LSL_OK;
 }
 
+// Node::featureMatching, BRUTEFORCE branch (src/node.cpp:606-641) on the frames' point features.
+extern "C" int lsl_match_points(lsl_ctx* ctx, const lsl_frame* query, const lsl_frame* train, uint32_t seed, lsl_match* out,
+                                int cap, int* n) {
+  if (!ctx || !query || !train || !n) return LSL_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int id_q = 1, id_t = 0;
+  int rc = setup_pairs(ctx, 1, &query, &train, &id_q, &id_t, &seed, nullptr, -1);
+  if (rc) return rc;
+  int mq = 0, dim = 1;
+  if ((rc = setup_ppairs(ctx, 1, &query, &train, -1, &mq, &dim))) return rc;
+  clear_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
+  if ((rc = lsl_launch_match_points(ctx, 1, mq, dim))) return rc;
+  int32_t nm = 0;
+  LSL_CUDA(cudaMemcpyAsync(&nm, ctx->hw.npmatch, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  LSL_CUDA(cudaStreamSynchronize(ctx->stream));
+  collect_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
+  *n = nm;
+  ctx->stats.pairs += 1; ctx->stats.matches += nm;
+  if (nm > cap || (nm && !out)) return LSL_ERR_CAPACITY;
+  if (nm) {
+    LSL_CUDA(cudaMemcpyAsync(out, ctx->hw.pmatches, sizeof(lsl_match) * nm, cudaMemcpyDeviceToHost, ctx->stream));
+    LSL_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += sizeof(lsl_match) * nm;
+  }
+  return LSL_OK;
+}
+
+static int fetch_psel(lsl_ctx* ctx, const LslPairPts& d, int which, int count, const std::vector<lsl_match>& all, lsl_match* out) {
+  if (!count) return LSL_OK;
+  std::vector<int32_t> idx(count);
+  LSL_CUDA(cudaMemcpyAsync(idx.data(), ctx->hw.hs.psel + d.pm_off * 3 + (size_t)which * d.cap_pm, 4 * count, cudaMemcpyDeviceToHost, ctx->stream));
+  LSL_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < count; ++i) out[i] = all[idx[i]];
+  ctx->stats.d2h_bytes += 4 * count;
+  return LSL_OK;
+}
+
 extern "C" int lsl_pose_ransac(lsl_ctx* ctx, const lsl_frame* train, const lsl_frame* query, int id_train, int id_query,
                                const lsl_match* pt_matches, int npt, const lsl_match* ln_matches, int nln, uint32_t seed,
                                lsl_pose_rec* rec, lsl_match* inliers_out, int cap, int* n_inl, lsl_match* ransac_inliers_out,
                                int cap2, int* n_rinl) {
-  (void)pt_matches;
-  if (!ctx || !train || !query || !rec || nln < 0 || (nln && !ln_matches)) return LSL_ERR_ARG;
-  if (npt != 0) { ctx->err = "point matches are not part of this build (line-only path)"; return LSL_ERR_ARG; }
-  if (nln > LSL_MAX_MATCH) return LSL_ERR_CAPACITY;
+  if (!ctx || !train || !query || !rec || nln < 0 || (nln && !ln_matches) || npt < 0 || (npt && !pt_matches)) return LSL_ERR_ARG;
+  if (nln > LSL_MAX_MATCH || npt > LSL_MAX_POINTS) return LSL_ERR_CAPACITY;
   for (int i = 0; i < nln; ++i)
     if (ln_matches[i].queryIdx < 0 || ln_matches[i].queryIdx >= query->nlines || ln_matches[i].trainIdx < 0 ||
         ln_matches[i].trainIdx >= train->nlines) return LSL_ERR_ARG;
+  for (int i = 0; i < npt; ++i)
+    if (pt_matches[i].queryIdx < 0 || pt_matches[i].queryIdx >= query->npoints || pt_matches[i].trainIdx < 0 ||
+        pt_matches[i].trainIdx >= train->npoints) return LSL_ERR_ARG;
   cudaSetDevice(ctx->device);
   int rc = setup_pairs(ctx, 1, &query, &train, &id_query, &id_train, &seed, nullptr, nln);
   if (rc) return rc;
+  const bool hybrid = npt > 0;
+  ctx->hw.last_hybrid = hybrid;
+  if (hybrid) {
+    if ((rc = setup_ppairs(ctx, 1, &query, &train, npt, nullptr, nullptr))) return rc;
+    int32_t np = npt;
+    LSL_CUDA(cudaMemcpyAsync(ctx->hw.npmatch, &np, 4, cudaMemcpyHostToDevice, ctx->stream));
+    LSL_CUDA(cudaMemcpyAsync(ctx->hw.pmatches, pt_matches, sizeof(lsl_match) * npt, cudaMemcpyHostToDevice, ctx->stream));
+    // matchNodePair order: featureMatching has consumed one rand() per point match before the RANSAC draws
+    if ((rc = upload_fresh_rng(ctx, seed, npt))) return rc;
+    ctx->stats.h2d_bytes += sizeof(lsl_match) * npt;
+  }
   int32_t nm = nln;
   LSL_CUDA(cudaMemcpyAsync(ctx->pw.nmatch, &nm, 4, cudaMemcpyHostToDevice, ctx->stream));
   if (nln) LSL_CUDA(cudaMemcpyAsync(ctx->pw.matches, ln_matches, sizeof(lsl_match) * nln, cudaMemcpyHostToDevice, ctx->stream));
   ctx->stats.h2d_bytes += sizeof(lsl_match) * nln;
   clear_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
-  if ((rc = lsl_launch_pose(ctx, 1))) return rc;
+  if (hybrid) { if ((rc = lsl_launch_pose_hybrid(ctx, 1, ctx->cam_fx, ctx->cam_dt))) return rc; }
+  else if ((rc = lsl_launch_pose(ctx, 1))) return rc;
   if ((rc = fetch_counts(ctx, 1))) return rc;
+  if (hybrid && (rc = fetch_counts_hyb(ctx, 1))) return rc;
   LSL_CUDA(cudaMemcpyAsync(rec, ctx->pw.recs, sizeof(lsl_pose_rec), cudaMemcpyDeviceToHost, ctx->stream));
   LSL_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->pw.h_nmatch[0] = nln;
+  if (hybrid) ctx->hw.h_npmatch[0] = npt;
   collect_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
   ctx->stats.pairs += 1; ctx->stats.d2h_bytes += sizeof(lsl_pose_rec);
   std::vector<lsl_match> all(ln_matches, ln_matches + nln);
@@ -541,12 +704,20 @@ extern "C" int lsl_match_pair_batch(lsl_ctx* ctx, int npairs, const lsl_frame* c
   cudaSetDevice(ctx->device);
   int rc = setup_pairs(ctx, npairs, queries, trains, id_query, id_train, seeds, nullptr, -1);
   if (rc) return rc;
+  bool hybrid = false;   // any frame with point features -> Node::matchNodePair with both modalities
+  for (int i = 0; i < npairs; ++i) hybrid = hybrid || (queries[i]->npoints > 0 && trains[i]->npoints > 0);
+  ctx->hw.last_hybrid = hybrid;
+  int mq = 0, dim = 1;
+  if (hybrid && (rc = setup_ppairs(ctx, npairs, queries, trains, -1, &mq, &dim))) return rc;
   clear_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
   cudaEventRecord(ctx->ev0, ctx->stream);
+  if (hybrid && (rc = lsl_launch_match_points(ctx, npairs, mq, dim))) return rc;   // featureMatching first (node.cpp:1504)
   if ((rc = lsl_launch_match(ctx, npairs))) return rc;
-  if ((rc = lsl_launch_pose(ctx, npairs))) return rc;
+  if (hybrid) { if ((rc = lsl_launch_pose_hybrid(ctx, npairs, ctx->cam_fx, ctx->cam_dt))) return rc; }
+  else if ((rc = lsl_launch_pose(ctx, npairs))) return rc;
   cudaEventRecord(ctx->ev3, ctx->stream);
   if ((rc = fetch_counts(ctx, npairs))) return rc;
+  if (hybrid && (rc = fetch_counts_hyb(ctx, npairs))) return rc;
   LSL_CUDA(cudaMemcpyAsync(out, ctx->pw.recs, sizeof(lsl_pose_rec) * npairs, cudaMemcpyDeviceToHost, ctx->stream));
   LSL_CUDA(cudaStreamSynchronize(ctx->stream));
   cudaEventElapsedTime(&ctx->ms_total, ctx->ev0, ctx->ev3);
@@ -557,8 +728,23 @@ extern "C" int lsl_match_pair_batch(lsl_ctx* ctx, int npairs, const lsl_frame* c
 }
 
 extern "C" int lsl_pair_matches(lsl_ctx* ctx, int pair, int what, lsl_match* out, int cap, int* n) {
-  if (!ctx || !n || pair < 0 || pair >= (int)ctx->pw.h_nmatch.size() || what < 0 || what > 2) return LSL_ERR_ARG;
+  if (!ctx || !n || pair < 0 || pair >= (int)ctx->pw.h_nmatch.size() || what < 0 || what > 5) return LSL_ERR_ARG;
   cudaSetDevice(ctx->device);
+  if (what >= 3) {   // point lists: 3 all point matches, 4 refined point inliers, 5 point inliers of the best hypothesis
+    const LslHybWork& h = ctx->hw;
+    if (!h.last_hybrid || pair >= (int)h.h_npmatch.size()) { *n = 0; return LSL_OK; }
+    const LslPairPts& d = h.h_ppairs[pair];
+    int nm = h.h_npmatch[pair];
+    int cnt = what == 3 ? nm : (what == 4 ? h.h_npinl[pair] : h.h_nprinl[pair]);
+    *n = cnt;
+    if (cnt > cap || (cnt && !out)) return LSL_ERR_CAPACITY;
+    if (!cnt) return LSL_OK;
+    std::vector<lsl_match> all(nm);
+    LSL_CUDA(cudaMemcpyAsync(all.data(), h.pmatches + d.pm_off, sizeof(lsl_match) * nm, cudaMemcpyDeviceToHost, ctx->stream));
+    LSL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (what == 3) { memcpy(out, all.data(), sizeof(lsl_match) * nm); return LSL_OK; }
+    return fetch_psel(ctx, d, what == 4 ? 1 : 0, cnt, all, out);
+  }
   const LslPairDesc& d = ctx->pw.h_pairs[pair];
   int nm = ctx->pw.h_nmatch[pair];
   int cnt = what == 0 ? nm : (what == 1 ? ctx->pw.h_ninl[pair] : ctx->pw.h_nrinl[pair]);

@@ -11,6 +11,7 @@
 #define LSL_MAX_SMP 101        // samples per line (line_sample_max_num + 1)
 #define LSL_NOTDEF (-1024.0)   // external/lsd/lsd.cpp:102
 #define LSL_MAX_MATCH 1024     // line matches per pair
+#define LSL_MAX_POINTS 2048    // point features per frame (max_keypoints is 600 in the reference)
 
 struct LslDims {
   int W, H;      // input image
@@ -99,10 +100,44 @@ struct LslPairWork {
   std::vector<int32_t> h_nmatch, h_ninl, h_nrinl;
 };
 
+// ---- point features of a pair (k_hybrid.cu) ----
+struct LslPairPts {
+  const float* qx;   // query feature_locations_3d_ [nqp][4]
+  const float* tx;   // train
+  const float* qd;   // query feature_descriptors_ [nqp][dim]
+  const float* td;
+  int nqp, ntp, dim, cap_pm;   // cap_pm = nqp: upper bound of the point match count
+  size_t pm_off;     // offset of this pair's point-match-sized slices
+  size_t knn_off;    // offset of this pair's per-query-row nearest-neighbour records
+};
+struct LslHybScratch {
+  double* pmd;       // [PM][22]  gathered per-point-match data (k_hybrid.cu:PMD_STRIDE)
+  double* pd2;       // [PM]      errorFunction2 values of the last scoring pass
+  int32_t* psel;     // [PM][3]   RANSAC / refined / trial point inlier index lists
+  double* plm;       // [PM][160] LM blocks of the point landmarks (k_hybrid.cu:PLM_STRIDE)
+  int32_t* pokf;     // [PM]
+  uint8_t* ptidx;    // [pairs][max_iter][2] rand()%nPt draws of getTransform_Lns_Pts_pcl
+  int32_t* rng;      // [pairs][33] glibc rand() state after featureMatching
+  int32_t* n_pinl;   // [pairs]
+  int32_t* n_prinl;  // [pairs]
+};
+struct LslHybWork {
+  LslPairPts* d_ppairs;
+  void* knn;            // [sum nqp] {float d1, d2; int i1}
+  lsl_match* pmatches;  // [PM]
+  int32_t* npmatch;     // [pairs]
+  LslHybScratch hs;
+  size_t cap_pairs, cap_pm, cap_knn;
+  int max_iter;
+  std::vector<LslPairPts> h_ppairs;
+  std::vector<int32_t> h_npmatch, h_npinl, h_nprinl;
+  bool last_hybrid;     // the last pair call ran the point + line path
+};
+
 // Kernel ids for the per-kernel device timers (CUDA events on the context stream)
 enum LslKernelId {
   LSL_K_GRAY = 0, LSL_K_XPASS, LSL_K_YPASS, LSL_K_LLANGLE, LSL_K_SEEDS, LSL_K_SOBEL, LSL_K_REGION, LSL_K_RANSAC3D,
-  LSL_K_MSLD, LSL_K_RANDFILL, LSL_K_MLE, LSL_K_GATHER, LSL_K_MATCH, LSL_K_POSE, LSL_K_COUNT
+  LSL_K_MSLD, LSL_K_RANDFILL, LSL_K_MLE, LSL_K_GATHER, LSL_K_MATCH, LSL_K_POSE, LSL_K_MATCHPTS, LSL_K_POSEHYB, LSL_K_COUNT
 };
 
 // Line records of all frames of one extract call live in ONE device allocation (stream-ordered pool);
@@ -123,6 +158,10 @@ struct lsl_frame {
   std::vector<double> segs;
   std::vector<int32_t> dbg_npts, dbg_inl, dbg_seg, dbg_lm;
   bool have_dbg;
+  // point features handed in by the caller (lsl_frame_set_points); device copies
+  int npoints, pdim;
+  float* d_xyz1;   // [npoints][4]
+  float* d_desc;   // [npoints][pdim]
 };
 
 struct lsl_ctx {
@@ -142,6 +181,8 @@ struct lsl_ctx {
   LslWork wk;
   void* wk_block; size_t wk_bytes;
   LslPairWork pw;
+  LslHybWork hw;
+  double cam_fx, cam_dt;     // focal length / asynch time used by the point-edge information (compPt3dCov)
   uint8_t* h_pin; size_t h_pin_bytes;   // pinned staging
   std::string err;
   lsl_stats stats;
@@ -169,3 +210,5 @@ int lsl_prepare_taps(lsl_ctx* ctx);
 int lsl_launch_gather(lsl_ctx* ctx, int n, lsl_line_rec* dst);
 int lsl_launch_match(lsl_ctx* ctx, int npairs);
 int lsl_launch_pose(lsl_ctx* ctx, int npairs);
+int lsl_launch_match_points(lsl_ctx* ctx, int npairs, int max_nq, int dim);
+int lsl_launch_pose_hybrid(lsl_ctx* ctx, int npairs, double fx, double dt);

@@ -713,7 +713,8 @@ void getTransform_PtsLines_ransac(const std::vector<Line>& train, const std::vec
   float refined_tf[16];
   memcpy(refined_tf, tf_best, sizeof(tf_best));
   refine_pose_hybrid(train, query, train_pts, query_pts, out.pt_ransac_inliers, out.ransac_inliers, refined_tf, 25, fx, asynch_dt, P);
-  double refined_rmse = sqrt(sum_squared_error / (double)(best_pt.size() + best_ln.size()));
+  // float / size_t -> float division, std::sqrt(float) (lineslam.h:35 `using namespace std`), motion.cpp:731
+  double refined_rmse = (double)sqrtf(sum_squared_error / (float)(best_pt.size() + best_ln.size()));
   std::vector<Match> refined_pt, refined_ln;
   for (int it = 0; it < 20; ++it) {
     ScoreH sc;

@@ -1,0 +1,121 @@
+"""GPU parity of the point + line pair stage through the C ABI.
+
+Tier-E: point-match index pairs and distances (Node::featureMatching), best RANSAC hypothesis, point and line
+inlier sets of the best hypothesis. Tier-T (north star 1e-5 rad / 1e-4 m): refined pose; the device follows the
+oracle's operation order, so the refined quantities are also compared bit for bit.
+"""
+import numpy as np
+import pytest
+
+from test_gpu_pair import _pose_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hyb(api, oracle):
+    from lineslam_b200 import synth
+    n = 3
+    imgs, deps, poses = synth.make_stream(n, scene_seed=2000, traj=synth.trajectory_orbit, stride=3)
+    K = synth.camera_K()
+    ctx = api.Context(max_batch=n, max_w=640, max_h=480, debug=True)
+    frames = ctx.extract_batch(imgs, deps, K, seeds=[1, 2, 3])
+    lines = [f.lines() for f in frames]
+    pts = [synth.make_points(2000, 3 * i, deps[i], *poses[i], K) for i in range(n)]
+    # a few features without depth (NaN z) as the reference keeps them (src/misc.cpp:716-722)
+    for x, d, _ in pts:
+        x[5::37, 2] = np.nan
+    for f, (x, d, _) in zip(frames, pts):
+        f.set_points(x, d)
+    yield ctx, frames, lines, pts, poses
+    ctx.close()
+
+
+def test_featureMatching(api, oracle, hyb):
+    ctx, frames, lines, pts, poses = hyb
+    for (q, t, seed) in [(1, 0, 1), (2, 1, 7), (0, 2, 3)]:
+        got = ctx.match_points(frames[q], frames[t], seed)
+        ref = oracle.featureMatching(pts[q][1], pts[t][1], ctx.params.nn_distance_ratio, seed)
+        assert len(ref) > 100
+        assert np.array_equal(got, ref), (q, t)
+    # ragged / degenerate: fewer than two train rows -> no matches (knnMatch k = 2)
+    one = ctx.frame_from_lines(lines[0][:0]).set_points(pts[0][0][:1], pts[0][1][:1])
+    assert len(ctx.match_points(frames[1], one, 1)) == 0
+    assert len(ctx.match_points(one, frames[1], 1)) == len(oracle.featureMatching(pts[0][1][:1], pts[1][1], 0.5, 1))
+
+
+def _check_hybrid(ctx, rec_g, inl_g, rinl_g, out):
+    rec_o = out["rec"]
+    assert rec_g["best_iter"] == rec_o["best_iter"]
+    assert np.array_equal(rinl_g, out["ln_ransac_inliers"])                  # Tier-E
+    assert np.array_equal(ctx.pair_matches(0, 5), out["pt_ransac_inliers"])  # Tier-E
+    assert _pose_close(rec_g["tf"], rec_o["tf"])                             # Tier-T
+    assert rec_g["found"] == rec_o["found"]
+    assert np.array_equal(inl_g, out["ln_inliers"])
+    assert np.array_equal(ctx.pair_matches(0, 4), out["pt_inliers"])
+    assert list(rec_g["pad"][:3]) == list(rec_o["pad"][:3])
+    assert rec_g["rmse"] == rec_o["rmse"]
+    assert np.array_equal(rec_g["tf"], rec_o["tf"])
+
+
+def test_pose_ransac_hybrid(api, oracle, hyb):
+    from lineslam_b200 import synth
+    ctx, frames, lines, pts, poses = hyb
+    for (q, t, seed) in [(1, 0, 1), (2, 1, 5), (2, 0, 9)]:
+        pm = oracle.featureMatching(pts[q][1], pts[t][1], 0.5, seed)
+        lm = oracle.lineMatching(lines[q], lines[t], True)
+        out = oracle.pose_ransac_hybrid(lines[t], lines[q], pts[t][0], pts[q][0], pm, lm, id_train=t, id_query=q, seed=seed,
+                                        skip_draws=len(pm))
+        rec_g, inl_g, rinl_g = ctx.pose_ransac(frames[t], frames[q], lm, id_train=t, id_query=q, seed=seed, pt_matches=pm)
+        assert out["rec"]["found"] == 1 and len(out["pt_inliers"]) > 50
+        _check_hybrid(ctx, rec_g, inl_g, rinl_g, out)
+        T = synth.relative_pose_q2t(*poses[q], *poses[t])
+        assert np.abs(rec_g["tf"].reshape(4, 4)[:3, 3] - T[:3, 3]).max() < 0.03
+    # points only (no line matches): every sample goes through the Kabsch solver
+    pm = oracle.featureMatching(pts[1][1], pts[0][1], 0.5, 2)
+    out = oracle.pose_ransac_hybrid(lines[0], lines[1], pts[0][0], pts[1][0], pm, lines[0][:0].view(np.uint8)[:0].view(pm.dtype),
+                                    seed=2, skip_draws=len(pm))
+    rec_g, inl_g, rinl_g = ctx.pose_ransac(frames[0], frames[1], None, seed=2, pt_matches=pm)
+    _check_hybrid(ctx, rec_g, inl_g, rinl_g, out)
+
+
+def test_matchNodePair_hybrid_batch(api, oracle, hyb):
+    ctx, frames, lines, pts, poses = hyb
+    qs, ts, seeds = [1, 2, 2], [0, 1, 0], [21, 22, 23]
+    recs = ctx.match_pair_batch([frames[q] for q in qs], [frames[t] for t in ts], qs, ts, seeds)
+    for k, (q, t) in enumerate(zip(qs, ts)):
+        pm = oracle.featureMatching(pts[q][1], pts[t][1], 0.5, seeds[k])
+        lm = oracle.lineMatching(lines[q], lines[t], True)
+        out = oracle.pose_ransac_hybrid(lines[t], lines[q], pts[t][0], pts[q][0], pm, lm, id_train=t, id_query=q,
+                                        seed=seeds[k], skip_draws=len(pm))
+        assert np.array_equal(ctx.pair_matches(k, 3), pm)
+        assert np.array_equal(ctx.pair_matches(k, 0), lm)
+        assert np.array_equal(ctx.pair_matches(k, 5), out["pt_ransac_inliers"])
+        assert np.array_equal(ctx.pair_matches(k, 2), out["ln_ransac_inliers"])
+        assert np.array_equal(ctx.pair_matches(k, 4), out["pt_inliers"])
+        assert np.array_equal(ctx.pair_matches(k, 1), out["ln_inliers"])
+        for name in ("found", "n_line_matches", "n_ransac_inliers", "n_inliers", "best_iter"):
+            assert recs[k][name] == out["rec"][name], (k, name)
+        assert _pose_close(recs[k]["tf"], out["rec"]["tf"])
+    n0 = api.Node(ctx, None, None, None, node_id=0, seed=1, frame=frames[0])
+    n1 = api.Node(ctx, None, None, None, node_id=1, seed=1, frame=frames[1])
+    mr = n1.matchNodePair(n0, seed=21)
+    assert mr.found and len(mr.inlier_matches) > 50 and len(mr.inlier_line_matches) > 10
+    assert np.array_equal(mr.final_trafo.ravel(), recs[0]["tf"])
+    w = len(mr.inlier_matches) + len(mr.inlier_line_matches)
+    assert np.isclose(mr.informationMatrix[0, 0], w / mr.rmse ** 2)
+
+
+def test_hybrid_kernel_without_point_matches_equals_line_kernel(api, oracle, hyb):
+    """Frames that carry points whose descriptors match nothing: the point + line kernel must reproduce the
+    line-only path exactly (same rand() stream, same refinement)."""
+    ctx, frames, lines, pts, poses = hyb
+    rng = np.random.default_rng(0)
+    junk = [ctx.frame_from_lines(lines[i]).set_points(pts[i][0][:40], np.abs(rng.normal(size=(40, 128))).astype(np.float32) + 5)
+            for i in range(2)]
+    recs = ctx.match_pair_batch([junk[1]], [junk[0]], [1], [0], [5])
+    assert len(ctx.pair_matches(0, 3)) == 0
+    lm = oracle.lineMatching(lines[1], lines[0], True)
+    rec_o, inl_o, rinl_o, _ = oracle.pose_ransac(lines[0], lines[1], lm, id_train=0, id_query=1, seed=5)
+    assert np.array_equal(ctx.pair_matches(0, 2), rinl_o) and np.array_equal(ctx.pair_matches(0, 1), inl_o)
+    assert np.array_equal(recs[0]["tf"], rec_o["tf"]) and recs[0]["rmse"] == rec_o["rmse"]
