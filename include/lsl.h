@@ -131,6 +131,15 @@ int lsl_pose_ransac(lsl_ctx* ctx, const lsl_frame* train, const lsl_frame* query
                     lsl_pose_rec* rec, lsl_match* inliers_out, int cap, int* n_inl,
                     lsl_match* ransac_inliers_out, int cap2, int* n_rinl);
 
+/* computeRelativeMotion_Ransac (src/line/utils.h, src/line/motion.cpp:367-526): line-only RANSAC on the matched
+ * line pairs (Euclidean consensus: pt2line3d_dist_relmotion, line3d_angle_relmotion) followed by
+ * optimizeRelmotion (motion.cpp:98-139: dlevmar_dif on quaternion + translation, 50 iterations) and consensus
+ * growing. R (row-major 3x3), t: x_train = R x_query + t. conset receives the indices into ln_matches.
+ * *have = 0 when no hypothesis has support (R, t untouched). */
+int lsl_relmotion_ransac(lsl_ctx* ctx, const lsl_frame* train, const lsl_frame* query, const lsl_match* ln_matches, int nln,
+                         uint32_t seed, double R[9], double t[3], int32_t* conset, int cap, int* n_conset, int* lm_calls,
+                         int* have);
+
 /* Node::matchNodePair (src/node.h:107, src/node.cpp:1494-1545) for npairs independent pairs, the
  * unit GraphManager::nodeComparisons maps over (src/graph_manager.cpp:555): featureMatching (when both frames
  * carry point features) + lineMatching + pose RANSAC + refinement on the device, one 128-byte record per pair back. */

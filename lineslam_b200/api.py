@@ -199,6 +199,15 @@ class Context:
                                      C.byref(n1), ptr(rinl), cap, C.byref(n2)), self._h)
         return rec[0].copy(), inl[:n1.value].copy(), rinl[:n2.value].copy()
 
+    def relmotion_ransac(self, train: "Frame", query: "Frame", ln_matches, seed=1):
+        """computeRelativeMotion_Ransac + optimizeRelmotion (src/line/motion.cpp:367-526) on the matched line pairs."""
+        m = np.ascontiguousarray(ln_matches, MATCH_DTYPE)
+        R = np.zeros(9); t = np.zeros(3); con = np.zeros(max(len(m), 1), np.int32)
+        n, calls, have = C.c_int(0), C.c_int(0), C.c_int(0)
+        _check(lib().lsl_relmotion_ransac(self._h, train._h, query._h, ptr(m) if len(m) else None, len(m), C.c_uint32(seed),
+                                          ptr(R), ptr(t), ptr(con), len(con), C.byref(n), C.byref(calls), C.byref(have)), self._h)
+        return dict(R=R.reshape(3, 3), t=t, conset=con[:n.value].copy(), lm_calls=calls.value, have=bool(have.value))
+
     def match_pair_batch(self, queries, trains, id_query, id_train, seeds):
         """Node::matchNodePair for a batch of independent pairs (graph_manager.cpp:555). Returns POSE_DTYPE[n]."""
         n = len(queries)

@@ -891,3 +891,448 @@ int lsl_launch_pose_hybrid(lsl_ctx* ctx, int npairs, double fx, double dt) {
   LSL_CUDA(cudaGetLastError());
   return LSL_OK;
 }
+
+// =====================================================================================================
+// computeRelativeMotion_Ransac (src/line/motion.cpp:367-526): line-only RANSAC with Euclidean consensus and the
+// levmar refinement optimizeRelmotion (motion.cpp:98-139; dlevmar_dif m = 7, cost motion.cpp:60-96).
+// One CTA per problem. The LM follows oracle/oracle_extract.cpp:dlevmar_dif_restated (pinned against the
+// reference's levmar build): residuals / Jacobian rows over the threads, ordered sums on dedicated threads,
+// the 7x7 Crout LU (Axb_core.c:1140-1277) and the 4-accumulator norm (misc_core.c:721-809) on thread 0.
+#define RM_THREADS 128
+
+
+__device__ __forceinline__ double dist3d_pt_line_d(const double* X, const double* A, const double* B) {  // utils.cpp:626-636
+  double AB[3] = {A[0] - B[0], A[1] - B[1], A[2] - B[2]};
+  double nab = sqrt(AB[0] * AB[0] + AB[1] * AB[1] + AB[2] * AB[2]);
+  if (nab < 1e-10) return -1;
+  double XA[3] = {X[0] - A[0], X[1] - A[1], X[2] - A[2]};
+  double ax = sqrt(XA[0] * XA[0] + XA[1] * XA[1] + XA[2] * XA[2]);
+  double inv = 1 / nab;
+  double nv[3] = {(B[0] - A[0]) * inv, (B[1] - A[1]) * inv, (B[2] - A[2]) * inv};
+  double d = XA[0] * nv[0] + XA[1] * nv[1] + XA[2] * nv[2];
+  return sqrt(fabs(ax * ax - d * d));
+}
+__device__ __forceinline__ bool rm_consistent(const double* g, const double* R, const double* t, double distThresh, double angThresh) {
+  const double PI_T = 3.14159265;
+  const double *aAp = g, *aBp = g + 3, *bAp = g + 6, *bBp = g + 9;
+  double aA[3], aB[3], RaAB[3];
+  double aAB[3] = {aAp[0] - aBp[0], aAp[1] - aBp[1], aAp[2] - aBp[2]};
+  double bAB[3] = {bAp[0] - bBp[0], bAp[1] - bBp[1], bAp[2] - bBp[2]};
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    aA[r] = ((R[r * 3] * aAp[0] + R[r * 3 + 1] * aAp[1]) + R[r * 3 + 2] * aAp[2]) + t[r];
+    aB[r] = ((R[r * 3] * aBp[0] + R[r * 3 + 1] * aBp[1]) + R[r * 3 + 2] * aBp[2]) + t[r];
+    RaAB[r] = (R[r * 3] * aAB[0] + R[r * 3 + 1] * aAB[1]) + R[r * 3 + 2] * aAB[2];
+  }
+  double dist = 0.5 * dist3d_pt_line_d(aA, bAp, bBp) + 0.5 * dist3d_pt_line_d(aB, bAp, bBp);
+  double dt = (RaAB[0] * bAB[0] + RaAB[1] * bAB[1]) + RaAB[2] * bAB[2];
+  double na = sqrt(aAB[0] * aAB[0] + aAB[1] * aAB[1] + aAB[2] * aAB[2]);
+  double nb = sqrt(bAB[0] * bAB[0] + bAB[1] * bAB[1] + bAB[2] * bAB[2]);
+  double angle = 180 * lsl_acos(fabs(dt / na / nb)) / PI_T;
+  return dist < distThresh && angle < angThresh;
+}
+// costFun_optimizeRelmotion for one pair (motion.cpp:60-96)
+__device__ double rm_cost_one(const double* g, const double* R, const double* t) {
+  const double *aAp = g, *aBp = g + 3, *bAp = g + 6, *bBp = g + 9;
+  double aA[3], aB[3], bA[3], bB[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    aA[r] = (R[r * 3] * aAp[0] + R[r * 3 + 1] * aAp[1] + R[r * 3 + 2] * aAp[2]) + t[r];
+    aB[r] = (R[r * 3] * aBp[0] + R[r * 3 + 1] * aBp[1] + R[r * 3 + 2] * aBp[2]) + t[r];
+  }
+  double dA[3] = {bAp[0] - t[0], bAp[1] - t[1], bAp[2] - t[2]}, dB[3] = {bBp[0] - t[0], bBp[1] - t[1], bBp[2] - t[2]};
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    bA[r] = R[r] * dA[0] + R[3 + r] * dA[1] + R[6 + r] * dA[2];
+    bB[r] = R[r] * dB[0] + R[3 + r] * dB[1] + R[6 + r] * dB[2];
+  }
+  return 0.25 * (mah_dist3d_pt_line(bAp, g + 30, aA, aB) + mah_dist3d_pt_line(bBp, g + 39, aA, aB) +
+                 mah_dist3d_pt_line(aAp, g + 12, bA, bB) + mah_dist3d_pt_line(aBp, g + 21, bA, bB));
+}
+__device__ void rm_cost(const double* g_all, const int32_t* sub, int n, const double* p, double* out) {
+  double R[9];
+  q2r(p, R);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = rm_cost_one(g_all + (size_t)sub[i] * RM_STRIDE, R, p + 4);
+}
+// LEVMAR_L2NRMXMY with x = 0 (misc_core.c:721-809), serial
+__device__ double rm_l2nrm(double* e, const double* y, int n) {
+  double sum0 = 0.0, sum1 = 0.0, sum2 = 0.0, sum3 = 0.0;
+  const int blockn = (n >> 3) << 3;
+#define EI(j) (e[j] = 0.0 - y[j], e[j] * e[j])
+  for (int i = blockn - 1; i > 0; i -= 8) {
+    sum0 += EI(i); sum1 += EI(i - 1); sum2 += EI(i - 2); sum3 += EI(i - 3);
+    sum0 += EI(i - 4); sum1 += EI(i - 5); sum2 += EI(i - 6); sum3 += EI(i - 7);
+  }
+  int i = blockn;
+  if (i < n) {
+    switch (n - i) {
+      case 7: sum0 += EI(i); ++i;
+      case 6: sum1 += EI(i); ++i;
+      case 5: sum2 += EI(i); ++i;
+      case 4: sum3 += EI(i); ++i;
+      case 3: sum0 += EI(i); ++i;
+      case 2: sum1 += EI(i); ++i;
+      case 1: sum2 += EI(i);
+    }
+  }
+#undef EI
+  return sum0 + sum1 + sum2 + sum3;
+}
+// AX_EQ_B_LU (Axb_core.c:1140-1277) for m = 7, serial; A is JtJ with mu already on the diagonal
+__device__ int rm_lu7(const double* A, const double* B, double* x) {
+  const int m = RM_M;
+  double a[RM_M * RM_M], work[RM_M];
+  int idx[RM_M];
+  int maxi = -1;
+  for (int i = 0; i < m * m; ++i) a[i] = A[i];
+  for (int i = 0; i < m; ++i) x[i] = B[i];
+  for (int i = 0; i < m; ++i) {
+    double max = 0.0, tmp;
+    for (int j = 0; j < m; ++j)
+      if ((tmp = fabs(a[i * m + j])) > max) max = tmp;
+    if (max == 0.0) return 0;
+    work[i] = 1.0 / max;
+  }
+  for (int j = 0; j < m; ++j) {
+    for (int i = 0; i < j; ++i) {
+      double sum = a[i * m + j];
+      for (int k = 0; k < i; ++k) sum -= a[i * m + k] * a[k * m + j];
+      a[i * m + j] = sum;
+    }
+    double max = 0.0, tmp;
+    for (int i = j; i < m; ++i) {
+      double sum = a[i * m + j];
+      for (int k = 0; k < j; ++k) sum -= a[i * m + k] * a[k * m + j];
+      a[i * m + j] = sum;
+      if ((tmp = work[i] * fabs(sum)) >= max) { max = tmp; maxi = i; }
+    }
+    if (j != maxi) {
+      for (int k = 0; k < m; ++k) { double t = a[maxi * m + k]; a[maxi * m + k] = a[j * m + k]; a[j * m + k] = t; }
+      work[maxi] = work[j];
+    }
+    idx[j] = maxi;
+    if (a[j * m + j] == 0.0) a[j * m + j] = DBL_EPSILON;
+    if (j != m - 1) {
+      double tmp2 = 1.0 / (a[j * m + j]);
+      for (int i = j + 1; i < m; ++i) a[i * m + j] *= tmp2;
+    }
+  }
+  int k = 0;
+  for (int i = 0; i < m; ++i) {
+    int j = idx[i];
+    double sum = x[j];
+    x[j] = x[i];
+    if (k != 0)
+      for (j = k - 1; j < i; ++j) sum -= a[i * m + j] * x[j];
+    else if (sum != 0.0) k = i + 1;
+    x[i] = sum;
+  }
+  for (int i = m - 1; i >= 0; --i) {
+    double sum = x[i];
+    for (int j = i + 1; j < m; ++j) sum -= a[i * m + j] * x[j];
+    x[i] = sum / a[i * m + i];
+  }
+  return 1;
+}
+
+struct RmLmShared {
+  double p[RM_M], pDp[RM_M], Dp[RM_M], jacTe[RM_M], diag[RM_M], JtJ[RM_M * RM_M], ptmp[RM_M];
+  double p_eL2, pDp_eL2, Dp_L2, fd;
+  int issolved;
+};
+// optimizeRelmotion: dlevmar_dif(m = 7, n, itmax 50, opts {1e-3, 1e-10, 1e-20, 1e-20, 1e-6}) on the subset `sub`;
+// R, t (shared memory) in / out. Whole CTA.
+__device__ void rm_optimize(const double* g_all, const int32_t* sub, int n, double* R, double* t, double* hx, double* wrk, double* e,
+                            double* wrk2, double* jac, RmLmShared& S) {
+  const int tid = threadIdx.x, m = RM_M;
+  if (tid == 0) {  // r2q (utils.cpp:1696-1707)
+    double tr = R[0] + R[4] + R[8];
+    double r = sqrt(1 + tr);
+    double s = 0.5 / r;
+    S.p[0] = 0.5 * r; S.p[1] = (R[7] - R[5]) * s; S.p[2] = (R[2] - R[6]) * s; S.p[3] = (R[3] - R[1]) * s;
+    S.p[4] = t[0]; S.p[5] = t[1]; S.p[6] = t[2];
+  }
+  __syncthreads();
+  const double tau = 1E-03, eps1 = 1E-10, eps2 = 1E-20, eps2_sq = 1E-20 * 1E-20, eps3 = 1E-20, delta = 1E-06;
+  const int itmax = 50;
+  if (n >= m) {
+    double mu = 0, jacTe_inf = 0, p_L2 = 0, tmp, p_eL2, dF, dL;
+    int nu = 20, nu2, stop = 0, K = 10, updjac = 0, updp = 1, newjac = 0, k;
+    rm_cost(g_all, sub, n, S.p, hx);
+    __syncthreads();
+    if (tid == 0) S.p_eL2 = rm_l2nrm(e, hx, n);
+    __syncthreads();
+    p_eL2 = S.p_eL2;
+    if (!isfinite(p_eL2)) stop = 7;
+    for (k = 0; k < itmax && !stop; ++k) {
+      if (p_eL2 <= eps3) { stop = 6; break; }
+      if ((updp && nu > 16) || updjac == K) {
+        for (int j = 0; j < m; ++j) {  // LEVMAR_FDIF_FORW_JAC_APPROX (misc_core.c:137-172)
+          if (tid == 0) {
+            double d = 1E-04 * S.p[j];
+            d = fabs(d);
+            if (d < delta) d = delta;
+            for (int c = 0; c < m; ++c) S.ptmp[c] = S.p[c];
+            S.ptmp[j] = S.p[j] + d;
+            S.fd = 1.0 / d;
+          }
+          __syncthreads();
+          rm_cost(g_all, sub, n, S.ptmp, wrk);
+          __syncthreads();
+          const double dinv = S.fd;
+          for (int i = tid; i < n; i += blockDim.x) jac[(size_t)i * m + j] = (wrk[i] - hx[i]) * dinv;
+          __syncthreads();
+        }
+        nu = 2; updjac = 0; updp = 0; newjac = 1;
+      }
+      if (newjac) {
+        newjac = 0;
+        // J^T J (lower triangle) and J^T e, accumulated for l = n-1 .. 0 (lm_core.c:618-639): one accumulator per thread
+        if (tid < 35) {
+          double acc = 0.0;
+          if (tid < 28) {
+            int i = 0, r = tid;
+            while (r > i) { r -= i + 1; ++i; }  // tid -> (i, j = r), j <= i
+            for (int l = n - 1; l >= 0; --l) acc += jac[(size_t)l * m + r] * jac[(size_t)l * m + i];
+            S.JtJ[i * m + r] = acc; S.JtJ[r * m + i] = acc;
+          } else {
+            const int i = tid - 28;
+            for (int l = n - 1; l >= 0; --l) acc += jac[(size_t)l * m + i] * e[l];
+            S.jacTe[i] = acc;
+          }
+        }
+        __syncthreads();
+        p_L2 = jacTe_inf = 0.0;
+        for (int i = 0; i < m; ++i) {
+          if (jacTe_inf < (tmp = fabs(S.jacTe[i]))) jacTe_inf = tmp;
+          p_L2 += S.p[i] * S.p[i];
+        }
+        if (tid < m) S.diag[tid] = S.JtJ[tid * m + tid];
+        __syncthreads();
+      }
+      if (jacTe_inf <= eps1) { stop = 1; break; }
+      if (k == 0) {
+        tmp = DBL_MIN;
+        for (int i = 0; i < m; ++i)
+          if (S.diag[i] > tmp) tmp = S.diag[i];
+        mu = tau * tmp;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        for (int i = 0; i < m; ++i) S.JtJ[i * m + i] += mu;
+        S.issolved = rm_lu7(S.JtJ, S.jacTe, S.Dp);
+        if (S.issolved) {
+          double d2 = 0.0;
+          for (int i = 0; i < m; ++i) { double v = S.Dp[i]; S.pDp[i] = S.p[i] + v; d2 += v * v; }
+          S.Dp_L2 = d2;
+        }
+      }
+      __syncthreads();
+      if (S.issolved) {
+        const double Dp_L2 = S.Dp_L2;
+        if (Dp_L2 <= eps2_sq * p_L2) { stop = 2; break; }
+        if (Dp_L2 >= (p_L2 + eps2) / (1E-12 * 1E-12)) { stop = 4; break; }
+        rm_cost(g_all, sub, n, S.pDp, wrk);
+        __syncthreads();
+        if (tid == 0) S.pDp_eL2 = rm_l2nrm(wrk2, wrk, n);
+        __syncthreads();
+        const double pDp_eL2 = S.pDp_eL2;
+        if (!isfinite(pDp_eL2)) { stop = 7; break; }
+        dF = p_eL2 - pDp_eL2;
+        if (updp || dF > 0) {  // Broyden rank-one update
+          for (int i = tid; i < n; i += blockDim.x) {
+            double tt = 0.0;
+            for (int l = 0; l < m; ++l) tt += jac[(size_t)i * m + l] * S.Dp[l];
+            tt = (wrk[i] - hx[i] - tt) / Dp_L2;
+            for (int j = 0; j < m; ++j) jac[(size_t)i * m + j] += tt * S.Dp[j];
+          }
+          ++updjac;
+          newjac = 1;
+        }
+        dL = 0.0;
+        for (int i = 0; i < m; ++i) dL += S.Dp[i] * (mu * S.Dp[i] + S.jacTe[i]);
+        if (dL > 0.0 && dF > 0.0) {
+          tmp = (2.0 * dF / dL - 1.0);
+          tmp = 1.0 - tmp * tmp * tmp;
+          mu = mu * ((tmp >= 0.3333333334) ? tmp : 0.3333333334);
+          nu = 2;
+          __syncthreads();
+          if (tid < m) S.p[tid] = S.pDp[tid];
+          for (int i = tid; i < n; i += blockDim.x) { e[i] = wrk2[i]; hx[i] = wrk[i]; }
+          p_eL2 = pDp_eL2;
+          updp = 1;
+          __syncthreads();
+          continue;
+        }
+      }
+      mu *= nu;
+      nu2 = nu << 1;
+      if (nu2 <= nu) { stop = 5; break; }
+      nu = nu2;
+      __syncthreads();
+      if (tid < m) S.JtJ[tid * m + tid] = S.diag[tid];
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    q2r(S.p, R);
+    t[0] = S.p[4]; t[1] = S.p[5]; t[2] = S.p[6];
+  }
+  __syncthreads();
+}
+
+// flags -> ordered index list (thread 0), returns the count
+__device__ int rm_compact(const int32_t* flag, int n, int32_t* out, int* s_cnt) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int c = 0;
+    for (int i = 0; i < n; ++i) if (flag[i]) out[c++] = i;
+    *s_cnt = c;
+  }
+  __syncthreads();
+  int c = *s_cnt;
+  __syncthreads();
+  return c;
+}
+
+__global__ void __launch_bounds__(RM_THREADS) relmotion_kernel(const LslPairDesc* __restrict__ pairs, const lsl_match* __restrict__ matches_all,
+                                                               const int32_t* __restrict__ nmatch, RmScratch rs, double distThresh,
+                                                               double angThresh, double cosDeg, int maxIters) {
+  __shared__ RmLmShared S;
+  __shared__ double s_R[9], s_t[3], s_Ro[9], s_to[3];
+  __shared__ int s_cnt, s_best;
+  __shared__ GRand s_rng;
+  __shared__ uint16_t s_idx[LSL_MAX_MATCH];
+  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = RM_THREADS / 32;
+  const LslPairDesc pd = pairs[pair];
+  const int n = min(nmatch[pair], pd.cap_m);
+  const lsl_match* ms = matches_all + pd.m_off;
+  double* g_all = rs.g + pd.m_off * RM_STRIDE;
+  double* hx = rs.hx + pd.m_off * 4;
+  double* wrk = hx + pd.cap_m; double* e = wrk + pd.cap_m; double* wrk2 = e + pd.cap_m;
+  double* jac = rs.jac + pd.m_off * RM_M;
+  int32_t* flag = rs.flag + pd.m_off;
+  int32_t* cur = rs.cur + pd.m_off * 2;
+  int32_t* trial = cur + pd.cap_m;
+  double* hyp = rs.hyp + (size_t)pair * rs.max_iter * 12;
+  int32_t* cnts = rs.cnts + (size_t)pair * rs.max_iter;
+  uint16_t* trip = rs.trip + (size_t)pair * rs.max_iter * 3;
+  double* outRt = rs.outRt + (size_t)pair * 12;
+  int32_t* outn = rs.outn + (size_t)pair * 4;
+  if (tid == 0) { outn[0] = 0; outn[1] = 0; outn[2] = 0; outn[3] = 0; }
+  if (n < 3) return;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const lsl_line_rec& a = pd.q[ms[i].queryIdx];
+    const lsl_line_rec& b = pd.t[ms[i].trainIdx];
+    double* g = g_all + (size_t)i * RM_STRIDE;
+    for (int k = 0; k < 3; ++k) { g[k] = a.A[k]; g[3 + k] = a.B[k]; g[6 + k] = b.A[k]; g[9 + k] = b.B[k]; }
+    for (int k = 0; k < 9; ++k) { g[12 + k] = a.DU_A[k]; g[21 + k] = a.DU_B[k]; g[30 + k] = b.DU_A[k]; g[39 + k] = b.DU_B[k]; }
+    double l[3] = {a.B[0] - a.A[0], a.B[1] - a.A[1], a.B[2] - a.A[2]};
+    double inv = 1 / sqrt(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]);
+    for (int k = 0; k < 3; ++k) g[48 + k] = l[k] * inv;
+  }
+  if (tid == 0) {
+    grand_seed(&s_rng, pd.seed);
+    for (int i = 0; i < n; ++i) s_idx[i] = (uint16_t)i;
+    for (int it = 0; it < maxIters; ++it) {
+      int left = n;
+      for (int k = 0; k < 3; ++k) {
+        int r = grand_next(&s_rng) % left;
+        uint16_t t = s_idx[k]; s_idx[k] = s_idx[k + r]; s_idx[k + r] = t;
+        --left;
+      }
+      trip[3 * it] = s_idx[0]; trip[3 * it + 1] = s_idx[1]; trip[3 * it + 2] = s_idx[2];
+    }
+  }
+  __syncthreads();
+  for (int h = tid; h < maxIters; h += blockDim.x) {
+    const double* g3[3] = {g_all + (size_t)trip[3 * h] * RM_STRIDE, g_all + (size_t)trip[3 * h + 1] * RM_STRIDE,
+                           g_all + (size_t)trip[3 * h + 2] * RM_STRIDE};
+    bool degenerate = true;
+    for (int i = 0; i < 3 && degenerate; ++i)
+      for (int j = i + 1; j < 3; ++j) {
+        const double* ui = g3[i] + 48; const double* uj = g3[j] + 48;
+        if (fabs(ui[0] * uj[0] + ui[1] * uj[1] + ui[2] * uj[2]) < cosDeg) { degenerate = false; break; }
+      }
+    if (degenerate) { cnts[h] = -1; continue; }
+    double R[9], t[3];
+    relmotion_svd3(g3, R, t);     // md layout qA qB tA tB == g[0..11]
+    double* o = hyp + (size_t)h * 12;
+    for (int k = 0; k < 9; ++k) o[k] = R[k];
+    for (int k = 0; k < 3; ++k) o[9 + k] = t[k];
+    cnts[h] = 0;
+  }
+  __syncthreads();
+  for (int h = warp; h < maxIters; h += nwarp) {
+    if (cnts[h] < 0) continue;
+    double Rt[12];
+    for (int k = 0; k < 12; ++k) Rt[k] = hyp[(size_t)h * 12 + k];
+    int c = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      int i = i0 + lane;
+      bool in = i < n && rm_consistent(g_all + (size_t)i * RM_STRIDE, Rt, Rt + 9, distThresh, angThresh);
+      c += __popc(__ballot_sync(FULL, in));
+    }
+    __syncwarp();
+    if (lane == 0) cnts[h] = c;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int best = 0, bh = 1 << 30;
+    for (int h = lane; h < maxIters; h += 32) { int c = cnts[h]; if (c > best) { best = c; bh = h; } }
+    for (int o = 16; o; o >>= 1) {
+      int b2 = __shfl_xor_sync(FULL, best, o), h2 = __shfl_xor_sync(FULL, bh, o);
+      if (b2 > best || (b2 == best && h2 < bh)) { best = b2; bh = h2; }
+    }
+    if (lane == 0) s_best = best > 0 ? bh : -1;
+  }
+  __syncthreads();
+  const int bh = s_best;
+  if (bh < 0) return;   // maxConSet.size() < 1
+  if (tid < 9) s_Ro[tid] = hyp[(size_t)bh * 12 + tid];
+  if (tid < 3) s_to[tid] = hyp[(size_t)bh * 12 + 9 + tid];
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) flag[i] = rm_consistent(g_all + (size_t)i * RM_STRIDE, s_Ro, s_to, distThresh, angThresh);
+  int ncur = rm_compact(flag, n, cur, &s_cnt);
+  int lm_calls = 0, nout = ncur;
+  if (ncur >= 4) {
+    if (tid < 9) s_R[tid] = s_Ro[tid];
+    if (tid < 3) s_t[tid] = s_to[tid];
+    __syncthreads();
+    rm_optimize(g_all, cur, ncur, s_R, s_t, hx, wrk, e, wrk2, jac, S); lm_calls++;
+    if (tid < 9) s_Ro[tid] = s_R[tid];      // Ro, to = first optimisation result; R = Ro, t = to
+    if (tid < 3) s_to[tid] = s_t[tid];
+    __syncthreads();
+    int nprev = 0;
+    while (true) {
+      for (int i = tid; i < n; i += blockDim.x) flag[i] = rm_consistent(g_all + (size_t)i * RM_STRIDE, s_R, s_t, distThresh, angThresh);
+      int nc = rm_compact(flag, n, trial, &s_cnt);
+      if (nc <= nprev) break;
+      nprev = nc;
+      for (int i = tid; i < nc; i += blockDim.x) cur[i] = trial[i];
+      if (tid < 9) s_Ro[tid] = s_R[tid];
+      if (tid < 3) s_to[tid] = s_t[tid];
+      __syncthreads();
+      rm_optimize(g_all, cur, nc, s_R, s_t, hx, wrk, e, wrk2, jac, S); lm_calls++;
+    }
+    nout = nprev;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int k = 0; k < 9; ++k) outRt[k] = s_Ro[k];
+    for (int k = 0; k < 3; ++k) outRt[9 + k] = s_to[k];
+    outn[0] = nout; outn[1] = lm_calls; outn[2] = 1;
+  }
+}
+
+int lsl_launch_relmotion(lsl_ctx* ctx, int npairs, RmScratch rs) {
+  const lsl_params& P = ctx->P;
+  const double PI_T = 3.14159265;
+  LSL_KSTART(ctx, LSL_K_RELMOTION);
+  relmotion_kernel<<<npairs, RM_THREADS, 0, ctx->stream>>>(ctx->pw.d_pairs, ctx->pw.matches, ctx->pw.nmatch, rs, P.pt2line3d_dist_relmotion,
+                                                          P.line3d_angle_relmotion, lsl_cos(5 * PI_T / 180), P.ransac_iters_line_motion);
+  LSL_KSTOP(ctx, LSL_K_RELMOTION);
+  LSL_CUDA(cudaGetLastError());
+  return LSL_OK;
+}

@@ -27,7 +27,7 @@ extern "C" const char* lsl_last_error(const lsl_ctx* ctx) { return ctx ? ctx->er
 static const char* const kKernelNames[LSL_K_COUNT] = {
     "gray_kernel", "xpass_kernel", "ypass_kernel", "ll_angle_kernel", "seed_list_kernel", "sobel5_kernel",
     "lsd_region_kernel", "line3d_ransac_kernel", "line_msld_kernel", "msld_randfill_kernel", "line_mle_kernel",
-    "gather_lines_kernel", "match_lines_kernel", "pose_kernel", "match_points_kernel", "pose_hybrid_kernel"};
+    "gather_lines_kernel", "match_lines_kernel", "pose_kernel", "match_points_kernel", "pose_hybrid_kernel", "relmotion_kernel"};
 extern "C" const char* lsl_kernel_name(int i) { return (i >= 0 && i < LSL_K_COUNT) ? kKernelNames[i] : ""; }
 
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -696,6 +696,63 @@ extern "C" int lsl_pose_ransac(lsl_ctx* ctx, const lsl_frame* train, const lsl_f
   if (inliers_out) { if (ni > cap) return LSL_ERR_CAPACITY; if ((rc = fetch_sel(ctx, ctx->pw.h_pairs[0], 1, ni, all, inliers_out))) return rc; }
   if (ransac_inliers_out) { if (nr > cap2) return LSL_ERR_CAPACITY; if ((rc = fetch_sel(ctx, ctx->pw.h_pairs[0], 0, nr, all, ransac_inliers_out))) return rc; }
   return LSL_OK;
+}
+
+// computeRelativeMotion_Ransac (src/line/motion.cpp:367-526) + optimizeRelmotion (motion.cpp:98-139) on the
+// matched line pairs of two frames: a = query lines, b = train lines, x_b = R x_a + t.
+extern "C" int lsl_relmotion_ransac(lsl_ctx* ctx, const lsl_frame* train, const lsl_frame* query, const lsl_match* ln_matches,
+                                    int nln, uint32_t seed, double R[9], double t[3], int32_t* conset, int cap, int* n_conset,
+                                    int* lm_calls, int* have) {
+  if (!ctx || !train || !query || nln < 0 || (nln && !ln_matches) || !R || !t || !n_conset) return LSL_ERR_ARG;
+  if (nln > LSL_MAX_MATCH) return LSL_ERR_CAPACITY;
+  for (int i = 0; i < nln; ++i)
+    if (ln_matches[i].queryIdx < 0 || ln_matches[i].queryIdx >= query->nlines || ln_matches[i].trainIdx < 0 ||
+        ln_matches[i].trainIdx >= train->nlines) return LSL_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int idq = 1, idt = 0;
+  int rc = setup_pairs(ctx, 1, &query, &train, &idq, &idt, &seed, nullptr, nln);
+  if (rc) return rc;
+  int32_t nm = nln;
+  cudaStream_t st = ctx->stream;
+  LSL_CUDA(cudaMemcpyAsync(ctx->pw.nmatch, &nm, 4, cudaMemcpyHostToDevice, st));
+  if (nln) LSL_CUDA(cudaMemcpyAsync(ctx->pw.matches, ln_matches, sizeof(lsl_match) * nln, cudaMemcpyHostToDevice, st));
+  const size_t M = nln > 0 ? nln : 1, it = ctx->P.ransac_iters_line_motion;
+  const size_t bytes = align_up(M * RM_STRIDE * 8) + align_up(M * 4 * 8) + align_up(M * RM_M * 8) + align_up(M * 4) + align_up(M * 2 * 4) +
+                       align_up(it * 12 * 8) + align_up(it * 4) + align_up(it * 3 * 2) + align_up(12 * 8) + align_up(16);
+  uint8_t* blk = nullptr;
+  LSL_CUDA(cudaMallocAsync((void**)&blk, bytes, st));
+  RmScratch rs;
+  size_t off = 0;
+  rs.g = (double*)(blk + off); off += align_up(M * RM_STRIDE * 8);
+  rs.hx = (double*)(blk + off); off += align_up(M * 4 * 8);
+  rs.jac = (double*)(blk + off); off += align_up(M * RM_M * 8);
+  rs.flag = (int32_t*)(blk + off); off += align_up(M * 4);
+  rs.cur = (int32_t*)(blk + off); off += align_up(M * 2 * 4);
+  rs.hyp = (double*)(blk + off); off += align_up(it * 12 * 8);
+  rs.cnts = (int32_t*)(blk + off); off += align_up(it * 4);
+  rs.trip = (uint16_t*)(blk + off); off += align_up(it * 3 * 2);
+  rs.outRt = (double*)(blk + off); off += align_up(12 * 8);
+  rs.outn = (int32_t*)(blk + off);
+  rs.max_iter = (int)it;
+  clear_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
+  if ((rc = lsl_launch_relmotion(ctx, 1, rs))) { cudaFreeAsync(blk, st); return rc; }
+  double Rt[12];
+  int32_t on[4];
+  LSL_CUDA(cudaMemcpyAsync(Rt, rs.outRt, sizeof(Rt), cudaMemcpyDeviceToHost, st));
+  LSL_CUDA(cudaMemcpyAsync(on, rs.outn, sizeof(on), cudaMemcpyDeviceToHost, st));
+  LSL_CUDA(cudaStreamSynchronize(st));
+  collect_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
+  *n_conset = on[0];
+  if (lm_calls) *lm_calls = on[1];
+  if (have) *have = on[2];
+  if (on[2]) { memcpy(R, Rt, 72); memcpy(t, Rt + 9, 24); }
+  int rcap = LSL_OK;
+  if (on[0] > cap || (on[0] && !conset)) rcap = LSL_ERR_CAPACITY;
+  else if (on[0]) LSL_CUDA(cudaMemcpyAsync(conset, rs.cur, 4 * on[0], cudaMemcpyDeviceToHost, st));
+  LSL_CUDA(cudaFreeAsync(blk, st));
+  LSL_CUDA(cudaStreamSynchronize(st));
+  ctx->stats.pairs += 1; ctx->stats.d2h_bytes += sizeof(Rt) + sizeof(on) + 4 * (size_t)on[0];
+  return rcap;
 }
 
 extern "C" int lsl_match_pair_batch(lsl_ctx* ctx, int npairs, const lsl_frame* const* queries, const lsl_frame* const* trains,

@@ -134,10 +134,27 @@ struct LslHybWork {
   bool last_hybrid;     // the last pair call ran the point + line path
 };
 
+// ---- computeRelativeMotion_Ransac scratch (k_hybrid.cu:relmotion_kernel), allocated per call ----
+#define RM_STRIDE 52   // aA aB bA bB (12) | a.DU_A a.DU_B b.DU_A b.DU_B (36) | a.u (3) | pad
+#define RM_M 7
+struct RmScratch {
+  double* g;       // [M][52] gathered pairs
+  double* hx;      // [M] x 4: hx, wrk, e, wrk2
+  double* jac;     // [M][7]
+  int32_t* flag;   // [M]
+  int32_t* cur;    // [M] x 2: current subset / trial consensus
+  double* hyp;     // [pairs][max_iter][12] R (9), t (3)
+  int32_t* cnts;   // [pairs][max_iter]
+  uint16_t* trip;  // [pairs][max_iter][3]
+  double* outRt;   // [pairs][12]
+  int32_t* outn;   // [pairs][4]: consensus size, LM calls, have, pad
+  int max_iter;
+};
+
 // Kernel ids for the per-kernel device timers (CUDA events on the context stream)
 enum LslKernelId {
   LSL_K_GRAY = 0, LSL_K_XPASS, LSL_K_YPASS, LSL_K_LLANGLE, LSL_K_SEEDS, LSL_K_SOBEL, LSL_K_REGION, LSL_K_RANSAC3D,
-  LSL_K_MSLD, LSL_K_RANDFILL, LSL_K_MLE, LSL_K_GATHER, LSL_K_MATCH, LSL_K_POSE, LSL_K_MATCHPTS, LSL_K_POSEHYB, LSL_K_COUNT
+  LSL_K_MSLD, LSL_K_RANDFILL, LSL_K_MLE, LSL_K_GATHER, LSL_K_MATCH, LSL_K_POSE, LSL_K_MATCHPTS, LSL_K_POSEHYB, LSL_K_RELMOTION, LSL_K_COUNT
 };
 
 // Line records of all frames of one extract call live in ONE device allocation (stream-ordered pool);
@@ -212,3 +229,4 @@ int lsl_launch_match(lsl_ctx* ctx, int npairs);
 int lsl_launch_pose(lsl_ctx* ctx, int npairs);
 int lsl_launch_match_points(lsl_ctx* ctx, int npairs, int max_nq, int dim);
 int lsl_launch_pose_hybrid(lsl_ctx* ctx, int npairs, double fx, double dt);
+int lsl_launch_relmotion(lsl_ctx* ctx, int npairs, RmScratch rs);

@@ -342,6 +342,9 @@ LSL_HD double lsl_atan2(double y, double x) {
   double corr = num.h / den.h;
   return two_sum(z0, corr).h;
 }
+// acos for |x| <= 1 through the correctly rounded atan2 (sqrt is IEEE): used only for angle thresholds
+// (src/line/motion.cpp:452). |x| > 1 (rounding) gives NaN like libm.
+LSL_HD double lsl_acos(double x) { return lsl_atan2(sqrt((1.0 - x) * (1.0 + x)), x); }
 LSL_HD double lsl_atan(double x) { return lsl_atan2(x, 1.0); }
 
 // ----------------------------------------------------------- pow / sinh ----

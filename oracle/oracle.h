@@ -132,6 +132,14 @@ void refine_pose_hybrid(const std::vector<Line>& train, const std::vector<Line>&
                         const Points& query_pts, const std::vector<Match>& pt_ms, const std::vector<Match>& ln_ms,
                         float tf[16], int iterations, double fx, double asynch_dt, const Params& P);
 
+// computeRelativeMotion_Ransac (src/line/motion.cpp:367-526): line-only RANSAC on paired 3D lines (a[i] <-> b[i],
+// x_b = R x_a + t) with Euclidean consensus, then optimizeRelmotion (motion.cpp:98-139: dlevmar_dif, m = 7
+// quaternion + translation, cost motion.cpp:60-96) and consensus growing. Returns the consensus index set.
+struct RelMotion { double R[9], t[3]; std::vector<int> conset; int lm_calls = 0; bool have = false; };
+void computeRelativeMotion_Ransac(const std::vector<Line>& a, const std::vector<Line>& b, uint32_t seed, const Params& P,
+                                  RelMotion& out);
+void optimizeRelmotion(const std::vector<Line>& a, const std::vector<Line>& b, double R[9], double t[3]);
+
 // sub-pieces exposed for unit tests
 void sobel5(const uint8_t* gray, int W, int H, std::vector<double>& gx, std::vector<double>& gy);
 int dlevmar_dif_restated(void (*func)(double*, double*, int, int, void*), double* p, double* x, int m,

@@ -212,6 +212,27 @@ void orc_kabsch(const float* from, const float* to, const float* w, int n, float
 }
 void orc_ldlt3_solve(const double* A, const double* b, double* x) { lslm::ldlt3_solve(A, b, x); }
 
+// computeRelativeMotion_Ransac (motion.cpp:367-526) on paired lines a[i] <-> b[i]; Rt = R (9) then t (3).
+int orc_relmotion_ransac(const lsl_line_rec* a, const lsl_line_rec* b, int n, uint32_t seed, const lsl_params* p,
+                         double* Rt, int32_t* conset, int* lm_calls, int* have) {
+  orc::Params P = toP(p);
+  std::vector<orc::Line> va(n), vb(n);
+  if (n) { memcpy(va.data(), a, sizeof(lsl_line_rec) * n); memcpy(vb.data(), b, sizeof(lsl_line_rec) * n); }
+  orc::RelMotion r;
+  orc::computeRelativeMotion_Ransac(va, vb, seed, P, r);
+  if (r.have) { memcpy(Rt, r.R, 72); memcpy(Rt + 9, r.t, 24); }
+  for (size_t i = 0; i < r.conset.size(); ++i) conset[i] = r.conset[i];
+  if (lm_calls) *lm_calls = r.lm_calls;
+  if (have) *have = r.have ? 1 : 0;
+  return (int)r.conset.size();
+}
+void orc_optimizeRelmotion(const lsl_line_rec* a, const lsl_line_rec* b, int n, double* Rt) {
+  std::vector<orc::Line> va(n), vb(n);
+  if (n) { memcpy(va.data(), a, sizeof(lsl_line_rec) * n); memcpy(vb.data(), b, sizeof(lsl_line_rec) * n); }
+  orc::optimizeRelmotion(va, vb, Rt, Rt + 9);
+}
+double orc_m_acos(double x) { return lslm::lsl_acos(x); }
+
 // levmar restatement probe: Rosenbrock-like known-answer problems are driven from tests through this.
 typedef void (*orc_lm_fn)(double*, double*, int, int, void*);
 int orc_dlevmar_dif(orc_lm_fn f, double* p, double* x, int m, int n, int itmax, const double* opts, double* info) {

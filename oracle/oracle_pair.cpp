@@ -742,4 +742,148 @@ void getTransform_Lines_ransac(const std::vector<Line>& train, const std::vector
   getTransform_PtsLines_ransac(train, query, none, none, id_train, id_query, std::vector<Match>(), all_ln, rng, 525.0, 0.0, P, out);
 }
 
+// ------------------------------------ line-only RANSAC + levmar refinement ----
+// dist3d_pt_line (utils.cpp:626-636)
+static double dist3d_pt_line(const double X[3], const double A[3], const double B[3]) {
+  double AB[3] = {A[0] - B[0], A[1] - B[1], A[2] - B[2]};
+  double nab = sqrt(AB[0] * AB[0] + AB[1] * AB[1] + AB[2] * AB[2]);
+  if (nab < 1e-10) return -1;
+  double XA[3] = {X[0] - A[0], X[1] - A[1], X[2] - A[2]};
+  double ax = sqrt(XA[0] * XA[0] + XA[1] * XA[1] + XA[2] * XA[2]);
+  double inv = 1 / nab;
+  double nv[3] = {(B[0] - A[0]) * inv, (B[1] - A[1]) * inv, (B[2] - A[2]) * inv};
+  double d = XA[0] * nv[0] + XA[1] * nv[1] + XA[2] * nv[2];
+  return sqrt(fabs(ax * ax - d * d));
+}
+// r2q (utils.cpp:1696-1707)
+static void r2q(const double R[9], double q[4]) {
+  double t = R[0] + R[4] + R[8];
+  double r = sqrt(1 + t);
+  double s = 0.5 / r;
+  q[0] = 0.5 * r; q[1] = (R[7] - R[5]) * s; q[2] = (R[2] - R[6]) * s; q[3] = (R[3] - R[1]) * s;
+}
+struct RelData { const std::vector<Line>* a; const std::vector<Line>* b; };
+// costFun_optimizeRelmotion (motion.cpp:60-96), OPT_USE_MAHDIST: cv::Mat products R*x + t and R^T*(x - t)
+static void relmotion_cost(double* p, double* error, int, int, void* adata) {
+  const RelData* d = (const RelData*)adata;
+  double R[9];
+  q2r(p, R);
+  const double* t = p + 4;
+  for (size_t i = 0; i < d->a->size(); ++i) {
+    const Line& a = (*d->a)[i];
+    const Line& b = (*d->b)[i];
+    double aA[3], aB[3], bA[3], bB[3];
+    for (int r = 0; r < 3; ++r) {
+      aA[r] = (R[r * 3] * a.A[0] + R[r * 3 + 1] * a.A[1] + R[r * 3 + 2] * a.A[2]) + t[r];
+      aB[r] = (R[r * 3] * a.B[0] + R[r * 3 + 1] * a.B[1] + R[r * 3 + 2] * a.B[2]) + t[r];
+    }
+    double dA[3] = {b.A[0] - t[0], b.A[1] - t[1], b.A[2] - t[2]}, dB[3] = {b.B[0] - t[0], b.B[1] - t[1], b.B[2] - t[2]};
+    for (int r = 0; r < 3; ++r) {
+      bA[r] = R[r] * dA[0] + R[3 + r] * dA[1] + R[6 + r] * dA[2];
+      bB[r] = R[r] * dB[0] + R[3 + r] * dB[1] + R[6 + r] * dB[2];
+    }
+    error[i] = 0.25 * (mah_dist3d_pt_line(b.A, b.DU_A, aA, aB) + mah_dist3d_pt_line(b.B, b.DU_B, aA, aB) +
+                       mah_dist3d_pt_line(a.A, a.DU_A, bA, bB) + mah_dist3d_pt_line(a.B, a.DU_B, bA, bB));
+  }
+}
+void optimizeRelmotion(const std::vector<Line>& a, const std::vector<Line>& b, double R[9], double t[3]) {
+  double q[4];
+  r2q(R, q);
+  double opts[5] = {1E-03, 1E-10, 1E-20, 1E-20, 1E-06}, info[10];
+  double para[7] = {q[0], q[1], q[2], q[3], t[0], t[1], t[2]};
+  std::vector<double> meas(a.size(), 0.0);
+  RelData data{&a, &b};
+  dlevmar_dif_restated(relmotion_cost, para, meas.data(), 7, (int)a.size(), 50, opts, info, &data);
+  q2r(para, R);
+  t[0] = para[4]; t[1] = para[5]; t[2] = para[6];
+}
+static void relmotion_consensus(const std::vector<Line>& a, const std::vector<Line>& b, const double R[9], const double t[3],
+                                double distThresh, double angThresh, std::vector<int>& inl) {
+  const double PI_T = 3.14159265;
+  inl.clear();
+  for (size_t i = 0; i < a.size(); ++i) {
+    double aA[3], aB[3], RaAB[3];
+    double aAB[3] = {a[i].A[0] - a[i].B[0], a[i].A[1] - a[i].B[1], a[i].A[2] - a[i].B[2]};
+    double bAB[3] = {b[i].A[0] - b[i].B[0], b[i].A[1] - b[i].B[1], b[i].A[2] - b[i].B[2]};
+    for (int r = 0; r < 3; ++r) {  // Eigen Matrix3d * Vector3d + Vector3d
+      aA[r] = ((R[r * 3] * a[i].A[0] + R[r * 3 + 1] * a[i].A[1]) + R[r * 3 + 2] * a[i].A[2]) + t[r];
+      aB[r] = ((R[r * 3] * a[i].B[0] + R[r * 3 + 1] * a[i].B[1]) + R[r * 3 + 2] * a[i].B[2]) + t[r];
+      RaAB[r] = (R[r * 3] * aAB[0] + R[r * 3 + 1] * aAB[1]) + R[r * 3 + 2] * aAB[2];
+    }
+    double dist = 0.5 * dist3d_pt_line(aA, b[i].A, b[i].B) + 0.5 * dist3d_pt_line(aB, b[i].A, b[i].B);
+    double dt = (RaAB[0] * bAB[0] + RaAB[1] * bAB[1]) + RaAB[2] * bAB[2];
+    double na = sqrt(aAB[0] * aAB[0] + aAB[1] * aAB[1] + aAB[2] * aAB[2]);
+    double nb = sqrt(bAB[0] * bAB[0] + bAB[1] * bAB[1] + bAB[2] * bAB[2]);
+    double angle = 180 * lsl_acos(fabs(dt / na / nb)) / PI_T;
+    if (dist < distThresh && angle < angThresh) inl.push_back((int)i);
+  }
+}
+void computeRelativeMotion_Ransac(const std::vector<Line>& a, const std::vector<Line>& b, uint32_t seed, const Params& P,
+                                  RelMotion& out) {
+  out = RelMotion();
+  const int n = (int)a.size();
+  if (n < 3 || (int)b.size() < 3) return;
+  const double PI_T = 3.14159265;
+  std::vector<double> au(3 * n);
+  for (int i = 0; i < n; ++i) {
+    double l[3] = {a[i].B[0] - a[i].A[0], a[i].B[1] - a[i].A[1], a[i].B[2] - a[i].A[2]};
+    double inv = 1 / sqrt(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]);
+    for (int k = 0; k < 3; ++k) au[3 * i + k] = l[k] * inv;
+  }
+  const int maxIters = P.ransac_iters_line_motion;
+  const double distThresh = P.pt2line3d_dist_relmotion, angThresh = P.line3d_angle_relmotion;
+  const double cosDeg = lsl_cos(5 * PI_T / 180);
+  std::vector<int> indexes(n);
+  for (int i = 0; i < n; ++i) indexes[i] = i;
+  GlibcRand rng; rng.seed(seed);
+  std::vector<int> maxConSet;
+  double bR[9], bt[3];
+  int iter = 0;
+  while (iter < maxIters) {
+    iter++;
+    int left = n;
+    for (int k = 0; k < 3; ++k) { int r = rng.next() % left; std::swap(indexes[k], indexes[k + r]); --left; }
+    bool degenerate = true;
+    for (int i = 0; i < 3 && degenerate; ++i)
+      for (int j = i + 1; j < 3; ++j) {
+        const double* ui = &au[3 * indexes[i]]; const double* uj = &au[3 * indexes[j]];
+        if (fabs(ui[0] * uj[0] + ui[1] * uj[1] + ui[2] * uj[2]) < cosDeg) { degenerate = false; break; }
+      }
+    if (degenerate) continue;
+    double qA[9], qB[9], tA[9], tB[9];
+    for (int k = 0; k < 3; ++k)
+      for (int c = 0; c < 3; ++c) {
+        qA[3 * k + c] = a[indexes[k]].A[c]; qB[3 * k + c] = a[indexes[k]].B[c];
+        tA[3 * k + c] = b[indexes[k]].A[c]; tB[3 * k + c] = b[indexes[k]].B[c];
+      }
+    double R[9], t[3];
+    relmotion_svd(qA, qB, tA, tB, 3, R, t);
+    std::vector<int> inlier;
+    relmotion_consensus(a, b, R, t, distThresh, angThresh, inlier);
+    if (inlier.size() > maxConSet.size()) { maxConSet = inlier; memcpy(bR, R, sizeof(bR)); memcpy(bt, t, sizeof(bt)); }
+    if (maxConSet.size() >= (size_t)n * 1) break;
+  }
+  out.conset = maxConSet;
+  if (maxConSet.size() < 1) return;
+  memcpy(out.R, bR, sizeof(bR)); memcpy(out.t, bt, sizeof(bt)); out.have = true;
+  if (maxConSet.size() < 4) return;
+  std::vector<Line> ina, inb;
+  for (int i : maxConSet) { ina.push_back(a[i]); inb.push_back(b[i]); }
+  optimizeRelmotion(ina, inb, out.R, out.t); out.lm_calls++;
+  double R[9], t[3];
+  memcpy(R, out.R, sizeof(R)); memcpy(t, out.t, sizeof(t));
+  std::vector<int> prevConSet;
+  while (1) {
+    std::vector<int> conset;
+    relmotion_consensus(a, b, R, t, distThresh, angThresh, conset);
+    if (conset.size() <= prevConSet.size()) break;
+    prevConSet = conset;
+    memcpy(out.R, R, sizeof(R)); memcpy(out.t, t, sizeof(t));
+    ina.clear(); inb.clear();
+    for (int i : prevConSet) { ina.push_back(a[i]); inb.push_back(b[i]); }
+    optimizeRelmotion(ina, inb, R, t); out.lm_calls++;
+  }
+  out.conset = prevConSet;
+}
+
 }  // namespace orc

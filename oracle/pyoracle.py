@@ -28,7 +28,7 @@ def lib():
     if _LIB is None:
         _LIB = C.CDLL(build())
         L = _LIB
-        for n in "exp log log10 sin cos sinh".split():
+        for n in "exp log log10 sin cos sinh acos".split():
             f = getattr(L, "orc_m_" + n); f.restype = C.c_double; f.argtypes = [C.c_double]
         for n in "atan2 pow".split():
             f = getattr(L, "orc_m_" + n); f.restype = C.c_double; f.argtypes = [C.c_double, C.c_double]
@@ -192,3 +192,20 @@ def ldlt3_solve(A, b):
     A = np.ascontiguousarray(A, np.float64); b = np.ascontiguousarray(b, np.float64); x = np.zeros(3)
     lib().orc_ldlt3_solve(ptr(A), ptr(b), ptr(x))
     return x
+
+
+def relmotion_ransac(a, b, seed=1, params=None):
+    """computeRelativeMotion_Ransac on paired line records a[i] <-> b[i] (x_b = R x_a + t)."""
+    p = params or default_params()
+    a = np.ascontiguousarray(a, LINE_DTYPE); b = np.ascontiguousarray(b, LINE_DTYPE)
+    Rt = np.zeros(12); con = np.zeros(max(len(a), 1), np.int32); calls = C.c_int(0); have = C.c_int(0)
+    n = lib().orc_relmotion_ransac(ptr(a), ptr(b), len(a), C.c_uint32(seed), C.byref(p), ptr(Rt), ptr(con), C.byref(calls),
+                                   C.byref(have))
+    return dict(R=Rt[:9].reshape(3, 3).copy(), t=Rt[9:].copy(), conset=con[:n].copy(), lm_calls=calls.value, have=bool(have.value))
+
+
+def optimizeRelmotion(a, b, R, t):
+    a = np.ascontiguousarray(a, LINE_DTYPE); b = np.ascontiguousarray(b, LINE_DTYPE)
+    Rt = np.concatenate([np.asarray(R, np.float64).ravel(), np.asarray(t, np.float64).ravel()])
+    lib().orc_optimizeRelmotion(ptr(a), ptr(b), len(a), ptr(Rt))
+    return Rt[:9].reshape(3, 3).copy(), Rt[9:].copy()

@@ -119,3 +119,25 @@ def test_hybrid_kernel_without_point_matches_equals_line_kernel(api, oracle, hyb
     rec_o, inl_o, rinl_o, _ = oracle.pose_ransac(lines[0], lines[1], lm, id_train=0, id_query=1, seed=5)
     assert np.array_equal(ctx.pair_matches(0, 2), rinl_o) and np.array_equal(ctx.pair_matches(0, 1), inl_o)
     assert np.array_equal(recs[0]["tf"], rec_o["tf"]) and recs[0]["rmse"] == rec_o["rmse"]
+
+
+def test_relmotion_ransac_levmar(api, oracle, hyb):
+    """computeRelativeMotion_Ransac + optimizeRelmotion (src/line/motion.cpp:367-526, 98-139):
+    consensus index set bit-exact, refined R, t bit-exact (same levmar operation order), and within the
+    north-star tolerance as the formal bar."""
+    ctx, frames, lines, pts, poses = hyb
+    for (q, t, seed) in [(1, 0, 3), (2, 1, 4), (2, 0, 8)]:
+        lm = oracle.lineMatching(lines[q], lines[t], True)
+        ref = oracle.relmotion_ransac(lines[q][lm["queryIdx"]], lines[t][lm["trainIdx"]], seed=seed)
+        got = ctx.relmotion_ransac(frames[t], frames[q], lm, seed=seed)
+        assert ref["have"] and ref["lm_calls"] >= 1 and len(ref["conset"]) > 20
+        assert got["have"] == ref["have"] and got["lm_calls"] == ref["lm_calls"]
+        assert np.array_equal(got["conset"], ref["conset"])
+        assert np.abs(got["R"] - ref["R"]).max() < 1e-5 and np.abs(got["t"] - ref["t"]).max() < 1e-4
+        assert np.array_equal(got["R"], ref["R"]) and np.array_equal(got["t"], ref["t"])
+    # fewer than three pairs -> empty consensus; three pairs -> no refinement (motion.cpp:370-374, 476-478)
+    lm = oracle.lineMatching(lines[1], lines[0], True)
+    assert len(ctx.relmotion_ransac(frames[0], frames[1], lm[:2])["conset"]) == 0
+    ref = oracle.relmotion_ransac(lines[1][lm["queryIdx"][:3]], lines[0][lm["trainIdx"][:3]], seed=1)
+    got = ctx.relmotion_ransac(frames[0], frames[1], lm[:3], seed=1)
+    assert np.array_equal(got["conset"], ref["conset"]) and got["lm_calls"] == ref["lm_calls"] == 0

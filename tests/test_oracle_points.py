@@ -101,3 +101,17 @@ def test_hybrid_ransac_recovers_ground_truth(oracle, hybrid_pair):
     only_l = oracle.pose_ransac_hybrid(lines[0], lines[1], x0[:0], x1[:0], pm[:0], lm, seed=4)
     rec_l, inl_l, rinl_l, _ = oracle.pose_ransac(lines[0], lines[1], lm, seed=4)
     assert np.array_equal(only_l["rec"]["tf"], rec_l["tf"]) and np.array_equal(only_l["ln_inliers"], inl_l)
+
+
+def test_relmotion_ransac_oracle(oracle, hybrid_pair):
+    """Row a27 on the CPU: the line-only RANSAC + levmar refinement recovers the synthetic motion."""
+    from lineslam_b200 import synth
+    lines, pts, poses = hybrid_pair
+    lm = oracle.lineMatching(lines[1], lines[0], True)
+    r = oracle.relmotion_ransac(lines[1][lm["queryIdx"]], lines[0][lm["trainIdx"]], seed=3)
+    T = synth.relative_pose_q2t(*poses[1], *poses[0])
+    assert r["have"] and len(r["conset"]) > 0.5 * len(lm) and r["lm_calls"] >= 1
+    assert np.abs(r["R"] - T[:3, :3]).max() < 0.01 and np.abs(r["t"] - T[:3, 3]).max() < 0.03
+    assert abs(np.linalg.det(r["R"]) - 1) < 1e-9
+    xs = np.linspace(-1, 1, 41)
+    assert max(abs(oracle.lib().orc_m_acos(x) - np.arccos(x)) for x in xs) < 1e-15
