@@ -469,9 +469,14 @@ __device__ double rect_improve(const FrameView& V, Rect* rec, double logNT, doub
 }
 
 // ------------------------------------------------------------- frame loop ----
-// LineSegmentDetection main loop (lsd.cpp:1995-2054). grid = frames, block = one warp.
-__global__ void __launch_bounds__(32) lsd_region_kernel(LslWork w, int xs, int ys, double ang_th, double density_th,
-                                                        double eps, double scale, double logNT, int min_reg_size) {
+// LineSegmentDetection main loop (lsd.cpp:1995-2054), split in three kernels:
+//   lsd_region_kernel   the order-dependent part (seed walk, region_grow, region2rect, refine: these read and
+//                       write `used`), one warp per frame; every region that survives refine() leaves its
+//                       rectangle in rects[] in sequence order;
+//   lsd_nfa_kernel      rect_improve + NFA validation (lsd.cpp:2024-2031) — no side effects on `used`, so all
+//                       candidate rectangles of all frames are validated in parallel, one warp each;
+//   lsd_compact_kernel  accepted rectangles -> output rows in sequence order (add_5tuple order, lsd.cpp:2033-2046).
+__global__ void __launch_bounds__(32) lsd_region_kernel(LslWork w, int xs, int ys, double ang_th, double density_th, int min_reg_size) {
   const int f = blockIdx.x, lane = threadIdx.x;
   const size_t po = (size_t)f * xs * ys;
   FrameView V;
@@ -480,7 +485,7 @@ __global__ void __launch_bounds__(32) lsd_region_kernel(LslWork w, int xs, int y
   V.used = w.used + po; V.reg = w.reg + po;
   const int32_t* seeds = w.seeds + po;
   const int nseeds = w.nseeds[f];
-  double* out = w.segs + (size_t)f * LSL_MAX_SEGS * 5;
+  double* rects = w.rects + (size_t)f * LSL_MAX_RECTS * 12;
   const double prec = LSL_PI * ang_th / 180.0;
   const double p = ang_th / 180.0;
   const bool fast_ok = prec > 1e-6 && prec < 1.4;
@@ -506,21 +511,69 @@ __global__ void __launch_bounds__(32) lsd_region_kernel(LslWork w, int xs, int y
       Rect rec;
       region2rect(V, n, reg_angle, prec, p, &rec);
       if (!refine(V, &n, prec, p, &rec, density_th)) continue;
-      double log_nfa = rect_improve(V, &rec, logNT, eps);
-      if (log_nfa <= eps) continue;
+      if (nout < LSL_MAX_RECTS) {
+        const double v[12] = {rec.x1, rec.y1, rec.x2, rec.y2, rec.width, rec.x, rec.y, rec.theta, rec.dx, rec.dy, rec.prec, rec.p};
+        double mine = v[0];
+#pragma unroll
+        for (int k = 1; k < 12; ++k) if (lane == k) mine = v[k];
+        if (lane < 12) rects[(size_t)nout * 12 + lane] = mine;
+      }
+      ++nout;
+    }
+  }
+  if (lane == 0) w.nrects[f] = nout;
+}
+
+__global__ void __launch_bounds__(128) lsd_nfa_kernel(LslWork w, int xs, int ys, double eps, double scale, double logNT) {
+  const int f = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t po = (size_t)f * xs * ys;
+  FrameView V;
+  V.xs = xs; V.ys = ys;
+  V.angles = w.angles + po; V.modgrad = w.modgrad + po; V.cs = w.cs + po;
+  V.used = w.used + po; V.reg = w.reg + po;
+  const int nr = min(w.nrects[f], LSL_MAX_RECTS);
+  double* rects = w.rects + (size_t)f * LSL_MAX_RECTS * 12;
+  uint8_t* ok = w.rect_ok + (size_t)f * LSL_MAX_RECTS;
+  for (int c = blockIdx.x * 4 + warp; c < nr; c += gridDim.x * 4) {
+    double* r = rects + (size_t)c * 12;
+    Rect rec;
+    rec.x1 = r[0]; rec.y1 = r[1]; rec.x2 = r[2]; rec.y2 = r[3]; rec.width = r[4]; rec.x = r[5]; rec.y = r[6];
+    rec.theta = r[7]; rec.dx = r[8]; rec.dy = r[9]; rec.prec = r[10]; rec.p = r[11];
+    __syncwarp();
+    double log_nfa = rect_improve(V, &rec, logNT, eps);
+    const bool acc = log_nfa > eps;
+    if (acc) {
       rec.x1 += 0.5; rec.y1 += 0.5; rec.x2 += 0.5; rec.y2 += 0.5;
       if (scale != 1.0) {
         rec.x1 /= scale; rec.y1 /= scale; rec.x2 /= scale; rec.y2 /= scale;
         rec.width /= scale;
       }
-      if (nout < LSL_MAX_SEGS && lane == 0) {
-        out[nout * 5 + 0] = rec.x1; out[nout * 5 + 1] = rec.y1; out[nout * 5 + 2] = rec.x2;
-        out[nout * 5 + 3] = rec.y2; out[nout * 5 + 4] = rec.width;
-      }
-      ++nout;
+      if (lane == 0) { r[0] = rec.x1; r[1] = rec.y1; r[2] = rec.x2; r[3] = rec.y2; r[4] = rec.width; }
     }
+    if (lane == 0) ok[c] = acc ? 1 : 0;
   }
-  if (lane == 0) w.nsegs[f] = nout;
+}
+
+__global__ void __launch_bounds__(32) lsd_compact_kernel(LslWork w) {
+  const int f = blockIdx.x, lane = threadIdx.x;
+  const int nraw = w.nrects[f];
+  const int nr = min(nraw, LSL_MAX_RECTS);
+  const double* rects = w.rects + (size_t)f * LSL_MAX_RECTS * 12;
+  const uint8_t* ok = w.rect_ok + (size_t)f * LSL_MAX_RECTS;
+  double* out = w.segs + (size_t)f * LSL_MAX_SEGS * 5;
+  int nout = 0;
+  for (int c0 = 0; c0 < nr; c0 += 32) {
+    const int c = c0 + lane;
+    const bool a = c < nr && ok[c] != 0;
+    const unsigned m = __ballot_sync(FULL, a);
+    const int pos = nout + __popc(m & ((1u << lane) - 1u));
+    if (a && pos < LSL_MAX_SEGS) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) out[(size_t)pos * 5 + k] = rects[(size_t)c * 12 + k];
+    }
+    nout += __popc(m);
+  }
+  if (lane == 0) w.nsegs[f] = nraw > LSL_MAX_RECTS ? LSL_MAX_SEGS + 1 : nout;   // overflow -> capacity error on the host
 }
 
 int lsl_launch_lsd(lsl_ctx* ctx, int n) {
@@ -532,9 +585,13 @@ int lsl_launch_lsd(lsl_ctx* ctx, int n) {
   double logNT = 5.0 * (lsl_log10((double)d.sw) + lsl_log10((double)d.sh)) / 2.0;
   int min_reg_size = (int)(-logNT / lsl_log10(p));
   LSL_KSTART(ctx, LSL_K_REGION);
-  lsd_region_kernel<<<n, 32, 0, ctx->stream>>>(w, d.sw, d.sh, P.lsd_ang_th, P.lsd_density_th, P.lsd_eps, P.lsd_scale,
-                                                logNT, min_reg_size);
+  lsd_region_kernel<<<n, 32, 0, ctx->stream>>>(w, d.sw, d.sh, P.lsd_ang_th, P.lsd_density_th, min_reg_size);
   LSL_KSTOP(ctx, LSL_K_REGION);
+  LSL_KSTART(ctx, LSL_K_NFA);
+  dim3 g(64, n);
+  lsd_nfa_kernel<<<g, 128, 0, ctx->stream>>>(w, d.sw, d.sh, P.lsd_eps, P.lsd_scale, logNT);
+  lsd_compact_kernel<<<n, 32, 0, ctx->stream>>>(w);
+  LSL_KSTOP(ctx, LSL_K_NFA);
   LSL_CUDA(cudaGetLastError());
   return LSL_OK;
 }

@@ -26,7 +26,7 @@ extern "C" const char* lsl_last_error(const lsl_ctx* ctx) { return ctx ? ctx->er
 
 static const char* const kKernelNames[LSL_K_COUNT] = {
     "gray_kernel", "xpass_kernel", "ypass_kernel", "ll_angle_kernel", "seed_list_kernel", "sobel5_kernel",
-    "lsd_region_kernel", "line3d_ransac_kernel", "line_msld_kernel", "msld_randfill_kernel", "line_mle_kernel",
+    "lsd_region_kernel", "lsd_nfa_kernel", "line3d_ransac_kernel", "line_msld_kernel", "msld_randfill_kernel", "line_mle_kernel",
     "gather_lines_kernel", "match_lines_kernel", "pose_kernel", "match_points_kernel", "pose_hybrid_kernel", "relmotion_kernel"};
 extern "C" const char* lsl_kernel_name(int i) { return (i >= 0 && i < LSL_K_COUNT) ? kKernelNames[i] : ""; }
 
@@ -59,6 +59,9 @@ static int carve(lsl_ctx* ctx, bool measure, size_t* total) {
   CARVE(seeds, int32_t, B * spix);
   CARVE(nseeds, int32_t, B);
   CARVE(reg, int32_t, B * spix);
+  CARVE(rects, double, (size_t)B * LSL_MAX_RECTS * 12);
+  CARVE(rect_ok, uint8_t, (size_t)B * LSL_MAX_RECTS);
+  CARVE(nrects, int32_t, B);
   CARVE(segs, double, (size_t)B * LSL_MAX_SEGS * 5);
   CARVE(nsegs, int32_t, B);
   CARVE(gx, int16_t, B * npix);

@@ -8,6 +8,7 @@
 
 #define LSL_MAX_SEGS 2048      // LSD segments per frame (ntuple_list rows)
 #define LSL_MAX_LINES 1024     // 3D lines kept per frame
+#define LSL_MAX_RECTS 4096     // regions per frame that reach the NFA validation
 #define LSL_MAX_SMP 101        // samples per line (line_sample_max_num + 1)
 #define LSL_NOTDEF (-1024.0)   // external/lsd/lsd.cpp:102
 #define LSL_MAX_MATCH 1024     // line matches per pair
@@ -43,6 +44,9 @@ struct LslWork {
   int32_t* seeds;   // [B][sh*sw]  x | y<<16 in list_p order
   int32_t* nseeds;  // [B]
   int32_t* reg;     // [B][sh*sw]  region pixel list x | y<<16
+  double* rects;    // [B][LSL_MAX_RECTS][12] candidate rectangles (struct rect of lsd.cpp:1075-1084) in sequence order
+  uint8_t* rect_ok; // [B][LSL_MAX_RECTS]     1 = passed the NFA validation
+  int32_t* nrects;  // [B]
   double* segs;     // [B][LSL_MAX_SEGS*5]
   int32_t* nsegs;   // [B]
   int16_t* gx;      // [B][H*W]  Sobel 5x5 d/dx (exact integers, |v| <= 6570)
@@ -153,7 +157,7 @@ struct RmScratch {
 
 // Kernel ids for the per-kernel device timers (CUDA events on the context stream)
 enum LslKernelId {
-  LSL_K_GRAY = 0, LSL_K_XPASS, LSL_K_YPASS, LSL_K_LLANGLE, LSL_K_SEEDS, LSL_K_SOBEL, LSL_K_REGION, LSL_K_RANSAC3D,
+  LSL_K_GRAY = 0, LSL_K_XPASS, LSL_K_YPASS, LSL_K_LLANGLE, LSL_K_SEEDS, LSL_K_SOBEL, LSL_K_REGION, LSL_K_NFA, LSL_K_RANSAC3D,
   LSL_K_MSLD, LSL_K_RANDFILL, LSL_K_MLE, LSL_K_GATHER, LSL_K_MATCH, LSL_K_POSE, LSL_K_MATCHPTS, LSL_K_POSEHYB, LSL_K_RELMOTION, LSL_K_COUNT
 };
 
