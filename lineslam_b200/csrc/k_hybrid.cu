@@ -129,7 +129,7 @@ __device__ void chi2_terms_pts(const PtView& P, int np, const Iso& w2n, const Is
 // getTransformFromHybridMatchesG2O restated for point + line landmarks (oracle/oracle_pair.cpp:refine_pose_hybrid).
 // Six threads per landmark; ordered sums over the landmarks (points first, then lines) on dedicated threads.
 __device__ void refine_pose_hybrid(const PtView& P, int np, const LmView& V, const double* md_all, int n, float* tf, int iterations,
-                                   const PoseParams& PP, double* s_red, double* s_S) {
+                                   const PoseParams& PP, double* s_red, double* s_S, Iso* s_ci) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   if (n + np == 0) return;
   Iso tfd, cam1, ident;
@@ -155,6 +155,17 @@ __device__ void refine_pose_hybrid(const PtView& P, int np, const LmView& V, con
     iso_inv(cam1, w2n);
     chi2_terms_pts(P, np, w2n, ident, P.X, PP);
     chi2_terms(V, md_all, n, w2n, ident, V.L, PP);
+    // the twelve perturbed camera poses (cam1 (+) +-delta e_d)^-1 are the same for every match: once per iteration
+    if (tid < 12) {
+      double u[6] = {0, 0, 0, 0, 0, 0};
+      const int d = tid >> 1;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) if (k == d) u[k] = (tid & 1) ? -del : del;
+      Iso c;
+      iso_oplus(cam1, u, c);
+      iso_inv(c, s_ci[tid]);
+    }
+    __syncthreads();
     // ---- points: numeric Jacobian columns, thread (match i, column d)
     for (int t = tid; t < 6 * np; t += nthr) {
       const int i = t / 6, d = t - 6 * i;
@@ -178,14 +189,9 @@ __device__ void refine_pose_hybrid(const PtView& P, int np, const LmView& V, con
           for (int k = 0; k < 3; ++k) Jm[side * 9 + k * 3 + d] = scalar * (e1[k] - e2[k]);
         }
         if (side) {
-          double u[6] = {0, 0, 0, 0, 0, 0}, e1[3], e2[3];
-          Iso c, ci;
-#pragma unroll
-          for (int k = 0; k < 6; ++k) if (k == d) u[k] = del;
-          iso_oplus(cam1, u, c); iso_inv(c, ci); pt_edge_error(ci, Xi, meas, e1);
-#pragma unroll
-          for (int k = 0; k < 6; ++k) if (k == d) u[k] = -del;
-          iso_oplus(cam1, u, c); iso_inv(c, ci); pt_edge_error(ci, Xi, meas, e2);
+          double e1[3], e2[3];
+          pt_edge_error(s_ci[2 * d], Xi, meas, e1);
+          pt_edge_error(s_ci[2 * d + 1], Xi, meas, e2);
 #pragma unroll
           for (int k = 0; k < 3; ++k) Jm[18 + k * 6 + d] = scalar * (e1[k] - e2[k]);
         }
@@ -227,14 +233,8 @@ __device__ void refine_pose_hybrid(const PtView& P, int np, const LmView& V, con
         if (side) {
 #pragma unroll
           for (int k = 0; k < 6; ++k) Lp[k] = Li[k];
-          double u[6] = {0, 0, 0, 0, 0, 0};
-          Iso c, ci;
-#pragma unroll
-          for (int k = 0; k < 6; ++k) if (k == d) u[k] = del;
-          iso_oplus(cam1, u, c); iso_inv(c, ci); edge_error(ci, Lp, meas, A1, A2, e1);
-#pragma unroll
-          for (int k = 0; k < 6; ++k) if (k == d) u[k] = -del;
-          iso_oplus(cam1, u, c); iso_inv(c, ci); edge_error(ci, Lp, meas, A1, A2, e2);
+          edge_error(s_ci[2 * d], Lp, meas, A1, A2, e1);
+          edge_error(s_ci[2 * d + 1], Lp, meas, A1, A2, e2);
 #pragma unroll
           for (int k = 0; k < 6; ++k) Jm[72 + k * 6 + d] = scalar * (e1[k] - e2[k]);
         }
@@ -627,6 +627,7 @@ __global__ void __launch_bounds__(POSE_THREADS, 1) pose_hybrid_kernel(const LslP
   __shared__ float s_tf[16];
   __shared__ double s_red[64];
   __shared__ double s_S[96];
+  __shared__ Iso s_ci[12];
   __shared__ int s_i[4];
   __shared__ double s_d[2];
   __shared__ GRand s_rng;
@@ -833,7 +834,7 @@ __global__ void __launch_bounds__(POSE_THREADS, 1) pose_hybrid_kernel(const LslP
   const float sum_squared_error = (float)sse;
   // ---- refinement (motion.cpp:726-839)
   V.sel = sel_r; P.sel = psel_r;
-  refine_pose_hybrid(P, bp_cnt, V, md_all, bl_cnt, s_tf, 25, PP, s_red, s_S);
+  refine_pose_hybrid(P, bp_cnt, V, md_all, bl_cnt, s_tf, 25, PP, s_red, s_S, s_ci);
   double refined_rmse = (double)sqrtf(sum_squared_error / (float)(bp_cnt + bl_cnt));
   int rp_cnt = 0, rl_cnt = 0;
   for (int it = 0; it < 20; ++it) {
@@ -847,7 +848,7 @@ __global__ void __launch_bounds__(POSE_THREADS, 1) pose_hybrid_kernel(const LslP
       refined_rmse = sqrt(tmp_sse / (double)(cp + cl));
       __syncthreads();
       V.sel = sel_f; P.sel = psel_f;
-      refine_pose_hybrid(P, rp_cnt, V, md_all, rl_cnt, s_tf, 20, PP, s_red, s_S);
+      refine_pose_hybrid(P, rp_cnt, V, md_all, rl_cnt, s_tf, 20, PP, s_red, s_S, s_ci);
     } else break;
   }
   __syncthreads();

@@ -101,36 +101,62 @@ __global__ void ypass_kernel(const double* __restrict__ aux, double* __restrict_
 }
 
 // ------------------------------------------------------------ ll_angle ----
-__global__ void ll_angle_kernel(const double* __restrict__ in, double* __restrict__ angles, double* __restrict__ modgrad,
-                                double2* __restrict__ cs, uint16_t* __restrict__ binT, int p, int n, double threshold,
-                                int n_bins, double max_grad) {
-  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
-  if (x >= p) return;
-  size_t base = (size_t)f * p * n, adr = (size_t)y * p + x;
-  double ang = LSL_NOTDEF, norm = 0.0;
+// ll_angle (lsd.cpp:670-794) on 32 x 32 tiles. The gradient pass is per pixel; the pixels above the gradient
+// threshold (a few percent of a frame) are compacted inside the tile so that the correctly rounded atan2 /
+// sincos run on dense warps; the bin plane is written column-major (the reference's x-outer / y-inner seed
+// order) through a shared-memory transpose, i.e. with coalesced stores.
+__global__ void __launch_bounds__(1024) ll_angle_kernel(const double* __restrict__ in, double* __restrict__ angles,
+                                                        double* __restrict__ modgrad, double2* __restrict__ cs,
+                                                        uint16_t* __restrict__ binT, int p, int n, double threshold,
+                                                        int n_bins, double max_grad) {
+  __shared__ uint16_t s_bin[32][33];
+  __shared__ uint16_t s_list[1024];
+  __shared__ double s_gx[1024], s_gy[1024];
+  __shared__ int s_cnt;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+  const int x = blockIdx.x * 32 + tx, y = blockIdx.y * 32 + ty, f = blockIdx.z;
+  const size_t base = (size_t)f * p * n;
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
   uint16_t bin = 0xFFFF;
-  double2 c2 = make_double2(2.0, 0.0);
-  if (x < p - 1 && y < n - 1) {
-    const double* I = in + base;
-    double com1 = I[adr + p + 1] - I[adr];
-    double com2 = I[adr + 1] - I[adr + p];
-    double gx = com1 + com2, gy = com1 - com2;
-    double norm2 = gx * gx + gy * gy;
-    norm = sqrt(norm2 / 4.0);
-    if (!(norm <= threshold)) {
-      ang = lsl_atan2(gx, -gy);
-      unsigned i = (unsigned)(norm * (double)n_bins / max_grad);
-      if (i >= (unsigned)n_bins) i = n_bins - 1;
-      bin = (uint16_t)i;
-      double s, c;
-      lsl_sincos(ang, &s, &c);
-      c2 = make_double2(c, s);
+  if (x < p && y < n) {
+    const size_t adr = (size_t)y * p + x;
+    double norm = 0.0;
+    bool valid = false;
+    if (x < p - 1 && y < n - 1) {
+      const double* I = in + base;
+      double com1 = I[adr + p + 1] - I[adr];
+      double com2 = I[adr + 1] - I[adr + p];
+      double gx = com1 + com2, gy = com1 - com2;
+      double norm2 = gx * gx + gy * gy;
+      norm = sqrt(norm2 / 4.0);
+      if (!(norm <= threshold)) {
+        valid = true;
+        unsigned i = (unsigned)(norm * (double)n_bins / max_grad);
+        if (i >= (unsigned)n_bins) i = n_bins - 1;
+        bin = (uint16_t)i;
+        int k = atomicAdd(&s_cnt, 1);
+        s_list[k] = (uint16_t)tid; s_gx[k] = gx; s_gy[k] = gy;
+      }
     }
+    modgrad[base + adr] = norm;
+    if (!valid) { angles[base + adr] = LSL_NOTDEF; cs[base + adr] = make_double2(2.0, 0.0); }
   }
-  angles[base + adr] = ang;
-  modgrad[base + adr] = norm;
-  cs[base + adr] = c2;
-  binT[base + (size_t)x * n + y] = bin;
+  s_bin[ty][tx] = bin;
+  __syncthreads();
+  const int cnt = s_cnt;
+  for (int k = tid; k < cnt; k += 1024) {
+    const int t = s_list[k];
+    const size_t adr = (size_t)(blockIdx.y * 32 + (t >> 5)) * p + (blockIdx.x * 32 + (t & 31));
+    double ang = lsl_atan2(s_gx[k], -s_gy[k]);
+    double sn, c;
+    lsl_sincos(ang, &sn, &c);
+    angles[base + adr] = ang;
+    cs[base + adr] = make_double2(c, sn);
+  }
+  // transposed store: thread (tx, ty) writes pixel (x0 + ty, y0 + tx) -> consecutive y for one x
+  const int xo = blockIdx.x * 32 + ty, yo = blockIdx.y * 32 + tx;
+  if (xo < p && yo < n) binT[base + (size_t)xo * n + yo] = s_bin[tx][ty];
 }
 
 // ---------------------------------------------------------- seed list ----
@@ -236,7 +262,8 @@ int lsl_launch_image(lsl_ctx* ctx, int n, const uint8_t* d_img, int channels) {
   double prec = LSL_PI * P.lsd_ang_th / 180.0;
   double rho = P.lsd_quant / lsl_sin(prec);
   LSL_KSTART(ctx, LSL_K_LLANGLE);
-  ll_angle_kernel<<<gyp, bx, 0, st>>>(w.scaled, w.angles, w.modgrad, w.cs, w.binT, d.sw, d.sh, rho, P.lsd_n_bins, P.lsd_max_grad);
+  dim3 gla((d.sw + 31) / 32, (d.sh + 31) / 32, n), bla(32, 32);
+  ll_angle_kernel<<<gla, bla, 0, st>>>(w.scaled, w.angles, w.modgrad, w.cs, w.binT, d.sw, d.sh, rho, P.lsd_n_bins, P.lsd_max_grad);
   LSL_KSTOP(ctx, LSL_K_LLANGLE);
   LSL_KSTART(ctx, LSL_K_SEEDS);
   seed_list_kernel<<<n, 256, P.lsd_n_bins * sizeof(int), st>>>(w.binT, w.seeds, w.nseeds, d.sw, d.sh, P.lsd_n_bins);

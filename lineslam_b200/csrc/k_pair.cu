@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) match_lines_kernel(const LslPairDesc* __r
 // column / block row); sums over the matches run as ordered chains on dedicated threads.
 // tf (12 floats, shared memory) in/out.
 __device__ void refine_pose(const LmView& V, const double* md_all, int n, float* tf, int iterations, const PoseParams& PP,
-                            double* s_red /* >= 64 doubles shared */, double* s_S /* 96 doubles shared */) {
+                            double* s_red /* >= 64 doubles shared */, double* s_S /* 96 doubles shared */, Iso* s_ci /* 12, shared */) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   if (n == 0) return;
   Iso tfd, cam1, ident;
@@ -166,6 +166,17 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
     Iso w2n;
     iso_inv(cam1, w2n);
     chi2_terms(V, md_all, n, w2n, ident, V.L, PP);
+    // the twelve perturbed camera poses (cam1 (+) +-delta e_d)^-1 are the same for every match: once per iteration
+    if (tid < 12) {
+      double u[6] = {0, 0, 0, 0, 0, 0};
+      const int d = tid >> 1;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) if (k == d) u[k] = (tid & 1) ? -del : del;
+      Iso c;
+      iso_oplus(cam1, u, c);
+      iso_inv(c, s_ci[tid]);
+    }
+    __syncthreads();
     // ---- numeric Jacobian columns: thread (match i, column d)
     for (int t = tid; t < 6 * n; t += nthr) {
       const int i = t / 6, d = t - 6 * i;
@@ -192,14 +203,8 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
         if (side) {
 #pragma unroll
           for (int k = 0; k < 6; ++k) Lp[k] = Li[k];
-          double u[6] = {0, 0, 0, 0, 0, 0};
-          Iso c, ci;
-#pragma unroll
-          for (int k = 0; k < 6; ++k) if (k == d) u[k] = del;
-          iso_oplus(cam1, u, c); iso_inv(c, ci); edge_error(ci, Lp, meas, A1, A2, e1);
-#pragma unroll
-          for (int k = 0; k < 6; ++k) if (k == d) u[k] = -del;
-          iso_oplus(cam1, u, c); iso_inv(c, ci); edge_error(ci, Lp, meas, A1, A2, e2);
+          edge_error(s_ci[2 * d], Lp, meas, A1, A2, e1);
+          edge_error(s_ci[2 * d + 1], Lp, meas, A1, A2, e2);
 #pragma unroll
           for (int k = 0; k < 6; ++k) Jm[72 + k * 6 + d] = scalar * (e1[k] - e2[k]);
         }
@@ -453,6 +458,7 @@ __global__ void __launch_bounds__(POSE_THREADS, 2) pose_kernel(const LslPairDesc
   __shared__ float s_tf[16];
   __shared__ double s_red[64];
   __shared__ double s_S[96];
+  __shared__ Iso s_ci[12];
   __shared__ int s_i[4];
   __shared__ double s_d[2];
   __shared__ GRand s_rng;
@@ -582,7 +588,7 @@ __global__ void __launch_bounds__(POSE_THREADS, 2) pose_kernel(const LslPairDesc
   const float sum_squared_error = (float)sse;
   // ---- refinement (motion.cpp:726-839)
   V.sel = sel_r;
-  refine_pose(V, md_all, best_cnt, s_tf, 25, PP, s_red, s_S);
+  refine_pose(V, md_all, best_cnt, s_tf, 25, PP, s_red, s_S, s_ci);
   double refined_rmse = (double)sqrtf(sum_squared_error / (float)best_cnt);   // float division + std::sqrt(float), motion.cpp:731
   int refined_cnt = 0;
   for (int it = 0; it < 20; ++it) {
@@ -594,7 +600,7 @@ __global__ void __launch_bounds__(POSE_THREADS, 2) pose_kernel(const LslPairDesc
       refined_rmse = sqrt(tmp_sse / (double)c);
       __syncthreads();
       V.sel = sel_f;
-      refine_pose(V, md_all, refined_cnt, s_tf, 20, PP, s_red, s_S);
+      refine_pose(V, md_all, refined_cnt, s_tf, 20, PP, s_red, s_S, s_ci);
     } else break;
   }
   __syncthreads();
