@@ -19,6 +19,7 @@ Only the cpu_baseline / --impl reference legs touch oracle/.
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -48,47 +49,67 @@ def make_unique_frames(u: int, rank: int):
     return imgs, deps, synth.camera_K(W, H)
 
 
-class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons every 200 ms while the timed region runs (B200_PROFILING.md). NVML in-process
-    (one init before the region): spawning nvidia-smi per sample stalls the CUDA driver for ~0.3 s a call."""
-    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+class ClockSampler:
+    """SM clock and throttle reasons every 500 ms while the timed regions run (B200_PROFILING.md recipe): ONE
+    long-lived `nvidia-smi -lms 500` child started before the warm-up (its start-up attaches to the driver once,
+    outside the timed regions) and killed afterwards. Rows are filtered to the timed regions by wall clock.
+    (An in-process NVML thread was measured to stall the CUDA driver for up to 1.7 s at random.)"""
+    FIELDS = ("timestamp,index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index: int):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
-        self.nv = None
+        import tempfile
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = vis.split(",")[index] if vis and index < len(vis.split(",")) else str(index)
+        self.path = tempfile.mktemp(prefix="lsl_clocks_", suffix=".csv")
+        self.windows = []
+        self.proc = None
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
-            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            self.nv = pynvml
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", phys, f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "500"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
-            self.nv = None
+            self.proc = None
 
-    def run(self):
-        while not self._halt.is_set():
-            try:
-                if self.nv is not None:
-                    sm = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
-                    try:
-                        mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                    except Exception:
-                        mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                    self.rows.append((float(sm), float(self.max), int(mask)))
-            except Exception:
-                pass
-            self._halt.wait(0.2)
+    def start(self):
+        time.sleep(1.5 if self.proc else 0.0)     # let the child finish its driver attach before any timing
+
+    def window(self, t0: float, t1: float):
+        self.windows.append((t0, t1))
 
     def stop(self):
-        self._halt.set()
-        self.join(timeout=6)
-        sm = [r[0] for r in self.rows]
-        reasons = sorted({n for r in self.rows for n, bit in self.REASONS if r[2] & bit})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.rows[0][1] if self.rows else None,
-                "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self.nv is not None else "unavailable"}
+        import datetime
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "unavailable"}
+        time.sleep(0.6)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for line in open(self.path, errors="ignore"):
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                clk, cmax = float(c[2]), float(c[3])
+            except Exception:
+                continue
+            if not any(a - 0.05 <= ts <= b + 0.05 for a, b in self.windows):
+                continue
+            sm.append(clk); mx = cmax
+            for name, v in zip(self.NAMES, c[4:8]):
+                if v.lower() == "active":
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm), "source": "nvidia-smi -lms 500"}
 
 
 # ------------------------------------------------------------------------------------------ CPU arm ----
@@ -188,6 +209,7 @@ def run_cuda(args, rank, world, local_rank):
     torch.cuda.synchronize()
 
     state = {"prev": None, "step": 0, "found": 0, "pairs": 0, "lines": 0}
+    per_step = []
     ktime = {}
 
     def one_step(e2e: bool):
@@ -229,14 +251,23 @@ def run_cuda(args, rank, world, local_rank):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        gc.collect()
+        gc.disable()              # no collector pauses inside the timed region (592 frame handles are created per step)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         t0 = time.perf_counter()
+        w0 = time.time()
+        per_step.clear()
         for _ in range(steps):
+            ts = time.perf_counter()
             one_step(e2e)
+            per_step.append(round(1e3 * (time.perf_counter() - ts), 2))
         e1.record(stream)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
+        if sampler:
+            sampler.window(w0, time.time())
+        gc.enable()
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], device="cuda")
@@ -246,12 +277,13 @@ def run_cuda(args, rank, world, local_rank):
         st1 = ctx.stats()
         return ms, wall, st0, st1
 
-    for _ in range(max(args.warmup, 3)):
-        one_step(False)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if rank == 0 and not os.environ.get("LSL_BENCH_NOCLOCKS") else None
     if sampler:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        one_step(False)
     ms_dev, wall_dev, s0, s1 = timed(False, args.steps)
+    steps_dev = list(per_step)
     kt = {k: float(np.mean(v)) for k, v in ktime.items() if v}
     found_frac = state["found"] / max(state["pairs"], 1)
     launches = int(s1.kernel_launches - s0.kernel_launches)
@@ -283,6 +315,7 @@ def run_cuda(args, rank, world, local_rank):
                     "h2d_bytes_per_step": int((h1.h2d_bytes - h0.h2d_bytes) // args.steps),
                     "d2h_bytes_per_step": int((h1.d2h_bytes - h0.d2h_bytes) // args.steps), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
+            "host_ms_each_step": {"value": steps_dev, "e2e": list(per_step)},
             "kernel_ms_per_step": kt,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None,

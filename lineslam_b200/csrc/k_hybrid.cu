@@ -868,6 +868,7 @@ int lsl_launch_match_points(lsl_ctx* ctx, int npairs, int max_nq, int dim) {
   if (max_nq > 0) {
     dim3 g((max_nq + 7) / 8, npairs);
     match_points_kernel<<<g, 256, 8 * dim * sizeof(float), ctx->stream>>>(h.d_ppairs, (Knn2*)h.knn);
+    ctx->stats.kernel_launches += 1;
   }
   match_points_accept_kernel<<<npairs, 32, 0, ctx->stream>>>(h.d_ppairs, ctx->pw.d_pairs, (const Knn2*)h.knn, h.pmatches, h.npmatch,
                                                             h.hs.rng, ctx->P.nn_distance_ratio);

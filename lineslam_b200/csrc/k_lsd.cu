@@ -591,6 +591,7 @@ int lsl_launch_lsd(lsl_ctx* ctx, int n) {
   dim3 g(64, n);
   lsd_nfa_kernel<<<g, 128, 0, ctx->stream>>>(w, d.sw, d.sh, P.lsd_eps, P.lsd_scale, logNT);
   lsd_compact_kernel<<<n, 32, 0, ctx->stream>>>(w);
+  ctx->stats.kernel_launches += 1;   // two launches inside one timing bracket
   LSL_KSTOP(ctx, LSL_K_NFA);
   LSL_CUDA(cudaGetLastError());
   return LSL_OK;
