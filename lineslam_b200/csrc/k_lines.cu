@@ -598,43 +598,39 @@ __device__ __forceinline__ void put6(double* a, int k, double v) {
   for (int c = 0; c < 6; ++c) if (k == c) a[c] = v;
 }
 
-// AX_EQ_B_LU for m = 6 (Axb_core.c:1140-1277) with the six rows on lanes 0..5 (Crout by columns, implicit
-// scaling, partial pivoting); every element sees the reference's operation order (k ascending), the lane
-// only decides where it is computed. Row swaps are lane-to-lane exchanges. The column / row loops are kept
-// rolled (run-time column index through sel6 / put6) so the solver stays small in the instruction cache.
-// The system is (JtJ + mu on the diagonal) x = Jte; on return every lane holds the full solution x[6].
-__device__ __noinline__ int ax_eq_b_lu6(const MleSmem& S, double mu, double* x) {
+// AX_EQ_B_LU for m = 6 (Axb_core.c:1140-1277: Crout LU with implicit scaling and partial pivoting, then the
+// permuted forward and the back substitution) in right-looking form on a shared-memory copy of the matrix.
+// Step j: pivot search over column j (the reference's last-maximum `>=` scan), row swap, scaling of the
+// column by 1 / pivot, then ALL trailing elements a[i][c] -= a[i][j] * a[j][c] (i, c > j) at once, one lane
+// each. Every element receives exactly the reference's updates (k ascending, separate multiply and subtract)
+// because the L entries travel with their row through the swaps; only where an operation is executed changes.
+// The two triangular solves are the reference's loops on lane 0. W = 48 doubles of warp-private scratch
+// (a 36 | work 6 | x 6). The system is (JtJ + mu on the diagonal) x = Jte; every lane receives x[6].
+__device__ __noinline__ int ax_eq_b_lu6(const MleSmem& S, double mu, double* W, double* x) {
   const int lane = threadIdx.x & 31;
-  const int row = lane < 6 ? lane : 5;   // lanes >= 6 shadow row 5 (results unused)
-  double a[6];
-#pragma unroll
-  for (int j = 0; j < 6; ++j) a[j] = S.JtJ[row * 6 + j];
-#pragma unroll
-  for (int j = 0; j < 6; ++j) if (j == row) a[j] = a[j] + mu;
-  double xr = S.Jte[row];
+  double* a = W; double* work = W + 36; double* xs = W + 42;
+  __syncwarp();
+  for (int e = lane; e < 36; e += 32) { const int r = e / 6, c = e - 6 * r; a[e] = (r == c) ? S.JtJ[e] + mu : S.JtJ[e]; }
+  if (lane < 6) xs[lane] = S.Jte[lane];
+  __syncwarp();
   double mx = 0.0, tmp;
+  if (lane < 6) {
 #pragma unroll
-  for (int j = 0; j < 6; ++j)
-    if ((tmp = fabs(a[j])) > mx) mx = tmp;
-  if (__ballot_sync(FULL, mx == 0.0) & 0x3fu) return 0;
-  double work = 1.0 / mx;
+    for (int j = 0; j < 6; ++j)
+      if ((tmp = fabs(a[lane * 6 + j])) > mx) mx = tmp;
+    work[lane] = 1.0 / mx;
+  }
+  if (__ballot_sync(FULL, lane < 6 && mx == 0.0)) return 0;
+  __syncwarp();
   int idxp = 0;   // idx[j] packed, 3 bits each
   int maxi = -1;
+  const int ui = 1 + lane / 5, uc = 1 + lane % 5;   // lanes 0..24 <-> element (ui, uc) of the trailing 5 x 5 block
 #pragma unroll 1
   for (int j = 0; j < 6; ++j) {
-    double sum = sel6(a, j);
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {           // a[i][j] -= a[i][k] * a[k][j], k < min(i, j); row k is final at step k
-      if (k < j) {
-        const double v = __shfl_sync(FULL, sum, k);
-        if (lane > k) sum -= a[k] * v;
-      }
-    }
-    put6(a, j, sum);
-    // pivot: last row i >= j with the largest work[i] * |sum| (the reference's `>=` scan), NaNs never win
-    tmp = work * fabs(sum);
-    double bv = (lane >= j && lane < 6 && tmp == tmp) ? tmp : -1.0;
+    // pivot: last row i >= j with the largest work[i] * |a[i][j]| (the reference's `>=` scan), NaNs never win
+    double bv = -1.0;
     int bi = lane;
+    if (lane >= j && lane < 6) { tmp = work[lane] * fabs(a[lane * 6 + j]); if (tmp == tmp) bv = tmp; }
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
       const double ov = __shfl_xor_sync(FULL, bv, o);
@@ -644,54 +640,46 @@ __device__ __noinline__ int ax_eq_b_lu6(const MleSmem& S, double mu, double* x) 
     bv = __shfl_sync(FULL, bv, 0); bi = __shfl_sync(FULL, bi, 0);
     if (bv >= 0.0) maxi = bi;
     if (j != maxi) {                         // uniform
-      const int partner = lane == j ? maxi : (lane == maxi ? j : lane);
-#pragma unroll
-      for (int c = 0; c < 6; ++c) a[c] = __shfl_sync(FULL, a[c], partner);
-      const double wj = __shfl_sync(FULL, work, j);
-      if (lane == maxi) work = wj;
+      if (lane < 6) { const double t = a[maxi * 6 + lane]; a[maxi * 6 + lane] = a[j * 6 + lane]; a[j * 6 + lane] = t; }
+      if (lane == 6) work[maxi] = work[j];
+      __syncwarp();
     }
     idxp |= (maxi & 7) << (3 * j);
-    double ajj = sel6(a, j);
-    if (lane == j && ajj == 0.0) { ajj = DBL_EPSILON; put6(a, j, ajj); }
+    double ajj = a[j * 6 + j];
+    if (ajj == 0.0) ajj = DBL_EPSILON;        // uniform value; lane 0 stores it
+    __syncwarp();
+    if (lane == 0) a[j * 6 + j] = ajj;
     if (j != 5) {
-      const double piv = __shfl_sync(FULL, ajj, j);
-      const double tmp2 = 1.0 / piv;
-      if (lane > j) put6(a, j, ajj * tmp2);
+      const double tmp2 = 1.0 / ajj;
+      if (lane > j && lane < 6) a[lane * 6 + j] *= tmp2;
+      __syncwarp();
+      if (lane < 25 && ui > j && uc > j) a[ui * 6 + uc] -= a[ui * 6 + j] * a[j * 6 + uc];
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    int k = 0;
+#pragma unroll 1
+    for (int i = 0; i < 6; ++i) {
+      int j = (idxp >> (3 * i)) & 7;
+      double sum = xs[j];
+      xs[j] = xs[i];
+      if (k != 0)
+        for (j = k - 1; j < i; ++j) sum -= a[i * 6 + j] * xs[j];
+      else if (sum != 0.0) k = i + 1;
+      xs[i] = sum;
+    }
+#pragma unroll 1
+    for (int i = 5; i >= 0; --i) {
+      double sum = xs[i];
+      for (int j = i + 1; j < 6; ++j) sum -= a[i * 6 + j] * xs[j];
+      xs[i] = sum / a[i * 6 + i];
     }
   }
-  // forward substitution with the row permutation
-  int k = 0;
-#pragma unroll 1
-  for (int i = 0; i < 6; ++i) {
-    const int jj = (idxp >> (3 * i)) & 7;
-    const double xi = __shfl_sync(FULL, xr, i);
-    double sum = __shfl_sync(FULL, xr, jj);   // sum = x[jj]; x[jj] = x[i]
-    if (lane == jj) xr = xi;
-    if (k != 0) {
+  __syncwarp();
 #pragma unroll
-      for (int j2 = 0; j2 < 5; ++j2) {
-        if (j2 < i) {
-          const double xv = __shfl_sync(FULL, xr, j2);
-          if (j2 >= k - 1) sum -= a[j2] * xv;   // meaningful on lane i (its row)
-        }
-      }
-    } else if (sum != 0.0) k = i + 1;
-    if (lane == i) xr = sum;
-  }
-#pragma unroll 1
-  for (int i = 5; i >= 0; --i) {
-    double sum = xr;
-#pragma unroll
-    for (int j = 1; j < 6; ++j) {
-      if (j > i) {
-        const double xv = __shfl_sync(FULL, xr, j);
-        sum -= a[j] * xv;
-      }
-    }
-    if (lane == i) xr = sum / sel6(a, i);
-  }
-#pragma unroll
-  for (int r = 0; r < 6; ++r) x[r] = __shfl_sync(FULL, xr, r);
+  for (int r = 0; r < 6; ++r) x[r] = xs[r];
+  __syncwarp();
   return 1;
 }
 
@@ -816,7 +804,7 @@ __global__ void __launch_bounds__(32, 13) line_mle_kernel(LslWork w, LineParams 
       mu = tau * tmp;
     }
     {
-      int issolved = ax_eq_b_lu6(S, mu, Dp);
+      int issolved = ax_eq_b_lu6(S, mu, Enew, Dp);   // the trial-residual buffer is dead until l2nrm_neg refills it
       if (issolved) {
         Dp_L2 = 0.0;
 #pragma unroll

@@ -250,7 +250,12 @@ static int extract_device(lsl_ctx* ctx, int n, const uint8_t* d_imgs, int channe
     blk = new (std::nothrow) LslLineBlock();
     if (!blk) return LSL_ERR_ARG;
     blk->refs = 0; blk->d = nullptr;
-    LSL_CUDA(cudaMallocAsync((void**)&blk->d, sizeof(lsl_line_rec) * tot, st));
+    // size classes of 16384 records (17 MB) with 1/8 headroom: consecutive batches of a stream then ask the stream-ordered
+    // pool for the same block size and reuse each other's freed blocks (an exact-fit request grew the pool by a fresh
+    // cudaMalloc whenever a batch carried a few more lines than any before it: sporadic 100-500 ms stalls)
+    const size_t want = (size_t)tot + (size_t)tot / 8;
+    const size_t recs_alloc = (want + 16383) / 16384 * 16384;
+    LSL_CUDA(cudaMallocAsync((void**)&blk->d, sizeof(lsl_line_rec) * recs_alloc, st));
     LSL_CUDA(cudaMemcpyAsync(ctx->d_goff, goff.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
     if ((rc = lsl_launch_gather(ctx, n, blk->d))) return rc;
   }
@@ -457,14 +462,14 @@ static int ensure_pair_ws(lsl_ctx* ctx, size_t npairs, size_t tot_m, size_t tot_
     p.cap_pairs = c; p.sc.max_iter = max_iter;
   }
   if (tot_m > p.cap_m) {
-    size_t c = tot_m + tot_m / 2;
+    size_t c = tot_m * 2;
     LSL_CUDA(cudaStreamSynchronize(ctx->stream));
     LSL_CUDA(regrow(&p.matches, c)); LSL_CUDA(regrow(&p.sc.md, c * 72)); LSL_CUDA(regrow(&p.sc.dab, c * 2));
     LSL_CUDA(regrow(&p.sc.sel, c * 3)); LSL_CUDA(regrow(&p.sc.lm, c * 306)); LSL_CUDA(regrow(&p.sc.okf, c));
     p.cap_m = c;
   }
   if (tot_d > p.cap_d) {
-    size_t c = tot_d + tot_d / 2;
+    size_t c = tot_d * 2;
     LSL_CUDA(cudaStreamSynchronize(ctx->stream));
     LSL_CUDA(regrow(&p.D, c));
     p.cap_d = c;

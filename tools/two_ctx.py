@@ -6,13 +6,15 @@ from lineslam_b200 import api
 import bench
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 592
 NCTX = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-STEPS = 4
+STEPS = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+STAGGER = float(sys.argv[4]) if len(sys.argv) > 4 else 0.0
 imgs, deps, K = bench.make_unique_frames(8, 0)
 order = bench.palindrome(8, B)
 bi = np.stack([imgs[i] for i in order]); bd = np.stack([deps[i] for i in order])
 di, dd = torch.from_numpy(bi).cuda(), torch.from_numpy(bd).cuda()
 ctxs = [api.Context(max_batch=B) for _ in range(NCTX)]
-def worker(ctx, nsteps, out):
+def worker(ctx, nsteps, out, delay=0.0):
+    time.sleep(delay)
     prev = None
     for s in range(nsteps):
         seeds = np.arange(1, B + 1, dtype=np.uint32)
@@ -28,7 +30,7 @@ for c in ctxs: worker(c, 2, [])   # warm-up
 torch.cuda.synchronize()
 outs = [[] for _ in ctxs]
 t0 = time.perf_counter()
-ths = [threading.Thread(target=worker, args=(c, STEPS, o)) for c, o in zip(ctxs, outs)]
+ths = [threading.Thread(target=worker, args=(c, STEPS, o, k * STAGGER)) for k, (c, o) in enumerate(zip(ctxs, outs))]
 for t in ths: t.start()
 for t in ths: t.join()
 torch.cuda.synchronize()
