@@ -142,8 +142,10 @@ class Context:
         depths = np.ascontiguousarray(depths, np.float32)
         n, H, W = depths.shape
         ch = 3 if imgs.ndim == 4 else 1
-        ip = (C.c_void_p * n)(*[imgs[i].ctypes.data for i in range(n)])
-        dp = (C.c_void_p * n)(*[depths[i].ctypes.data for i in range(n)])
+        # per-frame pointers without a Python loop (592 numpy slices cost ~10 ms per call)
+        ipa = np.uint64(imgs.ctypes.data) + np.arange(n, dtype=np.uint64) * np.uint64(imgs.strides[0])
+        dpa = np.uint64(depths.ctypes.data) + np.arange(n, dtype=np.uint64) * np.uint64(depths.strides[0])
+        ip, dp = ptr(ipa), ptr(dpa)
         sd = np.ascontiguousarray(seeds if seeds is not None else np.ones(n), np.uint32)
         Kc = np.ascontiguousarray(K, np.float64)
         out = (C.c_void_p * n)()

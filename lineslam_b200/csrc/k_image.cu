@@ -237,41 +237,53 @@ __global__ void sobel5_kernel(const uint8_t* __restrict__ gray, int16_t* __restr
   gy[(size_t)f * W * H + (size_t)y * W + x] = (int16_t)sy;
 }
 
-// Copies channel 0 when the caller already has a gray plane (channels == 1).
-int lsl_launch_image(lsl_ctx* ctx, int n, const uint8_t* d_img, int channels) {
+// Image stage for the frames [f0, f0 + n) of the batch (the host-buffer path calls it per upload chunk so that
+// the RGB upload of the next chunk overlaps these kernels). channels == 1: the caller already has a gray plane.
+int lsl_launch_image(lsl_ctx* ctx, int f0, int n, const uint8_t* d_img, int channels) {
   const LslDims& d = ctx->dims;
   const lsl_params& P = ctx->P;
-  LslWork& w = ctx->wk;
+  const LslWork& w = ctx->wk;
   cudaStream_t st = ctx->stream;
-  size_t npix = (size_t)d.W * d.H;
+  const size_t npix = (size_t)d.W * d.H, spix = (size_t)d.sw * d.sh, apix = (size_t)d.H * d.sw;
+  uint8_t* gray = w.gray + f0 * npix;
+  const uint8_t* img = d_img + (size_t)f0 * npix * channels;
   if (channels == 3) {
     long n4 = (long)(npix * n / 4);
     LSL_KSTART(ctx, LSL_K_GRAY);
-    gray_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(d_img, w.gray, n4);
+    gray_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(img, gray, n4);
     LSL_KSTOP(ctx, LSL_K_GRAY);
   } else {
-    LSL_CUDA(cudaMemcpyAsync(w.gray, d_img, npix * n, cudaMemcpyDeviceToDevice, st));
+    LSL_CUDA(cudaMemcpyAsync(gray, img, npix * n, cudaMemcpyDeviceToDevice, st));
   }
   dim3 bx(128), gxp((d.sw + 127) / 128, d.H, n), gyp((d.sw + 127) / 128, d.sh, n);
   LSL_KSTART(ctx, LSL_K_XPASS);
-  xpass_kernel<<<gxp, bx, 0, st>>>(w.gray, w.aux, ctx->taps.kx, ctx->taps.xc, d.W, d.H, d.sw, ctx->taps.h, ctx->taps.n);
+  xpass_kernel<<<gxp, bx, 0, st>>>(gray, w.aux + f0 * apix, ctx->taps.kx, ctx->taps.xc, d.W, d.H, d.sw, ctx->taps.h, ctx->taps.n);
   LSL_KSTOP(ctx, LSL_K_XPASS);
   LSL_KSTART(ctx, LSL_K_YPASS);
-  ypass_kernel<<<gyp, bx, 0, st>>>(w.aux, w.scaled, ctx->taps.ky, ctx->taps.yc, d.H, d.sw, d.sh, ctx->taps.h, ctx->taps.n);
+  ypass_kernel<<<gyp, bx, 0, st>>>(w.aux + f0 * apix, w.scaled + f0 * spix, ctx->taps.ky, ctx->taps.yc, d.H, d.sw, d.sh, ctx->taps.h, ctx->taps.n);
   LSL_KSTOP(ctx, LSL_K_YPASS);
   double prec = LSL_PI * P.lsd_ang_th / 180.0;
   double rho = P.lsd_quant / lsl_sin(prec);
   LSL_KSTART(ctx, LSL_K_LLANGLE);
   dim3 gla((d.sw + 31) / 32, (d.sh + 31) / 32, n), bla(32, 32);
-  ll_angle_kernel<<<gla, bla, 0, st>>>(w.scaled, w.angles, w.modgrad, w.cs, w.binT, d.sw, d.sh, rho, P.lsd_n_bins, P.lsd_max_grad);
+  ll_angle_kernel<<<gla, bla, 0, st>>>(w.scaled + f0 * spix, w.angles + f0 * spix, w.modgrad + f0 * spix, w.cs + f0 * spix,
+                                      w.binT + f0 * spix, d.sw, d.sh, rho, P.lsd_n_bins, P.lsd_max_grad);
   LSL_KSTOP(ctx, LSL_K_LLANGLE);
-  LSL_KSTART(ctx, LSL_K_SEEDS);
-  seed_list_kernel<<<n, 256, P.lsd_n_bins * sizeof(int), st>>>(w.binT, w.seeds, w.nseeds, d.sw, d.sh, P.lsd_n_bins);
-  LSL_KSTOP(ctx, LSL_K_SEEDS);
   dim3 bs(32, 16), gs((d.W + 31) / 32, (d.H + 15) / 16, n);
   LSL_KSTART(ctx, LSL_K_SOBEL);
-  sobel5_kernel<<<gs, bs, 0, st>>>(w.gray, w.gx, w.gy, d.W, d.H);
+  sobel5_kernel<<<gs, bs, 0, st>>>(gray, w.gx + f0 * npix, w.gy + f0 * npix, d.W, d.H);
   LSL_KSTOP(ctx, LSL_K_SOBEL);
+  LSL_CUDA(cudaGetLastError());
+  return LSL_OK;
+}
+
+// Seed lists of all n frames (one CTA per frame, latency-bound: launched once per batch, not per upload chunk)
+int lsl_launch_seeds(lsl_ctx* ctx, int n) {
+  const LslDims& d = ctx->dims;
+  const LslWork& w = ctx->wk;
+  LSL_KSTART(ctx, LSL_K_SEEDS);
+  seed_list_kernel<<<n, 256, ctx->P.lsd_n_bins * sizeof(int), ctx->stream>>>(w.binT, w.seeds, w.nseeds, d.sw, d.sh, ctx->P.lsd_n_bins);
+  LSL_KSTOP(ctx, LSL_K_SEEDS);
   LSL_CUDA(cudaGetLastError());
   return LSL_OK;
 }

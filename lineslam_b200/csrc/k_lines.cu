@@ -929,6 +929,7 @@ int lsl_launch_lines(lsl_ctx* ctx, int n, const float* d_depth, const double K[9
   LP.sample_min = P.line_sample_min_num; LP.sample_max = P.line_sample_max_num; LP.ransac_iters = P.ransac_iters_extract_line;
   LP.ncells = P.num_cells_lineseg_range; LP.mle_iters = P.line3d_mle_iter_num; LP.msld_s = d.msld_s;
   LP.W = d.W; LP.H = d.H;
+  if (ctx->depth_async) { LSL_CUDA(cudaStreamWaitEvent(st, ctx->ev_depth, 0)); ctx->depth_async = false; }
   LSL_KSTART(ctx, LSL_K_RANSAC3D);
   line3d_ransac_kernel<<<n, 128, 0, st>>>(w, LP, d_depth);
   LSL_KSTOP(ctx, LSL_K_RANSAC3D);

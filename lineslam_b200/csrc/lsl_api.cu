@@ -136,6 +136,11 @@ extern "C" int lsl_ctx_create(lsl_ctx** out, const lsl_params* params, int cuda_
       ctx->P.num_cells_lineseg_range < 10) { delete ctx; return LSL_ERR_ARG; }
   cudaError_t e = cudaSetDevice(cuda_device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_depth, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  ctx->depth_async = false; ctx->img_chunks = 0;
+  for (int c = 0; c < 8 && e == cudaSuccess; ++c) e = cudaEventCreateWithFlags(&ctx->ev_img[c], cudaEventDisableTiming);
   ctx->stream = ctx->own_stream;
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev3);
@@ -173,6 +178,8 @@ extern "C" void lsl_ctx_destroy(lsl_ctx* ctx) {
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev3);
   for (int k = 0; k < LSL_K_COUNT; ++k) { cudaEventDestroy(ctx->kev[k][0]); cudaEventDestroy(ctx->kev[k][1]); }
   cudaStreamDestroy(ctx->own_stream);
+  cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->ev_depth); cudaEventDestroy(ctx->ev_fork);
+  for (int c = 0; c < 8; ++c) cudaEventDestroy(ctx->ev_img[c]);
   delete ctx;
 }
 
@@ -230,7 +237,17 @@ static int extract_device(lsl_ctx* ctx, int n, const uint8_t* d_imgs, int channe
   LSL_CUDA(cudaMemcpyAsync(w.seeds_rng, sd.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
   clear_ktimes(ctx, 0, LSL_K_MATCH);
   cudaEventRecord(ctx->ev0, st);
-  if ((rc = lsl_launch_image(ctx, n, d_imgs, channels))) return rc;
+  if (ctx->img_chunks > 0) {   // host-buffer path: image stage per upload chunk (the next chunk's copy runs underneath)
+    const int C = ctx->img_chunks;
+    ctx->img_chunks = 0;
+    for (int c = 0; c < C; ++c) {
+      const int f0 = (int)((long)n * c / C), f1 = (int)((long)n * (c + 1) / C);
+      if (f1 == f0) continue;
+      LSL_CUDA(cudaStreamWaitEvent(st, ctx->ev_img[c], 0));
+      if ((rc = lsl_launch_image(ctx, f0, f1 - f0, d_imgs, channels))) return rc;
+    }
+  } else if ((rc = lsl_launch_image(ctx, 0, n, d_imgs, channels))) return rc;
+  if ((rc = lsl_launch_seeds(ctx, n))) return rc;
   if ((rc = lsl_launch_lsd(ctx, n))) return rc;
   if ((rc = lsl_launch_lines(ctx, n, d_depths, K, dt))) return rc;
   // ---- counts back (8 bytes per frame), then one dense block for the records of the whole batch
@@ -322,8 +339,20 @@ extern "C" int lsl_extract_batch(lsl_ctx* ctx, int n, const uint8_t* const* imgs
     bool contiguous = true;
     for (int i = 1; i < n; ++i) contiguous &= (imgs[i] == imgs[0] + ib * i) && ((const uint8_t*)depths[i] == (const uint8_t*)depths[0] + db * i);
     if (contiguous) {
-      LSL_CUDA(cudaMemcpyAsync(ctx->wk.img, imgs[0], ib * n, cudaMemcpyHostToDevice, ctx->stream));
-      LSL_CUDA(cudaMemcpyAsync(ctx->wk.depth, depths[0], db * n, cudaMemcpyHostToDevice, ctx->stream));
+      // the depth planes are first read by the 3D-line stage: their upload runs on the copy stream underneath the
+      // image / LSD kernels (the RANSAC launch waits for ev_depth)
+      LSL_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+      LSL_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
+      const int C = n >= 32 ? 4 : 1;   // RGB planes in C chunks: chunk c + 1 uploads while the image kernels of chunk c run
+      for (int c = 0; c < C; ++c) {
+        const size_t f0 = (size_t)n * c / C, f1 = (size_t)n * (c + 1) / C;
+        if (f1 > f0) LSL_CUDA(cudaMemcpyAsync(ctx->wk.img + ib * f0, imgs[0] + ib * f0, ib * (f1 - f0), cudaMemcpyHostToDevice, ctx->copy_stream));
+        LSL_CUDA(cudaEventRecord(ctx->ev_img[c], ctx->copy_stream));
+      }
+      ctx->img_chunks = C;
+      LSL_CUDA(cudaMemcpyAsync(ctx->wk.depth, depths[0], db * n, cudaMemcpyHostToDevice, ctx->copy_stream));
+      LSL_CUDA(cudaEventRecord(ctx->ev_depth, ctx->copy_stream));
+      ctx->depth_async = true;
     } else {
       for (int i = 0; i < n; ++i) {
         LSL_CUDA(cudaMemcpyAsync(ctx->wk.img + ib * i, imgs[i], ib, cudaMemcpyHostToDevice, ctx->stream));

@@ -191,6 +191,11 @@ struct lsl_ctx {
   cudaStream_t stream;       // stream every call of this context runs on
   cudaStream_t own_stream;   // created with the context; `stream` may be replaced by lsl_ctx_set_stream
   cudaEvent_t ev0, ev3;      // whole-call bracket
+  cudaStream_t copy_stream;  // depth upload of the host-buffer path (overlaps the image / LSD kernels)
+  cudaEvent_t ev_depth, ev_fork;
+  bool depth_async;          // the 3D-line stage must wait for ev_depth
+  int img_chunks;            // > 0: the RGB planes arrive in this many upload chunks (events ev_img[c]) on the copy stream
+  cudaEvent_t ev_img[8];
   cudaEvent_t kev[LSL_K_COUNT][2];
   bool kran[LSL_K_COUNT];
   float kms[LSL_K_COUNT];
@@ -224,7 +229,8 @@ struct lsl_ctx {
   } while (0)
 
 // kernel launchers (one per .cu)
-int lsl_launch_image(lsl_ctx* ctx, int n, const uint8_t* d_img, int channels);
+int lsl_launch_image(lsl_ctx* ctx, int f0, int n, const uint8_t* d_img, int channels);
+int lsl_launch_seeds(lsl_ctx* ctx, int n);
 int lsl_launch_lsd(lsl_ctx* ctx, int n);
 int lsl_launch_lines(lsl_ctx* ctx, int n, const float* d_depth, const double K[9], double dt);
 int lsl_prepare_taps(lsl_ctx* ctx);
