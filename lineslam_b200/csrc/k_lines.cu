@@ -586,18 +586,6 @@ __device__ __noinline__ double l2nrm_neg(double* E, const double* y, int n) {
   return s0 + s1 + s2 + s3;
 }
 
-// a[k] / a[k] = v for a run-time k without local memory (k is warp-uniform)
-__device__ __forceinline__ double sel6(const double* a, int k) {
-  double v = a[0];
-#pragma unroll
-  for (int c = 1; c < 6; ++c) if (k == c) v = a[c];
-  return v;
-}
-__device__ __forceinline__ void put6(double* a, int k, double v) {
-#pragma unroll
-  for (int c = 0; c < 6; ++c) if (k == c) a[c] = v;
-}
-
 // AX_EQ_B_LU for m = 6 (Axb_core.c:1140-1277: Crout LU with implicit scaling and partial pivoting, then the
 // permuted forward and the back substitution) in right-looking form on a shared-memory copy of the matrix.
 // Step j: pivot search over column j (the reference's last-maximum `>=` scan), row swap, scaling of the
@@ -683,7 +671,10 @@ __device__ __noinline__ int ax_eq_b_lu6(const MleSmem& S, double mu, double* W, 
   return 1;
 }
 
-__global__ void __launch_bounds__(32, 13) line_mle_kernel(LslWork w, LineParams P) {
+#ifndef MLE_MINB
+#define MLE_MINB 11
+#endif
+__global__ void __launch_bounds__(32, MLE_MINB) line_mle_kernel(LslWork w, LineParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MleSmem& S = *reinterpret_cast<MleSmem*>(smem_raw);
   const int f = blockIdx.y, lane = threadIdx.x;
@@ -941,6 +932,14 @@ int lsl_launch_lines(lsl_ctx* ctx, int n, const float* d_depth, const double K[9
   msld_randfill_kernel<<<(n + 63) / 64, 64, 0, st>>>(w, w.msld_fail, n);
   LSL_KSTOP(ctx, LSL_K_RANDFILL);
   LSL_KSTART(ctx, LSL_K_MLE);
+  {
+    static bool once = false;
+    if (!once) {   // leave the rest of the 256 KB to L1: the LM's local-memory working set lives there
+      int carve = (int)((MLE_MINB * (sizeof(MleSmem) + 1024) * 100 + 233471) / 233472);
+      cudaFuncSetAttribute(line_mle_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve > 100 ? 100 : carve);
+      once = true;
+    }
+  }
   line_mle_kernel<<<gl, 32, sizeof(MleSmem), st>>>(w, LP);
   LSL_KSTOP(ctx, LSL_K_MLE);
   LSL_CUDA(cudaGetLastError());
