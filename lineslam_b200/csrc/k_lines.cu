@@ -148,7 +148,10 @@ __device__ void line3d_pca(const double* s_pos, const uint32_t* mask, int cnt, d
   drct[0] = V[0]; drct[1] = V[3]; drct[2] = V[6];
 }
 
-__global__ void __launch_bounds__(128) line3d_ransac_kernel(LslWork w, LineParams P, const float* __restrict__ depth_all) {
+#ifndef RANSAC_MINB
+#define RANSAC_MINB 4
+#endif
+__global__ void __launch_bounds__(128, RANSAC_MINB) line3d_ransac_kernel(LslWork w, LineParams P, const float* __restrict__ depth_all) {
   __shared__ double s_pos[LSL_MAX_SMP * 3];
   __shared__ double s_DU[LSL_MAX_SMP * 9];
   __shared__ int s_idx[LSL_MAX_SMP];
