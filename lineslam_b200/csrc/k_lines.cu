@@ -638,38 +638,59 @@ __device__ __noinline__ int ax_eq_b_lu6(const MleSmem& S, double mu, double* W, 
     idxp |= (maxi & 7) << (3 * j);
     double ajj = a[j * 6 + j];
     if (ajj == 0.0) ajj = DBL_EPSILON;        // uniform value; lane 0 stores it
+    // column scaling (lanes 25..29 <-> rows j+1..5) and the trailing update (lanes 0..24) in one phase: all loads,
+    // one barrier, all stores; the update multiplies by the same scaled L entry the scaling lane stores
+    const int si = j + 1 + (lane - 25);
+    const bool scl = lane >= 25 && si < 6 && j != 5, upd = lane < 25 && ui > j && uc > j;
+    double lij = 0.0, ujc = 0.0, cur = 0.0;
+    if (scl) lij = a[si * 6 + j];
+    if (upd) { lij = a[ui * 6 + j]; ujc = a[j * 6 + uc]; cur = a[ui * 6 + uc]; }
     __syncwarp();
     if (lane == 0) a[j * 6 + j] = ajj;
     if (j != 5) {
       const double tmp2 = 1.0 / ajj;
-      if (lane > j && lane < 6) a[lane * 6 + j] *= tmp2;
-      __syncwarp();
-      if (lane < 25 && ui > j && uc > j) a[ui * 6 + uc] -= a[ui * 6 + j] * a[j * 6 + uc];
+      lij *= tmp2;
+      if (scl) a[si * 6 + j] = lij;
+      if (upd) a[ui * 6 + uc] = cur - lij * ujc;
     }
     __syncwarp();
   }
-  if (lane == 0) {
-    int k = 0;
-#pragma unroll 1
-    for (int i = 0; i < 6; ++i) {
-      int j = (idxp >> (3 * i)) & 7;
-      double sum = xs[j];
-      xs[j] = xs[i];
-      if (k != 0)
-        for (j = k - 1; j < i; ++j) sum -= a[i * 6 + j] * xs[j];
-      else if (sum != 0.0) k = i + 1;
-      xs[i] = sum;
-    }
-#pragma unroll 1
-    for (int i = 5; i >= 0; --i) {
-      double sum = xs[i];
-      for (int j = i + 1; j < 6; ++j) sum -= a[i * 6 + j] * xs[j];
-      xs[i] = sum / a[i * 6 + i];
-    }
-  }
-  __syncwarp();
+  // the two triangular solves: the reference's loops on registers, fully unrolled (static indices; the permuted
+  // right-hand side x[idx[i]] <-> x[i] and the leading-zero skip `k` become selects / predicates). Every lane runs
+  // them redundantly on its own copy, so no broadcast is needed afterwards.
+  {
+    double u[6][6], xr[6];
 #pragma unroll
-  for (int r = 0; r < 6; ++r) x[r] = xs[r];
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) u[i][j] = a[i * 6 + j];
+      xr[i] = xs[i];
+    }
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int jj = (idxp >> (3 * i)) & 7;
+      double sum = xr[i];
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+        if (r == jj) { sum = xr[r]; xr[r] = xr[i]; }
+      if (k != 0) {
+#pragma unroll
+        for (int j2 = 0; j2 < i; ++j2)
+          if (j2 >= k - 1) sum -= u[i][j2] * xr[j2];
+      } else if (sum != 0.0) k = i + 1;
+      xr[i] = sum;
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+      double sum = xr[i];
+#pragma unroll
+      for (int j2 = i + 1; j2 < 6; ++j2) sum -= u[i][j2] * xr[j2];
+      xr[i] = sum / u[i][i];
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) x[r] = xr[r];
+  }
   __syncwarp();
   return 1;
 }

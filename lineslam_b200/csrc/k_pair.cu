@@ -11,6 +11,13 @@
 // Pairs are independent (GraphManager::nodeComparisons maps over them, src/graph_manager.cpp:555), so a
 // batch of pairs is a grid of CTAs. Sums that feed decisions run in the reference's order.
 #include "pair_common.cuh"
+#include <stdio.h>
+#ifdef POSE_PROFILE
+__device__ unsigned long long g_pose_prof[16];
+#define PT(k) do { __syncthreads(); if (threadIdx.x == 0) { long long now_ = clock64(); atomicAdd(&g_pose_prof[k], (unsigned long long)(now_ - t_last_)); t_last_ = now_; } } while (0)
+#else
+#define PT(k)
+#endif
 
 // ------------------------------------------------------------ lineMatching ----
 __device__ __forceinline__ double cvnorm_diff72(const double* a, const double* b) {
@@ -145,7 +152,7 @@ __global__ void __launch_bounds__(256) match_lines_kernel(const LslPairDesc* __r
 // column / block row); sums over the matches run as ordered chains on dedicated threads.
 // tf (12 floats, shared memory) in/out.
 __device__ void refine_pose(const LmView& V, const double* md_all, int n, float* tf, int iterations, const PoseParams& PP,
-                            double* s_red /* >= 64 doubles shared */, double* s_S /* 96 doubles shared */, Iso* s_ci /* 12, shared */) {
+                            double* s_red /* >= 64 doubles shared */, double* s_S /* 96 doubles shared */, Iso* s_ci /* 12, shared */, long long& t_last_) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   if (n == 0) return;
   Iso tfd, cam1, ident;
@@ -166,6 +173,7 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
     Iso w2n;
     iso_inv(cam1, w2n);
     chi2_terms(V, md_all, n, w2n, ident, V.L, PP);
+    PT(4);
     // the twelve perturbed camera poses (cam1 (+) +-delta e_d)^-1 are the same for every match: once per iteration
     if (tid < 12) {
       double u[6] = {0, 0, 0, 0, 0, 0};
@@ -225,6 +233,7 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
       }
     }
     __syncthreads();
+    PT(5);
     // ---- block rows: thread (match i, row a)
     for (int t = tid; t < 6 * n; t += nthr) {
       const int i = t / 6, a = t - 6 * i;
@@ -268,6 +277,7 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
       for (int c = 0; c < 6; ++c) hll[a * 6 + c] = hrow[c];
     }
     __syncthreads();
+    PT(6);
     // ordered sums over the matches: Hpp (36), bp (6) on threads 0..41; chi2 on thread 64
     if (tid < 36) s_S[tid] = chain_sum<false>(0.0, V.contrib + tid, 42, n);
     else if (tid < 42) s_S[tid] = chain_sum<true>(0.0, V.contrib + tid, 42, n);
@@ -294,6 +304,7 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
       lambda = tau * maxDiag;
       ni = 2;
     }
+    PT(7);
     double rho = 0;
     int qmax = 0;
     do {
@@ -307,6 +318,7 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
         for (int k = 0; k < 6; ++k) V.HllInv[36 * i + k * 6 + c] = Rc[k];
       }
       __syncthreads();
+      PT(8);
       // Schur terms: thread (match i, row a)
       for (int t = tid; t < 6 * n; t += nthr) {
         const int i = t / 6, a = t - 6 * i;
@@ -333,6 +345,7 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
         }
       }
       __syncthreads();
+      PT(9);
       if (tid < 42) {
         double s0 = tid < 36 ? Hpp[tid] : bp[tid - 36];
         if (tid < 36 && (tid / 6 == tid % 6)) s0 += lambda;
@@ -352,6 +365,7 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
         for (int k = 0; k < 6; ++k) s_S[48 + k * 6 + tid] = Rc[k];
       }
       __syncthreads();
+      PT(10);
       double dp[6];
 #pragma unroll
       for (int a = 0; a < 6; ++a) {
@@ -383,6 +397,7 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
       iso_oplus(cam1, dp, camNew);
       iso_inv(camNew, w2nNew);
       __syncthreads();
+      PT(11);
       chi2_terms(V, md_all, n, w2nNew, ident, V.Lnew, PP);
       if (tid == nthr - 1) s_red[3] = chain_sum<false>(scale, V.terms, 1, 6 * n);   // overlaps the chi2 terms of the other warps
       __syncthreads();
@@ -391,6 +406,7 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
       scale = s_red[3];
       double tempChi = s_red[4];
       __syncthreads();
+      PT(12);
       if (!ok) tempChi = DBL_MAX;
       rho = (currentChi - tempChi);
       scale += 1e-3;
@@ -468,6 +484,7 @@ __global__ void __launch_bounds__(POSE_THREADS, 2) pose_kernel(const LslPairDesc
   const int nm = min(nmatch[pair], pd.cap_m);
   const lsl_match* ms = matches_all + pd.m_off;
   lsl_pose_rec* rec = out + pair;
+  long long t_last_ = clock64(); (void)t_last_;
   // per-pair slices of the scratch
   double* md_all = sc.md + pd.m_off * MD_STRIDE;
   double* da_s = sc.dab + pd.m_off * 2;
@@ -526,6 +543,7 @@ __global__ void __launch_bounds__(POSE_THREADS, 2) pose_kernel(const LslPairDesc
     }
   }
   __syncthreads();
+  PT(0);
   // ---- minimal solutions (getTransform_Line_svd, motion.cpp:581-603)
   for (int h = tid; h < maxIter; h += blockDim.x) {
     const double* mdp[3] = {md_all + (size_t)trip[3 * h] * MD_STRIDE, md_all + (size_t)trip[3 * h + 1] * MD_STRIDE,
@@ -536,6 +554,7 @@ __global__ void __launch_bounds__(POSE_THREADS, 2) pose_kernel(const LslPairDesc
     for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) tf[r * 4 + c] = (float)R[r * 3 + c]; tf[r * 4 + 3] = (float)t[r]; }
   }
   __syncthreads();
+  PT(1);
   // ---- scoring: warp per hypothesis, lanes over matches
   for (int h = warp; h < maxIter; h += nwarp) {
     const float* tfh = tfs + (size_t)h * 12;
@@ -556,6 +575,7 @@ __global__ void __launch_bounds__(POSE_THREADS, 2) pose_kernel(const LslPairDesc
     if (lane == 0) cnts[h] = c;
   }
   __syncthreads();
+  PT(2);
   // ---- first best (strict >, motion.cpp:714-720)
   if (warp == 0) {
     int best = 0, bh = 1 << 30;
@@ -586,21 +606,24 @@ __global__ void __launch_bounds__(POSE_THREADS, 2) pose_kernel(const LslPairDesc
     for (int i = 0; i < 16; ++i) tr[i] = s_tf[i];
   }
   const float sum_squared_error = (float)sse;
+  PT(3);
   // ---- refinement (motion.cpp:726-839)
   V.sel = sel_r;
-  refine_pose(V, md_all, best_cnt, s_tf, 25, PP, s_red, s_S, s_ci);
+  refine_pose(V, md_all, best_cnt, s_tf, 25, PP, s_red, s_S, s_ci, t_last_);
   double refined_rmse = (double)sqrtf(sum_squared_error / (float)best_cnt);   // float division + std::sqrt(float), motion.cpp:731
   int refined_cnt = 0;
   for (int it = 0; it < 20; ++it) {
     double tmp_sse;
+    PT(13);
     int c = score_all(md_all, nm, s_tf, PP.thr, da_s, db_s, sel_t, false, &tmp_sse, s_i, s_d);
+    PT(14);
     if (c * line_weight > refined_cnt * line_weight) {
       for (int i = tid; i < c; i += blockDim.x) sel_f[i] = sel_t[i];
       refined_cnt = c;
       refined_rmse = sqrt(tmp_sse / (double)c);
       __syncthreads();
       V.sel = sel_f;
-      refine_pose(V, md_all, refined_cnt, s_tf, 20, PP, s_red, s_S, s_ci);
+      refine_pose(V, md_all, refined_cnt, s_tf, 20, PP, s_red, s_S, s_ci, t_last_);
     } else break;
   }
   __syncthreads();
@@ -634,5 +657,18 @@ int lsl_launch_pose(lsl_ctx* ctx, int npairs) {
   pose_kernel<<<npairs, POSE_THREADS, 0, ctx->stream>>>(ctx->pw.d_pairs, ctx->pw.matches, ctx->pw.nmatch, ctx->pw.sc, PP, ctx->pw.recs);
   LSL_KSTOP(ctx, LSL_K_POSE);
   LSL_CUDA(cudaGetLastError());
+#ifdef POSE_PROFILE
+  {
+    cudaStreamSynchronize(ctx->stream);
+    unsigned long long h[16];
+    cudaMemcpyFromSymbol(h, g_pose_prof, sizeof(h));
+    static const char* nm_[16] = {"gather+samples", "minimal solves", "scoring", "best+score_all", "lm chi2", "lm jacobians", "lm block rows",
+                                  "lm chain Hpp", "lm inverse", "lm schur", "lm chain S+solve", "lm update", "lm trial chi2", "loop misc", "score_all", "-"};
+    double tot = 0; for (int i = 0; i < 15; ++i) tot += (double)h[i];
+    for (int i = 0; i < 15; ++i) fprintf(stderr, "pose phase %-18s %6.2f %%  %.3f ms/pair\n", nm_[i], 100.0 * h[i] / tot, h[i] / 1.965e6 / npairs);
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_pose_prof, z, sizeof(z));
+  }
+#endif
   return LSL_OK;
 }
