@@ -7,6 +7,7 @@
 // All of these are HBM/L2-streaming stencils; arithmetic follows the reference's operation order
 // exactly (compiled with --fmad=false) so every plane is bit-identical to the CPU path.
 #include "lsl_internal.h"
+#include <cuda/barrier>
 #include "shared/lsl_math.h"
 
 using namespace lslm;
@@ -98,6 +99,51 @@ __global__ void ypass_kernel(const double* __restrict__ aux, double* __restrict_
     sum += a[(size_t)j * sw + x] * ky[y * 8 + i];
   }
   out[((size_t)f * sh + y) * sw + x] = sum;
+}
+
+// y pass with TMA staging (sm_100a): one CTA produces YP_R consecutive output rows x 128 columns. The aux rows
+// those outputs tap (rows yc[y0]-h .. yc[y0+YP_R-1]+h, folded by the symmetric boundary) are fetched ONCE into
+// shared memory by bulk asynchronous copies (cp.async.bulk.shared::cluster.global, one 1 KB row segment each,
+// completion counted on an mbarrier) instead of seven global loads per output; the sum keeps the reference's tap
+// order i = 0..6 (lsd.cpp:625-640). Needs sw even (16-byte segments); otherwise ypass_kernel is used.
+#define YP_R 8
+#define YP_ROWS 24
+__global__ void __launch_bounds__(512) ypass_tma_kernel(const double* __restrict__ aux, double* __restrict__ out,
+                                                        const double* __restrict__ ky, const int* __restrict__ yc, int H, int sw,
+                                                        int sh, int h, int ntap) {
+  __shared__ __align__(128) double tile[YP_ROWS][128];
+#pragma nv_diag_suppress static_var_with_dynamic_init
+  __shared__ cuda::barrier<cuda::thread_scope_block> bar;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 128 + tx;
+  const int x0 = blockIdx.x * 128, y0 = blockIdx.y * YP_R, f = blockIdx.z;
+  const int y1 = min(y0 + YP_R, sh) - 1;
+  const double* a = aux + (size_t)f * H * sw;
+  const int jlo = yc[y0] - h, jhi = yc[y1] + h;          // unfolded row range of this CTA
+  const int nrows = jhi - jlo + 1;                        // <= YP_ROWS (checked on the host)
+  const int ncol = min(128, sw - x0);
+  if (tid == 0) {
+    init(&bar, 512);
+    cuda::device::experimental::fence_proxy_async_shared_cta();
+  }
+  __syncthreads();
+  cuda::barrier<cuda::thread_scope_block>::arrival_token token;
+  if (tid == 0) {
+    const size_t bytes = (size_t)ncol * sizeof(double);
+    for (int r = 0; r < nrows; ++r)
+      cuda::device::memcpy_async_tx(&tile[r][0], a + (size_t)sym_index(jlo + r, H) * sw + x0, cuda::aligned_size_t<16>(bytes), bar);
+    token = cuda::device::barrier_arrive_tx(bar, 1, bytes * nrows);
+  } else token = bar.arrive();
+  bar.wait(std::move(token));
+  if (tx < ncol) {
+    for (int yy = ty; yy < YP_R; yy += 4) {
+      const int y = y0 + yy;
+      if (y >= sh) break;
+      const int c = yc[y];
+      double sum = 0.0;
+      for (int i = 0; i < ntap; ++i) sum += tile[c - h + i - jlo][tx] * ky[y * 8 + i];
+      out[((size_t)f * sh + y) * sw + x0 + tx] = sum;
+    }
+  }
 }
 
 // ------------------------------------------------------------ ll_angle ----
@@ -260,7 +306,12 @@ int lsl_launch_image(lsl_ctx* ctx, int f0, int n, const uint8_t* d_img, int chan
   xpass_kernel<<<gxp, bx, 0, st>>>(gray, w.aux + f0 * apix, ctx->taps.kx, ctx->taps.xc, d.W, d.H, d.sw, ctx->taps.h, ctx->taps.n);
   LSL_KSTOP(ctx, LSL_K_XPASS);
   LSL_KSTART(ctx, LSL_K_YPASS);
-  ypass_kernel<<<gyp, bx, 0, st>>>(w.aux + f0 * apix, w.scaled + f0 * spix, ctx->taps.ky, ctx->taps.yc, d.H, d.sw, d.sh, ctx->taps.h, ctx->taps.n);
+  // rows tapped by YP_R consecutive outputs: ceil(YP_R / scale) + 2 h + 2 must fit the staged tile
+  if ((d.sw & 1) == 0 && (int)ceil(YP_R / P.lsd_scale) + 2 * ctx->taps.h + 2 <= YP_ROWS) {
+    dim3 byt(128, 4), gyt((d.sw + 127) / 128, (d.sh + YP_R - 1) / YP_R, n);
+    ypass_tma_kernel<<<gyt, byt, 0, st>>>(w.aux + f0 * apix, w.scaled + f0 * spix, ctx->taps.ky, ctx->taps.yc, d.H, d.sw, d.sh, ctx->taps.h, ctx->taps.n);
+  } else
+    ypass_kernel<<<gyp, bx, 0, st>>>(w.aux + f0 * apix, w.scaled + f0 * spix, ctx->taps.ky, ctx->taps.yc, d.H, d.sw, d.sh, ctx->taps.h, ctx->taps.n);
   LSL_KSTOP(ctx, LSL_K_YPASS);
   double prec = LSL_PI * P.lsd_ang_th / 180.0;
   double rho = P.lsd_quant / lsl_sin(prec);
