@@ -595,20 +595,21 @@ __device__ __noinline__ double l2nrm_neg(double* E, const double* y, int n) {
 // column by 1 / pivot, then ALL trailing elements a[i][c] -= a[i][j] * a[j][c] (i, c > j) at once, one lane
 // each. Every element receives exactly the reference's updates (k ascending, separate multiply and subtract)
 // because the L entries travel with their row through the swaps; only where an operation is executed changes.
-// The two triangular solves are the reference's loops on lane 0. W = 48 doubles of warp-private scratch
+// The two triangular solves are the reference's loops on registers. W = 48 doubles of warp-private scratch
 // (a 36 | work 6 | x 6). The system is (JtJ + mu on the diagonal) x = Jte; every lane receives x[6].
 __device__ __noinline__ int ax_eq_b_lu6(const MleSmem& S, double mu, double* W, double* x) {
   const int lane = threadIdx.x & 31;
   double* a = W; double* work = W + 36; double* xs = W + 42;
   __syncwarp();
   for (int e = lane; e < 36; e += 32) { const int r = e / 6, c = e - 6 * r; a[e] = (r == c) ? S.JtJ[e] + mu : S.JtJ[e]; }
-  if (lane < 6) xs[lane] = S.Jte[lane];
-  __syncwarp();
   double mx = 0.0, tmp;
   if (lane < 6) {
+    xs[lane] = S.Jte[lane];
 #pragma unroll
-    for (int j = 0; j < 6; ++j)
-      if ((tmp = fabs(a[lane * 6 + j])) > mx) mx = tmp;
+    for (int j = 0; j < 6; ++j) {
+      const double v = (j == lane) ? S.JtJ[lane * 6 + j] + mu : S.JtJ[lane * 6 + j];
+      if ((tmp = fabs(v)) > mx) mx = tmp;
+    }
     work[lane] = 1.0 / mx;
   }
   if (__ballot_sync(FULL, lane < 6 && mx == 0.0)) return 0;
@@ -618,19 +619,18 @@ __device__ __noinline__ int ax_eq_b_lu6(const MleSmem& S, double mu, double* W, 
   const int ui = 1 + lane / 5, uc = 1 + lane % 5;   // lanes 0..24 <-> element (ui, uc) of the trailing 5 x 5 block
 #pragma unroll 1
   for (int j = 0; j < 6; ++j) {
-    // pivot: last row i >= j with the largest work[i] * |a[i][j]| (the reference's `>=` scan), NaNs never win
-    double bv = -1.0;
-    int bi = lane;
-    if (lane >= j && lane < 6) { tmp = work[lane] * fabs(a[lane * 6 + j]); if (tmp == tmp) bv = tmp; }
+    // pivot: the reference's scan over the rows i >= j (`>=`: the last maximum wins, NaNs never do), run redundantly
+    // by every lane on the shared-memory column (six independent loads) instead of a shuffle reduction
+    {
+      double pmax = 0.0;
 #pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-      const double ov = __shfl_xor_sync(FULL, bv, o);
-      const int oi = __shfl_xor_sync(FULL, bi, o);
-      if (ov > bv || (ov == bv && oi > bi)) { bv = ov; bi = oi; }
+      for (int i = 0; i < 6; ++i) {
+        const double t = work[i] * fabs(a[i * 6 + j]);
+        if (i >= j && t >= pmax) { pmax = t; maxi = i; }
+      }
     }
-    bv = __shfl_sync(FULL, bv, 0); bi = __shfl_sync(FULL, bi, 0);
-    if (bv >= 0.0) maxi = bi;
     if (j != maxi) {                         // uniform
+      __syncwarp();                          // every lane has read the column and the weights
       if (lane < 6) { const double t = a[maxi * 6 + lane]; a[maxi * 6 + lane] = a[j * 6 + lane]; a[j * 6 + lane] = t; }
       if (lane == 6) work[maxi] = work[j];
       __syncwarp();
