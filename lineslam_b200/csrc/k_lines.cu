@@ -579,12 +579,12 @@ __device__ __noinline__ double l2nrm_neg(double* E, const double* y, int n) {
     s += t0 * t0; s += t1 * t1; s += t2 * t2; s += t3 * t3;
   }
   for (; i >= 0; i -= 4) { double t0 = E[i]; s += t0 * t0; }
+  // remainder (switch fall-through of the reference): element blockn + t goes to accumulator (7 - rem + t) & 3,
+  // i.e. accumulator a takes t = (a + rem + 1) & 3 and t + 4, in that order
   const int rem = n - blockn;
-  for (int t = 0; t < rem; ++t) {
-    const int c = rem - t;                                    // switch case label of element blockn + t
-    const int acc = (c == 7 || c == 3) ? 0 : ((c == 6 || c == 2) ? 1 : ((c == 5 || c == 1) ? 2 : 3));
-    if (acc == a) { double t0 = E[blockn + t]; s += t0 * t0; }
-  }
+  const int t0r = (a + rem + 1) & 3;
+  if (t0r < rem) { const double v = E[blockn + t0r]; s += v * v; }
+  if (t0r + 4 < rem) { const double v = E[blockn + t0r + 4]; s += v * v; }
   const double s0 = __shfl_sync(FULL, s, 0), s1 = __shfl_sync(FULL, s, 1), s2 = __shfl_sync(FULL, s, 2), s3 = __shfl_sync(FULL, s, 3);
   return s0 + s1 + s2 + s3;
 }
@@ -703,6 +703,8 @@ __global__ void __launch_bounds__(32, MLE_MINB) line_mle_kernel(LslWork w, LineP
   MleSmem& S = *reinterpret_cast<MleSmem*>(smem_raw);
   const int f = blockIdx.y, lane = threadIdx.x;
   const int nl = min(w.nlines[f], LSL_MAX_LINES);
+  int tri_i = 0, tri_j = lane;                         // lanes 0..20 <-> lower-triangle element (tri_i, tri_j), tri_j <= tri_i
+  while (tri_j > tri_i) { tri_j -= tri_i + 1; ++tri_i; }
   for (int li = blockIdx.x; li < nl; li += gridDim.x) {
   __syncwarp();
   lsl_line_rec* L = w.lines + (size_t)f * LSL_MAX_LINES + li;
@@ -784,11 +786,8 @@ __global__ void __launch_bounds__(32, MLE_MINB) line_mle_kernel(LslWork w, LineP
       if (lane < 27) {
         double acc = 0.0;
         const double* ja; const double* jb; int sb;
-        if (lane < 21) {
-          int i = 0, r = lane;
-          while (r > i) { r -= i + 1; ++i; }  // lane -> (i, j), j <= i
-          ja = S.jac + r; jb = S.jac + i; sb = m;
-        } else { ja = S.jac + (lane - 21); jb = Ecur; sb = 1; }
+        if (lane < 21) { ja = S.jac + tri_j; jb = S.jac + tri_i; sb = m; }
+        else { ja = S.jac + (lane - 21); jb = Ecur; sb = 1; }
         int l = n - 1;
         for (; l >= 3; l -= 4) {
           double t0 = ja[l * m] * jb[l * sb], t1 = ja[(l - 1) * m] * jb[(l - 1) * sb], t2 = ja[(l - 2) * m] * jb[(l - 2) * sb],
@@ -796,11 +795,8 @@ __global__ void __launch_bounds__(32, MLE_MINB) line_mle_kernel(LslWork w, LineP
           acc += t0; acc += t1; acc += t2; acc += t3;
         }
         for (; l >= 0; --l) acc += ja[l * m] * jb[l * sb];
-        if (lane < 21) {
-          int i = 0, r = lane;
-          while (r > i) { r -= i + 1; ++i; }
-          S.JtJ[i * m + r] = acc; S.JtJ[r * m + i] = acc;
-        } else S.Jte[lane - 21] = acc;
+        if (lane < 21) { S.JtJ[tri_i * m + tri_j] = acc; S.JtJ[tri_j * m + tri_i] = acc; }
+        else S.Jte[lane - 21] = acc;
       }
       __syncwarp();
       p_L2 = jacTe_inf = 0.0;
@@ -879,7 +875,7 @@ __global__ void __launch_bounds__(32, MLE_MINB) line_mle_kernel(LslWork w, LineP
     int ha = 0, hb = 0;
     double* Jt = S.jac;  // 32 x 18 doubles <= 101 x 6
     __syncwarp();
-    if (lane < 21) { int i = 0, r = lane; while (r > i) { r -= i + 1; ++i; } ha = i; hb = r; }
+    if (lane < 21) { ha = tri_i; hb = tri_j; }
 #pragma unroll 1
     for (int q4 = 0; q4 < 4; ++q4) {
       const int i0 = 32 * q4;
