@@ -614,7 +614,6 @@ __device__ __noinline__ int ax_eq_b_lu6(const MleSmem& S, double mu, double* W, 
   }
   if (__ballot_sync(FULL, lane < 6 && mx == 0.0)) return 0;
   __syncwarp();
-  int idxp = 0;   // idx[j] packed, 3 bits each
   int maxi = -1;
   const int ui = 1 + lane / 5, uc = 1 + lane % 5;   // lanes 0..24 <-> element (ui, uc) of the trailing 5 x 5 block
 #pragma unroll 1
@@ -633,9 +632,9 @@ __device__ __noinline__ int ax_eq_b_lu6(const MleSmem& S, double mu, double* W, 
       __syncwarp();                          // every lane has read the column and the weights
       if (lane < 6) { const double t = a[maxi * 6 + lane]; a[maxi * 6 + lane] = a[j * 6 + lane]; a[j * 6 + lane] = t; }
       if (lane == 6) work[maxi] = work[j];
+      if (lane == 7) { const double t = xs[maxi]; xs[maxi] = xs[j]; xs[j] = t; }   // the same row swap on the right-hand side
       __syncwarp();
     }
-    idxp |= (maxi & 7) << (3 * j);
     double ajj = a[j * 6 + j];
     if (ajj == 0.0) ajj = DBL_EPSILON;        // uniform value; lane 0 stores it
     // column scaling (lanes 25..29 <-> rows j+1..5) and the trailing update (lanes 0..24) in one phase: all loads,
@@ -666,14 +665,12 @@ __device__ __noinline__ int ax_eq_b_lu6(const MleSmem& S, double mu, double* W, 
       for (int j = 0; j < 6; ++j) u[i][j] = a[i * 6 + j];
       xr[i] = xs[i];
     }
+    // forward substitution: the reference interleaves x[idx[i]] <-> x[i] with the row sums; idx[i] >= i, so that is
+    // the row permutation applied first (done on xs during the elimination) followed by the plain L solve
     int k = 0;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-      const int jj = (idxp >> (3 * i)) & 7;
       double sum = xr[i];
-#pragma unroll
-      for (int r = 0; r < 6; ++r)
-        if (r == jj) { sum = xr[r]; xr[r] = xr[i]; }
       if (k != 0) {
 #pragma unroll
         for (int j2 = 0; j2 < i; ++j2)
