@@ -206,47 +206,64 @@ __global__ void __launch_bounds__(1024) ll_angle_kernel(const double* __restrict
 }
 
 // ---------------------------------------------------------- seed list ----
-// One CTA per frame. Pass A: histogram of bins (smem atomics, order-free). Pass B (warp 0): walk the
-// pixels in the reference's x-outer / y-inner order and scatter stably, bins 1023 .. 1 concatenated
-// (lsd.cpp:777-787; bin 0 would only be appended if it were the highest non-empty bin, which needs
-// norm < max_grad/n_bins <= threshold and therefore never holds a seed).
-__global__ void seed_list_kernel(const uint16_t* __restrict__ binT, int32_t* __restrict__ seeds, int32_t* __restrict__ nseeds,
-                                 int p, int n, int n_bins) {
-  extern __shared__ int s_cnt[];  // n_bins counters, then cursors
-  int f = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+// One CTA (8 warps) per frame reproduces list_p of ll_angle (lsd.cpp:723-787): pixels in the reference's
+// x-outer / y-inner order, bucketed by gradient bin, bins 1023 .. 1 concatenated (bin 0 would only be appended if
+// it were the highest non-empty bin, which needs norm < max_grad/n_bins <= threshold and therefore never holds a
+// seed). The pixel range is cut into 8 contiguous segments, one per warp: pass A counts the bins of every segment
+// (shared-memory atomics, order-free), pass B turns the counts into start cursors (bin-major, then segment order),
+// pass C lets every warp scatter its own segment stably (ballot + match_any keep the in-segment order).
+#define SEED_WARPS 8
+__global__ void __launch_bounds__(32 * SEED_WARPS) seed_list_kernel(const uint16_t* __restrict__ binT, int32_t* __restrict__ seeds,
+                                                                   int32_t* __restrict__ nseeds, int p, int n, int n_bins) {
+  extern __shared__ int s_cnt[];  // [SEED_WARPS][n_bins] counts -> cursors, then [n_bins] bin starts
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint16_t* B = binT + (size_t)f * p * n;
   int32_t* S = seeds + (size_t)f * p * n;
-  int total = p * n;
-  for (int i = tid; i < n_bins; i += nthr) s_cnt[i] = 0;
+  const int total = p * n;
+  const int seg = ((total + SEED_WARPS - 1) / SEED_WARPS + 31) & ~31;   // segment length, multiple of 32
+  const int lo = min(warp * seg, total), hi = min(lo + seg, total);
+  int* cnt = s_cnt + warp * n_bins;
+  int* start = s_cnt + SEED_WARPS * n_bins;
+  for (int i = tid; i < SEED_WARPS * n_bins; i += 32 * SEED_WARPS) s_cnt[i] = 0;
   __syncthreads();
-  for (int i = tid; i < total; i += nthr) {
+  for (int i = lo + lane; i < hi; i += 32) {
     uint16_t b = B[i];
-    if (b != 0xFFFF && b != 0) atomicAdd(&s_cnt[b], 1);
+    if (b != 0xFFFF && b != 0) atomicAdd(&cnt[b], 1);
+  }
+  __syncthreads();
+  // bin totals
+  for (int b = tid; b < n_bins; b += 32 * SEED_WARPS) {
+    int t = 0;
+    for (int w = 0; w < SEED_WARPS; ++w) t += s_cnt[w * n_bins + b];
+    start[b] = t;
   }
   __syncthreads();
   if (tid == 0) {
     int run = 0;
-    for (int b = n_bins - 1; b >= 1; --b) { int c = s_cnt[b]; s_cnt[b] = run; run += c; }
+    for (int b = n_bins - 1; b >= 1; --b) { int c = start[b]; start[b] = run; run += c; }
     nseeds[f] = run;
   }
   __syncthreads();
-  if (tid < 32) {
-    unsigned lt = (1u << tid) - 1u;
-    for (int i0 = 0; i0 < total; i0 += 32) {
-      int i = i0 + tid;
-      uint16_t b = i < total ? B[i] : (uint16_t)0xFFFF;
-      bool valid = (b != 0xFFFF && b != 0);
-      unsigned vm = __ballot_sync(0xffffffffu, valid);
-      if (valid) {
-        unsigned grp = __match_any_sync(vm, (unsigned)b);
-        int pos = s_cnt[b] + __popc(grp & lt);
-        int x = i / n, y = i - x * n;
-        S[pos] = x | (y << 16);
-        __syncwarp(vm);
-        if ((grp & lt) == 0) s_cnt[b] += __popc(grp);
-      }
-      __syncwarp();
+  for (int b = tid; b < n_bins; b += 32 * SEED_WARPS) {
+    int run = start[b];
+    for (int w = 0; w < SEED_WARPS; ++w) { int c = s_cnt[w * n_bins + b]; s_cnt[w * n_bins + b] = run; run += c; }
+  }
+  __syncthreads();
+  const unsigned lt = (1u << lane) - 1u;
+  for (int i0 = lo; i0 < hi; i0 += 32) {
+    int i = i0 + lane;
+    uint16_t b = i < hi ? B[i] : (uint16_t)0xFFFF;
+    bool valid = (b != 0xFFFF && b != 0);
+    unsigned vm = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+      unsigned grp = __match_any_sync(vm, (unsigned)b);
+      int pos = cnt[b] + __popc(grp & lt);
+      int x = i / n, y = i - x * n;
+      S[pos] = x | (y << 16);
+      __syncwarp(vm);
+      if ((grp & lt) == 0) cnt[b] += __popc(grp);
     }
+    __syncwarp();
   }
 }
 
@@ -332,8 +349,10 @@ int lsl_launch_image(lsl_ctx* ctx, int f0, int n, const uint8_t* d_img, int chan
 int lsl_launch_seeds(lsl_ctx* ctx, int n) {
   const LslDims& d = ctx->dims;
   const LslWork& w = ctx->wk;
+  const size_t seed_smem = (SEED_WARPS + 1) * ctx->P.lsd_n_bins * sizeof(int);
+  if (seed_smem > 48 * 1024) cudaFuncSetAttribute(seed_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem);
   LSL_KSTART(ctx, LSL_K_SEEDS);
-  seed_list_kernel<<<n, 256, ctx->P.lsd_n_bins * sizeof(int), ctx->stream>>>(w.binT, w.seeds, w.nseeds, d.sw, d.sh, ctx->P.lsd_n_bins);
+  seed_list_kernel<<<n, 32 * SEED_WARPS, seed_smem, ctx->stream>>>(w.binT, w.seeds, w.nseeds, d.sw, d.sh, ctx->P.lsd_n_bins);
   LSL_KSTOP(ctx, LSL_K_SEEDS);
   LSL_CUDA(cudaGetLastError());
   return LSL_OK;
