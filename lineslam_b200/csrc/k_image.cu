@@ -14,7 +14,9 @@ using namespace lslm;
 
 // ---------------------------------------------------------------- taps ----
 // gaussian_kernel (lsd.cpp:466-489) evaluated once per output coordinate, as the reference does.
-__global__ void taps_kernel(double* __restrict__ k, int* __restrict__ c, int nout, double scale, double sigma, int h) {
+// Tap i of output x is stored at k[x * sx + i * si]: (8, 1) = one row of taps per output (y table, read uniformly by a
+// warp), (1, nout) = tap-major (x table: a warp reads consecutive doubles).
+__global__ void taps_kernel(double* __restrict__ k, int* __restrict__ c, int nout, double scale, double sigma, int h, int sx, int si) {
   int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= nout) return;
   double xx = (double)x / scale;
@@ -29,7 +31,7 @@ __global__ void taps_kernel(double* __restrict__ k, int* __restrict__ c, int nou
   }
   if (sum >= 0.0)
     for (int i = 0; i < n; ++i) v[i] /= sum;
-  for (int i = 0; i < 8; ++i) k[x * 8 + i] = i < n ? v[i] : 0.0;
+  for (int i = 0; i < 8; ++i) k[(size_t)x * sx + (size_t)i * si] = i < n ? v[i] : 0.0;
   c[x] = xc;
 }
 
@@ -41,8 +43,8 @@ int lsl_prepare_taps(lsl_ctx* ctx) {
   int h = (int)ceil(sigma * sqrt(2.0 * 3.0 * 2.302585092994046));
   if (1 + 2 * h > 8) { ctx->err = "gaussian kernel wider than 8 taps"; return LSL_ERR_ARG; }
   ctx->taps.h = h; ctx->taps.n = 1 + 2 * h;
-  taps_kernel<<<(d.sw + 127) / 128, 128, 0, ctx->stream>>>(ctx->taps.kx, ctx->taps.xc, d.sw, P.lsd_scale, sigma, h);
-  taps_kernel<<<(d.sh + 127) / 128, 128, 0, ctx->stream>>>(ctx->taps.ky, ctx->taps.yc, d.sh, P.lsd_scale, sigma, h);
+  taps_kernel<<<(d.sw + 127) / 128, 128, 0, ctx->stream>>>(ctx->taps.kx, ctx->taps.xc, d.sw, P.lsd_scale, sigma, h, 1, d.sw);
+  taps_kernel<<<(d.sh + 127) / 128, 128, 0, ctx->stream>>>(ctx->taps.ky, ctx->taps.yc, d.sh, P.lsd_scale, sigma, h, 8, 1);
   ctx->stats.kernel_launches += 2;
   LSL_CUDA(cudaGetLastError());
   return LSL_OK;
@@ -74,18 +76,30 @@ __device__ __forceinline__ int sym_index(int j, int n) {  // lsd.cpp:596-599 sym
   if (j >= n) j = n2 - 1 - j;
   return j;
 }
-__global__ void xpass_kernel(const uint8_t* __restrict__ gray, double* __restrict__ aux, const double* __restrict__ kx,
-                             const int* __restrict__ xc, int W, int H, int sw, int h, int ntap) {
-  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
-  if (x >= sw) return;
+// x pass: 4 outputs of one row per thread (128 apart, so that a warp writes consecutive doubles), the tap
+// loop unrolled for the 7-tap kernel of sigma 0.75 (NT = 0: generic tap count). Sum order i = 0..ntap-1 (lsd.cpp:600-615).
+template <int NT>
+__global__ void __launch_bounds__(128) xpass_kernel(const uint8_t* __restrict__ gray, double* __restrict__ aux, const double* __restrict__ kx,
+                                                    const int* __restrict__ xc, int W, int H, int sw, int h, int ntap_rt) {
+  const int ntap = NT ? NT : ntap_rt;
+  const int x0 = blockIdx.x * 512 + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
   const uint8_t* row = gray + ((size_t)f * H + y) * W;
-  int c = xc[x];
-  double sum = 0.0;
-  for (int i = 0; i < ntap; ++i) {
-    int j = sym_index(c - h + i, W);
-    sum += (double)row[j] * kx[x * 8 + i];
+  double* out = aux + ((size_t)f * H + y) * sw;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int x = x0 + q * 128;           // coalesced: lanes write consecutive outputs
+    if (x >= sw) break;
+    const int c = xc[x] - h;
+    double sum = 0.0;
+    if (c >= 0 && c + ntap <= W) {          // interior: no boundary folding
+#pragma unroll
+      for (int i = 0; i < ntap; ++i) sum += (double)row[c + i] * kx[i * sw + x];
+    } else {
+#pragma unroll
+      for (int i = 0; i < ntap; ++i) sum += (double)row[sym_index(c + i, W)] * kx[i * sw + x];
+    }
+    out[x] = sum;
   }
-  aux[((size_t)f * H + y) * sw + x] = sum;
 }
 __global__ void ypass_kernel(const double* __restrict__ aux, double* __restrict__ out, const double* __restrict__ ky,
                              const int* __restrict__ yc, int H, int sw, int sh, int h, int ntap) {
@@ -318,9 +332,10 @@ int lsl_launch_image(lsl_ctx* ctx, int f0, int n, const uint8_t* d_img, int chan
   } else {
     LSL_CUDA(cudaMemcpyAsync(gray, img, npix * n, cudaMemcpyDeviceToDevice, st));
   }
-  dim3 bx(128), gxp((d.sw + 127) / 128, d.H, n), gyp((d.sw + 127) / 128, d.sh, n);
+  dim3 bx(128), gxp((d.sw + 511) / 512, d.H, n), gyp((d.sw + 127) / 128, d.sh, n);
   LSL_KSTART(ctx, LSL_K_XPASS);
-  xpass_kernel<<<gxp, bx, 0, st>>>(gray, w.aux + f0 * apix, ctx->taps.kx, ctx->taps.xc, d.W, d.H, d.sw, ctx->taps.h, ctx->taps.n);
+  if (ctx->taps.n == 7) xpass_kernel<7><<<gxp, bx, 0, st>>>(gray, w.aux + f0 * apix, ctx->taps.kx, ctx->taps.xc, d.W, d.H, d.sw, ctx->taps.h, 7);
+  else xpass_kernel<0><<<gxp, bx, 0, st>>>(gray, w.aux + f0 * apix, ctx->taps.kx, ctx->taps.xc, d.W, d.H, d.sw, ctx->taps.h, ctx->taps.n);
   LSL_KSTOP(ctx, LSL_K_XPASS);
   LSL_KSTART(ctx, LSL_K_YPASS);
   // rows tapped by YP_R consecutive outputs: ceil(YP_R / scale) + 2 h + 2 must fit the staged tile

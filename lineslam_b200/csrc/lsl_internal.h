@@ -22,7 +22,7 @@ struct LslDims {
 
 // Gaussian sampler tap tables (one set per context, depend on W,H,scale,sigma_scale only)
 struct LslTaps {
-  double* kx;  // [sw][8]  7 normalised taps (+pad) per output column  (lsd.cpp:581-585)
+  double* kx;  // [8][sw]  7 normalised taps (+pad) per output column, tap-major (lsd.cpp:581-585)
   int* xc;     // [sw]     centre pixel per output column
   double* ky;  // [sh][8]
   int* yc;     // [sh]
