@@ -72,8 +72,14 @@ LSL_HD dd fast_two_sum(double a, double b) {  // requires |a| >= |b| (or a == 0)
   double s = a + b;
   return mkdd(s, b - (s - a));
 }
+// p + e = a * b exactly (error-free product). Host: Dekker / Veltkamp splitting (no FMA is assumed: the reference
+// build has none). Device: one explicit fused multiply-add — the error term of a product is representable, so both
+// forms return the same (p, e) bit for bit for every product whose halves neither overflow nor underflow.
 LSL_HD dd two_prod(double a, double b) {
   double p = a * b;
+#if defined(__CUDA_ARCH__)
+  return mkdd(p, __fma_rn(a, b, -p));
+#endif
   double t = 134217729.0 * a, ah = t - (t - a), al = a - ah;
   t = 134217729.0 * b; double bh = t - (t - b), bl = b - bh;
   return mkdd(p, ((ah * bh - p) + ah * bl + al * bh) + al * bl);
