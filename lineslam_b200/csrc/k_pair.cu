@@ -468,7 +468,7 @@ __device__ int score_all(const double* md_all, int nm, const float* tf, double t
   return c;
 }
 
-__global__ void __launch_bounds__(POSE_THREADS, 2) pose_kernel(const LslPairDesc* __restrict__ pairs, const lsl_match* __restrict__ matches_all,
+__global__ void __launch_bounds__(POSE_THREADS, POSE_MINB) pose_kernel(const LslPairDesc* __restrict__ pairs, const lsl_match* __restrict__ matches_all,
                                                             const int32_t* __restrict__ nmatch, LslPairScratch sc, PoseParams PP,
                                                             lsl_pose_rec* __restrict__ out) {
   __shared__ float s_tf[16];

@@ -16,6 +16,9 @@ using namespace lslm;
 #ifndef POSE_THREADS
 #define POSE_THREADS 256
 #endif
+#ifndef POSE_MINB
+#define POSE_MINB 2
+#endif
 #define MD_STRIDE 72  // doubles of gathered data per line match
 
 // ------------------------------------------------------- minimal solver ----

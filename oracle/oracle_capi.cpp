@@ -232,6 +232,8 @@ void orc_optimizeRelmotion(const lsl_line_rec* a, const lsl_line_rec* b, int n, 
   orc::optimizeRelmotion(va, vb, Rt, Rt + 9);
 }
 double orc_m_acos(double x) { return lslm::lsl_acos(x); }
+// error-free product probe (Dekker splitting on the host; the device uses one FMA — tests/test_oracle_units.py)
+void orc_m_two_prod(double a, double b, double* pe) { lslm::dd r = lslm::two_prod(a, b); pe[0] = r.h; pe[1] = r.l; }
 
 // levmar restatement probe: Rosenbrock-like known-answer problems are driven from tests through this.
 typedef void (*orc_lm_fn)(double*, double*, int, int, void*);
