@@ -103,6 +103,7 @@ __device__ __forceinline__ double pt_chi2(const double* e, const double* Om, dou
 // LM scratch of the point landmarks ([field][match] blocks in the pair's slice)
 struct PtView {
   double *X, *Xnew, *Hxx, *Hpx, *bx, *Inv, *contrib, *dx, *terms, *chi;   // 3,3,9,18,3,9,42,3,3,2
+  size_t cap;    // contrib is stored [42][cap]
   double *J;     // 64 per match: Jl(newer) 9 | Jl(older) 9 | Jp 18 | e 2x3 | WOe 2x3 | r1 2 | pad
   int32_t* sel;  // [np] index into the pair's point match list
   int32_t* okf;
@@ -260,7 +261,7 @@ __device__ void refine_pose_hybrid(const PtView& P, int np, const LmView& V, con
       const int i = t / 6, a = t - 6 * i;
       const double* pmd = P.pmd + (size_t)P.sel[i] * PMD_STRIDE;
       const double* Jm = P.J + (size_t)64 * i;
-      double* cp = P.contrib + 42 * i;
+      double* cp = P.contrib + i; const size_t cs = P.cap;
       if (a < 3) {
         double b = 0, hrow[3] = {0, 0, 0};
 #pragma unroll
@@ -310,13 +311,13 @@ __device__ void refine_pose_hybrid(const PtView& P, int np, const LmView& V, con
         double sp = 0;
 #pragma unroll
         for (int k = 0; k < 3; ++k) sp += Jp[k * 6 + a] * WOe[k];
-        cp[36 + a] = sp;
+        cp[(36 + a) * cs] = sp;
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
           double h = 0;
 #pragma unroll
           for (int k = 0; k < 3; ++k) h += PtO[k] * Jp[k * 6 + c];
-          cp[a * 6 + c] = h;
+          cp[(a * 6 + c) * cs] = h;
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -331,7 +332,7 @@ __device__ void refine_pose_hybrid(const PtView& P, int np, const LmView& V, con
     for (int t = tid; t < 6 * n; t += nthr) {
       const int i = t / 6, a = t - 6 * i;
       const double* Jm = V.J + (size_t)124 * i;
-      double* hll = V.Hll + 36 * i; double* hpl = V.Hpl + 36 * i; double* cp = V.contrib + 42 * i;
+      double* hll = V.Hll + 36 * i; double* hpl = V.Hpl + 36 * i; double* cp = V.contrib + i; const size_t cs = V.cap;
       double b = 0, hrow[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
       for (int side = 0; side < 2; ++side) {
@@ -354,13 +355,13 @@ __device__ void refine_pose_hybrid(const PtView& P, int np, const LmView& V, con
           double sp = 0;
 #pragma unroll
           for (int k = 0; k < 6; ++k) sp += Jp[k * 6 + a] * (wgt * e[k]);
-          cp[36 + a] = sp;
+          cp[(36 + a) * cs] = sp;
 #pragma unroll
           for (int c = 0; c < 6; ++c) {
             double h = 0, g = 0;
 #pragma unroll
             for (int k = 0; k < 6; ++k) { h += Jp[k * 6 + a] * wgt * Jp[k * 6 + c]; g += Jp[k * 6 + a] * wgt * Jl[k * 6 + c]; }
-            cp[a * 6 + c] = h;
+            cp[(a * 6 + c) * cs] = h;
             hpl[a * 6 + c] = 0.0 + g;
           }
         }
@@ -371,8 +372,8 @@ __device__ void refine_pose_hybrid(const PtView& P, int np, const LmView& V, con
     }
     __syncthreads();
     // ordered sums over the landmarks (points, then lines): Hpp (36), bp (6) on threads 0..41; chi2 on thread 64
-    if (tid < 36) s_S[tid] = chain_sum<false>(chain_sum<false>(0.0, P.contrib + tid, 42, np), V.contrib + tid, 42, n);
-    else if (tid < 42) s_S[tid] = chain_sum<true>(chain_sum<true>(0.0, P.contrib + tid, 42, np), V.contrib + tid, 42, n);
+    if (tid < 36) s_S[tid] = chain_sum<false>(chain_sum<false>(0.0, P.contrib + (size_t)tid * P.cap, 1, np), V.contrib + (size_t)tid * V.cap, 1, n);
+    else if (tid < 42) s_S[tid] = chain_sum<true>(chain_sum<true>(0.0, P.contrib + (size_t)tid * P.cap, 1, np), V.contrib + (size_t)tid * V.cap, 1, n);
     else if (tid == 64) s_red[0] = chain_sum<false>(chain_sum<false>(0.0, P.chi, 1, 2 * np), V.chi, 1, 2 * n);
     __syncthreads();
     double Hpp[36], bp[6];
@@ -422,7 +423,7 @@ __device__ void refine_pose_hybrid(const PtView& P, int np, const LmView& V, con
       for (int t = tid; t < 6 * np; t += nthr) {
         const int i = t / 6, a = t - 6 * i;
         const double* hi = P.Inv + 9 * i; const double* hpx = P.Hpx + 18 * i;
-        double* cp = P.contrib + 42 * i;
+        double* cp = P.contrib + i; const size_t cs = P.cap;
         double T[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -434,19 +435,19 @@ __device__ void refine_pose_hybrid(const PtView& P, int np, const LmView& V, con
         double s = 0;
 #pragma unroll
         for (int k = 0; k < 3; ++k) s += T[k] * P.bx[3 * i + k];
-        cp[36 + a] = s;
+        cp[(36 + a) * cs] = s;
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
           double h = 0;
 #pragma unroll
           for (int k = 0; k < 3; ++k) h += T[k] * hpx[c * 3 + k];
-          cp[a * 6 + c] = h;
+          cp[(a * 6 + c) * cs] = h;
         }
       }
       for (int t = tid; t < 6 * n; t += nthr) {
         const int i = t / 6, a = t - 6 * i;
         const double* hi = V.HllInv + 36 * i; const double* hpl = V.Hpl + 36 * i;
-        double* cp = V.contrib + 42 * i;
+        double* cp = V.contrib + i; const size_t cs = V.cap;
         double T[6];
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
@@ -458,20 +459,20 @@ __device__ void refine_pose_hybrid(const PtView& P, int np, const LmView& V, con
         double s = 0;
 #pragma unroll
         for (int k = 0; k < 6; ++k) s += T[k] * V.bl[6 * i + k];
-        cp[36 + a] = s;
+        cp[(36 + a) * cs] = s;
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
           double h = 0;
 #pragma unroll
           for (int k = 0; k < 6; ++k) h += T[k] * hpl[c * 6 + k];
-          cp[a * 6 + c] = h;
+          cp[(a * 6 + c) * cs] = h;
         }
       }
       __syncthreads();
       if (tid < 42) {
         double s0 = tid < 36 ? Hpp[tid] : bp[tid - 36];
         if (tid < 36 && (tid / 6 == tid % 6)) s0 += lambda;
-        s_S[tid] = chain_sum<true>(chain_sum<true>(s0, P.contrib + tid, 42, np), V.contrib + tid, 42, n);
+        s_S[tid] = chain_sum<true>(chain_sum<true>(s0, P.contrib + (size_t)tid * P.cap, 1, np), V.contrib + (size_t)tid * V.cap, 1, n);
       } else if (tid == 64) {
         int ok = 1;
         for (int i = 0; i < np; ++i) ok &= P.okf[i];
@@ -662,6 +663,7 @@ __global__ void __launch_bounds__(POSE_THREADS, 1) pose_hybrid_kernel(const LslP
     V.L = lm; V.Lnew = V.L + 6 * c; V.Hll = V.Lnew + 6 * c; V.Hpl = V.Hll + 36 * c; V.bl = V.Hpl + 36 * c;
     V.HllInv = V.bl + 6 * c; V.contrib = V.HllInv + 36 * c; V.dl = V.contrib + 42 * c; V.terms = V.dl + 6 * c; V.chi = V.terms + 6 * c;
     V.J = V.chi + 2 * c;
+    V.cap = c;
     V.okf = sc.okf + pd.m_off;
     V.sel = sel_r;
   }
@@ -670,6 +672,7 @@ __global__ void __launch_bounds__(POSE_THREADS, 1) pose_hybrid_kernel(const LslP
     double* lm = hs.plm + pq.pm_off * PLM_STRIDE;
     const size_t c = pq.cap_pm;
     P.X = lm; P.Xnew = P.X + 3 * c; P.Hxx = P.Xnew + 3 * c; P.Hpx = P.Hxx + 9 * c; P.bx = P.Hpx + 18 * c; P.Inv = P.bx + 3 * c;
+    P.cap = c;
     P.contrib = P.Inv + 9 * c; P.dx = P.contrib + 42 * c; P.terms = P.dx + 3 * c; P.chi = P.terms + 3 * c; P.J = P.chi + 2 * c;
     P.okf = hs.pokf + pq.pm_off;
     P.sel = psel_r;

@@ -157,9 +157,10 @@ __global__ void __launch_bounds__(128, RANSAC_MINB) line3d_ransac_kernel(LslWork
   __shared__ int s_idx[LSL_MAX_SMP];
   __shared__ int s_hA[RANSAC_CH], s_hB[RANSAC_CH], s_hcnt[RANSAC_CH];
   __shared__ uint32_t s_hmask[RANSAC_CH][4];
-  __shared__ uint32_t s_best[4];
-  __shared__ int s_wcnt[4];
-  __shared__ int s_flag[4];  // 0: done, 1: accepted
+  // 16-byte aligned: the compiler merges neighbouring 4-byte reads into LDS.128 and would otherwise straddle two arrays
+  __shared__ __align__(16) uint32_t s_best[4];
+  __shared__ __align__(16) int s_wcnt[4];
+  __shared__ __align__(16) int s_flag[4];  // 0: done, 1: accepted
   __shared__ GRand s_rng, s_snap;
 
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -337,6 +338,7 @@ __global__ void __launch_bounds__(128, RANSAC_MINB) line3d_ransac_kernel(LslWork
           return dot3(pm, d);
         }, &e1, &e2);
         for (int k = 0; k < 3; ++k) { A3[k] = s_pos[3 * e1 + k]; B3[k] = s_pos[3 * e2 + k]; }
+        __syncwarp();   // all lanes have read s_best (top of this block) before lanes 0..3 replace it
         if (lane < 4) s_best[lane] = cur[lane];
         double dAB[3] = {A3[0] - B3[0], A3[1] - B3[1], A3[2] - B3[2]};
         accept = ((double)best_cnt / numSmp > P.collin_ratio) && (norm3(dAB) > P.len3d_thres);
@@ -535,11 +537,12 @@ __global__ void msld_randfill_kernel(LslWork w, const int32_t* __restrict__ msld
 // One warp per line. Lane `lane` owns the points i = lane + 32 q (q < 4): their positions, residuals hx / wrk
 // live in registers; the covariance factors DU, the Jacobian and the two residual-difference vectors that other
 // lanes must read (J^T e, the ordered norms) live in shared memory.
+#define MLE_JS 6   // row stride of jac (7 removes the 2-way bank conflicts of the row accesses but measured 2 ms slower)
 struct MleSmem {
   double pos[LSL_MAX_SMP * 3];
   double DU[LSL_MAX_SMP * 9];
   double eA[LSL_MAX_SMP], eB[LSL_MAX_SMP];  // e of the current estimate / of the trial point (roles swap on accept)
-  double jac[LSL_MAX_SMP * 6];
+  double jac[LSL_MAX_SMP * MLE_JS];
   double JtJ[36], Jte[6];
   double cinv1[9], cinv2[9];
 };  // the 32 x 18 tile of MleLine3dCov reuses `jac` once the LM has finished
@@ -771,27 +774,28 @@ __global__ void __launch_bounds__(32, MLE_MINB) line_mle_kernel(LslWork w, LineP
         mle_cost(S, n, idx1, idx2, pp, wrk);
         d = 1.0 / d;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { const int i = lane + 32 * q; if (i < n) S.jac[i * m + j] = (wrk[q] - hx[q]) * d; }
+        for (int q = 0; q < 4; ++q) { const int i = lane + 32 * q; if (i < n) S.jac[i * MLE_JS + j] = (wrk[q] - hx[q]) * d; }
       }
       __syncwarp();
       nu = 2; updjac = 0; updp = 0; newjac = 1;
     }
     if (newjac) {
       newjac = 0;
+      __syncwarp();   // every lane has read the previous J^T e (dL above) before lanes 21..26 overwrite it
       // J^T J (lower triangle) and J^T e, each accumulator summed for l = n-1 .. 0 (lm_core.c:618-639);
       // four products are formed ahead of the dependent adds
       if (lane < 27) {
         double acc = 0.0;
         const double* ja; const double* jb; int sb;
-        if (lane < 21) { ja = S.jac + tri_j; jb = S.jac + tri_i; sb = m; }
+        if (lane < 21) { ja = S.jac + tri_j; jb = S.jac + tri_i; sb = MLE_JS; }
         else { ja = S.jac + (lane - 21); jb = Ecur; sb = 1; }
         int l = n - 1;
         for (; l >= 3; l -= 4) {
-          double t0 = ja[l * m] * jb[l * sb], t1 = ja[(l - 1) * m] * jb[(l - 1) * sb], t2 = ja[(l - 2) * m] * jb[(l - 2) * sb],
-                 t3 = ja[(l - 3) * m] * jb[(l - 3) * sb];
+          double t0 = ja[l * MLE_JS] * jb[l * sb], t1 = ja[(l - 1) * MLE_JS] * jb[(l - 1) * sb], t2 = ja[(l - 2) * MLE_JS] * jb[(l - 2) * sb],
+                 t3 = ja[(l - 3) * MLE_JS] * jb[(l - 3) * sb];
           acc += t0; acc += t1; acc += t2; acc += t3;
         }
-        for (; l >= 0; --l) acc += ja[l * m] * jb[l * sb];
+        for (; l >= 0; --l) acc += ja[l * MLE_JS] * jb[l * sb];
         if (lane < 21) { S.JtJ[tri_i * m + tri_j] = acc; S.JtJ[tri_j * m + tri_i] = acc; }
         else S.Jte[lane - 21] = acc;
       }
@@ -830,10 +834,10 @@ __global__ void __launch_bounds__(32, MLE_MINB) line_mle_kernel(LslWork w, LineP
             if (i >= n) break;
             double t = 0.0;
 #pragma unroll
-            for (int l = 0; l < m; ++l) t += S.jac[i * m + l] * Dp[l];
+            for (int l = 0; l < m; ++l) t += S.jac[i * MLE_JS + l] * Dp[l];
             t = (wrk[q] - hx[q] - t) / Dp_L2;
 #pragma unroll
-            for (int j = 0; j < m; ++j) S.jac[i * m + j] += t * Dp[j];
+            for (int j = 0; j < m; ++j) S.jac[i * MLE_JS + j] += t * Dp[j];
           }
           __syncwarp();
           ++updjac;

@@ -89,11 +89,15 @@ __device__ __forceinline__ double warp_min_except(const double* D, size_t stride
 __global__ void __launch_bounds__(256) match_lines_kernel(const LslPairDesc* __restrict__ pairs, double* __restrict__ Dall,
                                                           lsl_match* __restrict__ matches_all, int32_t* __restrict__ nmatch,
                                                           double cosT) {
-  __shared__ int s_warp_cnt[8];
-  __shared__ int s_base;
+  // one 64-byte block: [0..7] per-warp hit flags, [8] running output position, rest padding (the compiler reads
+  // neighbouring ints with LDS.128; the padding keeps those reads inside the allocation)
+  __shared__ __align__(16) int s_sh[16];
+  int* s_warp_cnt = s_sh;
+  int& s_base = s_sh[8];
   const LslPairDesc pd = pairs[blockIdx.x];
   const int n1 = pd.nq, n2 = pd.nt, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   lsl_match* out = matches_all + pd.m_off;
+  if (tid < 16) s_sh[tid] = 0;
   if (n1 == 0 || n2 == 0) { if (tid == 0) nmatch[blockIdx.x] = 0; return; }
   double* D = Dall + pd.d_off;
   double lineDistThresh, descDiffThresh, lineOverlapThresh;
@@ -238,7 +242,7 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
     for (int t = tid; t < 6 * n; t += nthr) {
       const int i = t / 6, a = t - 6 * i;
       const double* Jm = V.J + (size_t)124 * i;
-      double* hll = V.Hll + 36 * i; double* hpl = V.Hpl + 36 * i; double* cp = V.contrib + 42 * i;
+      double* hll = V.Hll + 36 * i; double* hpl = V.Hpl + 36 * i; double* cp = V.contrib + i; const size_t cs = V.cap;
       double b = 0, hrow[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
       for (int side = 0; side < 2; ++side) {
@@ -261,13 +265,13 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
           double sp = 0;
 #pragma unroll
           for (int k = 0; k < 6; ++k) sp += Jp[k * 6 + a] * (wgt * e[k]);
-          cp[36 + a] = sp;
+          cp[(36 + a) * cs] = sp;
 #pragma unroll
           for (int c = 0; c < 6; ++c) {
             double h = 0, g = 0;
 #pragma unroll
             for (int k = 0; k < 6; ++k) { h += Jp[k * 6 + a] * wgt * Jp[k * 6 + c]; g += Jp[k * 6 + a] * wgt * Jl[k * 6 + c]; }
-            cp[a * 6 + c] = h;
+            cp[(a * 6 + c) * cs] = h;
             hpl[a * 6 + c] = 0.0 + g;
           }
         }
@@ -279,8 +283,8 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
     __syncthreads();
     PT(6);
     // ordered sums over the matches: Hpp (36), bp (6) on threads 0..41; chi2 on thread 64
-    if (tid < 36) s_S[tid] = chain_sum<false>(0.0, V.contrib + tid, 42, n);
-    else if (tid < 42) s_S[tid] = chain_sum<true>(0.0, V.contrib + tid, 42, n);
+    if (tid < 36) s_S[tid] = chain_sum<false>(0.0, V.contrib + (size_t)tid * V.cap, 1, n);
+    else if (tid < 42) s_S[tid] = chain_sum<true>(0.0, V.contrib + (size_t)tid * V.cap, 1, n);
     else if (tid == 64) s_red[0] = chain_sum<false>(0.0, V.chi, 1, 2 * n);
     __syncthreads();
     double Hpp[36], bp[6];
@@ -323,7 +327,7 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
       for (int t = tid; t < 6 * n; t += nthr) {
         const int i = t / 6, a = t - 6 * i;
         const double* hi = V.HllInv + 36 * i; const double* hpl = V.Hpl + 36 * i;
-        double* cp = V.contrib + 42 * i;
+        double* cp = V.contrib + i; const size_t cs = V.cap;
         double T[6];
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
@@ -335,13 +339,13 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
         double s = 0;
 #pragma unroll
         for (int k = 0; k < 6; ++k) s += T[k] * V.bl[6 * i + k];
-        cp[36 + a] = s;
+        cp[(36 + a) * cs] = s;
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
           double h = 0;
 #pragma unroll
           for (int k = 0; k < 6; ++k) h += T[k] * hpl[c * 6 + k];
-          cp[a * 6 + c] = h;
+          cp[(a * 6 + c) * cs] = h;
         }
       }
       __syncthreads();
@@ -349,7 +353,7 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
       if (tid < 42) {
         double s0 = tid < 36 ? Hpp[tid] : bp[tid - 36];
         if (tid < 36 && (tid / 6 == tid % 6)) s0 += lambda;
-        s_S[tid] = chain_sum<true>(s0, V.contrib + tid, 42, n);
+        s_S[tid] = chain_sum<true>(s0, V.contrib + (size_t)tid * V.cap, 1, n);
       } else if (tid == 64) {
         int ok = 1;
         for (int i = 0; i < n; ++i) ok &= V.okf[i];
@@ -502,6 +506,7 @@ __global__ void __launch_bounds__(POSE_THREADS, POSE_MINB) pose_kernel(const Lsl
     V.L = lm; V.Lnew = V.L + 6 * c; V.Hll = V.Lnew + 6 * c; V.Hpl = V.Hll + 36 * c; V.bl = V.Hpl + 36 * c;
     V.HllInv = V.bl + 6 * c; V.contrib = V.HllInv + 36 * c; V.dl = V.contrib + 42 * c; V.terms = V.dl + 6 * c; V.chi = V.terms + 6 * c;
     V.J = V.chi + 2 * c;
+    V.cap = c;
     V.okf = sc.okf + pd.m_off;
     V.sel = sel_r;
   }

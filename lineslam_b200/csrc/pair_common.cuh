@@ -186,6 +186,7 @@ struct PoseParams {
 #define LM_STRIDE 306
 struct LmView {
   double *L, *Lnew, *Hll, *Hpl, *bl, *HllInv, *contrib, *dl, *terms, *chi;  // 6,6,36,36,6,36,42,6,6,2 per match
+  size_t cap;     // matches per pair slice; `contrib` is stored [42][cap] (the ordered chain sums read contiguous memory)
   double *J;      // 124 per match: Jl(newer) 36 | Jl(older) 36 | Jp 36 | e(newer) 6 | e(older) 6 | wgt 2 | pad 2
   int32_t* sel;   // [n] index into the pair's match list
   int32_t* okf;   // [n]
