@@ -92,9 +92,11 @@ __device__ int region_grow(const FrameView& V, int seed, double prec, double tan
     bool cand = lane < 9 && lane != 4 && xx >= 0 && yy >= 0 && xx < xs && yy < ys;
     int idx = xx + yy * xs;
     double2 c2 = make_double2(2.0, 0.0);
-    if (cand) {
-      cand = V.used[idx] == 0;
-      if (cand) { c2 = V.cs[idx]; cand = c2.x <= 1.5; }
+    if (cand) {   // both loads are issued together: one memory latency per step instead of two dependent ones
+      const uint8_t u = V.used[idx];
+      const double2 cc = V.cs[idx];
+      cand = (u == 0) && (cc.x <= 1.5);
+      if (cand) c2 = cc;
     }
     unsigned mask = __ballot_sync(FULL, cand);
     while (mask) {
