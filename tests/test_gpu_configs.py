@@ -90,3 +90,26 @@ def test_1280x960_pair(api, oracle):
     T = synth.relative_pose_q2t(*poses[1], *poses[0])
     assert np.abs(recs[0]["tf"].reshape(4, 4)[:3, 3] - T[:3, 3]).max() < 0.03
     ctx.close()
+
+
+@pytest.mark.parametrize("W,H", [(324, 242), (332, 250), (200, 152)])
+def test_odd_sizes(api, oracle, W, H):
+    """Sizes whose 0.8x scaled width is odd or not a multiple of 32/128 (partial tiles everywhere, the y pass falls
+    back from the TMA kernel when the scaled width is odd): every stage and the final records stay bit-exact."""
+    from lineslam_b200 import synth
+    imgs, deps, poses = synth.make_stream(2, scene_seed=2003, W=W, H=H)
+    K = synth.camera_K(W, H)
+    p = api.default_params()
+    p.min_feature_matches = 10
+    ctx = api.Context(params=p, max_batch=2, max_w=W, max_h=H, debug=True)
+    frames = ctx.extract_batch(imgs, deps, K, seeds=[3, 4])
+    sw, sh = int(np.floor(W * 0.8)), int(np.floor(H * 0.8))
+    segs, dbg = oracle.lsd(oracle.gray(imgs[0]), debug=True)
+    assert np.array_equal(ctx.debug_read(1, np.float64, sw * sh).reshape(sh, sw), dbg["scaled"])
+    assert np.array_equal(ctx.debug_read(2, np.float64, sw * sh).reshape(sh, sw), dbg["angles"])
+    assert np.array_equal(ctx.debug_read(4, np.int32, sw * sh), dbg["seeds"])
+    for i in range(2):
+        ref, dref = oracle.detect3DLines(imgs[i], deps[i], K, seed=3 + i, params=p, debug=True)
+        assert np.array_equal(frames[i].segments(), dref["segs"])
+        _compare(frames[i].lines(), ref, frames[i].debug(), dref, f"odd{W}x{H}_{i}")
+    ctx.close()
