@@ -22,7 +22,9 @@
 using namespace lslm;
 
 #define FULL 0xffffffffu
+#ifndef RANSAC_CH
 #define RANSAC_CH 8  // hypotheses evaluated per round
+#endif
 
 struct LineParams {
   double len2d_thres, sample_interval, collin_ratio, len3d_thres, mah_thres, support_ratio, depth_scaling;
