@@ -544,6 +544,8 @@ struct MleSmem {
   double pos[LSL_MAX_SMP * 3];
   double DU[LSL_MAX_SMP * 9];
   double eA[LSL_MAX_SMP], eB[LSL_MAX_SMP];  // e of the current estimate / of the trial point (roles swap on accept)
+  double hA[LSL_MAX_SMP], hB[LSL_MAX_SMP];  // residual vectors hx / wrk (roles swap on accept); shared, not thread-local:
+                                            // arrays handed to the non-inlined helpers would otherwise live in local memory
   double jac[LSL_MAX_SMP * MLE_JS];
   double JtJ[36], Jte[6];
   double cinv1[9], cinv2[9];
@@ -552,8 +554,10 @@ struct MleSmem {
 // costFun_MLEstimateLine3d (utils.cpp:954-978) for the points a lane owns. Deliberately NOT inlined and not
 // unrolled: the LM loop is instruction-fetch bound when its body outgrows the instruction cache (ncu: 50 % of
 // the stall samples were `no_instructions` with three inlined, four-way unrolled copies).
-__device__ __noinline__ void mle_cost(const MleSmem& S, int n, int idx1, int idx2, const double* p, double* r) {
+__device__ __noinline__ void mle_cost(const MleSmem& S, int n, int idx1, int idx2, double p0, double p1, double p2, double p3,
+                                      double p4, double p5, double* r /* shared, [n] */) {
   const int lane = threadIdx.x & 31;
+  const double p[6] = {p0, p1, p2, p3, p4, p5};
 #pragma unroll 1
   for (int q = 0; q < 4; ++q) {
     const int i = lane + 32 * q;
@@ -562,7 +566,7 @@ __device__ __noinline__ void mle_cost(const MleSmem& S, int n, int idx1, int idx
     double v = mah_dist3d_pt_line(S.pos + 3 * ic, S.DU + 9 * ic, p, p + 3);
     if (i == idx1) v = mah_sq_pt(p, S.pos + 3 * ic, S.cinv1);
     else if (i == idx2) v = mah_sq_pt(p + 3, S.pos + 3 * ic, S.cinv2);
-    r[q] = v;
+    if (i < n) r[i] = v;
   }
 }
 
@@ -570,10 +574,10 @@ __device__ __noinline__ void mle_cost(const MleSmem& S, int n, int idx1, int idx
 // of 8 and the remainder upwards. Accumulator a sees the indices congruent to 3 - a (mod 4) below
 // blockn = 8 floor(n / 8) in descending order, then its share of the remainder; lanes 0..3 run one accumulator
 // each and the four partial sums are added left to right.
-__device__ __noinline__ double l2nrm_neg(double* E, const double* y, int n) {
+__device__ __noinline__ double l2nrm_neg(double* E, const double* y /* shared, [n] */, int n) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) { const int i = lane + 32 * q; if (i < n) E[i] = 0.0 - y[q]; }
+  for (int q = 0; q < 4; ++q) { const int i = lane + 32 * q; if (i < n) E[i] = 0.0 - y[i]; }   // own points: no barrier needed before
   __syncwarp();
   const int a = lane & 3;
   const int blockn = (n >> 3) << 3;
@@ -752,11 +756,12 @@ __global__ void __launch_bounds__(32, MLE_MINB) line_mle_kernel(LslWork w, LineP
   double mu = 0, jacTe_inf = 0, p_L2 = 0, tmp, p_eL2, pDp_eL2, Dp_L2 = DBL_MAX, dF, dL;
   int nu = 20, nu2, stop = 0, K = 10, updjac = 0, updp = 1, newjac = 0, k = 0;
   int lm_ret = -1;
-  double hx[4], wrk[4];
+  double* hx = S.hA;     // hx of the current estimate
+  double* wrk = S.hB;    // of the trial / perturbed point
   double* Ecur = S.eA;   // e = x - hx of the current estimate
   double* Enew = S.eB;   // of the trial point
   if (n >= m) {
-  mle_cost(S, n, idx1, idx2, p, hx);
+  mle_cost(S, n, idx1, idx2, p[0], p[1], p[2], p[3], p[4], p[5], hx);
   p_eL2 = l2nrm_neg(Ecur, hx, n);
   if (!isfinite(p_eL2)) stop = 7;
   for (k = 0; k < itmax && !stop; ++k) {
@@ -773,10 +778,10 @@ __global__ void __launch_bounds__(32, MLE_MINB) line_mle_kernel(LslWork w, LineP
         double pp[6];
 #pragma unroll
         for (int c = 0; c < 6; ++c) pp[c] = (c == j) ? p[c] + d : p[c];
-        mle_cost(S, n, idx1, idx2, pp, wrk);
+        mle_cost(S, n, idx1, idx2, pp[0], pp[1], pp[2], pp[3], pp[4], pp[5], wrk);
         d = 1.0 / d;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { const int i = lane + 32 * q; if (i < n) S.jac[i * MLE_JS + j] = (wrk[q] - hx[q]) * d; }
+        for (int q = 0; q < 4; ++q) { const int i = lane + 32 * q; if (i < n) S.jac[i * MLE_JS + j] = (wrk[i] - hx[i]) * d; }
       }
       __syncwarp();
       nu = 2; updjac = 0; updp = 0; newjac = 1;
@@ -825,7 +830,7 @@ __global__ void __launch_bounds__(32, MLE_MINB) line_mle_kernel(LslWork w, LineP
         for (int i = 0; i < m; ++i) { pDp[i] = p[i] + (tmp = Dp[i]); Dp_L2 += tmp * tmp; }
         if (Dp_L2 <= eps2_sq * p_L2) { stop = 2; break; }
         if (Dp_L2 >= (p_L2 + eps2) / (1E-12 * 1E-12)) { stop = 4; break; }
-        mle_cost(S, n, idx1, idx2, pDp, wrk);
+        mle_cost(S, n, idx1, idx2, pDp[0], pDp[1], pDp[2], pDp[3], pDp[4], pDp[5], wrk);
         pDp_eL2 = l2nrm_neg(Enew, wrk, n);
         if (!isfinite(pDp_eL2)) { stop = 7; break; }
         dF = p_eL2 - pDp_eL2;
@@ -837,7 +842,7 @@ __global__ void __launch_bounds__(32, MLE_MINB) line_mle_kernel(LslWork w, LineP
             double t = 0.0;
 #pragma unroll
             for (int l = 0; l < m; ++l) t += S.jac[i * MLE_JS + l] * Dp[l];
-            t = (wrk[q] - hx[q] - t) / Dp_L2;
+            t = (wrk[i] - hx[i] - t) / Dp_L2;
 #pragma unroll
             for (int j = 0; j < m; ++j) S.jac[i * MLE_JS + j] += t * Dp[j];
           }
@@ -855,8 +860,7 @@ __global__ void __launch_bounds__(32, MLE_MINB) line_mle_kernel(LslWork w, LineP
           nu = 2;
 #pragma unroll
           for (int i = 0; i < m; ++i) p[i] = pDp[i];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) hx[q] = wrk[q];
+          { double* t = hx; hx = wrk; wrk = t; }
           { double* t = Ecur; Ecur = Enew; Enew = t; }
           p_eL2 = pDp_eL2;
           updp = 1;
