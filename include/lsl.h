@@ -102,6 +102,9 @@ int lsl_frame_segments(const lsl_frame* f, double* dst, int cap, int* n);
 /* Builds a frame from caller-supplied records (e.g. features cached by the host). */
 int lsl_frame_from_lines(lsl_ctx* ctx, const lsl_line_rec* recs, int n, lsl_frame** out);
 void lsl_frame_free(lsl_frame* f);
+/* vector<FrameLine>().swap(node->lines) of the clear_past_point_cloud sweep (src/graph_manager.cpp:845-857): the
+ * frame keeps its point features but has no lines afterwards (device records released). */
+int lsl_frame_clear_lines(lsl_frame* f);
 
 /* Node::lineMatching (src/node.h:288, src/node.cpp:1619-1694): query = this, train = other. */
 int lsl_match_lines(lsl_ctx* ctx, const lsl_frame* query, const lsl_frame* train, int adjacent,

@@ -434,6 +434,18 @@ extern "C" void lsl_frame_free(lsl_frame* f) {
   if (f->d_desc) cudaFree(f->d_desc);
   delete f;
 }
+extern "C" int lsl_frame_clear_lines(lsl_frame* f) {
+  if (!f) return LSL_ERR_ARG;
+  if (f->d_lines) {
+    cudaSetDevice(f->ctx->device);
+    if (f->blk) {
+      if (--f->blk->refs == 0) { cudaFreeAsync(f->blk->d, f->ctx->stream); delete f->blk; }
+    } else cudaFree(f->d_lines);
+  }
+  f->d_lines = nullptr; f->blk = nullptr; f->nlines = 0;
+  f->lines.clear(); f->have_host = true;
+  return LSL_OK;
+}
 // Point features of a frame (inputs of the hot path: Node::feature_locations_3d_ and feature_descriptors_,
 // src/node.h; SIFT/SURF rows after squareroot_descriptor_space). Copies to the device; replaces earlier points.
 extern "C" int lsl_frame_set_points(lsl_ctx* ctx, lsl_frame* f, const float* xyz1, const float* desc, int n, int dim) {
