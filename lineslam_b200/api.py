@@ -48,6 +48,7 @@ def lib():
         L.lsl_frame_free.argtypes = [C.c_void_p]
         L.lsl_frame_free.restype = None
         L.lsl_frame_num_lines.argtypes = [C.c_void_p]
+        L.lsl_frame_clear_lines.argtypes = [C.c_void_p]
         L.lsl_kernel_name.restype = C.c_char_p
         L.lsl_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         _LIB = L
@@ -301,6 +302,10 @@ class Frame:
         lm = np.zeros(max(n, 1), np.int32)
         _check(lib().lsl_frame_debug(self._h, ptr(npts), ptr(idx), ptr(seg), ptr(lm)))
         return dict(n_inl=npts[:n], inl_idx=idx[:n], seg_of_line=seg[:n], lm_iters=lm[:n])
+
+    def clear_lines(self):
+        """vector<FrameLine>().swap(lines) of the clear_past_point_cloud sweep (src/graph_manager.cpp:845-857)."""
+        _check(lib().lsl_frame_clear_lines(self._h))
 
     def free(self):
         if self._h:
