@@ -1,0 +1,316 @@
+// k_tum.cu — TUM raw-directory ingest (include/lsl_tum.h): syncidx.txt parsing, PNG container +
+// DEFLATE on host threads (zlib), scan-line unfiltering and layout conversion on the device.
+//
+//   K19  png_unfilter_kernel   one CTA per image, one thread per scan line. PNG's filters make pixel (x, y) depend on
+//        its left, upper and upper-left neighbours, so the rows advance as a wavefront: thread y reconstructs pixel
+//        x = t - y at step t, reads the pixel above from the slot thread y - 1 published one step earlier (shared
+//        memory, double-buffered by step parity) and keeps its own left pixel and the previous "above" in registers.
+//        W + H - 1 steps per image instead of W * H serial byte operations; the output is written in the layout the
+//        extraction kernels read (BGR u8 like cv::imread(…, 1), or float metres with NaN for "no reading").
+//
+// HBM traffic per VGA frame: 0.92 + 0.61 MB of filtered scan lines in, 0.92 MB BGR + 1.23 MB float depth out.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+#include <zlib.h>
+#include "lsl_internal.h"
+#include "../../include/lsl_tum.h"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------- device ----
+__device__ __forceinline__ unsigned paeth(unsigned a, unsigned b, unsigned c) {
+  const int p = (int)a + (int)b - (int)c;
+  const int pa = abs(p - (int)a), pb = abs(p - (int)b), pc = abs(p - (int)c);
+  return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+
+// KIND 0: colour / grey 8-bit -> BGR u8 [H][W][3];  KIND 1: grey 16-bit (big endian) -> f32 metres [H][W]
+template <int BPP, int KIND>
+__global__ void __launch_bounds__(1024) png_unfilter_kernel(const uint8_t* __restrict__ filt_all, size_t filt_img_bytes,
+                                                            uint8_t* __restrict__ out_all, size_t out_img_bytes, int W, int H,
+                                                            float depth_scale) {
+  extern __shared__ uint32_t s_pub[];   // [2][H]: the pixel each row reconstructed in the previous / current step
+  const int y = threadIdx.x;
+  const size_t stride = 1 + (size_t)W * BPP;
+  const uint8_t* row = filt_all + (size_t)blockIdx.x * filt_img_bytes + (size_t)(y < H ? y : 0) * stride;
+  uint8_t* out = out_all + (size_t)blockIdx.x * out_img_bytes;
+  const int ft = (y < H) ? row[0] : 0;
+  uint32_t a = 0, c = 0;
+  const int steps = W + H - 1;
+  for (int t = 0; t < steps; ++t) {
+    const int x = t - y;
+    if (y < H && x >= 0 && x < W) {
+      const uint32_t b = (y > 0) ? s_pub[((t - 1) & 1) * H + (y - 1)] : 0u;
+      uint32_t r = 0;
+#pragma unroll
+      for (int j = 0; j < BPP; ++j) {
+        const unsigned f = __ldg(row + 1 + (size_t)x * BPP + j);
+        const unsigned aj = (a >> (8 * j)) & 255u, bj = (b >> (8 * j)) & 255u, cj = (c >> (8 * j)) & 255u;
+        unsigned pred;
+        switch (ft) {
+          case 1: pred = aj; break;
+          case 2: pred = bj; break;
+          case 3: pred = (aj + bj) >> 1; break;
+          case 4: pred = paeth(aj, bj, cj); break;
+          default: pred = 0; break;
+        }
+        r |= ((f + pred) & 255u) << (8 * j);
+      }
+      s_pub[(t & 1) * H + y] = r;
+      const size_t px = (size_t)y * W + x;
+      if (KIND == 0) {
+        const uint8_t c0 = (uint8_t)(r & 255u), c1 = (uint8_t)((r >> 8) & 255u), c2 = (uint8_t)((r >> 16) & 255u);
+        if (BPP >= 3) { out[px * 3] = c2; out[px * 3 + 1] = c1; out[px * 3 + 2] = c0; }   // file order RGB(A) -> BGR
+        else { out[px * 3] = c0; out[px * 3 + 1] = c0; out[px * 3 + 2] = c0; }            // grey -> three equal planes
+      } else {
+        const unsigned v = ((r & 255u) << 8) | ((r >> 8) & 255u);   // network byte order
+        const float d = (float)v;                                   // convertTo(CV_32FC1): exact for 16 bits
+        // values < 1e-5 -> quiet NaN (openni_listener.cpp:1238-1241), then MatExpr "/ 5000.0" = float multiply by
+        // (float)(1 / 5000.0). x86 keeps the NaN's bits through the multiply (0x7fc00000); the GPU would canonicalise
+        // them to 0x7fffffff, so the NaN is stored as the reference leaves it.
+        reinterpret_cast<float*>(out)[px] = ((double)d < 1e-5) ? __int_as_float(0x7fc00000) : d * depth_scale;
+      }
+      c = b; a = r;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host ----
+uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+struct PngView {
+  int W = 0, H = 0, ch = 0, bits = 0;
+  std::vector<std::pair<const uint8_t*, size_t>> idat;
+};
+
+bool png_parse(const uint8_t* p, size_t len, PngView* v, std::string* err) {
+  static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+  if (!p || len < 8 + 25 || std::memcmp(p, sig, 8) != 0) { *err = "not a PNG file"; return false; }
+  size_t off = 8;
+  bool have_ihdr = false, end = false;
+  while (!end && off + 12 <= len) {
+    const uint32_t clen = be32(p + off);
+    const uint8_t* type = p + off + 4;
+    if ((size_t)clen > len - off - 12) { *err = "truncated PNG chunk"; return false; }
+    const uint8_t* data = p + off + 8;
+    if (!std::memcmp(type, "IHDR", 4)) {
+      if (clen != 13) { *err = "bad IHDR"; return false; }
+      v->W = (int)be32(data); v->H = (int)be32(data + 4); v->bits = data[8];
+      const int ctype = data[9];
+      if (data[10] != 0 || data[11] != 0) { *err = "unknown PNG compression / filter method"; return false; }
+      if (data[12] != 0) { *err = "interlaced PNG not supported"; return false; }
+      if (ctype == 0 && (v->bits == 8 || v->bits == 16)) v->ch = 1;
+      else if (ctype == 2 && v->bits == 8) v->ch = 3;
+      else if (ctype == 6 && v->bits == 8) v->ch = 4;
+      else { *err = "PNG colour type / bit depth not supported (grey 8/16, RGB 8, RGBA 8)"; return false; }
+      have_ihdr = true;
+    } else if (!std::memcmp(type, "IDAT", 4)) {
+      v->idat.emplace_back(data, (size_t)clen);
+    } else if (!std::memcmp(type, "IEND", 4)) end = true;
+    off += 12 + (size_t)clen;
+  }
+  if (!have_ihdr || v->idat.empty()) { *err = "PNG without IHDR / IDAT"; return false; }
+  return true;
+}
+
+// inflates the concatenated IDAT stream into dst; must yield exactly `want` bytes
+bool png_inflate(const PngView& v, uint8_t* dst, size_t want, std::string* err) {
+  z_stream zs;
+  std::memset(&zs, 0, sizeof zs);
+  if (inflateInit(&zs) != Z_OK) { *err = "inflateInit failed"; return false; }
+  zs.next_out = dst; zs.avail_out = (uInt)want;
+  int rc = Z_OK;
+  for (size_t k = 0; k < v.idat.size() && rc != Z_STREAM_END; ++k) {
+    zs.next_in = const_cast<Bytef*>(v.idat[k].first); zs.avail_in = (uInt)v.idat[k].second;
+    rc = inflate(&zs, Z_NO_FLUSH);
+    if (rc != Z_OK && rc != Z_STREAM_END && !(rc == Z_BUF_ERROR && zs.avail_in == 0)) break;
+    if (rc == Z_BUF_ERROR) rc = Z_OK;
+  }
+  const size_t got = want - zs.avail_out;
+  inflateEnd(&zs);
+  if (rc != Z_STREAM_END || got != want) { *err = "corrupt or short PNG data stream"; return false; }
+  return true;
+}
+
+struct TumScratch {
+  uint8_t* h_filt = nullptr; size_t h_cap = 0;   // pinned staging of the filtered scan lines
+  uint8_t* d_filt = nullptr; size_t d_cap = 0;
+  uint8_t* d_bgr = nullptr; size_t bgr_cap = 0;  // lsl_extract_tum_batch only
+  float* d_depth = nullptr; size_t depth_cap = 0;
+};
+std::mutex g_mu;
+std::map<lsl_ctx*, TumScratch> g_scratch;
+
+template <typename T>
+bool grow_dev(T** p, size_t* cap, size_t need) {
+  if (*cap >= need) return true;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  if (cudaMalloc((void**)p, need) != cudaSuccess) return false;
+  *cap = need;
+  return true;
+}
+
+template <int BPP, int KIND>
+void launch_unfilter(cudaStream_t st, int n, const uint8_t* d_filt, size_t filt_img, uint8_t* out, size_t out_img, int W, int H) {
+  const int threads = (H + 31) & ~31;
+  png_unfilter_kernel<BPP, KIND><<<n, threads, 2 * (size_t)H * sizeof(uint32_t), st>>>(d_filt, filt_img, out, out_img, W, H,
+                                                                                    (float)(1.0 / 5000.0));
+}
+
+// one list of n same-sized PNGs -> device; kind 0 colour (any supported 8-bit type), 1 depth (grey 16)
+int decode_list(lsl_ctx* ctx, TumScratch& S, int n, const uint8_t* const* png, const size_t* len, int W, int H, int kind, void* d_out) {
+  std::vector<PngView> views((size_t)n);
+  int ch = 0;
+  for (int i = 0; i < n; ++i) {
+    std::string err;
+    if (!png_parse(png[i], len[i], &views[(size_t)i], &err)) { ctx->err = "image " + std::to_string(i) + ": " + err; return LSL_ERR_ARG; }
+    const PngView& v = views[(size_t)i];
+    if (v.W != W || v.H != H) { ctx->err = "image " + std::to_string(i) + ": size differs from W x H"; return LSL_ERR_ARG; }
+    if (kind == 1 ? !(v.ch == 1 && v.bits == 16) : v.bits != 8) {
+      ctx->err = "image " + std::to_string(i) + (kind == 1 ? ": depth PNG must be 16-bit grey" : ": colour PNG must be 8 bits per sample");
+      return LSL_ERR_ARG;
+    }
+    if (i == 0) ch = v.ch;
+    else if (v.ch != ch) { ctx->err = "images of one batch must share the PNG colour type"; return LSL_ERR_ARG; }
+  }
+  const int bpp = kind == 1 ? 2 : ch;
+  const size_t img_bytes = (size_t)H * (1 + (size_t)W * bpp), total = img_bytes * (size_t)n;
+  if (S.h_cap < total) {
+    if (S.h_filt) cudaFreeHost(S.h_filt);
+    S.h_filt = nullptr; S.h_cap = 0;
+    LSL_CUDA(cudaHostAlloc((void**)&S.h_filt, total, cudaHostAllocDefault));
+    S.h_cap = total;
+  }
+  if (!grow_dev(&S.d_filt, &S.d_cap, total)) { ctx->err = "cudaMalloc of the PNG staging buffer failed"; return LSL_ERR_CUDA; }
+  // DEFLATE on host threads, one image at a time per thread
+  std::atomic<int> next(0), bad(-1);
+  std::vector<std::string> errs((size_t)n);
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt == 0) nt = 4;
+  if (nt > (unsigned)n) nt = (unsigned)n;
+  auto work = [&]() {
+    for (int i; (i = next.fetch_add(1)) < n;)
+      if (!png_inflate(views[(size_t)i], S.h_filt + img_bytes * (size_t)i, img_bytes, &errs[(size_t)i])) bad.store(i);
+  };
+  std::vector<std::thread> pool;
+  for (unsigned k = 1; k < nt; ++k) pool.emplace_back(work);
+  work();
+  for (auto& th : pool) th.join();
+  if (bad.load() >= 0) { ctx->err = "image " + std::to_string(bad.load()) + ": " + errs[(size_t)bad.load()]; return LSL_ERR_ARG; }
+  for (int i = 0; i < n; ++i)     // filter-type bytes must be 0..4
+    for (int y = 0; y < H; ++y)
+      if (S.h_filt[img_bytes * (size_t)i + (size_t)y * (1 + (size_t)W * bpp)] > 4) { ctx->err = "image " + std::to_string(i) + ": bad PNG filter type"; return LSL_ERR_ARG; }
+  LSL_CUDA(cudaMemcpyAsync(S.d_filt, S.h_filt, total, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->stats.h2d_bytes += (int64_t)total;
+  LSL_KSTART(ctx, LSL_K_PNG);
+  uint8_t* o = (uint8_t*)d_out;
+  const size_t out_img = kind == 1 ? (size_t)W * H * sizeof(float) : (size_t)W * H * 3;
+  if (kind == 1) launch_unfilter<2, 1>(ctx->stream, n, S.d_filt, img_bytes, o, out_img, W, H);
+  else if (bpp == 3) launch_unfilter<3, 0>(ctx->stream, n, S.d_filt, img_bytes, o, out_img, W, H);
+  else if (bpp == 4) launch_unfilter<4, 0>(ctx->stream, n, S.d_filt, img_bytes, o, out_img, W, H);
+  else launch_unfilter<1, 0>(ctx->stream, n, S.d_filt, img_bytes, o, out_img, W, H);
+  LSL_KSTOP(ctx, LSL_K_PNG);
+  LSL_CUDA(cudaGetLastError());
+  // the pinned staging buffer is reused by the next list: wait for the upload (the kernel itself stays asynchronous)
+  LSL_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->kev[LSL_K_PNG][0], ctx->kev[LSL_K_PNG][1]);
+  ctx->kms[LSL_K_PNG] = (kind == 1 ? ctx->kms[LSL_K_PNG] : 0.f) + ms;   // colour + depth launches of one decode call add up
+  return LSL_OK;
+}
+
+}  // namespace
+
+extern "C" int lsl_tum_read_syncidx(const char* dirname, lsl_tum_entry* dst, int cap, int* n) {
+  if (!dirname || !n) return LSL_ERR_ARG;
+  *n = 0;
+  const std::string path = std::string(dirname) + "/syncidx.txt";
+  FILE* f = std::fopen(path.c_str(), "r");
+  if (!f) return LSL_OK;   // like the reference: a missing list is an empty list (openni_listener.cpp:1206)
+  char tok[4][256];
+  int k = 0, groups = 0, rc = LSL_OK;
+  char buf[256];
+  while (std::fscanf(f, "%255s", buf) == 1) {     // `fsync >> tmp`: whitespace-separated tokens
+    std::memcpy(tok[k], buf, sizeof buf);
+    if (++k == 4) {
+      k = 0;
+      if (dst && groups < cap) {
+        lsl_tum_entry& e = dst[groups];
+        e.ts_rgb = std::atof(tok[0]); e.ts_depth = std::atof(tok[2]);
+        std::memcpy(e.rgb, tok[1], 256); std::memcpy(e.depth, tok[3], 256);
+      } else rc = LSL_ERR_CAPACITY;
+      ++groups;
+    }
+  }
+  std::fclose(f);
+  *n = groups;
+  return rc;
+}
+
+extern "C" int lsl_png_info(const uint8_t* png, size_t len, int* W, int* H, int* channels, int* bit_depth) {
+  PngView v; std::string err;
+  if (!png_parse(png, len, &v, &err)) return LSL_ERR_ARG;
+  if (W) *W = v.W;
+  if (H) *H = v.H;
+  if (channels) *channels = v.ch;
+  if (bit_depth) *bit_depth = v.bits;
+  return LSL_OK;
+}
+
+extern "C" int lsl_tum_decode_batch(lsl_ctx* ctx, int n, const uint8_t* const* rgb_png, const size_t* rgb_len,
+                                    const uint8_t* const* depth_png, const size_t* depth_len, int W, int H,
+                                    uint8_t* d_bgr, float* d_depth) {
+  if (!ctx || n < 0 || W <= 0 || H <= 0) return LSL_ERR_ARG;
+  if (H > 1024) { ctx->err = "PNG decode: H > 1024 rows"; return LSL_ERR_CAPACITY; }
+  if ((rgb_png && (!rgb_len || !d_bgr)) || (depth_png && (!depth_len || !d_depth))) return LSL_ERR_ARG;
+  if (n == 0) return LSL_OK;
+  cudaSetDevice(ctx->device);
+  std::lock_guard<std::mutex> lk(g_mu);
+  TumScratch& S = g_scratch[ctx];
+  int rc = LSL_OK;
+  if (rgb_png && (rc = decode_list(ctx, S, n, rgb_png, rgb_len, W, H, 0, d_bgr)) != LSL_OK) return rc;
+  if (depth_png && (rc = decode_list(ctx, S, n, depth_png, depth_len, W, H, 1, d_depth)) != LSL_OK) return rc;
+  return LSL_OK;
+}
+
+extern "C" int lsl_extract_tum_batch(lsl_ctx* ctx, int n, const uint8_t* const* rgb_png, const size_t* rgb_len,
+                                     const uint8_t* const* depth_png, const size_t* depth_len, int W, int H, const double K[9],
+                                     double asynch_dt_s, const uint32_t* rand_seeds, lsl_frame** out) {
+  if (!ctx || n <= 0 || !rgb_png || !depth_png || !out) return LSL_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  uint8_t* d_bgr; float* d_depth;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TumScratch& S = g_scratch[ctx];
+    if (!grow_dev(&S.d_bgr, &S.bgr_cap, (size_t)n * W * H * 3) || !grow_dev(&S.d_depth, &S.depth_cap, (size_t)n * W * H * sizeof(float))) {
+      ctx->err = "cudaMalloc of the decoded image buffers failed";
+      return LSL_ERR_CUDA;
+    }
+    d_bgr = S.d_bgr; d_depth = S.d_depth;
+  }
+  int rc = lsl_tum_decode_batch(ctx, n, rgb_png, rgb_len, depth_png, depth_len, W, H, d_bgr, d_depth);
+  if (rc != LSL_OK) return rc;
+  static const double Ktum[9] = {525, 0, 319.5, 0, 525, 239.5, 0, 0, 1};   // openni_listener.cpp:1256-1260
+  return lsl_extract_batch_dev(ctx, n, d_bgr, 3, d_depth, W, H, K ? K : Ktum, asynch_dt_s, rand_seeds, out);
+}
+
+extern "C" void lsl_tum_release(lsl_ctx* ctx) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_scratch.find(ctx);
+  if (it == g_scratch.end()) return;
+  TumScratch& S = it->second;
+  if (ctx) cudaSetDevice(ctx->device);
+  if (S.h_filt) cudaFreeHost(S.h_filt);
+  if (S.d_filt) cudaFree(S.d_filt);
+  if (S.d_bgr) cudaFree(S.d_bgr);
+  if (S.d_depth) cudaFree(S.d_depth);
+  g_scratch.erase(it);
+}

@@ -27,7 +27,7 @@ extern "C" const char* lsl_last_error(const lsl_ctx* ctx) { return ctx ? ctx->er
 static const char* const kKernelNames[LSL_K_COUNT] = {
     "gray_kernel", "xpass_kernel", "ypass_kernel", "ll_angle_kernel", "seed_list_kernel", "sobel5_kernel",
     "lsd_region_kernel", "lsd_nfa_kernel", "line3d_ransac_kernel", "line_msld_kernel", "msld_randfill_kernel", "line_mle_kernel",
-    "gather_lines_kernel", "match_lines_kernel", "pose_kernel", "match_points_kernel", "pose_hybrid_kernel", "relmotion_kernel"};
+    "gather_lines_kernel", "match_lines_kernel", "pose_kernel", "match_points_kernel", "pose_hybrid_kernel", "relmotion_kernel", "png_unfilter_kernel"};
 extern "C" const char* lsl_kernel_name(int i) { return (i >= 0 && i < LSL_K_COUNT) ? kKernelNames[i] : ""; }
 
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -632,12 +632,12 @@ extern "C" int lsl_match_lines(lsl_ctx* ctx, const lsl_frame* query, const lsl_f
   int adj = adjacent ? 1 : 0;
   int rc = setup_pairs(ctx, 1, &query, &train, nullptr, nullptr, nullptr, &adj, -1);
   if (rc) return rc;
-  clear_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
+  clear_ktimes(ctx, LSL_K_MATCH, LSL_K_PNG);
   if ((rc = lsl_launch_match(ctx, 1))) return rc;
   int32_t nm = 0;
   LSL_CUDA(cudaMemcpyAsync(&nm, ctx->pw.nmatch, 4, cudaMemcpyDeviceToHost, ctx->stream));
   LSL_CUDA(cudaStreamSynchronize(ctx->stream));
-  collect_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
+  collect_ktimes(ctx, LSL_K_MATCH, LSL_K_PNG);
   *n = nm;
   ctx->stats.pairs += 1; ctx->stats.matches += nm;
   if (nm > cap || (nm && !out)) return LSL_ERR_CAPACITY;
@@ -670,12 +670,12 @@ extern "C" int lsl_match_points(lsl_ctx* ctx, const lsl_frame* query, const lsl_
   if (rc) return rc;
   int mq = 0, dim = 1;
   if ((rc = setup_ppairs(ctx, 1, &query, &train, -1, &mq, &dim))) return rc;
-  clear_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
+  clear_ktimes(ctx, LSL_K_MATCH, LSL_K_PNG);
   if ((rc = lsl_launch_match_points(ctx, 1, mq, dim))) return rc;
   int32_t nm = 0;
   LSL_CUDA(cudaMemcpyAsync(&nm, ctx->hw.npmatch, 4, cudaMemcpyDeviceToHost, ctx->stream));
   LSL_CUDA(cudaStreamSynchronize(ctx->stream));
-  collect_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
+  collect_ktimes(ctx, LSL_K_MATCH, LSL_K_PNG);
   *n = nm;
   ctx->stats.pairs += 1; ctx->stats.matches += nm;
   if (nm > cap || (nm && !out)) return LSL_ERR_CAPACITY;
@@ -727,7 +727,7 @@ extern "C" int lsl_pose_ransac(lsl_ctx* ctx, const lsl_frame* train, const lsl_f
   LSL_CUDA(cudaMemcpyAsync(ctx->pw.nmatch, &nm, 4, cudaMemcpyHostToDevice, ctx->stream));
   if (nln) LSL_CUDA(cudaMemcpyAsync(ctx->pw.matches, ln_matches, sizeof(lsl_match) * nln, cudaMemcpyHostToDevice, ctx->stream));
   ctx->stats.h2d_bytes += sizeof(lsl_match) * nln;
-  clear_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
+  clear_ktimes(ctx, LSL_K_MATCH, LSL_K_PNG);
   if (hybrid) { if ((rc = lsl_launch_pose_hybrid(ctx, 1, ctx->cam_fx, ctx->cam_dt))) return rc; }
   else if ((rc = lsl_launch_pose(ctx, 1))) return rc;
   if ((rc = fetch_counts(ctx, 1))) return rc;
@@ -736,7 +736,7 @@ extern "C" int lsl_pose_ransac(lsl_ctx* ctx, const lsl_frame* train, const lsl_f
   LSL_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->pw.h_nmatch[0] = nln;
   if (hybrid) ctx->hw.h_npmatch[0] = npt;
-  collect_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
+  collect_ktimes(ctx, LSL_K_MATCH, LSL_K_PNG);
   ctx->stats.pairs += 1; ctx->stats.d2h_bytes += sizeof(lsl_pose_rec);
   std::vector<lsl_match> all(ln_matches, ln_matches + nln);
   int ni = ctx->pw.h_ninl[0], nr = ctx->pw.h_nrinl[0];
@@ -783,14 +783,14 @@ extern "C" int lsl_relmotion_ransac(lsl_ctx* ctx, const lsl_frame* train, const 
   rs.outRt = (double*)(blk + off); off += align_up(12 * 8);
   rs.outn = (int32_t*)(blk + off);
   rs.max_iter = (int)it;
-  clear_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
+  clear_ktimes(ctx, LSL_K_MATCH, LSL_K_PNG);
   if ((rc = lsl_launch_relmotion(ctx, 1, rs))) { cudaFreeAsync(blk, st); return rc; }
   double Rt[12];
   int32_t on[4];
   LSL_CUDA(cudaMemcpyAsync(Rt, rs.outRt, sizeof(Rt), cudaMemcpyDeviceToHost, st));
   LSL_CUDA(cudaMemcpyAsync(on, rs.outn, sizeof(on), cudaMemcpyDeviceToHost, st));
   LSL_CUDA(cudaStreamSynchronize(st));
-  collect_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
+  collect_ktimes(ctx, LSL_K_MATCH, LSL_K_PNG);
   *n_conset = on[0];
   if (lm_calls) *lm_calls = on[1];
   if (have) *have = on[2];
@@ -815,7 +815,7 @@ extern "C" int lsl_match_pair_batch(lsl_ctx* ctx, int npairs, const lsl_frame* c
   ctx->hw.last_hybrid = hybrid;
   int mq = 0, dim = 1;
   if (hybrid && (rc = setup_ppairs(ctx, npairs, queries, trains, -1, &mq, &dim))) return rc;
-  clear_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
+  clear_ktimes(ctx, LSL_K_MATCH, LSL_K_PNG);
   cudaEventRecord(ctx->ev0, ctx->stream);
   if (hybrid && (rc = lsl_launch_match_points(ctx, npairs, mq, dim))) return rc;   // featureMatching first (node.cpp:1504)
   if ((rc = lsl_launch_match(ctx, npairs))) return rc;
@@ -827,7 +827,7 @@ extern "C" int lsl_match_pair_batch(lsl_ctx* ctx, int npairs, const lsl_frame* c
   LSL_CUDA(cudaMemcpyAsync(out, ctx->pw.recs, sizeof(lsl_pose_rec) * npairs, cudaMemcpyDeviceToHost, ctx->stream));
   LSL_CUDA(cudaStreamSynchronize(ctx->stream));
   cudaEventElapsedTime(&ctx->ms_total, ctx->ev0, ctx->ev3);
-  collect_ktimes(ctx, LSL_K_MATCH, LSL_K_COUNT);
+  collect_ktimes(ctx, LSL_K_MATCH, LSL_K_PNG);
   ctx->stats.pairs += npairs; ctx->stats.d2h_bytes += (sizeof(lsl_pose_rec) + 12) * npairs;
   for (int i = 0; i < npairs; ++i) ctx->stats.matches += ctx->pw.h_nmatch[i];
   return LSL_OK;

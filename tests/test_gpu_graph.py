@@ -84,9 +84,10 @@ def test_add_frame_flow(api, two_sets, clear_past, tmp_path):
         assert nd["estimate"].tolist() == [float(x) for x in ogm.vertices[o.vertex_id]]
         assert bool(nd["has_lines"]) == o.has_lines and bool(nd["valid_tf_estimate"]) == o.valid_tf_estimate
     if clear_past:
-        # the reference's quirk: only the newest node keeps its lines, so nothing but the predecessor ever registers
+        # the reference's quirk: only the newest node keeps its lines, so nothing but the predecessor (and the frame
+        # itself, when the Dijkstra neighbourhood hands it back as its own candidate) ever registers
         assert all(nodes[i].frame.num_lines == 0 for i in range(N - 1)) and nodes[N - 1].frame.num_lines > 0
-        assert all(abs(e.id1 - e.id2) == 1 for e in want_e if e.info >= 0)
+        assert all(abs(e.id1 - e.id2) <= 1 for e in want_e if e.info >= 0)
     else:
         assert len(want_e) > 2 * N                            # predecessors + geodesic / sampled candidates register
         # chained estimates follow the synthetic ground truth at the centimetre level
