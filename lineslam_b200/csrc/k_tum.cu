@@ -1,6 +1,10 @@
-// k_tum.cu — TUM raw-directory ingest (include/lsl_tum.h): syncidx.txt parsing, PNG container +
-// DEFLATE on host threads (zlib), scan-line unfiltering and layout conversion on the device.
+// k_tum.cu — TUM raw-directory ingest (include/lsl_tum.h): syncidx.txt parsing and the PNG
+// container on the host (chunk walk, IDAT payloads gathered into one pinned buffer); DEFLATE, scan-line unfiltering
+// and layout conversion on the device. What crosses PCIe is the COMPRESSED data (≈0.4 MB per VGA image).
 //
+//   K18  png_inflate_kernel    one warp per zlib stream (shared/lsl_inflate.h): all lanes walk the stream convergently
+//        (bit reader in registers, Huffman tables in shared memory built by lane 0), lane 0 stores literals, the warp
+//        shares LZ77 copies. DEFLATE is bit-serial inside a stream; the parallelism is the 2 x batch streams in flight.
 //   K19  png_unfilter_kernel   one CTA per image, one thread per scan line. PNG's filters make pixel (x, y) depend on
 //        its left, upper and upper-left neighbours, so the rows advance as a wavefront: thread y reconstructs pixel
 //        x = t - y at step t, reads the pixel above from the slot thread y - 1 published one step earlier (shared
@@ -9,21 +13,48 @@
 //        extraction kernels read (BGR u8 like cv::imread(…, 1), or float metres with NaN for "no reading").
 //
 // HBM traffic per VGA frame: 0.92 + 0.61 MB of filtered scan lines in, 0.92 MB BGR + 1.23 MB float depth out.
-#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <map>
 #include <mutex>
 #include <string>
-#include <thread>
 #include <vector>
-#include <zlib.h>
 #include "lsl_internal.h"
+#include "shared/lsl_inflate.h"
 #include "../../include/lsl_tum.h"
 
 namespace {
 
 // ---------------------------------------------------------------------------------------------- device ----
+struct InflateOpsWarp {
+  int lane;
+  __device__ __forceinline__ bool leader() const { return lane == 0; }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+  __device__ __forceinline__ void put(uint8_t* out, size_t pos, uint8_t v) const { if (lane == 0) out[pos] = v; }
+  __device__ __forceinline__ void copy(uint8_t* out, size_t pos, int dist, int n) const {
+    __syncwarp();                                   // the bytes the match refers to are visible to every lane
+    const uint8_t* win = out + pos - dist;
+    for (int i = lane; i < n; i += 32) out[pos + i] = win[dist >= n ? i : i % dist];
+    __syncwarp();
+  }
+  __device__ __forceinline__ void stored(uint8_t* out, size_t pos, const uint8_t* src, uint32_t n) const {
+    for (uint32_t i = lane; i < n; i += 32) out[pos + i] = src[i];
+    __syncwarp();
+  }
+};
+
+// status[img]: 0 or the negative code of lslm::inflate_zlib
+__global__ void __launch_bounds__(32) png_inflate_kernel(const uint8_t* __restrict__ z_all, const size_t* __restrict__ z_off,
+                                                         uint8_t* filt_all, size_t filt_img_bytes, int* __restrict__ status) {
+  __shared__ lslm::InflateScratch S;
+  const int img = blockIdx.x;
+  InflateOpsWarp ops;
+  ops.lane = threadIdx.x;
+  const int rc = lslm::inflate_zlib(z_all + z_off[img], z_off[img + 1] - z_off[img], filt_all + (size_t)img * filt_img_bytes,
+                                    filt_img_bytes, &S, ops);
+  if (threadIdx.x == 0) status[img] = rc;
+}
+
 __device__ __forceinline__ unsigned paeth(unsigned a, unsigned b, unsigned c) {
   const int p = (int)a + (int)b - (int)c;
   const int pa = abs(p - (int)a), pb = abs(p - (int)b), pc = abs(p - (int)c);
@@ -34,13 +65,14 @@ __device__ __forceinline__ unsigned paeth(unsigned a, unsigned b, unsigned c) {
 template <int BPP, int KIND>
 __global__ void __launch_bounds__(1024) png_unfilter_kernel(const uint8_t* __restrict__ filt_all, size_t filt_img_bytes,
                                                             uint8_t* __restrict__ out_all, size_t out_img_bytes, int W, int H,
-                                                            float depth_scale) {
+                                                            float depth_scale, int* __restrict__ status) {
   extern __shared__ uint32_t s_pub[];   // [2][H]: the pixel each row reconstructed in the previous / current step
   const int y = threadIdx.x;
   const size_t stride = 1 + (size_t)W * BPP;
   const uint8_t* row = filt_all + (size_t)blockIdx.x * filt_img_bytes + (size_t)(y < H ? y : 0) * stride;
   uint8_t* out = out_all + (size_t)blockIdx.x * out_img_bytes;
   const int ft = (y < H) ? row[0] : 0;
+  if (ft > 4) status[blockIdx.x] = -9;      // not a PNG filter type (the row is then passed through unfiltered)
   uint32_t a = 0, c = 0;
   const int steps = W + H - 1;
   for (int t = 0; t < steps; ++t) {
@@ -120,28 +152,10 @@ bool png_parse(const uint8_t* p, size_t len, PngView* v, std::string* err) {
   return true;
 }
 
-// inflates the concatenated IDAT stream into dst; must yield exactly `want` bytes
-bool png_inflate(const PngView& v, uint8_t* dst, size_t want, std::string* err) {
-  z_stream zs;
-  std::memset(&zs, 0, sizeof zs);
-  if (inflateInit(&zs) != Z_OK) { *err = "inflateInit failed"; return false; }
-  zs.next_out = dst; zs.avail_out = (uInt)want;
-  int rc = Z_OK;
-  for (size_t k = 0; k < v.idat.size() && rc != Z_STREAM_END; ++k) {
-    zs.next_in = const_cast<Bytef*>(v.idat[k].first); zs.avail_in = (uInt)v.idat[k].second;
-    rc = inflate(&zs, Z_NO_FLUSH);
-    if (rc != Z_OK && rc != Z_STREAM_END && !(rc == Z_BUF_ERROR && zs.avail_in == 0)) break;
-    if (rc == Z_BUF_ERROR) rc = Z_OK;
-  }
-  const size_t got = want - zs.avail_out;
-  inflateEnd(&zs);
-  if (rc != Z_STREAM_END || got != want) { *err = "corrupt or short PNG data stream"; return false; }
-  return true;
-}
-
 struct TumScratch {
-  uint8_t* h_filt = nullptr; size_t h_cap = 0;   // pinned staging of the filtered scan lines
-  uint8_t* d_filt = nullptr; size_t d_cap = 0;
+  uint8_t* h_z = nullptr; size_t h_cap = 0;      // pinned staging: [offsets (n + 1) size_t | status n int | compressed streams]
+  uint8_t* d_z = nullptr; size_t dz_cap = 0;     // the same block on the device
+  uint8_t* d_filt = nullptr; size_t d_cap = 0;   // inflated (still filtered) scan lines
   uint8_t* d_bgr = nullptr; size_t bgr_cap = 0;  // lsl_extract_tum_batch only
   float* d_depth = nullptr; size_t depth_cap = 0;
 };
@@ -159,16 +173,33 @@ bool grow_dev(T** p, size_t* cap, size_t need) {
 }
 
 template <int BPP, int KIND>
-void launch_unfilter(cudaStream_t st, int n, const uint8_t* d_filt, size_t filt_img, uint8_t* out, size_t out_img, int W, int H) {
+void launch_unfilter(cudaStream_t st, int n, const uint8_t* d_filt, size_t filt_img, uint8_t* out, size_t out_img, int W, int H,
+                     int* d_status) {
   const int threads = (H + 31) & ~31;
   png_unfilter_kernel<BPP, KIND><<<n, threads, 2 * (size_t)H * sizeof(uint32_t), st>>>(d_filt, filt_img, out, out_img, W, H,
-                                                                                    (float)(1.0 / 5000.0));
+                                                                                    (float)(1.0 / 5000.0), d_status);
+}
+
+const char* inflate_error(int rc) {
+  switch (rc) {
+    case -1: return "bad zlib header";
+    case -2: return "bad DEFLATE block type";
+    case -3: return "bad stored block";
+    case -4: return "bad Huffman code lengths";
+    case -5: return "bad symbol or distance";
+    case -6: return "corrupt data stream (more data than W x H needs)";
+    case -7: return "truncated data stream";
+    case -8: return "short data stream (fewer bytes than W x H needs)";
+    case -9: return "bad PNG filter type";
+    default: return "corrupt data stream";
+  }
 }
 
 // one list of n same-sized PNGs -> device; kind 0 colour (any supported 8-bit type), 1 depth (grey 16)
 int decode_list(lsl_ctx* ctx, TumScratch& S, int n, const uint8_t* const* png, const size_t* len, int W, int H, int kind, void* d_out) {
   std::vector<PngView> views((size_t)n);
   int ch = 0;
+  size_t zbytes = 0;
   for (int i = 0; i < n; ++i) {
     std::string err;
     if (!png_parse(png[i], len[i], &views[(size_t)i], &err)) { ctx->err = "image " + std::to_string(i) + ": " + err; return LSL_ERR_ARG; }
@@ -180,50 +211,63 @@ int decode_list(lsl_ctx* ctx, TumScratch& S, int n, const uint8_t* const* png, c
     }
     if (i == 0) ch = v.ch;
     else if (v.ch != ch) { ctx->err = "images of one batch must share the PNG colour type"; return LSL_ERR_ARG; }
+    for (const auto& c : v.idat) zbytes += c.second;
+    zbytes = (zbytes + 15) & ~(size_t)15;
   }
   const int bpp = kind == 1 ? 2 : ch;
-  const size_t img_bytes = (size_t)H * (1 + (size_t)W * bpp), total = img_bytes * (size_t)n;
+  const size_t img_bytes = (size_t)H * (1 + (size_t)W * bpp);
+  const size_t head = (((size_t)(n + 1) * sizeof(size_t) + (size_t)n * sizeof(int)) + 15) & ~(size_t)15;
+  const size_t total = head + zbytes;
   if (S.h_cap < total) {
-    if (S.h_filt) cudaFreeHost(S.h_filt);
-    S.h_filt = nullptr; S.h_cap = 0;
-    LSL_CUDA(cudaHostAlloc((void**)&S.h_filt, total, cudaHostAllocDefault));
+    if (S.h_z) cudaFreeHost(S.h_z);
+    S.h_z = nullptr; S.h_cap = 0;
+    LSL_CUDA(cudaHostAlloc((void**)&S.h_z, total, cudaHostAllocDefault));
     S.h_cap = total;
   }
-  if (!grow_dev(&S.d_filt, &S.d_cap, total)) { ctx->err = "cudaMalloc of the PNG staging buffer failed"; return LSL_ERR_CUDA; }
-  // DEFLATE on host threads, one image at a time per thread
-  std::atomic<int> next(0), bad(-1);
-  std::vector<std::string> errs((size_t)n);
-  unsigned nt = std::thread::hardware_concurrency();
-  if (nt == 0) nt = 4;
-  if (nt > (unsigned)n) nt = (unsigned)n;
-  auto work = [&]() {
-    for (int i; (i = next.fetch_add(1)) < n;)
-      if (!png_inflate(views[(size_t)i], S.h_filt + img_bytes * (size_t)i, img_bytes, &errs[(size_t)i])) bad.store(i);
-  };
-  std::vector<std::thread> pool;
-  for (unsigned k = 1; k < nt; ++k) pool.emplace_back(work);
-  work();
-  for (auto& th : pool) th.join();
-  if (bad.load() >= 0) { ctx->err = "image " + std::to_string(bad.load()) + ": " + errs[(size_t)bad.load()]; return LSL_ERR_ARG; }
-  for (int i = 0; i < n; ++i)     // filter-type bytes must be 0..4
-    for (int y = 0; y < H; ++y)
-      if (S.h_filt[img_bytes * (size_t)i + (size_t)y * (1 + (size_t)W * bpp)] > 4) { ctx->err = "image " + std::to_string(i) + ": bad PNG filter type"; return LSL_ERR_ARG; }
-  LSL_CUDA(cudaMemcpyAsync(S.d_filt, S.h_filt, total, cudaMemcpyHostToDevice, ctx->stream));
+  if (!grow_dev(&S.d_z, &S.dz_cap, total) || !grow_dev(&S.d_filt, &S.d_cap, img_bytes * (size_t)n)) {
+    ctx->err = "cudaMalloc of the PNG staging buffers failed";
+    return LSL_ERR_CUDA;
+  }
+  // gather: the IDAT payloads of one image form one zlib stream (PNG §10.1), streams 16-byte aligned
+  size_t* h_off = reinterpret_cast<size_t*>(S.h_z);
+  int* h_status = reinterpret_cast<int*>(S.h_z + (size_t)(n + 1) * sizeof(size_t));
+  size_t off = head;
+  for (int i = 0; i < n; ++i) {
+    h_off[i] = off;
+    for (const auto& c : views[(size_t)i].idat) { std::memcpy(S.h_z + off, c.first, c.second); off += c.second; }
+    const size_t pad = (16 - (off & 15)) & 15;      // < 16 zero bytes behind the Adler-32 trailer: never decoded, the
+    std::memset(S.h_z + off, 0, pad);               // final block ends the stream before them
+    off += pad;
+    h_status[i] = 0;
+  }
+  h_off[n] = off;
+  LSL_CUDA(cudaMemcpyAsync(S.d_z, S.h_z, total, cudaMemcpyHostToDevice, ctx->stream));
   ctx->stats.h2d_bytes += (int64_t)total;
+  const size_t* d_off = reinterpret_cast<const size_t*>(S.d_z);
+  int* d_status = reinterpret_cast<int*>(S.d_z + (size_t)(n + 1) * sizeof(size_t));
+  LSL_KSTART(ctx, LSL_K_INFLATE);
+  png_inflate_kernel<<<n, 32, 0, ctx->stream>>>(S.d_z, d_off, S.d_filt, img_bytes, d_status);
+  LSL_KSTOP(ctx, LSL_K_INFLATE);
   LSL_KSTART(ctx, LSL_K_PNG);
   uint8_t* o = (uint8_t*)d_out;
   const size_t out_img = kind == 1 ? (size_t)W * H * sizeof(float) : (size_t)W * H * 3;
-  if (kind == 1) launch_unfilter<2, 1>(ctx->stream, n, S.d_filt, img_bytes, o, out_img, W, H);
-  else if (bpp == 3) launch_unfilter<3, 0>(ctx->stream, n, S.d_filt, img_bytes, o, out_img, W, H);
-  else if (bpp == 4) launch_unfilter<4, 0>(ctx->stream, n, S.d_filt, img_bytes, o, out_img, W, H);
-  else launch_unfilter<1, 0>(ctx->stream, n, S.d_filt, img_bytes, o, out_img, W, H);
+  if (kind == 1) launch_unfilter<2, 1>(ctx->stream, n, S.d_filt, img_bytes, o, out_img, W, H, d_status);
+  else if (bpp == 3) launch_unfilter<3, 0>(ctx->stream, n, S.d_filt, img_bytes, o, out_img, W, H, d_status);
+  else if (bpp == 4) launch_unfilter<4, 0>(ctx->stream, n, S.d_filt, img_bytes, o, out_img, W, H, d_status);
+  else launch_unfilter<1, 0>(ctx->stream, n, S.d_filt, img_bytes, o, out_img, W, H, d_status);
   LSL_KSTOP(ctx, LSL_K_PNG);
   LSL_CUDA(cudaGetLastError());
-  // the pinned staging buffer is reused by the next list: wait for the upload (the kernel itself stays asynchronous)
+  LSL_CUDA(cudaMemcpyAsync(h_status, d_status, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->stats.d2h_bytes += (int64_t)n * (int64_t)sizeof(int);
+  // the pinned staging block is reused by the next list, and the status words decide the return value
   LSL_CUDA(cudaStreamSynchronize(ctx->stream));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ctx->kev[LSL_K_PNG][0], ctx->kev[LSL_K_PNG][1]);
   ctx->kms[LSL_K_PNG] = (kind == 1 ? ctx->kms[LSL_K_PNG] : 0.f) + ms;   // colour + depth launches of one decode call add up
+  cudaEventElapsedTime(&ms, ctx->kev[LSL_K_INFLATE][0], ctx->kev[LSL_K_INFLATE][1]);
+  ctx->kms[LSL_K_INFLATE] = (kind == 1 ? ctx->kms[LSL_K_INFLATE] : 0.f) + ms;
+  for (int i = 0; i < n; ++i)
+    if (h_status[i] != 0) { ctx->err = "image " + std::to_string(i) + ": " + inflate_error(h_status[i]); return LSL_ERR_ARG; }
   return LSL_OK;
 }
 
@@ -308,7 +352,8 @@ extern "C" void lsl_tum_release(lsl_ctx* ctx) {
   if (it == g_scratch.end()) return;
   TumScratch& S = it->second;
   if (ctx) cudaSetDevice(ctx->device);
-  if (S.h_filt) cudaFreeHost(S.h_filt);
+  if (S.h_z) cudaFreeHost(S.h_z);
+  if (S.d_z) cudaFree(S.d_z);
   if (S.d_filt) cudaFree(S.d_filt);
   if (S.d_bgr) cudaFree(S.d_bgr);
   if (S.d_depth) cudaFree(S.d_depth);
