@@ -7,11 +7,13 @@
  *   rgb PNG              cv::imread(name, 1): 8-bit, 3 channels in BGR order whatever the file holds (:1233)
  *   depth PNG            16-bit grey; convertTo(CV_32FC1), values < 1e-5 -> NaN, then "/ 5000.0" (:1234-1244)
  *
- * Split of the PNG decode: the DEFLATE stream is bit-serial and is inflated on host threads (zlib); everything after
- * it — scan-line unfiltering (None/Sub/Up/Average/Paeth), RGB->BGR / grey replication, big-endian 16-bit -> float
- * metres with the NaN rule — runs on the device in png_unfilter_kernel, which writes the exact buffers
- * lsl_extract_batch_dev consumes. What crosses PCIe is the filtered scan lines (H*(1+W*bpp) bytes per image: 0.92 MB
- * + 0.61 MB per VGA frame instead of 0.92 MB + 1.23 MB of float depth).
+ * Split of the PNG decode: the host only walks the PNG container (signature, IHDR, IDAT chunk boundaries) and gathers
+ * the compressed payloads into one pinned block; the zlib / DEFLATE stream is decoded on the device, one warp per
+ * image (png_inflate_kernel), followed by scan-line unfiltering (None/Sub/Up/Average/Paeth) as a row wavefront,
+ * RGB->BGR / grey replication and big-endian 16-bit -> float metres with the NaN rule (png_unfilter_kernel), which
+ * writes the exact buffers lsl_extract_batch_dev consumes. What crosses PCIe is the COMPRESSED data (about 0.4 MB +
+ * 0.45 MB per VGA frame instead of 0.92 MB + 1.23 MB of decoded planes). Not verified: chunk CRCs and the Adler-32
+ * trailer (the decoder checks the block structure, every code and distance, and the exact output length).
  *
  * "/ 5000.0" on a CV_32F cv::Mat is OpenCV 2.4's MatExpr scale: convertTo(CV_32F, alpha = 1/5000.0) whose 32f->32f
  * kernel multiplies in float by (float)alpha. OpenCV is not in this image: that reading is UNVERIFIED (the alternative,

@@ -26,20 +26,70 @@
 namespace {
 
 // ---------------------------------------------------------------------------------------------- device ----
+// Output side of the decoder on the device: the last LSL_INF_RING bytes of the stream live in a shared-memory ring
+// (DEFLATE matches reach at most 32 KB back), literals and match copies touch only the ring, and every completed
+// LSL_INF_CHUNK bytes leave for global memory as one coalesced 16-byte-per-lane store pass. Without the ring every
+// match copy was a round trip to L2 for bytes this warp had just written (357 ms per 2 x 592 VGA images).
+#define LSL_INF_RING 36864    // 18 chunks: >= 32768 + one chunk + the longest match, and a multiple of the chunk
+#define LSL_INF_CHUNK 2048
+// stores output bytes [first, first + LSL_INF_CHUNK) from the ring; rare (once per 2 KB), kept out of line (and free of
+// the ops object, which must stay in registers) so that the literal loop stays small
+__device__ __noinline__ void inflate_flush_chunk(const uint8_t* ring, uint8_t* out, uint32_t first, int lane) {
+  __syncwarp();
+  const uint4* src = reinterpret_cast<const uint4*>(ring + first % LSL_INF_RING);   // chunks never wrap
+  uint8_t* dst = out + first;
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    for (int k = lane; k < LSL_INF_CHUNK / 16; k += 32) reinterpret_cast<uint4*>(dst)[k] = src[k];
+  } else {
+    const uint8_t* sb = reinterpret_cast<const uint8_t*>(src);
+    for (int k = lane; k < LSL_INF_CHUNK; k += 32) dst[k] = sb[k];
+  }
+}
+
 struct InflateOpsWarp {
   int lane;
+  uint8_t* ring;        // shared memory, LSL_INF_RING bytes, 16-byte aligned
+  uint32_t rp;          // ring index of the next output byte (= pos % LSL_INF_RING, kept incrementally)
+  uint32_t next_flush;  // output position at which the next chunk is complete (multiple of LSL_INF_CHUNK)
   __device__ __forceinline__ bool leader() const { return lane == 0; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
-  __device__ __forceinline__ void put(uint8_t* out, size_t pos, uint8_t v) const { if (lane == 0) out[pos] = v; }
-  __device__ __forceinline__ void copy(uint8_t* out, size_t pos, int dist, int n) const {
-    __syncwarp();                                   // the bytes the match refers to are visible to every lane
-    const uint8_t* win = out + pos - dist;
-    for (int i = lane; i < n; i += 32) out[pos + i] = win[dist >= n ? i : i % dist];
-    __syncwarp();
+  __device__ __forceinline__ void flush_chunk(uint8_t* out) {
+    inflate_flush_chunk(ring, out, next_flush - LSL_INF_CHUNK, lane);
+    next_flush += LSL_INF_CHUNK;
   }
-  __device__ __forceinline__ void stored(uint8_t* out, size_t pos, const uint8_t* src, uint32_t n) const {
-    for (uint32_t i = lane; i < n; i += 32) out[pos + i] = src[i];
+  __device__ __forceinline__ void put(uint8_t* out, uint32_t pos, uint8_t v) {
+    if (lane == 0) ring[rp] = v;
+    rp = (rp + 1 == LSL_INF_RING) ? 0 : rp + 1;
+    if (pos + 1 == next_flush) flush_chunk(out);
+  }
+  __device__ __forceinline__ void copy(uint8_t* out, uint32_t pos, int dist, int n) {
+    __syncwarp();                                   // the bytes the match refers to are visible to every lane
+    const uint32_t sbase = rp + LSL_INF_RING - (uint32_t)dist;    // < 2 * LSL_INF_RING
+    for (int i = lane; i < n; i += 32) {
+      uint32_t s = sbase + (uint32_t)(dist >= n ? i : i % dist);
+      if (s >= LSL_INF_RING) s -= LSL_INF_RING;
+      uint32_t d = rp + (uint32_t)i;
+      if (d >= LSL_INF_RING) d -= LSL_INF_RING;
+      ring[d] = ring[s];
+    }
     __syncwarp();
+    rp += (uint32_t)n;
+    if (rp >= LSL_INF_RING) rp -= LSL_INF_RING;
+    while (pos + (uint32_t)n >= next_flush) flush_chunk(out);
+  }
+  __device__ __forceinline__ void stored(uint8_t* out, uint32_t pos, const uint8_t* src, uint32_t n) {
+    for (uint32_t done = 0; done < n;) {             // at most one chunk at a time so that the ring never overflows
+      const uint32_t m = min(n - done, (uint32_t)LSL_INF_CHUNK);
+      __syncwarp();
+      for (uint32_t i = lane; i < m; i += 32) ring[(rp + i) % LSL_INF_RING] = src[done + i];
+      done += m;
+      rp = (rp + m) % LSL_INF_RING;
+      while (pos + done >= next_flush) flush_chunk(out);
+    }
+  }
+  __device__ __forceinline__ void finish(uint8_t* out, uint32_t pos) {
+    __syncwarp();
+    for (uint32_t i = next_flush - LSL_INF_CHUNK + lane; i < pos; i += 32) out[i] = ring[i % LSL_INF_RING];
   }
 };
 
@@ -47,9 +97,10 @@ struct InflateOpsWarp {
 __global__ void __launch_bounds__(32) png_inflate_kernel(const uint8_t* __restrict__ z_all, const size_t* __restrict__ z_off,
                                                          uint8_t* filt_all, size_t filt_img_bytes, int* __restrict__ status) {
   __shared__ lslm::InflateScratch S;
+  extern __shared__ __align__(16) uint8_t s_ring[];
   const int img = blockIdx.x;
   InflateOpsWarp ops;
-  ops.lane = threadIdx.x;
+  ops.lane = threadIdx.x; ops.ring = s_ring; ops.rp = 0; ops.next_flush = LSL_INF_CHUNK;
   const int rc = lslm::inflate_zlib(z_all + z_off[img], z_off[img + 1] - z_off[img], filt_all + (size_t)img * filt_img_bytes,
                                     filt_img_bytes, &S, ops);
   if (threadIdx.x == 0) status[img] = rc;
@@ -152,12 +203,13 @@ bool png_parse(const uint8_t* p, size_t len, PngView* v, std::string* err) {
   return true;
 }
 
-struct TumScratch {
-  uint8_t* h_z = nullptr; size_t h_cap = 0;      // pinned staging: [offsets (n + 1) size_t | status n int | compressed streams]
-  uint8_t* d_z = nullptr; size_t dz_cap = 0;     // the same block on the device
-  uint8_t* d_filt = nullptr; size_t d_cap = 0;   // inflated (still filtered) scan lines
+struct TumScratch {   // staging per list kind (0 colour, 1 depth) so that the two lists are in flight together
+  uint8_t* h_z[2] = {nullptr, nullptr}; size_t h_cap[2] = {0, 0};     // pinned: [offsets (n + 1) size_t | status n int | compressed streams]
+  uint8_t* d_z[2] = {nullptr, nullptr}; size_t dz_cap[2] = {0, 0};    // the same block on the device
+  uint8_t* d_filt[2] = {nullptr, nullptr}; size_t d_cap[2] = {0, 0};  // inflated (still filtered) scan lines
   uint8_t* d_bgr = nullptr; size_t bgr_cap = 0;  // lsl_extract_tum_batch only
   float* d_depth = nullptr; size_t depth_cap = 0;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 std::mutex g_mu;
 std::map<lsl_ctx*, TumScratch> g_scratch;
@@ -196,7 +248,9 @@ const char* inflate_error(int rc) {
 }
 
 // one list of n same-sized PNGs -> device; kind 0 colour (any supported 8-bit type), 1 depth (grey 16)
-int decode_list(lsl_ctx* ctx, TumScratch& S, int n, const uint8_t* const* png, const size_t* len, int W, int H, int kind, void* d_out) {
+// Enqueues gather -> H2D -> inflate -> unfilter -> status D2H on `st`; the caller synchronises and calls check_list.
+int decode_list(lsl_ctx* ctx, TumScratch& S, cudaStream_t st, int n, const uint8_t* const* png, const size_t* len, int W, int H, int kind,
+                void* d_out) {
   std::vector<PngView> views((size_t)n);
   int ch = 0;
   size_t zbytes = 0;
@@ -218,56 +272,69 @@ int decode_list(lsl_ctx* ctx, TumScratch& S, int n, const uint8_t* const* png, c
   const size_t img_bytes = (size_t)H * (1 + (size_t)W * bpp);
   const size_t head = (((size_t)(n + 1) * sizeof(size_t) + (size_t)n * sizeof(int)) + 15) & ~(size_t)15;
   const size_t total = head + zbytes;
-  if (S.h_cap < total) {
-    if (S.h_z) cudaFreeHost(S.h_z);
-    S.h_z = nullptr; S.h_cap = 0;
-    LSL_CUDA(cudaHostAlloc((void**)&S.h_z, total, cudaHostAllocDefault));
-    S.h_cap = total;
+  if (S.h_cap[kind] < total) {
+    if (S.h_z[kind]) cudaFreeHost(S.h_z[kind]);
+    S.h_z[kind] = nullptr; S.h_cap[kind] = 0;
+    LSL_CUDA(cudaHostAlloc((void**)&S.h_z[kind], total, cudaHostAllocDefault));
+    S.h_cap[kind] = total;
   }
-  if (!grow_dev(&S.d_z, &S.dz_cap, total) || !grow_dev(&S.d_filt, &S.d_cap, img_bytes * (size_t)n)) {
+  uint8_t* const hz = S.h_z[kind];
+  if (!grow_dev(&S.d_z[kind], &S.dz_cap[kind], total) || !grow_dev(&S.d_filt[kind], &S.d_cap[kind], img_bytes * (size_t)n)) {
     ctx->err = "cudaMalloc of the PNG staging buffers failed";
     return LSL_ERR_CUDA;
   }
   // gather: the IDAT payloads of one image form one zlib stream (PNG §10.1), streams 16-byte aligned
-  size_t* h_off = reinterpret_cast<size_t*>(S.h_z);
-  int* h_status = reinterpret_cast<int*>(S.h_z + (size_t)(n + 1) * sizeof(size_t));
+  uint8_t* const dz = S.d_z[kind];
+  uint8_t* const dfilt = S.d_filt[kind];
+  size_t* h_off = reinterpret_cast<size_t*>(hz);
+  int* h_status = reinterpret_cast<int*>(hz + (size_t)(n + 1) * sizeof(size_t));
   size_t off = head;
   for (int i = 0; i < n; ++i) {
     h_off[i] = off;
-    for (const auto& c : views[(size_t)i].idat) { std::memcpy(S.h_z + off, c.first, c.second); off += c.second; }
+    for (const auto& c : views[(size_t)i].idat) { std::memcpy(hz + off, c.first, c.second); off += c.second; }
     const size_t pad = (16 - (off & 15)) & 15;      // < 16 zero bytes behind the Adler-32 trailer: never decoded, the
-    std::memset(S.h_z + off, 0, pad);               // final block ends the stream before them
+    std::memset(hz + off, 0, pad);                  // final block ends the stream before them
     off += pad;
     h_status[i] = 0;
   }
   h_off[n] = off;
-  LSL_CUDA(cudaMemcpyAsync(S.d_z, S.h_z, total, cudaMemcpyHostToDevice, ctx->stream));
+  LSL_CUDA(cudaMemcpyAsync(dz, hz, total, cudaMemcpyHostToDevice, st));
   ctx->stats.h2d_bytes += (int64_t)total;
-  const size_t* d_off = reinterpret_cast<const size_t*>(S.d_z);
-  int* d_status = reinterpret_cast<int*>(S.d_z + (size_t)(n + 1) * sizeof(size_t));
-  LSL_KSTART(ctx, LSL_K_INFLATE);
-  png_inflate_kernel<<<n, 32, 0, ctx->stream>>>(S.d_z, d_off, S.d_filt, img_bytes, d_status);
-  LSL_KSTOP(ctx, LSL_K_INFLATE);
-  LSL_KSTART(ctx, LSL_K_PNG);
+  const size_t* d_off = reinterpret_cast<const size_t*>(dz);
+  int* d_status = reinterpret_cast<int*>(dz + (size_t)(n + 1) * sizeof(size_t));
+  const int k_inf = kind == 1 ? LSL_K_INFLATE_D : LSL_K_INFLATE, k_unf = kind == 1 ? LSL_K_PNG_D : LSL_K_PNG;
+  cudaEventRecord(ctx->kev[k_inf][0], st);
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(png_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LSL_INF_RING); attr_set = true; }
+  png_inflate_kernel<<<n, 32, LSL_INF_RING, st>>>(dz, d_off, dfilt, img_bytes, d_status);
+  cudaEventRecord(ctx->kev[k_inf][1], st);
+  cudaEventRecord(ctx->kev[k_unf][0], st);
   uint8_t* o = (uint8_t*)d_out;
   const size_t out_img = kind == 1 ? (size_t)W * H * sizeof(float) : (size_t)W * H * 3;
-  if (kind == 1) launch_unfilter<2, 1>(ctx->stream, n, S.d_filt, img_bytes, o, out_img, W, H, d_status);
-  else if (bpp == 3) launch_unfilter<3, 0>(ctx->stream, n, S.d_filt, img_bytes, o, out_img, W, H, d_status);
-  else if (bpp == 4) launch_unfilter<4, 0>(ctx->stream, n, S.d_filt, img_bytes, o, out_img, W, H, d_status);
-  else launch_unfilter<1, 0>(ctx->stream, n, S.d_filt, img_bytes, o, out_img, W, H, d_status);
-  LSL_KSTOP(ctx, LSL_K_PNG);
+  if (kind == 1) launch_unfilter<2, 1>(st, n, dfilt, img_bytes, o, out_img, W, H, d_status);
+  else if (bpp == 3) launch_unfilter<3, 0>(st, n, dfilt, img_bytes, o, out_img, W, H, d_status);
+  else if (bpp == 4) launch_unfilter<4, 0>(st, n, dfilt, img_bytes, o, out_img, W, H, d_status);
+  else launch_unfilter<1, 0>(st, n, dfilt, img_bytes, o, out_img, W, H, d_status);
+  cudaEventRecord(ctx->kev[k_unf][1], st);
+  ctx->kran[k_inf] = ctx->kran[k_unf] = true;
+  ctx->stats.kernel_launches += 2;
   LSL_CUDA(cudaGetLastError());
-  LSL_CUDA(cudaMemcpyAsync(h_status, d_status, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  LSL_CUDA(cudaMemcpyAsync(h_status, d_status, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
   ctx->stats.d2h_bytes += (int64_t)n * (int64_t)sizeof(int);
-  // the pinned staging block is reused by the next list, and the status words decide the return value
-  LSL_CUDA(cudaStreamSynchronize(ctx->stream));
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, ctx->kev[LSL_K_PNG][0], ctx->kev[LSL_K_PNG][1]);
-  ctx->kms[LSL_K_PNG] = (kind == 1 ? ctx->kms[LSL_K_PNG] : 0.f) + ms;   // colour + depth launches of one decode call add up
-  cudaEventElapsedTime(&ms, ctx->kev[LSL_K_INFLATE][0], ctx->kev[LSL_K_INFLATE][1]);
-  ctx->kms[LSL_K_INFLATE] = (kind == 1 ? ctx->kms[LSL_K_INFLATE] : 0.f) + ms;
+  return LSL_OK;
+}
+
+// after the stream(s) have been synchronised: kernel times and the per-image status words of one list
+int check_list(lsl_ctx* ctx, TumScratch& S, int n, int kind) {
+  const int k_inf = kind == 1 ? LSL_K_INFLATE_D : LSL_K_INFLATE, k_unf = kind == 1 ? LSL_K_PNG_D : LSL_K_PNG;
+  cudaEventElapsedTime(&ctx->kms[k_inf], ctx->kev[k_inf][0], ctx->kev[k_inf][1]);
+  cudaEventElapsedTime(&ctx->kms[k_unf], ctx->kev[k_unf][0], ctx->kev[k_unf][1]);
+  const int* h_status = reinterpret_cast<const int*>(S.h_z[kind] + (size_t)(n + 1) * sizeof(size_t));
   for (int i = 0; i < n; ++i)
-    if (h_status[i] != 0) { ctx->err = "image " + std::to_string(i) + ": " + inflate_error(h_status[i]); return LSL_ERR_ARG; }
+    if (h_status[i] != 0) {
+      ctx->err = std::string(kind == 1 ? "depth" : "colour") + " image " + std::to_string(i) + ": " + inflate_error(h_status[i]);
+      return LSL_ERR_ARG;
+    }
   return LSL_OK;
 }
 
@@ -320,8 +387,28 @@ extern "C" int lsl_tum_decode_batch(lsl_ctx* ctx, int n, const uint8_t* const* r
   std::lock_guard<std::mutex> lk(g_mu);
   TumScratch& S = g_scratch[ctx];
   int rc = LSL_OK;
-  if (rgb_png && (rc = decode_list(ctx, S, n, rgb_png, rgb_len, W, H, 0, d_bgr)) != LSL_OK) return rc;
-  if (depth_png && (rc = decode_list(ctx, S, n, depth_png, depth_len, W, H, 1, d_depth)) != LSL_OK) return rc;
+  // colour list on the context's stream, depth list on its copy stream: the host gathers the second list while the
+  // first one is being inflated, and the two inflate kernels share the SMs (5 streams per SM fit, a list brings 4)
+  const bool both = rgb_png && depth_png;
+  cudaStream_t st_d = ctx->stream;
+  if (both) {
+    if (!S.ev_fork) { LSL_CUDA(cudaEventCreateWithFlags(&S.ev_fork, cudaEventDisableTiming)); LSL_CUDA(cudaEventCreateWithFlags(&S.ev_join, cudaEventDisableTiming)); }
+    st_d = ctx->copy_stream;
+    LSL_CUDA(cudaEventRecord(S.ev_fork, ctx->stream));
+    LSL_CUDA(cudaStreamWaitEvent(st_d, S.ev_fork, 0));
+  }
+  if (rgb_png) rc = decode_list(ctx, S, ctx->stream, n, rgb_png, rgb_len, W, H, 0, d_bgr);
+  if (rc == LSL_OK && depth_png) rc = decode_list(ctx, S, st_d, n, depth_png, depth_len, W, H, 1, d_depth);
+  if (both) {
+    cudaEventRecord(S.ev_join, st_d);
+    cudaStreamWaitEvent(ctx->stream, S.ev_join, 0);
+  }
+  // the pinned staging blocks are reused by the next call, and the status words decide the return value
+  const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (rc != LSL_OK) return rc;
+  if (e != cudaSuccess) { ctx->err = std::string("PNG decode: ") + cudaGetErrorString(e); return LSL_ERR_CUDA; }
+  if (rgb_png && (rc = check_list(ctx, S, n, 0)) != LSL_OK) return rc;
+  if (depth_png && (rc = check_list(ctx, S, n, 1)) != LSL_OK) return rc;
   return LSL_OK;
 }
 
@@ -352,9 +439,13 @@ extern "C" void lsl_tum_release(lsl_ctx* ctx) {
   if (it == g_scratch.end()) return;
   TumScratch& S = it->second;
   if (ctx) cudaSetDevice(ctx->device);
-  if (S.h_z) cudaFreeHost(S.h_z);
-  if (S.d_z) cudaFree(S.d_z);
-  if (S.d_filt) cudaFree(S.d_filt);
+  for (int k = 0; k < 2; ++k) {
+    if (S.h_z[k]) cudaFreeHost(S.h_z[k]);
+    if (S.d_z[k]) cudaFree(S.d_z[k]);
+    if (S.d_filt[k]) cudaFree(S.d_filt[k]);
+  }
+  if (S.ev_fork) cudaEventDestroy(S.ev_fork);
+  if (S.ev_join) cudaEventDestroy(S.ev_join);
   if (S.d_bgr) cudaFree(S.d_bgr);
   if (S.d_depth) cudaFree(S.d_depth);
   g_scratch.erase(it);

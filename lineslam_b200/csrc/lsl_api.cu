@@ -27,7 +27,7 @@ extern "C" const char* lsl_last_error(const lsl_ctx* ctx) { return ctx ? ctx->er
 static const char* const kKernelNames[LSL_K_COUNT] = {
     "gray_kernel", "xpass_kernel", "ypass_kernel", "ll_angle_kernel", "seed_list_kernel", "sobel5_kernel",
     "lsd_region_kernel", "lsd_nfa_kernel", "line3d_ransac_kernel", "line_msld_kernel", "msld_randfill_kernel", "line_mle_kernel",
-    "gather_lines_kernel", "match_lines_kernel", "pose_kernel", "match_points_kernel", "pose_hybrid_kernel", "relmotion_kernel", "png_unfilter_kernel", "png_inflate_kernel"};
+    "gather_lines_kernel", "match_lines_kernel", "pose_kernel", "match_points_kernel", "pose_hybrid_kernel", "relmotion_kernel", "png_unfilter_kernel", "png_inflate_kernel", "png_unfilter_kernel(depth)", "png_inflate_kernel(depth)"};
 extern "C" const char* lsl_kernel_name(int i) { return (i >= 0 && i < LSL_K_COUNT) ? kKernelNames[i] : ""; }
 
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }

@@ -158,7 +158,7 @@ struct RmScratch {
 // Kernel ids for the per-kernel device timers (CUDA events on the context stream)
 enum LslKernelId {
   LSL_K_GRAY = 0, LSL_K_XPASS, LSL_K_YPASS, LSL_K_LLANGLE, LSL_K_SEEDS, LSL_K_SOBEL, LSL_K_REGION, LSL_K_NFA, LSL_K_RANSAC3D,
-  LSL_K_MSLD, LSL_K_RANDFILL, LSL_K_MLE, LSL_K_GATHER, LSL_K_MATCH, LSL_K_POSE, LSL_K_MATCHPTS, LSL_K_POSEHYB, LSL_K_RELMOTION, LSL_K_PNG, LSL_K_INFLATE, LSL_K_COUNT
+  LSL_K_MSLD, LSL_K_RANDFILL, LSL_K_MLE, LSL_K_GATHER, LSL_K_MATCH, LSL_K_POSE, LSL_K_MATCHPTS, LSL_K_POSEHYB, LSL_K_RELMOTION, LSL_K_PNG, LSL_K_INFLATE, LSL_K_PNG_D, LSL_K_INFLATE_D, LSL_K_COUNT
 };
 
 // Line records of all frames of one extract call live in ONE device allocation (stream-ordered pool);

@@ -10,6 +10,7 @@
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
+#include <string.h>
 #include "lsl_math.h"
 
 #if defined(__CUDACC__)
@@ -36,19 +37,39 @@ struct InflateScratch {
 
 struct BitIn {
   const uint8_t* in;
-  size_t len, pos;
+  size_t len, pos;      // pos: next input byte that has not entered buf yet
   uint64_t buf;
   int cnt;
-  int overrun;
+  int overrun;          // bytes asked for past the end (zeros are supplied; a few are normal look-ahead)
+  uint32_t nextw;       // word at in + pos, loaded one refill early so that its latency hides behind decoding
+  bool have_next;
 };
 
-LSL_HD void bits_fill(BitIn* b) {   // at least 32 valid bits afterwards (zeros past the end, flagged)
-  while (b->cnt <= 56) {
-    uint64_t v = 0;
-    if (b->pos < b->len) v = b->in[b->pos]; else b->overrun++;
-    b->pos++;
-    b->buf |= v << b->cnt;
-    b->cnt += 8;
+LSL_HD uint32_t load_le32(const uint8_t* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(reinterpret_cast<const uint32_t*>(p));
+#else
+  uint32_t v; memcpy(&v, p, 4); return v;
+#endif
+}
+
+// at least 33 valid bits afterwards: aligned 32-bit words while two whole words remain, single bytes otherwise
+LSL_HD void bits_fill(BitIn* b) {
+  while (b->cnt <= 32) {
+    if ((((uintptr_t)(b->in + b->pos)) & 3) == 0 && b->pos + 8 <= b->len) {
+      if (!b->have_next) { b->nextw = load_le32(b->in + b->pos); b->have_next = true; }
+      const uint32_t w = b->nextw;
+      b->nextw = load_le32(b->in + b->pos + 4);
+      b->buf |= (uint64_t)w << b->cnt;
+      b->cnt += 32; b->pos += 4;
+    } else {
+      b->have_next = false;
+      uint64_t v = 0;
+      if (b->pos < b->len) v = b->in[b->pos]; else b->overrun++;
+      b->pos++;
+      b->buf |= v << b->cnt;
+      b->cnt += 8;
+    }
   }
 }
 LSL_HD uint32_t bits_get(BitIn* b, int n) {   // n <= 32, after bits_fill
@@ -107,18 +128,20 @@ LSL_HD int huff_decode(BitIn* b, const HuffTable* h) {
 struct InflateOpsSerial {
   LSL_HDM bool leader() const { return true; }   // the one thread that builds the shared tables
   LSL_HDM void sync() const {}                   // all threads of the group have passed this point, writes visible
-  LSL_HDM void put(uint8_t* out, size_t pos, uint8_t v) const { out[pos] = v; }
-  LSL_HDM void copy(uint8_t* out, size_t pos, int dist, int n) const { for (int i = 0; i < n; ++i) out[pos + i] = out[pos + i - dist]; }
-  LSL_HDM void stored(uint8_t* out, size_t pos, const uint8_t* src, uint32_t n) const { for (uint32_t i = 0; i < n; ++i) out[pos + i] = src[i]; }
+  LSL_HDM void finish(uint8_t*, uint32_t) const {} // everything handed to put / copy / stored is in `out` afterwards
+  LSL_HDM void put(uint8_t* out, uint32_t pos, uint8_t v) const { out[pos] = v; }
+  LSL_HDM void copy(uint8_t* out, uint32_t pos, int dist, int n) const { for (int i = 0; i < n; ++i) out[pos + i] = out[pos + i - dist]; }
+  LSL_HDM void stored(uint8_t* out, uint32_t pos, const uint8_t* src, uint32_t n) const { for (uint32_t i = 0; i < n; ++i) out[pos + i] = src[i]; }
 };
 
 template <typename Ops>
-LSL_HD int inflate_zlib(const uint8_t* in, size_t len, uint8_t* out, size_t want, InflateScratch* S, const Ops& ops) {
-  if (len < 6) return -1;
+LSL_HD int inflate_zlib(const uint8_t* in, size_t len, uint8_t* out, size_t want_bytes, InflateScratch* S, Ops& ops) {
+  if (len < 6 || want_bytes > 0xfffffff0u) return -1;
+  const uint32_t want = (uint32_t)want_bytes;        // positions are 32-bit: cheaper on the device
   if ((in[0] & 15) != 8 || (in[0] >> 4) > 7 || (in[1] & 32) || ((in[0] << 8) | in[1]) % 31 != 0) return -1;
   BitIn b;
-  b.in = in; b.len = len; b.pos = 2; b.buf = 0; b.cnt = 0; b.overrun = 0;
-  size_t pos = 0;
+  b.in = in; b.len = len; b.pos = 2; b.buf = 0; b.cnt = 0; b.overrun = 0; b.nextw = 0; b.have_next = false;
+  uint32_t pos = 0;
   int last = 0;
   const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
   while (!last) {
@@ -128,14 +151,15 @@ LSL_HD int inflate_zlib(const uint8_t* in, size_t len, uint8_t* out, size_t want
     const int type = (int)bits_get(&b, 2);
     if (type == 0) {                                    // stored
       bits_get(&b, b.cnt & 7);                          // to the byte boundary
+      bits_fill(&b);
       const uint32_t n = bits_get(&b, 16), nn = bits_get(&b, 16);
       if ((n ^ 0xffffu) != nn) return -3;
       size_t src = b.pos - (size_t)(b.cnt >> 3);        // bytes still in the bit buffer belong to the block
       if (src + n > len) return -7;
-      if (pos + n > want) return -6;
+      if (n > want - pos) return -6;
       ops.stored(out, pos, in + src, n);
       pos += n;
-      b.pos = src + n; b.buf = 0; b.cnt = 0;
+      b.pos = src + n; b.buf = 0; b.cnt = 0; b.have_next = false;
       continue;
     }
     if (type == 3) return -2;
@@ -211,14 +235,15 @@ LSL_HD int inflate_zlib(const uint8_t* in, size_t len, uint8_t* out, size_t want
       int dist;
       if (ds < 4) dist = 1 + ds;
       else { const int e = (ds >> 1) - 1; dist = 1 + ((2 + (ds & 1)) << e) + (int)bits_get(&b, e); }
-      if ((size_t)dist > pos) return -5;
-      if (pos + (size_t)mlen > want) return -6;
+      if ((uint32_t)dist > pos) return -5;
+      if ((uint32_t)mlen > want - pos) return -6;
       ops.copy(out, pos, dist, mlen);
-      pos += (size_t)mlen;
+      pos += (uint32_t)mlen;
     }
     if (b.overrun > 8) return -7;
   }
   if (b.overrun > 8) return -7;
+  ops.finish(out, pos);
   return pos == want ? 0 : -8;
 }
 

@@ -4,5 +4,6 @@
 
 extern "C" int lsl_inflate_host_check(const uint8_t* in, size_t len, uint8_t* out, size_t want) {
   static thread_local lslm::InflateScratch S;
-  return lslm::inflate_zlib(in, len, out, want, &S, lslm::InflateOpsSerial());
+  lslm::InflateOpsSerial ops;
+  return lslm::inflate_zlib(in, len, out, want, &S, ops);
 }

