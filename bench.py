@@ -36,9 +36,10 @@ W, H = 640, 480
 B_FRAME = W * H * (3 + 4)          # compulsory HBM bytes per extracted frame: RGB u8 + depth f32
 METRIC = "frame-pairs/sec (extract+match+RANSAC pose) on 640x480 RGB-D"
 # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture at batch 592
-# (profiles/r1_end_ncu_full_raw_b592.csv), per frame of the launch
-NCU_DRAM_BYTES_PER_FRAME = {"line_mle_kernel": (0.1960e9 + 0.3766e9) / 592, "lsd_region_kernel": (1.439e9 + 0.0898e9) / 592,
-                            "line3d_ransac_kernel": (0.3236e9 + 0.1164e9) / 592, "lsd_nfa_kernel": (0.2759e9 + 0.0110e9) / 592,
+# (profiles/r1_final2_ncu_full_raw_b592.csv for the first three kernels, profiles/r1_end_ncu_full_raw_b592.csv for the
+# others), per frame of the launch
+NCU_DRAM_BYTES_PER_FRAME = {"line_mle_kernel": (0.1764e9 + 0.1708e9) / 592, "lsd_region_kernel": (1.4525e9 + 0.0903e9) / 592,
+                            "line3d_ransac_kernel": (0.3238e9 + 0.1165e9) / 592, "lsd_nfa_kernel": (0.2759e9 + 0.0110e9) / 592,
                             "ll_angle_kernel": (0.9328e9 + 3.925e9) / 592, "line_msld_kernel": (0.6691e9 + 0.0586e9) / 592}
 
 
@@ -325,7 +326,7 @@ def run_cuda(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
                          "traffic": (NCU_DRAM_BYTES_PER_FRAME[dom] * B if dom in NCU_DRAM_BYTES_PER_FRAME else None),
-                         "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r1_end_ncu_full_raw_b592.csv)",
+                         "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r1_final2_ncu_full_raw_b592.csv)",
                          "algorithmic_bytes": B * B_FRAME,
                          "note": f"algorithmic bytes = {B} frames x {B_FRAME} B (RGB u8 + depth f32) per launch / CUDA-event time of "
                                  f"{dom}; peak = MEASURED_PEAKS.json hbm_gbs ({'measured' if peaks else 'fallback 6650 GB/s of B200_PROFILING.md'}); "
