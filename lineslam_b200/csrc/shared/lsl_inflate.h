@@ -184,23 +184,25 @@ LSL_HD int inflate_zlib(const uint8_t* in, size_t len, uint8_t* out, size_t want
       if (ops.leader()) S->status = huff_build(&S->lit, cl, 19);
       ops.sync();
       if (S->status != 0) return -4;                                 // the code-length code must be complete
-      // below, every thread stores the same value to the same slot and only re-reads slots it has already stored
-      int idx = 0;
+      // every thread walks the code lengths (its bit reader must advance; the previous length lives in a register),
+      // only the leader stores them
+      int idx = 0, prev = 0, len256 = 0;
+      const bool lead = ops.leader();
       while (idx < nlen + ndist) {
         bits_fill(&b);
         const int sym = huff_decode(&b, &S->lit);
         if (sym < 0) return -4;
-        if (sym < 16) S->lengths[idx++] = (uint8_t)sym;
-        else {
-          int rep, val = 0;
-          if (sym == 16) { if (idx == 0) return -4; val = S->lengths[idx - 1]; rep = 3 + (int)bits_get(&b, 2); }
-          else if (sym == 17) rep = 3 + (int)bits_get(&b, 3);
-          else rep = 11 + (int)bits_get(&b, 7);
-          if (idx + rep > nlen + ndist) return -4;
-          while (rep--) S->lengths[idx++] = (uint8_t)val;
-        }
+        int rep = 1, val = sym;
+        if (sym == 16) { if (idx == 0) return -4; val = prev; rep = 3 + (int)bits_get(&b, 2); }
+        else if (sym == 17) { val = 0; rep = 3 + (int)bits_get(&b, 3); }
+        else if (sym == 18) { val = 0; rep = 11 + (int)bits_get(&b, 7); }
+        if (idx + rep > nlen + ndist) return -4;
+        if (idx <= 256 && 256 < idx + rep) len256 = val;
+        if (lead) for (int k = 0; k < rep; ++k) S->lengths[idx + k] = (uint8_t)val;
+        idx += rep;
+        prev = val;
       }
-      if (S->lengths[256] == 0) return -4;
+      if (len256 == 0) return -4;                                    // no end-of-block code
       // the distance lengths sit behind the literal/length ones: build dist first (lit reuses the scratch table)
       ops.sync();
       if (ops.leader()) {
