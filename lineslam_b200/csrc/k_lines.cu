@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(128, RANSAC_MINB) line3d_ransac_kernel(LslWork
         double BA[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]};
         bool degenerate = norm3(BA) < 1e-10;
         int cnt = 0;
-#pragma unroll
+#pragma unroll 1   // rolled: four inlined copies of the distance made the RANSAC loop instruction-fetch bound (16.5 -> 14.1 ms)
         for (int wd = 0; wd < 4; ++wd) {
           int i = wd * 32 + lane;
           bool in = false;
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(128, RANSAC_MINB) line3d_ransac_kernel(LslWork
           for (int k = 0; k < 3; ++k) q2[k] = tm[k] + td[k];
           uint32_t nm[4];
           int cnt = 0;
-#pragma unroll
+#pragma unroll 1
           for (int wd = 0; wd < 4; ++wd) {
             int i = wd * 32 + lane;
             bool in = false;
@@ -583,10 +583,13 @@ __device__ __noinline__ double l2nrm_neg(double* E, const double* y /* shared, [
   const int blockn = (n >> 3) << 3;
   double s = 0.0;
   int i = blockn - 1 - a;
+  // (both loops rolled: the LM loop is instruction-fetch bound, its hot code must stay near the 32 KB L1.5 I-cache)
+#pragma unroll 1
   for (; i >= 12; i -= 16) {
     double t0 = E[i], t1 = E[i - 4], t2 = E[i - 8], t3 = E[i - 12];
     s += t0 * t0; s += t1 * t1; s += t2 * t2; s += t3 * t3;
   }
+#pragma unroll 1
   for (; i >= 0; i -= 4) { double t0 = E[i]; s += t0 * t0; }
   // remainder (switch fall-through of the reference): element blockn + t goes to accumulator (7 - rem + t) & 3,
   // i.e. accumulator a takes t = (a + rem + 1) & 3 and t + 4, in that order
@@ -797,11 +800,13 @@ __global__ void __launch_bounds__(32, MLE_MINB) line_mle_kernel(LslWork w, LineP
         if (lane < 21) { ja = S.jac + tri_j; jb = S.jac + tri_i; sb = MLE_JS; }
         else { ja = S.jac + (lane - 21); jb = Ecur; sb = 1; }
         int l = n - 1;
+#pragma unroll 1
         for (; l >= 3; l -= 4) {
           double t0 = ja[l * MLE_JS] * jb[l * sb], t1 = ja[(l - 1) * MLE_JS] * jb[(l - 1) * sb], t2 = ja[(l - 2) * MLE_JS] * jb[(l - 2) * sb],
                  t3 = ja[(l - 3) * MLE_JS] * jb[(l - 3) * sb];
           acc += t0; acc += t1; acc += t2; acc += t3;
         }
+#pragma unroll 1
         for (; l >= 0; --l) acc += ja[l * MLE_JS] * jb[l * sb];
         if (lane < 21) { S.JtJ[tri_i * m + tri_j] = acc; S.JtJ[tri_j * m + tri_i] = acc; }
         else S.Jte[lane - 21] = acc;

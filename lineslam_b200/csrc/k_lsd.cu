@@ -398,7 +398,9 @@ __device__ __forceinline__ double inter_hi(double x, double x1, double y1, doubl
   return y1 + (x - x1) * (y2 - y1) / (x2 - x1);
 }
 // lsd.cpp:1388-1410 with the rectangle iterator (:1165-1383) unrolled into per-lane columns.
-__device__ double rect_nfa(const FrameView& V, const Rect& r, double logNT) {
+// NOT inlined: rect_improve calls it from six places (21 after unrolling) and the kernel was instruction-fetch bound
+// (ncu: 40 % of the stall samples `no_instructions` at 19 288 SASS instructions).
+__device__ __noinline__ double rect_nfa(const FrameView& V, const Rect& r, double logNT) {
   const int lane = threadIdx.x & 31;
   double vx0[4], vy0[4], vx[4], vy[4];
   vx0[0] = r.x1 - r.dy * r.width / 2.0; vy0[0] = r.y1 + r.dx * r.width / 2.0;
@@ -438,6 +440,7 @@ __device__ double rect_improve(const FrameView& V, Rect* rec, double logNT, doub
   double log_nfa = rect_nfa(V, *rec, logNT), log_nfa_new;
   if (log_nfa > eps) return log_nfa;
   r = *rec;
+#pragma unroll 1
   for (int n = 0; n < 5; ++n) {
     r.p /= 2.0; r.prec = r.p * LSL_PI;
     log_nfa_new = rect_nfa(V, r, logNT);
@@ -445,6 +448,7 @@ __device__ double rect_improve(const FrameView& V, Rect* rec, double logNT, doub
   }
   if (log_nfa > eps) return log_nfa;
   r = *rec;
+#pragma unroll 1
   for (int n = 0; n < 5; ++n)
     if ((r.width - delta) >= 0.5) {
       r.width -= delta;
@@ -453,6 +457,7 @@ __device__ double rect_improve(const FrameView& V, Rect* rec, double logNT, doub
     }
   if (log_nfa > eps) return log_nfa;
   r = *rec;
+#pragma unroll 1
   for (int n = 0; n < 5; ++n)
     if ((r.width - delta) >= 0.5) {
       r.x1 += -r.dy * delta_2; r.y1 += r.dx * delta_2;
@@ -463,6 +468,7 @@ __device__ double rect_improve(const FrameView& V, Rect* rec, double logNT, doub
     }
   if (log_nfa > eps) return log_nfa;
   r = *rec;
+#pragma unroll 1
   for (int n = 0; n < 5; ++n)
     if ((r.width - delta) >= 0.5) {
       r.x1 -= -r.dy * delta_2; r.y1 -= r.dx * delta_2;
@@ -473,6 +479,7 @@ __device__ double rect_improve(const FrameView& V, Rect* rec, double logNT, doub
     }
   if (log_nfa > eps) return log_nfa;
   r = *rec;
+#pragma unroll 1
   for (int n = 0; n < 5; ++n) {
     r.p /= 2.0; r.prec = r.p * LSL_PI;
     log_nfa_new = rect_nfa(V, r, logNT);
