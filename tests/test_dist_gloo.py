@@ -67,3 +67,63 @@ def test_shard_helpers_edge_cases():
     assert [shard.shard_pairs(256, 8, r)[:2] for r in (0, 7)] == [(0, 32), (224, 256)]
     assert shard.shard_stream(10, 3, 1, 4) == [(4, 8)]
     assert len(shard.pad_records(np.zeros(0, shard.POSE_DTYPE), 3)) == 3
+
+
+def _graph_worker(rank, world, port, q):
+    """Loop-closure insertion with the candidates of every frame sharded over the ranks: each rank
+    registers its block of candidates, the 128-byte records are all-gathered, every rank commits the same list."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import test_graph as TG
+    from lineslam_b200 import graph as G, shard
+    from lineslam_b200.records import POSE_DTYPE
+    po, pp = TG._params(**TG.CASES["octomap_5_5_5"]["kw"])
+    rec, stamps, feats = TG._script(321, 60, motion=0.15)
+    gm = G.GraphManager(pp, 5)
+    found = []
+    for i in range(len(stamps)):
+        rec.cur[0] = i
+        action, nid, cmp_ = gm.node_begin(float(stamps[i]), feats[i], feats[i])
+        if action in (G.FIRST, G.SKIPPED):
+            found.append(action == G.FIRST); continue
+        r0 = rec(nid, cmp_) if action == G.COMPARE_PREDECESSOR else None     # the predecessor pair: every rank (cheap)
+        action, ids, res = gm.node_predecessor(r0)
+        if action == G.DROPPED:
+            found.append(bool(res.found_match)); continue
+        lo, hi, per = shard.shard_pairs(len(ids), world, rank)
+        mine = np.array([rec(nid, int(c)) for c in ids[lo:hi]], POSE_DTYPE) if hi > lo else np.zeros(0, POSE_DTYPE)
+        allr = shard.allgather_pose_records(shard.pad_records(mine, per)) if per > 0 else np.zeros(0, POSE_DTYPE)
+        allr = shard.drop_padding(allr)
+        found.append(bool(gm.node_commit(allr).found_match))
+    q.put((rank, found, gm.edges().tobytes(), gm.nodes().tobytes(), [int(k) for k in gm.keyframe_ids()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_candidates_give_the_unsharded_graph():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import test_graph as TG
+    world = 2
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    port = _free_port()
+    ps = [ctxm.Process(target=_graph_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    po, pp = TG._params(**TG.CASES["octomap_5_5_5"]["kw"])
+    rec, stamps, feats = TG._script(321, 60, motion=0.15)
+    gm, found, _ = TG._run_product(pp, 5, rec, stamps, feats)          # single process, unsharded
+    for rank, f, e, n, k in res:
+        assert f == found
+        assert e == gm.edges().tobytes() and n == gm.nodes().tobytes()
+        assert k == [int(x) for x in gm.keyframe_ids()]
+    assert len(gm.edges()) > 60
