@@ -46,17 +46,18 @@ NCU_DRAM_BYTES_PER_FRAME = {"line_mle_kernel": (0.1764e9 + 0.1708e9) / 592, "lsd
 def _hbm_peak(peaks, fallback: float = 6650.0) -> float:
     """HBM GB/s out of the driver-written MEASURED_PEAKS.json (key `hbm_gbs`; any numeric entry whose key names HBM /
     copy bandwidth is accepted, nested or not); the profiling recipe's fallback otherwise."""
-    def walk(d):
+    def walk(d, path=""):
         if isinstance(d, dict):
             for k, v in d.items():
-                kl = str(k).lower()
+                kl = path + "/" + str(k).lower()
                 if isinstance(v, (int, float)) and ("hbm" in kl or "copy" in kl) and v > 100:
-                    yield (0 if kl == "hbm_gbs" else 1, float(v))
+                    # exact key first, then sustained figures (the kernel is timed inside a long step), then the rest
+                    yield (0 if kl == "/hbm_gbs" else 1 if "sustain" in kl else 2, float(v))
                 else:
-                    yield from walk(v)
+                    yield from walk(v, kl)
         elif isinstance(d, list):
             for v in d:
-                yield from walk(v)
+                yield from walk(v, path)
     found = sorted(walk(peaks))
     return found[0][1] if found else fallback
 
