@@ -540,21 +540,26 @@ __global__ void msld_randfill_kernel(LslWork w, const int32_t* __restrict__ msld
 // live in registers; the covariance factors DU, the Jacobian and the two residual-difference vectors that other
 // lanes must read (J^T e, the ordered norms) live in shared memory.
 #define MLE_JS 6   // row stride of jac (7 removes the 2-way bank conflicts of the row accesses but measured 2 ms slower)
-struct MleSmem {
-  double pos[LSL_MAX_SMP * 3];
-  double DU[LSL_MAX_SMP * 9];
-  double eA[LSL_MAX_SMP], eB[LSL_MAX_SMP];  // e of the current estimate / of the trial point (roles swap on accept)
-  double hA[LSL_MAX_SMP], hB[LSL_MAX_SMP];  // residual vectors hx / wrk (roles swap on accept); shared, not thread-local:
-                                            // arrays handed to the non-inlined helpers would otherwise live in local memory
-  double jac[LSL_MAX_SMP * MLE_JS];
+// CAP = point capacity of the instance: LSL_MAX_SMP for the general kernel; a second instance with CAP = 64 exists for
+// the experiment LSL_MLE_SIZE_CLASSES (13 KB instead of 18 KB per warp -> more resident lines per SM), see the launcher.
+template <int CAP>
+struct MleSmemT {
+  double pos[CAP * 3];
+  double DU[CAP * 9];
+  double eA[CAP], eB[CAP];  // e of the current estimate / of the trial point (roles swap on accept)
+  double hA[CAP], hB[CAP];  // residual vectors hx / wrk (roles swap on accept); shared, not thread-local:
+                            // arrays handed to the non-inlined helpers would otherwise live in local memory
+  double jac[(CAP * MLE_JS > 32 * 18) ? CAP * MLE_JS : 32 * 18];   // also the 32 x 18 tile of MleLine3dCov after the LM
   double JtJ[36], Jte[6];
   double cinv1[9], cinv2[9];
-};  // the 32 x 18 tile of MleLine3dCov reuses `jac` once the LM has finished
+};
+typedef MleSmemT<LSL_MAX_SMP> MleSmem;
 
 // costFun_MLEstimateLine3d (utils.cpp:954-978) for the points a lane owns. Deliberately NOT inlined and not
 // unrolled: the LM loop is instruction-fetch bound when its body outgrows the instruction cache (ncu: 50 % of
 // the stall samples were `no_instructions` with three inlined, four-way unrolled copies).
-__device__ __noinline__ void mle_cost(const MleSmem& S, int n, int idx1, int idx2, double p0, double p1, double p2, double p3,
+template <int CAP>
+__device__ __noinline__ void mle_cost(const MleSmemT<CAP>& S, int n, int idx1, int idx2, double p0, double p1, double p2, double p3,
                                       double p4, double p5, double* r /* shared, [n] */) {
   const int lane = threadIdx.x & 31;
   const double p[6] = {p0, p1, p2, p3, p4, p5};
@@ -609,7 +614,8 @@ __device__ __noinline__ double l2nrm_neg(double* E, const double* y /* shared, [
 // because the L entries travel with their row through the swaps; only where an operation is executed changes.
 // The two triangular solves are the reference's loops on registers. W = 48 doubles of warp-private scratch
 // (a 36 | work 6 | x 6). The system is (JtJ + mu on the diagonal) x = Jte; every lane receives x[6].
-__device__ __noinline__ int ax_eq_b_lu6(const MleSmem& S, double mu, double* W, double* x) {
+template <int CAP>
+__device__ __noinline__ int ax_eq_b_lu6(const MleSmemT<CAP>& S, double mu, double* W, double* x) {
   const int lane = threadIdx.x & 31;
   double* a = W; double* work = W + 36; double* xs = W + 42;
   __syncwarp();
@@ -707,9 +713,12 @@ __device__ __noinline__ int ax_eq_b_lu6(const MleSmem& S, double mu, double* W, 
 #ifndef MLE_MINB
 #define MLE_MINB 11
 #endif
-__global__ void __launch_bounds__(32, MLE_MINB) line_mle_kernel(LslWork w, LineParams P) {
+// MODE 0: every line (the product path). MODE 1 / 2 (experiment): only the lines with n <= CAP / with n > MLE_SPLIT points.
+#define MLE_SPLIT 64
+template <int CAP, int MINB, int MODE>
+__global__ void __launch_bounds__(32, MINB) line_mle_kernel(LslWork w, LineParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  MleSmem& S = *reinterpret_cast<MleSmem*>(smem_raw);
+  MleSmemT<CAP>& S = *reinterpret_cast<MleSmemT<CAP>*>(smem_raw);
   const int f = blockIdx.y, lane = threadIdx.x;
   const int nl = min(w.nlines[f], LSL_MAX_LINES);
   int tri_i = 0, tri_j = lane;                         // lanes 0..20 <-> lower-triangle element (tri_i, tri_j), tri_j <= tri_i
@@ -718,6 +727,8 @@ __global__ void __launch_bounds__(32, MLE_MINB) line_mle_kernel(LslWork w, LineP
   __syncwarp();
   lsl_line_rec* L = w.lines + (size_t)f * LSL_MAX_LINES + li;
   const int n = w.npts[(size_t)f * LSL_MAX_LINES + li];
+  if (MODE == 1 && n > CAP) continue;          // uniform; compiled out of the product instance (MODE 0)
+  if (MODE == 2 && n <= MLE_SPLIT) continue;
   const double* gp = w.pts + ((size_t)f * LSL_MAX_LINES + li) * LSL_MAX_SMP * 3;
   const int m = 6;
   // points + their covariance factors (recomputed: same functions as the RANSAC stage)
@@ -965,14 +976,26 @@ int lsl_launch_lines(lsl_ctx* ctx, int n, const float* d_depth, const double K[9
   LSL_KSTOP(ctx, LSL_K_RANDFILL);
   LSL_KSTART(ctx, LSL_K_MLE);
   {
+    // Experiment switch for the next tuning step: LSL_MLE_SIZE_CLASSES=1 runs the lines with at
+    // most 64 points in an instance with 13 KB of shared memory per warp at 16 CTAs / SM and the rest in the general
+    // instance. Same arithmetic per line, so results are identical; off by default until it is measured.
+    static int classes = -1;
+    if (classes < 0) { const char* e = getenv("LSL_MLE_SIZE_CLASSES"); classes = (e && e[0] == '1') ? 1 : 0; }
     static bool once = false;
     if (!once) {   // leave the rest of the 256 KB to L1: the LM's local-memory working set lives there
       int carve = (int)((MLE_MINB * (sizeof(MleSmem) + 1024) * 100 + 233471) / 233472);
-      cudaFuncSetAttribute(line_mle_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve > 100 ? 100 : carve);
+      cudaFuncSetAttribute(line_mle_kernel<LSL_MAX_SMP, MLE_MINB, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, carve > 100 ? 100 : carve);
+      cudaFuncSetAttribute(line_mle_kernel<LSL_MAX_SMP, MLE_MINB, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, carve > 100 ? 100 : carve);
+      cudaFuncSetAttribute(line_mle_kernel<MLE_SPLIT, 16, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
       once = true;
     }
+    if (classes) {
+      line_mle_kernel<MLE_SPLIT, 16, 1><<<gl, 32, sizeof(MleSmemT<MLE_SPLIT>), st>>>(w, LP);
+      line_mle_kernel<LSL_MAX_SMP, MLE_MINB, 2><<<gl, 32, sizeof(MleSmem), st>>>(w, LP);
+    } else {
+      line_mle_kernel<LSL_MAX_SMP, MLE_MINB, 0><<<gl, 32, sizeof(MleSmem), st>>>(w, LP);
+    }
   }
-  line_mle_kernel<<<gl, 32, sizeof(MleSmem), st>>>(w, LP);
   LSL_KSTOP(ctx, LSL_K_MLE);
   LSL_CUDA(cudaGetLastError());
   return LSL_OK;
