@@ -171,3 +171,34 @@ def test_standalone_candidate_query_and_errors():
     with pytest.raises(Exception):
         pgm.getPotentialEdgeTargetsWithDijkstra(1, 1, 1, 10_000, False)
     pgm.close()
+
+
+def test_random_parameter_sweep_matches_oracle():
+    """Forty random parameter sets (candidate counts 0..6, geodesic depth 1..4, every flag combination, motion gates
+    on and off) x 50 frames: decisions, candidate lists, keyframes, edges and estimates equal the oracle's."""
+    master = np.random.default_rng(2026)
+    for trial in range(40):
+        kw = dict(predecessor_candidates=int(master.integers(1, 7)), neighbor_candidates=int(master.integers(0, 7)),
+                  min_sampled_candidates=int(master.integers(0, 7)), geodesic_depth=int(master.integers(1, 5)),
+                  keep_all_nodes=bool(master.integers(0, 2)), keep_good_nodes=bool(master.integers(0, 2)),
+                  clear_non_keyframes=bool(master.integers(0, 2)), clear_past_point_cloud=bool(master.integers(0, 2)),
+                  largest_loop=bool(master.integers(0, 2)),
+                  min_translation_meter=float(master.choice([0.0, 0.01, 0.05])), min_rotation_degree=float(master.choice([0.0, 0.5])),
+                  max_translation_meter=float(master.choice([1e10, 5.0])), max_rotation_degree=int(master.choice([360, 120])),
+                  min_matches=int(master.choice([20, 60])))
+        po, pp = _params(**kw)
+        rec, stamps, feats = _script(7000 + trial, 50, p_found=float(master.choice([0.5, 0.8, 1.0])), motion=float(master.choice([0.03, 0.1])),
+                                     p_few=float(master.choice([0.0, 0.15])))
+        seed = int(master.integers(1, 1000))
+        ogm, ofound = _run_oracle(po, seed, rec, stamps, feats)
+        pgm, pfound, pcands = _run_product(pp, seed, rec, stamps, feats)
+        assert pfound == ofound, (trial, kw)
+        assert pcands == ogm.log, (trial, kw)
+        assert [int(k) for k in pgm.keyframe_ids()] == ogm.keyframe_ids, (trial, kw)
+        e = pgm.edges()
+        assert [(int(x["id1"]), int(x["id2"])) for x in e] == [(o.id1, o.id2) for o in ogm.edges], (trial, kw)
+        for nd in pgm.nodes():
+            o = ogm.graph[int(nd["id"])]
+            assert nd["estimate"].tolist() == [float(x) for x in ogm.vertices[o.vertex_id]], (trial, kw)
+            assert (bool(nd["matchable"]), bool(nd["valid_tf_estimate"]), bool(nd["has_lines"])) == (o.matchable, o.valid_tf_estimate, o.has_lines)
+        pgm.close()
