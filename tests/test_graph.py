@@ -202,3 +202,20 @@ def test_random_parameter_sweep_matches_oracle():
             assert nd["estimate"].tolist() == [float(x) for x in ogm.vertices[o.vertex_id]], (trial, kw)
             assert (bool(nd["matchable"]), bool(nd["valid_tf_estimate"]), bool(nd["has_lines"])) == (o.matchable, o.valid_tf_estimate, o.has_lines)
         pgm.close()
+
+
+def test_new_initial_node_branch():
+    """graph_manager.cpp:816-823: with a single node in the graph and a failed comparison, a frame with more features
+    replaces the initial node (resetGraph + firstNode); later failures leave the graph alone."""
+    po, pp = _params(min_translation_meter=0.01, predecessor_candidates=2)
+    rec, stamps, feats = _script(11, 30, p_found=0.0)          # no pair ever registers
+    feats = [30] + [200] * 29
+    ogm, ofound = _run_oracle(po, 3, rec, stamps, feats)
+    pgm, pfound, pcands = _run_product(pp, 3, rec, stamps, feats)
+    assert ofound == pfound == [True, True] + [False] * 28
+    assert pcands == ogm.log
+    assert pgm.num_nodes() == len(ogm.graph) == 1
+    nd = pgm.nodes()[0]
+    assert (int(nd["n_feat2d"]), int(nd["seq_id"]), nd["stamp"]) == (200, ogm.graph[0].seq_id, ogm.graph[0].stamp)
+    assert [int(k) for k in pgm.keyframe_ids()] == ogm.keyframe_ids == [0]
+    pgm.close()
