@@ -425,6 +425,7 @@ extern "C" int lsl_graph_add_frame(lsl_graph* g, lsl_ctx* ctx, lsl_frame* frame,
   const lsl_pose_rec* pp = nullptr;
   if (action == LSL_GRAPH_COMPARE_PREDECESSOR) {
     const lsl_frame* q = frame; const lsl_frame* t = g->nodes[(size_t)cmp].frame;
+    if (!t) { g->phase = 0; g->pend_active = false; return LSL_ERR_ARG; }
     int32_t iq = nid, it = cmp;
     if ((rc = lsl_match_pair_batch(ctx, 1, &q, &t, &iq, &it, &seed, &prec)) != LSL_OK) { g->phase = 0; g->pend_active = false; return rc; }
     pp = &prec;
@@ -441,6 +442,7 @@ extern "C" int lsl_graph_add_frame(lsl_graph* g, lsl_ctx* ctx, lsl_frame* frame,
     for (int i = 0; i < n; ++i) {
       const Node& c = (ids[(size_t)i] == nid) ? g->pending() : g->nodes[(size_t)ids[(size_t)i]];
       ts[(size_t)i] = c.frame; it[(size_t)i] = ids[(size_t)i]; sd[(size_t)i] = seed + 1u + (uint32_t)i;
+      if (!c.frame) { g->phase = 0; g->pend_active = false; return LSL_ERR_ARG; }   // node inserted through the three-phase calls: no frame to register against
     }
     if ((rc = lsl_match_pair_batch(ctx, n, qs.data(), ts.data(), iq.data(), it.data(), sd.data(), recs.data())) != LSL_OK) {
       g->phase = 0; g->pend_active = false; return rc;
