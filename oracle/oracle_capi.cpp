@@ -8,6 +8,7 @@
 #include "../lineslam_b200/csrc/shared/lsl_math.h"
 #include "../lineslam_b200/csrc/shared/lsl_params_default.h"
 #include "../lineslam_b200/csrc/shared/lsl_points.h"
+#include "../lineslam_b200/csrc/shared/lsl_linalg.h"
 
 static orc::Params toP(const lsl_params* p) {
   orc::Params P;
@@ -270,5 +271,18 @@ double orc_stream_step(const uint8_t* img, int channels, const float* depth, int
   auto t1 = std::chrono::steady_clock::now();
   return std::chrono::duration<double>(t1 - t0).count();
 }
+
+// ---- third-party restatement probes (tests/test_oracle_cv2.py compares them with cv2 4.13) ----
+double orc_cvnorm(const double* v, int n) { return orc::cvnorm(v, n); }
+double orc_cvnorm_diff72(const double* a, const double* b) { return orc::cvnorm_diff72(a, b); }
+float orc_l2sqr_f(const float* a, const float* b, int n) { return lslm::l2sqr_f(a, b, n); }
+// RandomPoint3d ctor (cv::SVD of the 3x3 covariance, src/line/lineslam.h:59-81)
+void orc_cov_to_DU(const double* cov, double* DU, double* W_sqrt) { lslm::cov_to_DU(cov, DU, W_sqrt); }
+// cv::Mat::inv() on 3x3 (src/line/motion.cpp:363, utils.cpp:1012) and 6x6 (utils.cpp:1044); returns 0 if singular
+double orc_inv3(const double* a, double* r) { return lslm::inv3(a, r); }
+int orc_inv6(const double* a, double* r) { double A[36]; memcpy(A, a, sizeof(A)); return lslm::inv_lu<6>(A, r); }
+// cv::SVD of a symmetric 4x4 (Zhang's A in computeRelativeMotion_svd, motion.cpp:353): eigenvalues descending + vectors in columns
+void orc_jacobi4(const double* a, double* w, double* V) { double A[16]; memcpy(A, a, sizeof(A)); lslm::jacobi_sym<4>(A, w, V); }
+void orc_jacobi3(const double* a, double* w, double* V) { double A[9]; memcpy(A, a, sizeof(A)); lslm::jacobi_sym<3>(A, w, V); }
 
 }  // extern "C"

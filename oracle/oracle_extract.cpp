@@ -214,7 +214,7 @@ static void extract3dline_mahdist(const std::vector<Pt3>& pts, GlibcRand& rng, c
 // ------------------------------------------------------------------ MSLD ----
 // cv::norm(CV_64F vector): OpenCV 2.4 normL2_ pairs the squares two by two (UNVERIFIED,
 // source not in the container; see DESIGN.md "third-party arithmetic").
-static double cvnorm(const double* v, int len) {
+double cvnorm(const double* v, int len) {
   double result = 0;
   int i = 0;
   for (; i <= len - 4; i += 4) {

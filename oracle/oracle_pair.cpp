@@ -18,7 +18,7 @@ using namespace lslm;
 
 namespace orc {
 
-static double cvnorm_diff72(const double* a, const double* b) {  // cv::norm(a - b), see oracle_extract.cpp:cvnorm
+double cvnorm_diff72(const double* a, const double* b) {  // cv::norm(a - b), see oracle_extract.cpp:cvnorm
   double result = 0;
   for (int i = 0; i < 72; i += 4) {
     double v0 = a[i] - b[i], v1 = a[i + 1] - b[i + 1];

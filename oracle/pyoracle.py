@@ -33,6 +33,10 @@ def lib():
         for n in "atan2 pow".split():
             f = getattr(L, "orc_m_" + n); f.restype = C.c_double; f.argtypes = [C.c_double, C.c_double]
         L.orc_stream_step.restype = C.c_double
+        L.orc_cvnorm.restype = C.c_double
+        L.orc_cvnorm_diff72.restype = C.c_double
+        L.orc_l2sqr_f.restype = C.c_float
+        L.orc_inv3.restype = C.c_double
         L.orc_error_function2.restype = C.c_double
     return _LIB
 
@@ -209,3 +213,44 @@ def optimizeRelmotion(a, b, R, t):
     Rt = np.concatenate([np.asarray(R, np.float64).ravel(), np.asarray(t, np.float64).ravel()])
     lib().orc_optimizeRelmotion(ptr(a), ptr(b), len(a), ptr(Rt))
     return Rt[:9].reshape(3, 3).copy(), Rt[9:].copy()
+
+
+# ---- third-party restatement probes (compared with cv2 4.13 in tests/test_oracle_cv2.py) ----
+def cvnorm(v):
+    v = np.ascontiguousarray(v, np.float64)
+    return lib().orc_cvnorm(ptr(v), len(v))
+
+
+def cvnorm_diff72(a, b):
+    a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64)
+    return lib().orc_cvnorm_diff72(ptr(a), ptr(b))
+
+
+def l2sqr_f(a, b):
+    a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+    return float(lib().orc_l2sqr_f(ptr(a), ptr(b), len(a)))
+
+
+def cov_to_DU(cov):
+    c = np.ascontiguousarray(cov, np.float64); DU = np.zeros((3, 3)); W = np.zeros(3)
+    lib().orc_cov_to_DU(ptr(c), ptr(DU), ptr(W))
+    return DU, W
+
+
+def inv3(a):
+    a = np.ascontiguousarray(a, np.float64); r = np.zeros((3, 3))
+    det = lib().orc_inv3(ptr(a), ptr(r))
+    return r, det
+
+
+def inv6(a):
+    a = np.ascontiguousarray(a, np.float64); r = np.zeros((6, 6))
+    ok = lib().orc_inv6(ptr(a), ptr(r))
+    return r, ok
+
+
+def jacobi_sym(a):
+    a = np.ascontiguousarray(a, np.float64); n = a.shape[0]
+    w = np.zeros(n); V = np.zeros((n, n))
+    (lib().orc_jacobi4 if n == 4 else lib().orc_jacobi3)(ptr(a), ptr(w), ptr(V))
+    return w, V
