@@ -17,6 +17,7 @@
 #include "shared/lsl_linalg.h"
 #include "shared/lsl_math.h"
 #include "shared/lsl_rand.h"
+#include "shared/lsl_cvdraw.h"
 #include <float.h>
 
 using namespace lslm;
@@ -420,7 +421,7 @@ __global__ void __launch_bounds__(128) line_msld_kernel(LslWork w, LineParams P,
   {
     int x1 = (int)nearbyint(px), y1 = (int)nearbyint(py), x2 = (int)nearbyint(qx), y2 = (int)nearbyint(qy);
     long long sx = 0, sy = 0;
-    if ((unsigned)x1 < (unsigned)W && (unsigned)x2 < (unsigned)W && (unsigned)y1 < (unsigned)H && (unsigned)y2 < (unsigned)H) {
+    if (line_iter_endpoints(W, H, &x1, &y1, &x2, &y2)) {   // cv::LineIterator ctor: clipLine when an end point is outside
       int dx = x2 - x1, dy = y2 - y1;
       int stx = dx < 0 ? -1 : 1, sty = dy < 0 ? -1 : 1;
       dx = dx < 0 ? -dx : dx; dy = dy < 0 ? -dy : dy;

@@ -219,3 +219,23 @@ def make_points(scene_seed: int, frame_index: int, depth: np.ndarray, R_wc: np.n
     desc = np.abs(desc)
     desc = np.sqrt(desc / desc.sum(1, keepdims=True)).astype(np.float32)
     return np.ascontiguousarray(xyz1), np.ascontiguousarray(desc), idx
+
+
+def border_bands(seed: int, W: int = 320, H: int = 240) -> np.ndarray:
+    """Wide colour bands crossing the image border at shallow angles: LSD rectangles whose axis end points round to a
+    pixel outside the image (seeds 88 and 307 at 320x240), the case cv::LineIterator clips (tests only)."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    img = np.full((H, W, 3), int(rng.integers(60, 180)), np.uint8)
+    for _ in range(10):
+        side = rng.integers(0, 4)
+        a = rng.uniform(-0.35, 0.35) + (0 if side < 2 else np.pi / 2)
+        if side < 2:
+            c = np.array([rng.uniform(0, W), rng.choice([rng.uniform(-10, 25), rng.uniform(H - 25, H + 10)])])
+        else:
+            c = np.array([rng.choice([rng.uniform(-10, 25), rng.uniform(W - 25, W + 10)]), rng.uniform(0, H)])
+        L = rng.uniform(100, 300); wd = rng.uniform(25, 70)
+        d = np.array([np.cos(a), np.sin(a)]); n = np.array([-d[1], d[0]])
+        poly = np.array([c - d * L / 2 - n * wd / 2, c + d * L / 2 - n * wd / 2, c + d * L / 2 + n * wd / 2, c - d * L / 2 + n * wd / 2])
+        cv2.fillPoly(img, [np.round(poly).astype(np.int32)], tuple(int(v) for v in rng.integers(20, 235, 3)))
+    return np.clip(img + rng.normal(0, 1.5, img.shape), 0, 255).astype(np.uint8)

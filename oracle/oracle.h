@@ -141,6 +141,7 @@ void computeRelativeMotion_Ransac(const std::vector<Line>& a, const std::vector<
 void optimizeRelmotion(const std::vector<Line>& a, const std::vector<Line>& b, double R[9], double t[3]);
 
 // sub-pieces exposed for unit tests
+void get_gradient_probe(const double* xG, const double* yG, int W, int H, const double* pq, double* r);  // FrameLine::getGradient
 double cvnorm(const double* v, int len);                  // cv::norm of a CV_64F vector (OpenCV 2.4 normL2_)
 double cvnorm_diff72(const double* a, const double* b);   // cv::norm(des1 - des2), 72-D
 void sobel5(const uint8_t* gray, int W, int H, std::vector<double>& gx, std::vector<double>& gy);

@@ -9,6 +9,7 @@
 #include "../lineslam_b200/csrc/shared/lsl_params_default.h"
 #include "../lineslam_b200/csrc/shared/lsl_points.h"
 #include "../lineslam_b200/csrc/shared/lsl_linalg.h"
+#include "../lineslam_b200/csrc/shared/lsl_cvdraw.h"
 
 static orc::Params toP(const lsl_params* p) {
   orc::Params P;
@@ -284,5 +285,12 @@ int orc_inv6(const double* a, double* r) { double A[36]; memcpy(A, a, sizeof(A))
 // cv::SVD of a symmetric 4x4 (Zhang's A in computeRelativeMotion_svd, motion.cpp:353): eigenvalues descending + vectors in columns
 void orc_jacobi4(const double* a, double* w, double* V) { double A[16]; memcpy(A, a, sizeof(A)); lslm::jacobi_sym<4>(A, w, V); }
 void orc_jacobi3(const double* a, double* w, double* V) { double A[9]; memcpy(A, a, sizeof(A)); lslm::jacobi_sym<3>(A, w, V); }
+
+// cv::clipLine restatement probe; pts = x1 y1 x2 y2 in/out, returns the bool
+int orc_clip_line(int W, int H, int* pts) { return lslm::clip_line(W, H, pts, pts + 1, pts + 2, pts + 3) ? 1 : 0; }
+// FrameLine::getGradient probe: r (2) for the segment p -> q over the given f64 gradient planes
+void orc_get_gradient(const double* xG, const double* yG, int W, int H, const double* pq, double* r) {
+  orc::get_gradient_probe(xG, yG, W, H, pq, r);
+}
 
 }  // extern "C"

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include "../lineslam_b200/csrc/shared/lsl_math.h"
 #include "../lineslam_b200/csrc/shared/lsl_linalg.h"
+#include "../lineslam_b200/csrc/shared/lsl_cvdraw.h"
 
 using namespace lslm;
 
@@ -300,8 +301,8 @@ static void getGradient(Line& l, const double* xG, const double* yG, int W, int 
   int x1 = (int)nearbyint(l.p[0]), y1 = (int)nearbyint(l.p[1]);  // cvRound: half to even
   int x2 = (int)nearbyint(l.q[0]), y2 = (int)nearbyint(l.q[1]);
   double xSum = 0, ySum = 0;
-  if ((unsigned)x1 < (unsigned)W && (unsigned)x2 < (unsigned)W && (unsigned)y1 < (unsigned)H &&
-      (unsigned)y2 < (unsigned)H) {
+  // LineIterator ctor (OpenCV 2.4 drawing.cpp): end points outside the image -> cv::clipLine; count = 0 if nothing is left
+  if (lslm::line_iter_endpoints(W, H, &x1, &y1, &x2, &y2)) {
     int dx = x2 - x1, dy = y2 - y1;
     int sx = dx < 0 ? -1 : 1, sy = dy < 0 ? -1 : 1;
     dx = dx < 0 ? -dx : dx; dy = dy < 0 ? -dy : dy;
@@ -316,10 +317,17 @@ static void getGradient(Line& l, const double* xG, const double* yG, int W, int 
       err += minusDelta + (plusDelta & mask);
       if (steep) { y += sy; if (mask) x += sx; } else { x += sx; if (mask) y += sy; }
     }
-  }  // (endpoints outside the image never happen for LSD output; clipLine is not restated)
+  }
   double len = sqrt(xSum * xSum + ySum * ySum);
   l.r[0] = xSum / len;
   l.r[1] = ySum / len;
+}
+
+void get_gradient_probe(const double* xG, const double* yG, int W, int H, const double* pq, double* r) {
+  Line l;
+  l.p[0] = pq[0]; l.p[1] = pq[1]; l.q[0] = pq[2]; l.q[1] = pq[3];
+  getGradient(l, xG, yG, W, H);
+  r[0] = l.r[0]; r[1] = l.r[1];
 }
 
 // --------------------------------------------------------------- levmar ----

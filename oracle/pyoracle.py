@@ -254,3 +254,18 @@ def jacobi_sym(a):
     w = np.zeros(n); V = np.zeros((n, n))
     (lib().orc_jacobi4 if n == 4 else lib().orc_jacobi3)(ptr(a), ptr(w), ptr(V))
     return w, V
+
+
+def clip_line(W, H, pt1, pt2):
+    pts = np.array([pt1[0], pt1[1], pt2[0], pt2[1]], np.int32)
+    ok = lib().orc_clip_line(W, H, ptr(pts))
+    return bool(ok), (int(pts[0]), int(pts[1])), (int(pts[2]), int(pts[3]))
+
+
+def get_gradient(gx, gy, p, q):
+    """FrameLine::getGradient over f64 gradient planes; returns r (2)."""
+    gx = np.ascontiguousarray(gx, np.float64); gy = np.ascontiguousarray(gy, np.float64)
+    H, W = gx.shape
+    pq = np.array([p[0], p[1], q[0], q[1]], np.float64); r = np.zeros(2)
+    lib().orc_get_gradient(ptr(gx), ptr(gy), W, H, ptr(pq), ptr(r))
+    return r

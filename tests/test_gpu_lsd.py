@@ -71,3 +71,42 @@ def test_cuda_segments_equal_upstream_golden(api, stream4):
         gold = np.load(os.path.join(gold_dir, f"lsd_upstream_scene2000_f{i}.npy"))
         assert np.array_equal(frames[i].segments(), gold)
     ctx.close()
+
+
+def _golden(name):
+    import os
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)
+
+
+def test_cuda_segments_on_reference_tum_frame(api, oracle):
+    """The reference's own 640x480 TUM frame (external/lsd/lsd-1.5/1305031453.359684.png, committed under
+    tests/golden): device LSD rows == the rows of the UNMODIFIED upstream lsd.c, bit for bit (397 segments). A real
+    image exercises refine / reduce_region_radius / rect_improve far more than the rendered box room."""
+    import cv2
+    tum = cv2.imread(_golden("ref_tum_frame.png"), cv2.IMREAD_COLOR)
+    gold = np.load(_golden("lsd_upstream_ref_tum.npy"))
+    ctx = api.Context(max_batch=2, max_w=640, max_h=480, debug=True)
+    deps = np.ones((2, 480, 640), np.float32)
+    frames = ctx.extract_batch(np.stack([tum, tum[:, ::-1].copy()]), deps, np.array([[525., 0, 319.5], [0, 525., 239.5], [0, 0, 1]]))
+    got = frames[0].segments()
+    assert got.shape == gold.shape == (397, 5)
+    assert np.array_equal(got, gold)
+    # the mirrored frame against the oracle (a second real image)
+    assert np.array_equal(frames[1].segments(), oracle.lsd(oracle.gray(tum[:, ::-1].copy())))
+    ctx.close()
+
+
+def test_cuda_segments_on_reference_chairs(api, oracle):
+    """chairs.pgm (512x512 gray, 725 segments upstream): the device equals the oracle bit for bit and the upstream build
+    within the disclosed bound (glibc's libm is not correctly rounded: <= 4 ulp on <= 3 rows, tests/test_oracle_ref.py)."""
+    import cv2
+    chairs = cv2.imread(_golden("ref_chairs.png"), cv2.IMREAD_GRAYSCALE)
+    gold = np.load(_golden("lsd_upstream_ref_chairs.npy"))
+    ctx = api.Context(max_batch=1, max_w=512, max_h=512, debug=True)
+    fr = ctx.extract_batch(chairs[None], np.ones((1, 512, 512), np.float32), np.array([[500., 0, 255.5], [0, 500., 255.5], [0, 0, 1]]))[0]
+    got = fr.segments()
+    assert np.array_equal(got, oracle.lsd(chairs))
+    assert got.shape == gold.shape == (725, 5)
+    ulp = np.abs(got.view(np.int64) - gold.view(np.int64))
+    assert ulp.max() <= 4 and (ulp.max(axis=1) > 0).sum() <= 3
+    ctx.close()

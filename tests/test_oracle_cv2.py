@@ -171,3 +171,71 @@ def test_minMaxLoc_returns_first_minimum():
         first = int(np.flatnonzero(v[0] == v.min())[0])
         assert cv2.minMaxLoc(v)[2] == (first, 0)
         assert cv2.minMaxLoc(v.T.copy())[2] == (0, first)
+
+
+def test_clipLine_vs_cv2():
+    """cv::clipLine inside the cv::LineIterator constructor (FrameLine::getGradient, src/line/lineslam.cpp:529)."""
+    rng = np.random.default_rng(9)
+    W, H = 640, 480
+    cases = [((-3, 10), (50, 40)), ((600, 470), (660, 500)), ((-5, -5), (-1, 700)), ((639, 0), (640, 479)),
+             ((10, -1), (10, 480)), ((-1, 5), (640, 5)), ((700, 600), (800, 700)), ((0, 0), (639, 479))]
+    for _ in range(20000):
+        cases.append(((int(rng.integers(-60, 700)), int(rng.integers(-60, 540))),
+                      (int(rng.integers(-60, 700)), int(rng.integers(-60, 540)))))
+    for p1, p2 in cases:
+        ok, a, b = po.clip_line(W, H, p1, p2)
+        ok2, a2, b2 = cv2.clipLine((0, 0, W, H), p1, p2)
+        assert ok == ok2, (p1, p2)
+        if ok:
+            assert (a, b) == (tuple(a2), tuple(b2)), (p1, p2)
+
+
+def test_getGradient_border_segments():
+    """A segment whose rounded end point leaves the image is clipped and iterated (the reference), not skipped: r is the
+    normalised gradient sum over the Bresenham pixels between the cv2.clipLine'd end points; a segment entirely outside
+    gives count = 0 and r = NaN (0/0), as `xSum/len` does in the reference."""
+    rng = np.random.default_rng(10)
+    H, W = 120, 160
+    gx = rng.integers(-6570, 6571, (H, W)).astype(np.float64)
+    gy = rng.integers(-6570, 6571, (H, W)).astype(np.float64)
+
+    def expect(p, q):
+        p1 = (int(np.rint(p[0])), int(np.rint(p[1]))); p2 = (int(np.rint(q[0])), int(np.rint(q[1])))
+        inside = all(0 <= a[0] < W and 0 <= a[1] < H for a in (p1, p2))
+        if not inside:
+            ok, p1, p2 = cv2.clipLine((0, 0, W, H), p1, p2)
+            if not ok:
+                return None
+        (x1, y1), (x2, y2) = p1, p2
+        dx, dy = abs(x2 - x1), abs(y2 - y1)
+        sx, sy = (1 if x2 >= x1 else -1), (1 if y2 >= y1 else -1)
+        steep = dy > dx
+        dmaj, dmin = (dy, dx) if steep else (dx, dy)
+        err = dmaj - 2 * dmin
+        x, y, sxs, sys_ = x1, y1, 0.0, 0.0
+        for _ in range(dmaj + 1):
+            sxs += gx[y, x]; sys_ += gy[y, x]
+            mask = err < 0
+            err += -2 * dmin + (2 * dmaj if mask else 0)
+            if steep:
+                y += sy; x += sx if mask else 0
+            else:
+                x += sx; y += sy if mask else 0
+        n = np.sqrt(sxs * sxs + sys_ * sys_)
+        return np.array([sxs / n, sys_ / n])
+
+    segs = [((-2.4, 10.2), (50.3, 40.7)), ((150.2, 100.9), (161.7, 118.2)), ((159.6, 3.0), (100.0, 60.0)),
+            ((20.0, 119.6), (90.0, 60.0)), ((-0.6, -0.6), (30.0, 30.0)), ((170.0, 130.0), (200.0, 150.0)),
+            ((-0.4, 50.0), (80.0, 50.0))]
+    for _ in range(300):
+        segs.append(((rng.uniform(-8, W + 8), rng.uniform(-8, H + 8)), (rng.uniform(-8, W + 8), rng.uniform(-8, H + 8))))
+    n_clipped = 0
+    for p, q in segs:
+        r = po.get_gradient(gx, gy, p, q)
+        e = expect(p, q)
+        if e is None:
+            assert np.all(np.isnan(r))
+        else:
+            assert np.array_equal(r, e), (p, q)
+        n_clipped += any(not (0 <= np.rint(a[0]) < W and 0 <= np.rint(a[1]) < H) for a in (p, q))
+    assert n_clipped > 20

@@ -119,3 +119,25 @@ def test_levmar_restatement_on_line_mle_shape(oracle):
     ret_o = L.orc_dlevmar_dif(cb, p.ctypes.data_as(C.c_void_p), xx.ctypes.data_as(C.c_void_p), 6, n, 100,
                               o.ctypes.data_as(C.c_void_p), info.ctypes.data_as(C.c_void_p))
     assert ret_o == ret_r and np.array_equal(p, p_r) and np.array_equal(info, info_r)
+
+
+def _golden_images():
+    import cv2
+    chairs = cv2.imread(os.path.join(GOLD, "ref_chairs.png"), cv2.IMREAD_GRAYSCALE)
+    tum = cv2.imread(os.path.join(GOLD, "ref_tum_frame.png"), cv2.IMREAD_COLOR)
+    assert chairs is not None and chairs.shape == (512, 512) and tum is not None and tum.shape == (480, 640, 3)
+    return chairs, tum
+
+
+def test_lsd_oracle_on_committed_reference_images(oracle):
+    """Category-b fixtures: the reference's own images (tests/golden/ref_*.png) with the segment lists the unmodified
+    upstream lsd.c produced for them (tests/golden/make_golden.py). Runs without /root/reference."""
+    chairs, tum = _golden_images()
+    gold_t = np.load(os.path.join(GOLD, "lsd_upstream_ref_tum.npy"))
+    gold_c = np.load(os.path.join(GOLD, "lsd_upstream_ref_chairs.npy"))
+    assert len(gold_t) == 397 and len(gold_c) == 725
+    assert np.array_equal(oracle.lsd(oracle.gray(tum)), gold_t)            # 640x480 TUM frame: bit-exact
+    a = oracle.lsd(chairs)
+    assert a.shape == gold_c.shape
+    ulp = np.abs(a.view(np.int64) - gold_c.view(np.int64))                # chairs: glibc libm vs correctly rounded math
+    assert ulp.max() <= 4 and (ulp.max(axis=1) > 0).sum() <= 3
