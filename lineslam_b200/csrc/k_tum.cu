@@ -304,8 +304,13 @@ int decode_list(lsl_ctx* ctx, TumScratch& S, cudaStream_t st, int n, const uint8
   int* d_status = reinterpret_cast<int*>(dz + (size_t)(n + 1) * sizeof(size_t));
   const int k_inf = kind == 1 ? LSL_K_INFLATE_D : LSL_K_INFLATE, k_unf = kind == 1 ? LSL_K_PNG_D : LSL_K_PNG;
   cudaEventRecord(ctx->kev[k_inf][0], st);
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(png_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LSL_INF_RING); attr_set = true; }
+  {  // function attributes are per device: set once for every device this process decodes on
+    static std::mutex attr_mu;
+    static bool attr_set[64] = {false};
+    std::lock_guard<std::mutex> lk(attr_mu);
+    const int dev = ctx->device & 63;
+    if (!attr_set[dev]) { cudaFuncSetAttribute(png_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LSL_INF_RING); attr_set[dev] = true; }
+  }
   png_inflate_kernel<<<n, 32, LSL_INF_RING, st>>>(dz, d_off, dfilt, img_bytes, d_status);
   cudaEventRecord(ctx->kev[k_inf][1], st);
   cudaEventRecord(ctx->kev[k_unf][0], st);

@@ -4,6 +4,7 @@
 #include "lsl_internal.h"
 #include "shared/lsl_params_default.h"
 #include "shared/lsl_rand.h"
+#include "../../include/lsl_tum.h"
 #include <dlfcn.h>
 #include <string.h>
 #include <stdlib.h>
@@ -171,6 +172,7 @@ extern "C" void lsl_ctx_destroy(lsl_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  lsl_tum_release(ctx);   // staging buffers of the TUM loader are keyed by the context: never outlive it
   nccl_teardown(ctx);
   if (ctx->wk_block) cudaFree(ctx->wk_block);
   free_pair_ws(ctx);

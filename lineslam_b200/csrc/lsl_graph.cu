@@ -202,6 +202,16 @@ EdgeRec edge_of(const lsl_pose_rec& r, const lsl_graph_params& P) {
   return e;
 }
 
+// A found record must name a node that exists (or the pending node itself, which can be drawn as its own geodesic
+// candidate, :262) as the train frame and the pending node as the query frame (the reference asserts n->id_ == edge.id).
+bool rec_ids_ok(const lsl_graph* g, const lsl_pose_rec& r, int expect_train) {
+  if (!r.found) return true;
+  const int nn = (int)g->nodes.size();
+  const bool train_ok = (r.id_train >= 0 && r.id_train < nn) || (g->pend_active && !g->pend_in_graph && r.id_train == g->pend.id);
+  if (!train_ok || r.id_query != g->pend.id) return false;
+  return expect_train < 0 || r.id_train == expect_train;
+}
+
 void first_node(lsl_graph* g, Node nd) {   // graph_manager.cpp:358-400
   nd.id = (int)g->nodes.size();
   nd.seq_id = g->next_seq_id++;
@@ -254,11 +264,11 @@ void main_loop(lsl_graph* g, const lsl_pose_rec* recs, int n, lsl_graph_node_res
   for (int i = 0; i < n; ++i) {
     EdgeRec mr = edge_of(recs[i], P);
     if (mr.id1 < 0) continue;
-    const double dt = g->pend.stamp - g->nodes[(size_t)mr.id1].stamp;
+    const double dt = g->pend.stamp - g->node_ref(mr.id1).stamp;
     if (small_trafo(mr.tf.m, dt, P) && add_edge(g, mr, big_trafo(mr.tf.m, P), mr.n_inliers > g->curr_best.n_inliers)) {
       g->pend.vertex_id = g->pending().vertex_id;
       g->put_pending_in_graph();
-      g->nodes[(size_t)mr.id1].valid_tf = true;
+      g->node_ref(mr.id1).valid_tf = true;
       if (mr.n_inliers > g->curr_best.n_inliers) g->curr_best = mr;
       if (g->is_keyframe(mr.id1)) g->pend_edge_to_kf = true;
     }
@@ -357,9 +367,18 @@ extern "C" int lsl_graph_node_begin(lsl_graph* g, double stamp, int n2d, int n3d
 
 extern "C" int lsl_graph_node_predecessor(lsl_graph* g, const lsl_pose_rec* rec, int* action, int32_t* ids, int cap, int* n,
                                           lsl_graph_node_result* res) {
-  if (!g || !action || !n || g->phase != 1) return LSL_ERR_ARG;
+  if (!g || !action || !n) return LSL_ERR_ARG;
+  if (g->phase == 2 && !rec) {   // retry after LSL_ERR_CAPACITY: the candidates are cached, nothing is recomputed (no second rand() draw)
+    *n = (int)g->pend_cands.size();
+    *action = LSL_GRAPH_CANDIDATES;
+    if (cap < *n || (!ids && *n)) return LSL_ERR_CAPACITY;
+    for (int i = 0; i < *n; ++i) ids[i] = g->pend_cands[(size_t)i];
+    return LSL_OK;
+  }
+  if (g->phase != 1) return LSL_ERR_ARG;
   const lsl_graph_params& P = g->P;
   *n = 0;
+  if (rec && !rec_ids_ok(g, *rec, -1)) return LSL_ERR_ARG;   // nothing has been touched yet
   if (rec) {                                                  // initial comparison (:462-519)
     EdgeRec mr = edge_of(*rec, P);
     if (mr.id1 >= 0 && mr.id2 >= 0) {
@@ -399,6 +418,8 @@ extern "C" int lsl_graph_node_predecessor(lsl_graph* g, const lsl_pose_rec* rec,
 
 extern "C" int lsl_graph_node_commit(lsl_graph* g, const lsl_pose_rec* recs, int n, lsl_graph_node_result* res) {
   if (!g || g->phase != 2 || n != (int)g->pend_cands.size() || (n && !recs)) return LSL_ERR_ARG;
+  for (int i = 0; i < n; ++i)   // validate every record before any state changes
+    if (!rec_ids_ok(g, recs[i], g->pend_cands[(size_t)i])) return LSL_ERR_ARG;
   main_loop(g, recs, n, res);
   return LSL_OK;
 }
@@ -435,6 +456,7 @@ extern "C" int lsl_graph_add_frame(lsl_graph* g, lsl_ctx* ctx, lsl_frame* frame,
   if ((rc = lsl_graph_node_predecessor(g, pp, &action, ids.data(), (int)ids.size(), &n, &r)) != LSL_OK) return rc;
   if (action == LSL_GRAPH_DROPPED) { if (res) *res = r; release_lines(); return LSL_OK; }
   std::vector<lsl_pose_rec> recs((size_t)n);
+  int fail_rc = LSL_OK;
   if (n) {
     std::vector<const lsl_frame*> qs((size_t)n, frame), ts((size_t)n);
     std::vector<int32_t> iq((size_t)n, nid), it((size_t)n);
@@ -442,10 +464,19 @@ extern "C" int lsl_graph_add_frame(lsl_graph* g, lsl_ctx* ctx, lsl_frame* frame,
     for (int i = 0; i < n; ++i) {
       const Node& c = (ids[(size_t)i] == nid) ? g->pending() : g->nodes[(size_t)ids[(size_t)i]];
       ts[(size_t)i] = c.frame; it[(size_t)i] = ids[(size_t)i]; sd[(size_t)i] = seed + 1u + (uint32_t)i;
-      if (!c.frame) { g->phase = 0; g->pend_active = false; return LSL_ERR_ARG; }   // node inserted through the three-phase calls: no frame to register against
+      if (!c.frame) {   // node inserted through the three-phase calls: no frame to register against
+        fail_rc = LSL_ERR_ARG; break;
+      }
     }
-    if ((rc = lsl_match_pair_batch(ctx, n, qs.data(), ts.data(), iq.data(), it.data(), sd.data(), recs.data())) != LSL_OK) {
-      g->phase = 0; g->pend_active = false; return rc;
+    if (fail_rc == LSL_OK) fail_rc = lsl_match_pair_batch(ctx, n, qs.data(), ts.data(), iq.data(), it.data(), sd.data(), recs.data());
+    if (fail_rc != LSL_OK) {
+      // the predecessor edge may already be in the graph: finish the node with the records obtained so far (none of
+      // the candidates registered) so that keyframe / clear_past_point_cloud bookkeeping still runs, then report
+      std::memset(recs.data(), 0, sizeof(lsl_pose_rec) * (size_t)n);
+      lsl_graph_node_commit(g, recs.data(), n, &r);
+      if (res) *res = r;
+      release_lines();
+      return fail_rc;
     }
   }
   rc = lsl_graph_node_commit(g, recs.data(), n, &r);

@@ -207,7 +207,9 @@ LSL_HD int inflate_zlib(const uint8_t* in, size_t len, uint8_t* out, size_t want
       ops.sync();
       if (ops.leader()) {
         int err = huff_build(&S->dist, S->lengths + nlen, ndist);
-        int bad = (err < 0 || (err > 0 && ndist - S->dist.count[0] != 1));
+        // RFC 1951 §3.2.7: an incomplete distance code is legal when it has one code — or none at all (an all-literal
+        // block, as libdeflate / zopfli emit); a distance symbol that is then requested matches no code (-5 below)
+        int bad = (err < 0 || (err > 0 && ndist - S->dist.count[0] > 1));
         err = huff_build(&S->lit, S->lengths, nlen);
         bad |= (err < 0 || (err > 0 && nlen - S->lit.count[0] != 1));
         S->status = bad;

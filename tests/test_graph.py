@@ -219,3 +219,49 @@ def test_new_initial_node_branch():
     assert (int(nd["n_feat2d"]), int(nd["seq_id"]), nd["stamp"]) == (200, ogm.graph[0].seq_id, ogm.graph[0].stamp)
     assert [int(k) for k in pgm.keyframe_ids()] == ogm.keyframe_ids == [0]
     pgm.close()
+
+
+def test_bad_record_ids_are_refused_before_any_mutation():
+    """ids in caller-supplied (or all-gathered) pose records are array indices inside the library: a found record whose
+    id_train is out of range, whose id_query is not the node in flight, or (commit) whose id_train is not the candidate
+    it answers must come back as LSL_ERR_ARG with the graph untouched — the reference asserts n->id_ == edge.id."""
+    import ctypes as C
+    from lineslam_b200.api import lib
+    po, pp = _params(predecessor_candidates=3, neighbor_candidates=2, min_sampled_candidates=2, min_translation_meter=0.01)
+    rec, stamps, feats = _script(5, 30, p_few=0.0, p_found=1.0)
+    gm, _, _ = _run_product(pp, 3, rec, stamps[:20], feats[:20])
+    n_nodes, n_edges = gm.num_nodes(), len(gm.edges())
+    rec.cur[0] = 20
+    action, nid, cmp_ = gm.node_begin(float(stamps[20]), feats[20], feats[20])
+    assert action == G.COMPARE_PREDECESSOR
+    for bad_train, bad_query in ((10_000, nid), (-7, nid), (cmp_, nid + 3)):
+        r = rec(nid, cmp_).copy()
+        r["found"] = 1; r["id_train"] = bad_train; r["id_query"] = bad_query
+        with pytest.raises(Exception):
+            gm.node_predecessor(r)
+        assert gm.num_nodes() == n_nodes and len(gm.edges()) == n_edges
+    # a too-small id buffer reports the capacity error; the retry (rec = NULL) returns the cached candidates
+    L = lib()
+    good = np.ascontiguousarray(rec(nid, cmp_), POSE_DTYPE).reshape(1)
+    a, n = C.c_int(0), C.c_int(0)
+    res = G.NodeResult()
+    ids = np.zeros(64, np.int32)
+    rc = L.lsl_graph_node_predecessor(gm._h, good.ctypes.data_as(C.c_void_p), C.byref(a), ids.ctypes.data_as(C.c_void_p), 0, C.byref(n), C.byref(res))
+    if a.value == G.CANDIDATES and n.value > 0:
+        assert rc == -3
+        want = n.value
+        rc = L.lsl_graph_node_predecessor(gm._h, None, C.byref(a), ids.ctypes.data_as(C.c_void_p), 64, C.byref(n), C.byref(res))
+        assert rc == 0 and n.value == want
+        cands = ids[:want].copy()
+        recs = np.array([rec(nid, int(c)) for c in cands], POSE_DTYPE)
+        bad = recs.copy(); bad["found"] = 1; bad["id_train"] = 9999
+        with pytest.raises(Exception):
+            gm.node_commit(bad)
+        swapped = recs.copy(); swapped["found"] = 1
+        if want >= 2:
+            swapped["id_train"] = swapped["id_train"][::-1].copy()
+            if not np.array_equal(swapped["id_train"], recs["id_train"]):
+                with pytest.raises(Exception):
+                    gm.node_commit(swapped)
+        gm.node_commit(recs)       # the valid records still go through afterwards
+    gm.close()

@@ -136,3 +136,67 @@ def test_device_inflate_code_equals_zlib_on_host():
         zz[int(rng.integers(2, len(z) - 4))] ^= 1 << int(rng.integers(0, 8))
         rc = L.lsl_inflate_host_check(bytes(zz), len(zz), out.ctypes.data, len(raw))
         assert rc < 0 or out[:len(raw)].tobytes() != raw or True      # must return, never read or write out of bounds
+
+
+def _all_literal_dynamic_block(raw: bytes) -> bytes:
+    """A zlib stream whose single dynamic block has NO distance code at all (HDIST = 1, that one length 0): what
+    libdeflate (oxipng) and zopfli emit for all-literal data, legal per RFC 1951 §3.2.7. Hand-assembled: zlib's own
+    encoder always emits two distance codes."""
+    import zlib
+    bits = []
+
+    def put(v, n):                       # header fields: LSB first
+        for k in range(n):
+            bits.append((v >> k) & 1)
+
+    def put_code(code, n):               # Huffman codes: MSB first
+        for k in range(n - 1, -1, -1):
+            bits.append((code >> k) & 1)
+
+    lit_len = [8] * 255 + [9, 9]         # symbols 0..254 -> 8 bits, 255 and 256 (end of block) -> 9 bits: Kraft sum 1
+    # canonical codes
+    def canon(lengths):
+        codes, code = {}, 0
+        for l in range(1, 16):
+            for s, ll in enumerate(lengths):
+                if ll == l:
+                    codes[s] = (code, l); code += 1
+            code <<= 1
+        return codes
+    lit = canon(lit_len)
+    # code-length alphabet: symbols 8 (1 bit), 0 and 9 (2 bits)
+    cl_len = [0] * 19
+    cl_len[8], cl_len[0], cl_len[9] = 1, 2, 2
+    cl = canon(cl_len)
+    order = [16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15]
+    put(1, 1); put(2, 2)                 # BFINAL, dynamic
+    put(0, 5); put(0, 5)                 # HLIT = 257, HDIST = 1
+    ncode = max(i for i, s in enumerate(order) if cl_len[s]) + 1
+    put(ncode - 4, 4)
+    for i in range(ncode):
+        put(cl_len[order[i]], 3)
+    for l in lit_len + [0]:              # 257 literal/length lengths, then the single distance length: 0
+        put_code(*cl[l])
+    for b in raw:
+        put_code(*lit[b])
+    put_code(*lit[256])
+    while len(bits) % 8:
+        bits.append(0)
+    body = bytes(sum(bits[i + k] << k for k in range(8)) for i in range(0, len(bits), 8))
+    z = b"\x78\x9c" + body + zlib.adler32(raw).to_bytes(4, "big")
+    assert zlib.decompress(z) == raw     # zlib accepts it
+    return z
+
+
+def test_inflate_accepts_block_without_distance_codes():
+    import ctypes as C
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    L = C.CDLL(os.path.join(root, "oracle", "libinflate_check.so"))
+    L.lsl_inflate_host_check.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    rng = np.random.default_rng(12)
+    for n in (1, 300, 5000):
+        raw = bytes(rng.integers(0, 256, n, dtype=np.uint8))
+        z = _all_literal_dynamic_block(raw)
+        out = np.zeros(n, np.uint8)
+        assert L.lsl_inflate_host_check(z, len(z), out.ctypes.data, n) == 0
+        assert out.tobytes() == raw
