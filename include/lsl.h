@@ -3,7 +3,14 @@
  * Drop-in boundary for the reference's hot path. The reference has no FFI;
  * these entry points are what a maintainer binds from the C++ symbols listed beside each
  * function (see INTEGRATION.md for the adapter code). POD only, no exceptions, no exit():
- * every call returns 0 or a negative lsl_status. All entry points are re-entrant per context.
+ * every call returns 0 or a negative lsl_status.
+ *
+ * Threading: every entry point may be called from any host thread. Calls on ONE context are serialised
+ * by a per-context lock in arrival order (the reference calls detect3DLines on a QtConcurrent worker while QThreadPool
+ * threads run matchNodePair, src/node.cpp:214, src/graph_manager.cpp:555 — those callers work unchanged and get the
+ * results of a serial run); "last call" accessors (lsl_pair_matches, lsl_kernel_times, lsl_last_timing) refer to the
+ * last call that completed on the context, so a thread that needs them keeps its pair calls on a context of its own.
+ * Host threads that should overlap on the device use one context each (contexts share nothing but the device).
  *
  * RNG contract: the process-global rand() of the reference becomes an explicit
  * seed per call; the library replays glibc's TYPE_3 generator from that seed in the serial
@@ -89,6 +96,13 @@ int lsl_extract(lsl_ctx* ctx, const uint8_t* img, int channels, const float* dep
 int lsl_extract_batch(lsl_ctx* ctx, int n, const uint8_t* const* imgs, int channels,
                       const float* const* depths, int W, int H, const double K[9],
                       double asynch_dt_s, const uint32_t* rand_seeds, lsl_frame** out);
+/* Host buffers with the depth map as the sensor / the TUM PNG delivers it: 16-bit, 0 = no measurement. The conversion
+ * of src/openni_listener.cpp:1233-1244 (convertTo(CV_32FC1); values < 1e-5 -> NaN; "/ depth_factor" = float multiply by
+ * (float)(1 / depth_factor), 5000 for TUM) runs on the device, so a frame costs W*H*(channels + 2) bytes of PCIe instead of
+ * W*H*(channels + 4). Results are identical to lsl_extract_batch on the converted planes. */
+int lsl_extract_batch_u16(lsl_ctx* ctx, int n, const uint8_t* const* imgs, int channels, const uint16_t* const* depths,
+                          int W, int H, const double K[9], double asynch_dt_s, const uint32_t* rand_seeds,
+                          double depth_factor, lsl_frame** out);
 /* Inputs already resident in device memory: d_imgs = n*H*W*channels u8, d_depths = n*H*W f32. */
 int lsl_extract_batch_dev(lsl_ctx* ctx, int n, const uint8_t* d_imgs, int channels, const float* d_depths,
                           int W, int H, const double K[9], double asynch_dt_s, const uint32_t* rand_seeds,
@@ -114,6 +128,17 @@ int lsl_match_lines(lsl_ctx* ctx, const lsl_frame* query, const lsl_frame* train
  * Node::feature_descriptors_ (CV_32F rows, after squareroot_descriptor_space, src/node.cpp:304-310, 1823-1837).
  * They are INPUTS of the path (the detectors are out of scope); copied to the device, n <= 2048. */
 int lsl_frame_set_points(lsl_ctx* ctx, lsl_frame* f, const float* xyz1, const float* desc, int n, int dim);
+/* Same with the two conditioning choices of the reference's Node constructor behind the ABI:
+ *   desc_is_u8 = 1: binary rows (ORB, 32 bytes: src/features.cpp:174-211); featureMatching then runs the
+ *                   "BruteForce-HammingLUT" matcher (src/node.cpp:609-613): popcount distances as float, same k = 2 /
+ *                   ratio / unique-train / rand() jitter pass. dim = bytes per row (multiple of 4).
+ *   root_sift = 1:  squareroot_descriptor_space (src/node.cpp:304-310, 1823-1837) is applied ON THE DEVICE to the f32 rows
+ *                   (abs -> L1 normalise by the row's sequential float sum -> sqrt; zero rows untouched); pass the raw
+ *                   SIFT / SURF rows. Ignored for u8 rows (the reference does not condition ORB). */
+int lsl_frame_set_points_ex(lsl_ctx* ctx, lsl_frame* f, const float* xyz1, const void* desc, int n, int dim, int desc_is_u8,
+                            int root_sift);
+/* Copies the frame's (conditioned) descriptor rows back: n x dim floats, or n x dim bytes for u8 rows. */
+int lsl_frame_descriptors(lsl_ctx* ctx, const lsl_frame* f, void* dst, int64_t cap_bytes);
 int lsl_frame_num_points(const lsl_frame* f);
 /* fx = K(0,0) and Node::asynch_time_diff_sec_ used by the point-edge information matrices of the refinement
  * (compPt3dCov, src/transformation_estimation.cpp:243-262). Every extract call sets them from its K / dt. */

@@ -137,10 +137,12 @@ class Context:
             pass
 
     # ---- extraction -----------------------------------------------------------------------
-    def extract_batch(self, imgs, depths, K, seeds=None, dt=0.0):
-        """imgs: (n,H,W,3) or (n,H,W) u8 host array; depths: (n,H,W) f32. Returns [Frame]."""
+    def extract_batch(self, imgs, depths, K, seeds=None, dt=0.0, depth_factor=5000.0):
+        """imgs: (n,H,W,3) or (n,H,W) u8 host array; depths: (n,H,W) f32 metres, or uint16 raw sensor / TUM PNG values
+        (0 = invalid, metres = v / depth_factor: converted on the device, half the PCIe bytes). Returns [Frame]."""
         imgs = np.ascontiguousarray(imgs, np.uint8)
-        depths = np.ascontiguousarray(depths, np.float32)
+        u16 = np.asarray(depths).dtype == np.uint16
+        depths = np.ascontiguousarray(depths, np.uint16 if u16 else np.float32)
         n, H, W = depths.shape
         ch = 3 if imgs.ndim == 4 else 1
         # per-frame pointers without a Python loop (592 numpy slices cost ~10 ms per call)
@@ -150,7 +152,11 @@ class Context:
         sd = np.ascontiguousarray(seeds if seeds is not None else np.ones(n), np.uint32)
         Kc = np.ascontiguousarray(K, np.float64)
         out = (C.c_void_p * n)()
-        _check(lib().lsl_extract_batch(self._h, n, ip, ch, dp, W, H, ptr(Kc), C.c_double(dt), ptr(sd), out), self._h)
+        if u16:
+            _check(lib().lsl_extract_batch_u16(self._h, n, ip, ch, dp, W, H, ptr(Kc), C.c_double(dt), ptr(sd),
+                                               C.c_double(depth_factor), out), self._h)
+        else:
+            _check(lib().lsl_extract_batch(self._h, n, ip, ch, dp, W, H, ptr(Kc), C.c_double(dt), ptr(sd), out), self._h)
         return [Frame(self, out[i]) for i in range(n)]
 
     def extract_batch_dev(self, d_imgs: int, channels: int, d_depths: int, n: int, W: int, H: int, K, seeds=None,
@@ -272,12 +278,23 @@ class Frame:
     def num_points(self) -> int:
         return _check(lib().lsl_frame_num_points(self._h))
 
-    def set_points(self, xyz1, desc):
-        """feature_locations_3d_ (n,4) and feature_descriptors_ (n,dim) of the Node this frame belongs to."""
+    def set_points(self, xyz1, desc, root_sift: bool = False):
+        """feature_locations_3d_ (n,4) and feature_descriptors_ (n,dim) of the Node this frame belongs to. uint8 rows are
+        ORB descriptors (Hamming matcher); root_sift applies squareroot_descriptor_space on the device (f32 rows)."""
         x = np.ascontiguousarray(xyz1, np.float32).reshape(-1, 4)
-        d = np.ascontiguousarray(desc, np.float32).reshape(len(x), -1) if len(x) else np.zeros((0, 1), np.float32)
-        _check(lib().lsl_frame_set_points(self.ctx._h, self._h, ptr(x), ptr(d), len(x), d.shape[1]), self.ctx._h)
+        d = np.asarray(desc)
+        u8 = d.dtype == np.uint8
+        d = np.ascontiguousarray(d, np.uint8 if u8 else np.float32).reshape(len(x), -1) if len(x) else np.zeros((0, 4), np.float32)
+        _check(lib().lsl_frame_set_points_ex(self.ctx._h, self._h, ptr(x), ptr(d), len(x), d.shape[1], int(u8), int(root_sift)), self.ctx._h)
+        self._pdim, self._pu8 = d.shape[1], bool(u8)
         return self
+
+    def descriptors(self) -> np.ndarray:
+        """The frame's descriptor rows as the device holds them (after the optional RootSIFT conditioning)."""
+        n, dim, u8 = self.num_points, getattr(self, "_pdim", 0), getattr(self, "_pu8", False)
+        out = np.zeros((n, dim), np.uint8 if u8 else np.float32)
+        _check(lib().lsl_frame_descriptors(self.ctx._h, self._h, ptr(out), C.c_int64(out.nbytes)), self.ctx._h)
+        return out
 
     def lines(self) -> np.ndarray:
         n = self.num_lines

@@ -53,6 +53,48 @@ __global__ void __launch_bounds__(256) match_points_kernel(const LslPairPts* __r
   if (lane == 0) knn_all[pd.knn_off + i] = best;
 }
 
+// "BruteForce-HammingLUT" (ORB rows, src/node.cpp:609-613): the distance is the popcount of the XOR over the row, handed to
+// the ratio test as a float; same k = 2 rule (strict <, earlier train row first on ties). Rows are dim bytes (multiple of 4).
+__global__ void __launch_bounds__(256) match_points_hamming_kernel(const LslPairPts* __restrict__ pp, Knn2* __restrict__ knn_all) {
+  extern __shared__ float s_q[];   // [8][dim / 4] words
+  const LslPairPts pd = pp[blockIdx.y];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + warp;
+  if (i >= pd.nqp) return;
+  const int nw = pd.dim >> 2;
+  uint32_t* q = reinterpret_cast<uint32_t*>(s_q) + warp * nw;
+  const uint32_t* qd = reinterpret_cast<const uint32_t*>(pd.qd);
+  const uint32_t* td = reinterpret_cast<const uint32_t*>(pd.td);
+  for (int k = lane; k < nw; k += 32) q[k] = qd[(size_t)i * nw + k];
+  __syncwarp();
+  Knn2 best; best.d1 = FLT_MAX; best.d2 = FLT_MAX; best.i1 = 1 << 30;
+  for (int j = lane; j < pd.ntp; j += 32) {
+    int c = 0;
+    for (int k = 0; k < nw; ++k) c += __popc(q[k] ^ td[(size_t)j * nw + k]);
+    const float d = (float)c;
+    if (d < best.d1) { best.d2 = best.d1; best.d1 = d; best.i1 = j; }
+    else if (d < best.d2) best.d2 = d;
+  }
+  for (int o = 16; o; o >>= 1) {
+    Knn2 other;
+    other.d1 = __shfl_xor_sync(FULL, best.d1, o); other.d2 = __shfl_xor_sync(FULL, best.d2, o);
+    other.i1 = __shfl_xor_sync(FULL, best.i1, o);
+    best = knn_merge(best, other);
+  }
+  if (lane == 0) knn_all[pd.knn_off + i] = best;
+}
+
+// squareroot_descriptor_space (src/node.cpp:1823-1837) in place: thread per row (the L1 sum is a sequential float chain)
+__global__ void __launch_bounds__(128) rootsift_kernel(float* __restrict__ desc, int n, int dim) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  float* d = desc + (size_t)r * dim;
+  float sum = 0.f;
+  for (int c = 0; c < dim; ++c) { const float v = fabsf(d[c]); d[c] = v; sum = __fadd_rn(sum, v); }
+  if (sum == 0.f) return;
+  for (int c = 0; c < dim; ++c) d[c] = __fsqrt_rn(__fdiv_rn(d[c], sum));
+}
+
 // serial acceptance pass (row order): ratio test, unique trainIdx, distance jitter from rand()
 __global__ void __launch_bounds__(32) match_points_accept_kernel(const LslPairPts* __restrict__ pp, const LslPairDesc* __restrict__ pairs,
                                                                  const Knn2* __restrict__ knn_all, lsl_match* __restrict__ pm_all,
@@ -865,17 +907,25 @@ __global__ void __launch_bounds__(POSE_THREADS, 1) pose_hybrid_kernel(const LslP
 }
 
 // ------------------------------------------------------------- launchers ----
-int lsl_launch_match_points(lsl_ctx* ctx, int npairs, int max_nq, int dim) {
+int lsl_launch_match_points(lsl_ctx* ctx, int npairs, int max_nq, int dim, int kind) {
   LslHybWork& h = ctx->hw;
   LSL_KSTART(ctx, LSL_K_MATCHPTS);
   if (max_nq > 0) {
     dim3 g((max_nq + 7) / 8, npairs);
-    match_points_kernel<<<g, 256, 8 * dim * sizeof(float), ctx->stream>>>(h.d_ppairs, (Knn2*)h.knn);
+    if (kind == 1) match_points_hamming_kernel<<<g, 256, 8 * dim, ctx->stream>>>(h.d_ppairs, (Knn2*)h.knn);
+    else match_points_kernel<<<g, 256, 8 * dim * sizeof(float), ctx->stream>>>(h.d_ppairs, (Knn2*)h.knn);
     ctx->stats.kernel_launches += 1;
   }
   match_points_accept_kernel<<<npairs, 32, 0, ctx->stream>>>(h.d_ppairs, ctx->pw.d_pairs, (const Knn2*)h.knn, h.pmatches, h.npmatch,
                                                             h.hs.rng, ctx->P.nn_distance_ratio);
   LSL_KSTOP(ctx, LSL_K_MATCHPTS);
+  LSL_CUDA(cudaGetLastError());
+  return LSL_OK;
+}
+
+int lsl_launch_rootsift(lsl_ctx* ctx, float* d_desc, int n, int dim) {
+  rootsift_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_desc, n, dim);
+  ctx->stats.kernel_launches += 1;
   LSL_CUDA(cudaGetLastError());
   return LSL_OK;
 }

@@ -372,3 +372,37 @@ int lsl_launch_seeds(lsl_ctx* ctx, int n) {
   LSL_CUDA(cudaGetLastError());
   return LSL_OK;
 }
+
+
+// ---- raw 16-bit depth -> metres (src/openni_listener.cpp:1233-1244): convertTo(CV_32FC1), values < 1e-5 -> quiet NaN with
+// the bit pattern the x86 reference leaves (0x7fc00000), then the MatExpr "/ factor" = float multiply by (float)(1 / factor).
+// HBM streaming: 8 pixels (one 16-byte load, two 16-byte stores) per thread.
+__global__ void __launch_bounds__(256) depth_u16_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, size_t count, float scale) {
+  const size_t i8 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i8 + 8 <= count) {
+    const uint4 v = *reinterpret_cast<const uint4*>(in + i8);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a = (float)(w[k] & 0xffffu), b = (float)(w[k] >> 16);
+      o[2 * k] = ((double)a < 1e-5) ? __int_as_float(0x7fc00000) : __fmul_rn(a, scale);
+      o[2 * k + 1] = ((double)b < 1e-5) ? __int_as_float(0x7fc00000) : __fmul_rn(b, scale);
+    }
+    *reinterpret_cast<float4*>(out + i8) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(out + i8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  } else {
+    for (size_t i = i8; i < count; ++i) {
+      const float a = (float)in[i];
+      out[i] = ((double)a < 1e-5) ? __int_as_float(0x7fc00000) : __fmul_rn(a, scale);
+    }
+  }
+}
+
+int lsl_launch_depth_u16(lsl_ctx* ctx, cudaStream_t st, const uint16_t* d_in, float* d_out, size_t count, float scale) {
+  const size_t threads = (count + 7) / 8;
+  depth_u16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_in, d_out, count, scale);
+  ctx->stats.kernel_launches += 1;
+  LSL_CUDA(cudaGetLastError());
+  return LSL_OK;
+}

@@ -388,7 +388,7 @@ extern "C" int lsl_tum_decode_batch(lsl_ctx* ctx, int n, const uint8_t* const* r
   if (H > 1024) { ctx->err = "PNG decode: H > 1024 rows"; return LSL_ERR_CAPACITY; }
   if ((rgb_png && (!rgb_len || !d_bgr)) || (depth_png && (!depth_len || !d_depth))) return LSL_ERR_ARG;
   if (n == 0) return LSL_OK;
-  cudaSetDevice(ctx->device);
+  LSL_ENTER(ctx);
   std::lock_guard<std::mutex> lk(g_mu);
   TumScratch& S = g_scratch[ctx];
   int rc = LSL_OK;
@@ -421,7 +421,7 @@ extern "C" int lsl_extract_tum_batch(lsl_ctx* ctx, int n, const uint8_t* const* 
                                      const uint8_t* const* depth_png, const size_t* depth_len, int W, int H, const double K[9],
                                      double asynch_dt_s, const uint32_t* rand_seeds, lsl_frame** out) {
   if (!ctx || n <= 0 || !rgb_png || !depth_png || !out) return LSL_ERR_ARG;
-  cudaSetDevice(ctx->device);
+  LSL_ENTER(ctx);
   uint8_t* d_bgr; float* d_depth;
   {
     std::lock_guard<std::mutex> lk(g_mu);

@@ -126,6 +126,7 @@ extern "C" int lsl_ctx_create(lsl_ctx** out, const lsl_params* params, int cuda_
   ctx->hw.cap_pairs = ctx->hw.cap_pm = ctx->hw.cap_knn = 0; ctx->hw.max_iter = 0; ctx->hw.last_hybrid = false;
   ctx->cam_fx = 525.0; ctx->cam_dt = 0.0;   // K(0,0) of src/openni_listener.cpp:1256; replaced by the K of the last extract call
   ctx->h_pin = nullptr; ctx->h_pin_bytes = 0;
+  ctx->d_depth16 = nullptr; ctx->d_depth16_bytes = 0;
   memset(&ctx->stats, 0, sizeof(ctx->stats));
   memset(&ctx->dims, 0, sizeof(ctx->dims));
   memset(ctx->kran, 0, sizeof(ctx->kran));
@@ -177,6 +178,7 @@ extern "C" void lsl_ctx_destroy(lsl_ctx* ctx) {
   if (ctx->wk_block) cudaFree(ctx->wk_block);
   free_pair_ws(ctx);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  if (ctx->d_depth16) cudaFree(ctx->d_depth16);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev3);
   for (int k = 0; k < LSL_K_COUNT; ++k) { cudaEventDestroy(ctx->kev[k][0]); cudaEventDestroy(ctx->kev[k][1]); }
   cudaStreamDestroy(ctx->own_stream);
@@ -187,13 +189,14 @@ extern "C" void lsl_ctx_destroy(lsl_ctx* ctx) {
 
 extern "C" int lsl_ctx_set_stream(lsl_ctx* ctx, void* cuda_stream) {
   if (!ctx) return LSL_ERR_ARG;
-  cudaSetDevice(ctx->device);
+  LSL_ENTER(ctx);
   cudaStreamSynchronize(ctx->stream);
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
   return LSL_OK;
 }
 extern "C" int lsl_ctx_set_debug(lsl_ctx* ctx, int on) {
   if (!ctx) return LSL_ERR_ARG;
+  LSL_LOCK(ctx);
   ctx->debug = on ? 1 : 0;
   return LSL_OK;
 }
@@ -314,7 +317,7 @@ extern "C" int lsl_extract_batch_dev(lsl_ctx* ctx, int n, const uint8_t* d_imgs,
                                      int H, const double K[9], double dt, const uint32_t* seeds, lsl_frame** out) {
   if (!ctx || !d_imgs || !d_depths || !K || !out || n < 1 || (channels != 1 && channels != 3)) return LSL_ERR_ARG;
   if (n > ctx->max_batch) { ctx->err = "batch larger than the context's max_batch"; return LSL_ERR_CAPACITY; }
-  cudaSetDevice(ctx->device);
+  LSL_ENTER(ctx);
   return extract_device(ctx, n, d_imgs, channels, d_depths, W, H, K, dt, seeds, out);
 }
 
@@ -324,19 +327,34 @@ static bool is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
-extern "C" int lsl_extract_batch(lsl_ctx* ctx, int n, const uint8_t* const* imgs, int channels, const float* const* depths,
-                                 int W, int H, const double K[9], double dt, const uint32_t* seeds, lsl_frame** out) {
+// Host-buffer path shared by lsl_extract_batch (f32 depth, depth_elem = 4) and lsl_extract_batch_u16 (raw 16-bit depth,
+// depth_elem = 2: converted to metres on the device, on the copy stream right behind its upload).
+static int extract_host(lsl_ctx* ctx, int n, const uint8_t* const* imgs, int channels, const void* const* depths, int depth_elem,
+                        float depth_scale, int W, int H, const double K[9], double dt, const uint32_t* seeds, lsl_frame** out) {
   if (!ctx || !imgs || !depths || !K || !out || n < 1 || (channels != 1 && channels != 3)) return LSL_ERR_ARG;
   if (n > ctx->max_batch) { ctx->err = "batch larger than the context's max_batch"; return LSL_ERR_CAPACITY; }
-  cudaSetDevice(ctx->device);
+  LSL_ENTER(ctx);
   int rc = set_dims(ctx, W, H);
   if (rc) return rc;
-  const size_t ib = (size_t)W * H * channels, db = (size_t)W * H * sizeof(float);
+  const size_t npix = (size_t)W * H;
+  const size_t ib = npix * channels, db = npix * (size_t)depth_elem;
   for (int i = 0; i < n; ++i)
     if (!imgs[i] || !depths[i]) return LSL_ERR_ARG;
+  uint8_t* d_draw = (uint8_t*)ctx->wk.depth;   // where the uploaded depth bytes land
+  if (depth_elem == 2) {
+    if (ctx->d_depth16_bytes < db * n) {
+      LSL_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (ctx->d_depth16) cudaFree(ctx->d_depth16);
+      ctx->d_depth16 = nullptr; ctx->d_depth16_bytes = 0;
+      LSL_CUDA(cudaMalloc((void**)&ctx->d_depth16, db * (size_t)ctx->max_batch));
+      ctx->d_depth16_bytes = db * (size_t)ctx->max_batch;
+    }
+    d_draw = (uint8_t*)ctx->d_depth16;
+  }
   // page-locked caller buffers are copied straight from where they are; pageable ones are staged through
   // the context's pinned buffer so the copies stay asynchronous
   bool pinned = is_pinned(imgs[0]) && is_pinned(depths[0]);
+  cudaStream_t depth_stream = ctx->stream;
   if (pinned) {
     bool contiguous = true;
     for (int i = 1; i < n; ++i) contiguous &= (imgs[i] == imgs[0] + ib * i) && ((const uint8_t*)depths[i] == (const uint8_t*)depths[0] + db * i);
@@ -352,13 +370,13 @@ extern "C" int lsl_extract_batch(lsl_ctx* ctx, int n, const uint8_t* const* imgs
         LSL_CUDA(cudaEventRecord(ctx->ev_img[c], ctx->copy_stream));
       }
       ctx->img_chunks = C;
-      LSL_CUDA(cudaMemcpyAsync(ctx->wk.depth, depths[0], db * n, cudaMemcpyHostToDevice, ctx->copy_stream));
-      LSL_CUDA(cudaEventRecord(ctx->ev_depth, ctx->copy_stream));
+      LSL_CUDA(cudaMemcpyAsync(d_draw, depths[0], db * n, cudaMemcpyHostToDevice, ctx->copy_stream));
+      depth_stream = ctx->copy_stream;
       ctx->depth_async = true;
     } else {
       for (int i = 0; i < n; ++i) {
         LSL_CUDA(cudaMemcpyAsync(ctx->wk.img + ib * i, imgs[i], ib, cudaMemcpyHostToDevice, ctx->stream));
-        LSL_CUDA(cudaMemcpyAsync((uint8_t*)ctx->wk.depth + db * i, depths[i], db, cudaMemcpyHostToDevice, ctx->stream));
+        LSL_CUDA(cudaMemcpyAsync(d_draw + db * i, depths[i], db, cudaMemcpyHostToDevice, ctx->stream));
       }
     }
   } else {
@@ -369,10 +387,24 @@ extern "C" int lsl_extract_batch(lsl_ctx* ctx, int n, const uint8_t* const* imgs
       memcpy(hp + ib * n + db * i, depths[i], db);
     }
     LSL_CUDA(cudaMemcpyAsync(ctx->wk.img, hp, ib * n, cudaMemcpyHostToDevice, ctx->stream));
-    LSL_CUDA(cudaMemcpyAsync(ctx->wk.depth, hp + ib * n, db * n, cudaMemcpyHostToDevice, ctx->stream));
+    LSL_CUDA(cudaMemcpyAsync(d_draw, hp + ib * n, db * n, cudaMemcpyHostToDevice, ctx->stream));
   }
+  if (depth_elem == 2 && (rc = lsl_launch_depth_u16(ctx, depth_stream, ctx->d_depth16, ctx->wk.depth, npix * n, depth_scale))) return rc;
+  if (ctx->depth_async) LSL_CUDA(cudaEventRecord(ctx->ev_depth, ctx->copy_stream));
   ctx->stats.h2d_bytes += (ib + db) * n;
   return extract_device(ctx, n, ctx->wk.img, channels, ctx->wk.depth, W, H, K, dt, seeds, out);
+}
+
+extern "C" int lsl_extract_batch(lsl_ctx* ctx, int n, const uint8_t* const* imgs, int channels, const float* const* depths,
+                                 int W, int H, const double K[9], double dt, const uint32_t* seeds, lsl_frame** out) {
+  return extract_host(ctx, n, imgs, channels, (const void* const*)depths, 4, 1.f, W, H, K, dt, seeds, out);
+}
+
+extern "C" int lsl_extract_batch_u16(lsl_ctx* ctx, int n, const uint8_t* const* imgs, int channels, const uint16_t* const* depths,
+                                     int W, int H, const double K[9], double dt, const uint32_t* seeds, double depth_factor,
+                                     lsl_frame** out) {
+  if (!(depth_factor > 0)) return LSL_ERR_ARG;
+  return extract_host(ctx, n, imgs, channels, (const void* const*)depths, 2, (float)(1.0 / depth_factor), W, H, K, dt, seeds, out);
 }
 
 extern "C" int lsl_extract(lsl_ctx* ctx, const uint8_t* img, int channels, const float* depth, int W, int H,
@@ -389,7 +421,7 @@ extern "C" int lsl_frame_lines(const lsl_frame* fc, lsl_line_rec* dst, int cap, 
   if (!f->nlines) return LSL_OK;
   if (!f->have_host) {  // host mirror on first use
     lsl_ctx* ctx = f->ctx;
-    cudaSetDevice(ctx->device);
+    LSL_ENTER(ctx);
     f->lines.resize(f->nlines);
     LSL_CUDA(cudaMemcpyAsync(f->lines.data(), f->d_lines, sizeof(lsl_line_rec) * f->nlines, cudaMemcpyDeviceToHost, ctx->stream));
     LSL_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -409,7 +441,7 @@ extern "C" int lsl_frame_segments(const lsl_frame* f, double* dst, int cap, int*
 }
 extern "C" int lsl_frame_from_lines(lsl_ctx* ctx, const lsl_line_rec* recs, int n, lsl_frame** out) {
   if (!ctx || !out || n < 0 || (n && !recs) || n > LSL_MAX_LINES) return LSL_ERR_ARG;
-  cudaSetDevice(ctx->device);
+  LSL_ENTER(ctx);
   lsl_frame* fr = new (std::nothrow) lsl_frame();
   if (!fr) return LSL_ERR_ARG;
   fr->ctx = ctx; fr->nlines = n; fr->nsegs = 0; fr->d_lines = nullptr; fr->blk = nullptr;
@@ -427,7 +459,7 @@ extern "C" int lsl_frame_from_lines(lsl_ctx* ctx, const lsl_line_rec* recs, int 
 extern "C" void lsl_frame_free(lsl_frame* f) {
   if (!f) return;
   if (f->d_lines) {
-    cudaSetDevice(f->ctx->device);
+    LSL_ENTER(f->ctx);
     if (f->blk) {
       if (--f->blk->refs == 0) { cudaFreeAsync(f->blk->d, f->ctx->stream); delete f->blk; }
     } else cudaFree(f->d_lines);
@@ -439,7 +471,7 @@ extern "C" void lsl_frame_free(lsl_frame* f) {
 extern "C" int lsl_frame_clear_lines(lsl_frame* f) {
   if (!f) return LSL_ERR_ARG;
   if (f->d_lines) {
-    cudaSetDevice(f->ctx->device);
+    LSL_ENTER(f->ctx);
     if (f->blk) {
       if (--f->blk->refs == 0) { cudaFreeAsync(f->blk->d, f->ctx->stream); delete f->blk; }
     } else cudaFree(f->d_lines);
@@ -450,25 +482,44 @@ extern "C" int lsl_frame_clear_lines(lsl_frame* f) {
 }
 // Point features of a frame (inputs of the hot path: Node::feature_locations_3d_ and feature_descriptors_,
 // src/node.h; SIFT/SURF rows after squareroot_descriptor_space). Copies to the device; replaces earlier points.
-extern "C" int lsl_frame_set_points(lsl_ctx* ctx, lsl_frame* f, const float* xyz1, const float* desc, int n, int dim) {
+extern "C" int lsl_frame_set_points_ex(lsl_ctx* ctx, lsl_frame* f, const float* xyz1, const void* desc, int n, int dim, int desc_is_u8,
+                                       int root_sift) {
   if (!ctx || !f || n < 0 || n > LSL_MAX_POINTS || (n && (!xyz1 || !desc)) || dim < 1 || dim > 512) return LSL_ERR_ARG;
-  cudaSetDevice(ctx->device);
+  if (desc_is_u8 && (dim & 3)) { ctx->err = "binary descriptor rows must be a multiple of 4 bytes"; return LSL_ERR_ARG; }
+  LSL_ENTER(ctx);
   if (f->d_xyz1) { cudaFree(f->d_xyz1); f->d_xyz1 = nullptr; }
   if (f->d_desc) { cudaFree(f->d_desc); f->d_desc = nullptr; }
-  f->npoints = n; f->pdim = dim;
+  f->npoints = n; f->pdim = dim; f->pkind = desc_is_u8 ? 1 : 0;
   if (n) {
+    const size_t row = desc_is_u8 ? (size_t)dim : sizeof(float) * (size_t)dim;
     LSL_CUDA(cudaMalloc((void**)&f->d_xyz1, sizeof(float) * 4 * n));
-    LSL_CUDA(cudaMalloc((void**)&f->d_desc, sizeof(float) * (size_t)dim * n));
+    LSL_CUDA(cudaMalloc((void**)&f->d_desc, row * n));
     LSL_CUDA(cudaMemcpyAsync(f->d_xyz1, xyz1, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
-    LSL_CUDA(cudaMemcpyAsync(f->d_desc, desc, sizeof(float) * (size_t)dim * n, cudaMemcpyHostToDevice, ctx->stream));
+    LSL_CUDA(cudaMemcpyAsync(f->d_desc, desc, row * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (root_sift && !desc_is_u8) { int rc = lsl_launch_rootsift(ctx, f->d_desc, n, dim); if (rc) return rc; }
     LSL_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->stats.h2d_bytes += sizeof(float) * (size_t)(4 + dim) * n;
+    ctx->stats.h2d_bytes += sizeof(float) * 4 * (size_t)n + row * n;
   }
+  return LSL_OK;
+}
+extern "C" int lsl_frame_set_points(lsl_ctx* ctx, lsl_frame* f, const float* xyz1, const float* desc, int n, int dim) {
+  return lsl_frame_set_points_ex(ctx, f, xyz1, desc, n, dim, 0, 0);
+}
+extern "C" int lsl_frame_descriptors(lsl_ctx* ctx, const lsl_frame* f, void* dst, int64_t cap_bytes) {
+  if (!ctx || !f || (f->npoints && !dst)) return LSL_ERR_ARG;
+  const size_t bytes = (f->pkind ? (size_t)f->pdim : sizeof(float) * (size_t)f->pdim) * (size_t)f->npoints;
+  if ((int64_t)bytes > cap_bytes) return LSL_ERR_CAPACITY;
+  if (!bytes) return LSL_OK;
+  LSL_ENTER(ctx);
+  LSL_CUDA(cudaMemcpyAsync(dst, f->d_desc, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  LSL_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->stats.d2h_bytes += bytes;
   return LSL_OK;
 }
 extern "C" int lsl_frame_num_points(const lsl_frame* f) { return f ? f->npoints : LSL_ERR_ARG; }
 extern "C" int lsl_ctx_set_camera(lsl_ctx* ctx, double fx, double asynch_dt_s) {
   if (!ctx || !(fx > 0)) return LSL_ERR_ARG;
+  LSL_LOCK(ctx);
   ctx->cam_fx = fx; ctx->cam_dt = asynch_dt_s;
   return LSL_OK;
 }
@@ -549,11 +600,11 @@ static int setup_pairs(lsl_ctx* ctx, int npairs, const lsl_frame* const* queries
 
 // Point side of a batch: descriptors of the pairs' point sets and the point-match-sized scratch.
 static int setup_ppairs(lsl_ctx* ctx, int npairs, const lsl_frame* const* queries, const lsl_frame* const* trains,
-                        int cap_override, int* max_nq, int* dim_out) {
+                        int cap_override, int* max_nq, int* dim_out, int* kind_out = nullptr) {
   LslHybWork& h = ctx->hw;
   h.h_ppairs.resize(npairs);
   size_t pm_off = 0, knn_off = 0;
-  int mq = 0, dim = 0;
+  int mq = 0, dim = 0, kind = 0;
   for (int i = 0; i < npairs; ++i) {
     const lsl_frame* q = queries[i];
     const lsl_frame* t = trains[i];
@@ -562,7 +613,12 @@ static int setup_ppairs(lsl_ctx* ctx, int npairs, const lsl_frame* const* querie
     d.nqp = q->npoints; d.ntp = t->npoints;
     if (d.nqp && d.ntp && q->pdim != t->pdim) { ctx->err = "descriptor dimensions of the two frames differ"; return LSL_ERR_ARG; }
     d.dim = d.nqp ? q->pdim : t->pdim;
-    if (cap_override < 0 && d.nqp && d.ntp) { if (dim && d.dim != dim) { ctx->err = "mixed descriptor dimensions in one batch"; return LSL_ERR_ARG; } dim = d.dim; }
+    d.kind = d.nqp ? q->pkind : t->pkind; d.pad_ = 0;
+    if (d.nqp && d.ntp && q->pkind != t->pkind) { ctx->err = "descriptor types of the two frames differ"; return LSL_ERR_ARG; }
+    if (cap_override < 0 && d.nqp && d.ntp) {
+      if (dim && (d.dim != dim || d.kind != kind)) { ctx->err = "mixed descriptor dimensions / types in one batch"; return LSL_ERR_ARG; }
+      dim = d.dim; kind = d.kind;
+    }
     d.cap_pm = cap_override >= 0 ? cap_override : d.nqp;
     d.pm_off = pm_off; d.knn_off = knn_off;
     pm_off += (size_t)(d.cap_pm > 0 ? d.cap_pm : 1);
@@ -595,6 +651,7 @@ static int setup_ppairs(lsl_ctx* ctx, int npairs, const lsl_frame* const* querie
   LSL_CUDA(cudaMemcpyAsync(h.d_ppairs, h.h_ppairs.data(), sizeof(LslPairPts) * npairs, cudaMemcpyHostToDevice, ctx->stream));
   if (max_nq) *max_nq = mq;
   if (dim_out) *dim_out = dim ? dim : 1;
+  if (kind_out) *kind_out = kind;
   return LSL_OK;
 }
 // seeds the per-pair rand() state on the host (pose-only calls have no featureMatching pass before them)
@@ -630,7 +687,7 @@ static int fetch_counts(lsl_ctx* ctx, int npairs) {
 extern "C" int lsl_match_lines(lsl_ctx* ctx, const lsl_frame* query, const lsl_frame* train, int adjacent, lsl_match* out,
                                int cap, int* n) {
   if (!ctx || !query || !train || !n) return LSL_ERR_ARG;
-  cudaSetDevice(ctx->device);
+  LSL_ENTER(ctx);
   int adj = adjacent ? 1 : 0;
   int rc = setup_pairs(ctx, 1, &query, &train, nullptr, nullptr, nullptr, &adj, -1);
   if (rc) return rc;
@@ -666,14 +723,14 @@ static int fetch_sel(lsl_ctx* ctx, const LslPairDesc& d, int which, int count, c
 extern "C" int lsl_match_points(lsl_ctx* ctx, const lsl_frame* query, const lsl_frame* train, uint32_t seed, lsl_match* out,
                                 int cap, int* n) {
   if (!ctx || !query || !train || !n) return LSL_ERR_ARG;
-  cudaSetDevice(ctx->device);
+  LSL_ENTER(ctx);
   int id_q = 1, id_t = 0;
   int rc = setup_pairs(ctx, 1, &query, &train, &id_q, &id_t, &seed, nullptr, -1);
   if (rc) return rc;
-  int mq = 0, dim = 1;
-  if ((rc = setup_ppairs(ctx, 1, &query, &train, -1, &mq, &dim))) return rc;
+  int mq = 0, dim = 1, kind = 0;
+  if ((rc = setup_ppairs(ctx, 1, &query, &train, -1, &mq, &dim, &kind))) return rc;
   clear_ktimes(ctx, LSL_K_MATCH, LSL_K_PNG);
-  if ((rc = lsl_launch_match_points(ctx, 1, mq, dim))) return rc;
+  if ((rc = lsl_launch_match_points(ctx, 1, mq, dim, kind))) return rc;
   int32_t nm = 0;
   LSL_CUDA(cudaMemcpyAsync(&nm, ctx->hw.npmatch, 4, cudaMemcpyDeviceToHost, ctx->stream));
   LSL_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -711,7 +768,7 @@ extern "C" int lsl_pose_ransac(lsl_ctx* ctx, const lsl_frame* train, const lsl_f
   for (int i = 0; i < npt; ++i)
     if (pt_matches[i].queryIdx < 0 || pt_matches[i].queryIdx >= query->npoints || pt_matches[i].trainIdx < 0 ||
         pt_matches[i].trainIdx >= train->npoints) return LSL_ERR_ARG;
-  cudaSetDevice(ctx->device);
+  LSL_ENTER(ctx);
   int rc = setup_pairs(ctx, 1, &query, &train, &id_query, &id_train, &seed, nullptr, nln);
   if (rc) return rc;
   const bool hybrid = npt > 0;
@@ -759,7 +816,7 @@ extern "C" int lsl_relmotion_ransac(lsl_ctx* ctx, const lsl_frame* train, const 
   for (int i = 0; i < nln; ++i)
     if (ln_matches[i].queryIdx < 0 || ln_matches[i].queryIdx >= query->nlines || ln_matches[i].trainIdx < 0 ||
         ln_matches[i].trainIdx >= train->nlines) return LSL_ERR_ARG;
-  cudaSetDevice(ctx->device);
+  LSL_ENTER(ctx);
   int idq = 1, idt = 0;
   int rc = setup_pairs(ctx, 1, &query, &train, &idq, &idt, &seed, nullptr, nln);
   if (rc) return rc;
@@ -809,17 +866,17 @@ extern "C" int lsl_relmotion_ransac(lsl_ctx* ctx, const lsl_frame* train, const 
 extern "C" int lsl_match_pair_batch(lsl_ctx* ctx, int npairs, const lsl_frame* const* queries, const lsl_frame* const* trains,
                                     const int32_t* id_query, const int32_t* id_train, const uint32_t* seeds, lsl_pose_rec* out) {
   if (!ctx || npairs < 1 || !queries || !trains || !out) return LSL_ERR_ARG;
-  cudaSetDevice(ctx->device);
+  LSL_ENTER(ctx);
   int rc = setup_pairs(ctx, npairs, queries, trains, id_query, id_train, seeds, nullptr, -1);
   if (rc) return rc;
   bool hybrid = false;   // any frame with point features -> Node::matchNodePair with both modalities
   for (int i = 0; i < npairs; ++i) hybrid = hybrid || (queries[i]->npoints > 0 && trains[i]->npoints > 0);
   ctx->hw.last_hybrid = hybrid;
-  int mq = 0, dim = 1;
-  if (hybrid && (rc = setup_ppairs(ctx, npairs, queries, trains, -1, &mq, &dim))) return rc;
+  int mq = 0, dim = 1, kind = 0;
+  if (hybrid && (rc = setup_ppairs(ctx, npairs, queries, trains, -1, &mq, &dim, &kind))) return rc;
   clear_ktimes(ctx, LSL_K_MATCH, LSL_K_PNG);
   cudaEventRecord(ctx->ev0, ctx->stream);
-  if (hybrid && (rc = lsl_launch_match_points(ctx, npairs, mq, dim))) return rc;   // featureMatching first (node.cpp:1504)
+  if (hybrid && (rc = lsl_launch_match_points(ctx, npairs, mq, dim, kind))) return rc;   // featureMatching first (node.cpp:1504)
   if ((rc = lsl_launch_match(ctx, npairs))) return rc;
   if (hybrid) { if ((rc = lsl_launch_pose_hybrid(ctx, npairs, ctx->cam_fx, ctx->cam_dt))) return rc; }
   else if ((rc = lsl_launch_pose(ctx, npairs))) return rc;
@@ -837,7 +894,7 @@ extern "C" int lsl_match_pair_batch(lsl_ctx* ctx, int npairs, const lsl_frame* c
 
 extern "C" int lsl_pair_matches(lsl_ctx* ctx, int pair, int what, lsl_match* out, int cap, int* n) {
   if (!ctx || !n || pair < 0 || pair >= (int)ctx->pw.h_nmatch.size() || what < 0 || what > 5) return LSL_ERR_ARG;
-  cudaSetDevice(ctx->device);
+  LSL_ENTER(ctx);
   if (what >= 3) {   // point lists: 3 all point matches, 4 refined point inliers, 5 point inliers of the best hypothesis
     const LslHybWork& h = ctx->hw;
     if (!h.last_hybrid || pair >= (int)h.h_npmatch.size()) { *n = 0; return LSL_OK; }
@@ -896,7 +953,7 @@ extern "C" int lsl_comm_unique_id(void* id128) {
 }
 extern "C" int lsl_comm_init(lsl_ctx* ctx, const void* id128, int nranks, int rank) {
   if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return LSL_ERR_ARG;
-  cudaSetDevice(ctx->device);
+  LSL_ENTER(ctx);
   void* h = nccl_open(ctx);
   if (!h) { ctx->err = "libnccl not found (set LSL_NCCL_LIB)"; return LSL_ERR_NCCL; }
   nccl_init_rank_fn f = (nccl_init_rank_fn)dlsym(h, "ncclCommInitRank");
@@ -926,7 +983,7 @@ extern "C" int lsl_allgather_poses(lsl_ctx* ctx, void* nccl_comm, int nranks, co
   void* comm = nccl_comm ? nccl_comm : ctx->nccl_comm;
   if (!nccl_comm) nranks = ctx->nccl_nranks;
   if (!comm || nranks < 1) { ctx->err = "no communicator: call lsl_comm_init or pass an ncclComm_t"; return LSL_ERR_NCCL; }
-  cudaSetDevice(ctx->device);
+  LSL_ENTER(ctx);
   void* h = nccl_open(ctx);
   if (!h) return LSL_ERR_NCCL;
   nccl_allgather_fn ag = (nccl_allgather_fn)dlsym(h, "ncclAllGather");
@@ -952,17 +1009,20 @@ extern "C" int lsl_allgather_poses(lsl_ctx* ctx, void* nccl_comm, int nranks, co
 // ------------------------------------------------------------------ introspection ----
 extern "C" int lsl_get_stats(const lsl_ctx* ctx, lsl_stats* out) {
   if (!ctx || !out) return LSL_ERR_ARG;
+  LSL_LOCK(ctx);
   *out = ctx->stats;
   return LSL_OK;
 }
 extern "C" int lsl_last_timing(const lsl_ctx* ctx, float* ms_total, float* ms_rg) {
   if (!ctx) return LSL_ERR_ARG;
+  LSL_LOCK(ctx);
   if (ms_total) *ms_total = ctx->ms_total;
   if (ms_rg) *ms_rg = ctx->ms_rg;
   return LSL_OK;
 }
 extern "C" int lsl_kernel_times(const lsl_ctx* ctx, float* ms, int cap, int* n) {
   if (!ctx || !n) return LSL_ERR_ARG;
+  LSL_LOCK(ctx);
   *n = LSL_K_COUNT;
   if (cap < LSL_K_COUNT || !ms) return LSL_ERR_CAPACITY;
   for (int k = 0; k < LSL_K_COUNT; ++k) ms[k] = ctx->kran[k] ? ctx->kms[k] : 0.f;
@@ -971,7 +1031,7 @@ extern "C" int lsl_kernel_times(const lsl_ctx* ctx, float* ms, int cap, int* n) 
 
 extern "C" int64_t lsl_debug_read(lsl_ctx* ctx, int what, void* dst, int64_t cap_bytes) {
   if (!ctx || !dst) return LSL_ERR_ARG;
-  cudaSetDevice(ctx->device);
+  LSL_ENTER(ctx);
   const LslDims& d = ctx->dims;
   const LslWork& w = ctx->wk;
   const void* src = nullptr;

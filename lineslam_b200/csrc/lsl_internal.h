@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/lsl.h"
@@ -111,6 +112,7 @@ struct LslPairPts {
   const float* qd;   // query feature_descriptors_ [nqp][dim]
   const float* td;
   int nqp, ntp, dim, cap_pm;   // cap_pm = nqp: upper bound of the point match count
+  int kind, pad_;              // 0: f32 rows, L2 (BruteForce); 1: u8 rows of dim bytes, Hamming (BruteForce-HammingLUT)
   size_t pm_off;     // offset of this pair's point-match-sized slices
   size_t knn_off;    // offset of this pair's per-query-row nearest-neighbour records
 };
@@ -180,12 +182,16 @@ struct lsl_frame {
   std::vector<int32_t> dbg_npts, dbg_inl, dbg_seg, dbg_lm;
   bool have_dbg;
   // point features handed in by the caller (lsl_frame_set_points); device copies
-  int npoints, pdim;
+  int npoints, pdim, pkind;    // pkind 0: f32 descriptors, 1: u8 (ORB) rows of pdim bytes
   float* d_xyz1;   // [npoints][4]
   float* d_desc;   // [npoints][pdim]
 };
 
 struct lsl_ctx {
+  // every entry point that touches the context takes this lock (LSL_ENTER): calls from several host threads on ONE
+  // context are serialised in arrival order (recursive: lsl_extract -> lsl_extract_batch, lsl_graph_add_frame ->
+  // lsl_match_pair_batch); concurrency across host threads = one context per thread
+  mutable std::recursive_mutex mu;
   lsl_params P;
   int device, max_batch, max_w, max_h;
   cudaStream_t stream;       // stream every call of this context runs on
@@ -210,10 +216,14 @@ struct lsl_ctx {
   LslHybWork hw;
   double cam_fx, cam_dt;     // focal length / asynch time used by the point-edge information (compPt3dCov)
   uint8_t* h_pin; size_t h_pin_bytes;   // pinned staging
+  uint16_t* d_depth16; size_t d_depth16_bytes;   // raw 16-bit depth planes of lsl_extract_batch_u16 (allocated on first use)
   std::string err;
   lsl_stats stats;
   float ms_total, ms_rg;
 };
+
+#define LSL_LOCK(c) std::lock_guard<std::recursive_mutex> lsl_lock_((c)->mu)
+#define LSL_ENTER(c) LSL_LOCK(c); cudaSetDevice((c)->device)
 
 // device-time bracket of one kernel launch
 #define LSL_KSTART(ctx, id) do { cudaEventRecord((ctx)->kev[id][0], (ctx)->stream); } while (0)
@@ -235,8 +245,10 @@ int lsl_launch_lsd(lsl_ctx* ctx, int n);
 int lsl_launch_lines(lsl_ctx* ctx, int n, const float* d_depth, const double K[9], double dt);
 int lsl_prepare_taps(lsl_ctx* ctx);
 int lsl_launch_gather(lsl_ctx* ctx, int n, lsl_line_rec* dst);
+int lsl_launch_depth_u16(lsl_ctx* ctx, cudaStream_t st, const uint16_t* d_in, float* d_out, size_t count, float scale);
 int lsl_launch_match(lsl_ctx* ctx, int npairs);
 int lsl_launch_pose(lsl_ctx* ctx, int npairs);
-int lsl_launch_match_points(lsl_ctx* ctx, int npairs, int max_nq, int dim);
+int lsl_launch_match_points(lsl_ctx* ctx, int npairs, int max_nq, int dim, int kind);
+int lsl_launch_rootsift(lsl_ctx* ctx, float* d_desc, int n, int dim);
 int lsl_launch_pose_hybrid(lsl_ctx* ctx, int npairs, double fx, double dt);
 int lsl_launch_relmotion(lsl_ctx* ctx, int npairs, RmScratch rs);

@@ -100,6 +100,8 @@ struct Points { int n = 0, dim = 0; const float* xyz1 = nullptr; const float* de
 // Node::featureMatching, BRUTEFORCE branch (src/node.cpp:606-641): BFMatcher L2 knnMatch k = 2, ratio test,
 // unique trainIdx, distance = ratio + rand()/(1000 RAND_MAX); one rand() per accepted match.
 void featureMatching(const Points& query, const Points& train, double nn_ratio, GlibcRand& rng, std::vector<Match>& out);
+void featureMatching_hamming(const uint8_t* qd, int nq, const uint8_t* td, int nt, int nbytes, double nn_ratio, GlibcRand& rng,
+                             std::vector<Match>& out);   // ORB rows, BruteForce-HammingLUT (src/node.cpp:609-613)
 // squareroot_descriptor_space (src/node.cpp:1823-1837), in place
 void rootsift(float* desc, int n, int dim);
 

@@ -162,6 +162,14 @@ int orc_featureMatching(const float* qdesc, int nq, const float* tdesc, int nt, 
   return (int)m.size();
 }
 void orc_rootsift(float* desc, int n, int dim) { orc::rootsift(desc, n, dim); }
+int orc_featureMatching_hamming(const uint8_t* qd, int nq, const uint8_t* td, int nt, int nbytes, double nn_ratio, uint32_t seed,
+                                lsl_match* out, int cap) {
+  orc::GlibcRand r; r.seed(seed);
+  std::vector<orc::Match> m;
+  orc::featureMatching_hamming(qd, nq, td, nt, nbytes, nn_ratio, r, m);
+  for (int i = 0; i < (int)m.size() && i < cap; ++i) memcpy(&out[i], &m[i], sizeof(lsl_match));
+  return (int)m.size();
+}
 
 // getTransform_PtsLines_ransac with point + line matches. skip_draws: rand() calls already consumed from the
 // seed's stream (the featureMatching jitter of the same matchNodePair call). pad[0] = #point matches,

@@ -590,6 +590,35 @@ void featureMatching(const Points& q, const Points& t, double nn_ratio, GlibcRan
   }
 }
 
+// Node::featureMatching with feature_extractor_type ORB (src/node.cpp:606-641): "BruteForce-HammingLUT" — the distance of
+// two binary rows is the number of differing bits (a lookup table per byte), knnMatch hands it back as a float.
+void featureMatching_hamming(const uint8_t* qd, int nq, const uint8_t* td, int nt, int nbytes, double nn_ratio, GlibcRand& rng,
+                             std::vector<Match>& out) {
+  if (nq == 0 || nt < 2) return;
+  static uint8_t lut[256];
+  static bool init = false;
+  if (!init) { for (int v = 0; v < 256; ++v) { int c = 0; for (int b = 0; b < 8; ++b) c += (v >> b) & 1; lut[v] = (uint8_t)c; } init = true; }
+  std::vector<char> used(nt, 0);
+  for (int i = 0; i < nq; ++i) {
+    float d1 = FLT_MAX, d2 = FLT_MAX; int i1 = -1;
+    for (int j = 0; j < nt; ++j) {
+      int c = 0;
+      for (int k = 0; k < nbytes; ++k) c += lut[qd[(size_t)i * nbytes + k] ^ td[(size_t)j * nbytes + k]];
+      float d = (float)c;
+      if (d < d1) { d2 = d1; d1 = d; i1 = j; }
+      else if (d < d2) d2 = d;
+    }
+    float dist_ratio_fac = d1 / d2;
+    if (dist_ratio_fac < nn_ratio) {
+      if (used[i1]) continue;
+      used[i1] = 1;
+      Match m; m.queryIdx = i; m.trainIdx = i1;
+      m.distance = (float)(dist_ratio_fac + (float)rng.next() / (1000.0 * 2147483647));
+      out.push_back(m);
+    }
+  }
+}
+
 // ------------------------------------------ pose RANSAC (points + lines) ----
 static void tf_to_double(const float tf[16], double tfd[16]) { for (int i = 0; i < 16; ++i) tfd[i] = (double)tf[i]; }
 

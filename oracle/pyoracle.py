@@ -269,3 +269,12 @@ def get_gradient(gx, gy, p, q):
     pq = np.array([p[0], p[1], q[0], q[1]], np.float64); r = np.zeros(2)
     lib().orc_get_gradient(ptr(gx), ptr(gy), W, H, ptr(pq), ptr(r))
     return r
+
+
+def featureMatching_hamming(qdesc, tdesc, nn_ratio=0.5, seed=1):
+    """Node::featureMatching for ORB rows (BruteForce-HammingLUT)."""
+    q = np.ascontiguousarray(qdesc, np.uint8); t = np.ascontiguousarray(tdesc, np.uint8)
+    out = np.zeros(max(len(q), 1), MATCH_DTYPE)
+    n = lib().orc_featureMatching_hamming(ptr(q), len(q), ptr(t), len(t), q.shape[1], C.c_double(nn_ratio), C.c_uint32(seed),
+                                          ptr(out), len(out))
+    return out[:n].copy()

@@ -126,3 +126,30 @@ def test_border_segments_are_clipped_not_skipped(api, oracle):
                 assert np.all(np.isfinite(l["r"])) and abs(np.linalg.norm(l["des"]) - 1.0) < 1e-9
     assert outside >= 2
     ctx.close()
+
+
+def test_u16_depth_entry_equals_f32_entry(api, oracle, stream4):
+    """lsl_extract_batch_u16: the 16-bit depth of the sensor / TUM PNG converted on the device (0 -> NaN, x (float)(1/5000),
+    src/openni_listener.cpp:1233-1244) gives the records of the f32 entry on the host-converted planes, for pageable and
+    for pinned contiguous buffers (the two upload paths), and moves 2 instead of 4 depth bytes per pixel."""
+    import torch
+    imgs, deps, poses, K = stream4
+    raw = np.nan_to_num(deps * 5000.0, nan=0.0).round().astype(np.uint16)
+    raw[0, 100:140, 200:300] = 0
+    conv = raw.astype(np.float32)
+    conv = np.where(conv < 1e-5, np.float32(np.nan), conv * np.float32(1.0 / 5000.0)).astype(np.float32)
+    ctx = api.Context(max_batch=4, max_w=640, max_h=480, debug=True)
+    ref = ctx.extract_batch(imgs, conv, K, seeds=[1, 2, 3, 4])
+    ref_lines = [f.lines().copy() for f in ref]
+    orc = oracle.detect3DLines(imgs[0], conv[0], K, seed=1)
+    assert ref_lines[0].tobytes() == orc.tobytes()
+    s0 = ctx.stats().h2d_bytes
+    got = ctx.extract_batch(imgs, raw, K, seeds=[1, 2, 3, 4])
+    assert ctx.stats().h2d_bytes - s0 == 4 * 640 * 480 * (3 + 2)
+    for g, r in zip(got, ref_lines):
+        assert g.lines().tobytes() == r.tobytes()
+    pi, pd = torch.from_numpy(imgs.copy()).pin_memory(), torch.from_numpy(raw.view(np.int16).copy()).pin_memory()
+    got2 = ctx.extract_batch(pi.numpy(), pd.numpy().view(np.uint16), K, seeds=[1, 2, 3, 4])
+    for g, r in zip(got2, ref_lines):
+        assert g.lines().tobytes() == r.tobytes()
+    ctx.close()

@@ -141,3 +141,41 @@ def test_relmotion_ransac_levmar(api, oracle, hyb):
     ref = oracle.relmotion_ransac(lines[1][lm["queryIdx"][:3]], lines[0][lm["trainIdx"][:3]], seed=1)
     got = ctx.relmotion_ransac(frames[0], frames[1], lm[:3], seed=1)
     assert np.array_equal(got["conset"], ref["conset"]) and got["lm_calls"] == ref["lm_calls"] == 0
+
+
+def test_orb_hamming_branch_and_device_rootsift(api, oracle, hyb):
+    """a21 remainder: ORB rows through the BruteForce-HammingLUT matcher, and squareroot_descriptor_space applied on
+    the device (src/node.cpp:606-641, 304-310, 1823-1837)."""
+    ctx, frames, lines, pts, poses = hyb
+    rng = np.random.default_rng(31)
+    q = rng.integers(0, 256, (600, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (570, 32), dtype=np.uint8)
+    sel = rng.permutation(600)[:400]
+    t[:400] = q[sel]
+    t[:400] ^= ((rng.random((400, 32)) < 0.04) * rng.integers(0, 256, (400, 32))).astype(np.uint8)
+    t[9] = t[8]
+    xq = np.ones((600, 4), np.float32); xt = np.ones((570, 4), np.float32)
+    fq = ctx.frame_from_lines(lines[0][:0]).set_points(xq, q)
+    ft = ctx.frame_from_lines(lines[0][:0]).set_points(xt, t)
+    for seed in (1, 5):
+        got = ctx.match_points(fq, ft, seed)
+        ref = oracle.featureMatching_hamming(q, t, ctx.params.nn_distance_ratio, seed)
+        assert len(ref) > 200 and np.array_equal(got, ref)
+    assert np.array_equal(fq.descriptors(), q)
+    # mixing ORB and float rows in one pair is refused, not silently matched
+    with pytest.raises(Exception):
+        ctx.match_points(fq, frames[0], 1)
+    # RootSIFT on the device == the oracle's conditioning of the raw rows, and the matches that follow are identical
+    raw = [(rng.normal(size=(500, 128)) * rng.choice([0.1, 1.0, 30.0], size=(500, 1))).astype(np.float32) for _ in range(2)]
+    raw[1][:300] = raw[0][rng.permutation(500)[:300]] + rng.normal(0, 0.01, (300, 128)).astype(np.float32)
+    raw[0][3] = 0
+    x = np.ones((500, 4), np.float32)
+    fa = ctx.frame_from_lines(lines[0][:0]).set_points(x, raw[0], root_sift=True)
+    fb = ctx.frame_from_lines(lines[0][:0]).set_points(x, raw[1], root_sift=True)
+    ra, rb = oracle.rootsift(raw[0]), oracle.rootsift(raw[1])
+    assert np.array_equal(fa.descriptors(), ra) and np.array_equal(fb.descriptors(), rb)
+    got = ctx.match_points(fa, fb, 2)
+    ref = oracle.featureMatching(ra, rb, ctx.params.nn_distance_ratio, 2)
+    assert len(ref) > 100 and np.array_equal(got, ref)
+    for f in (fq, ft, fa, fb):
+        f.free()

@@ -239,3 +239,46 @@ def test_getGradient_border_segments():
             assert np.array_equal(r, e), (p, q)
         n_clipped += any(not (0 <= np.rint(a[0]) < W and 0 <= np.rint(a[1]) < H) for a in (p, q))
     assert n_clipped > 20
+
+
+def test_hamming_feature_matching_vs_cv2():
+    """feature_extractor_type ORB: "BruteForce-HammingLUT" knnMatch k = 2 + ratio / unique / jitter pass
+    (src/node.cpp:606-641). Integer distances: the whole match list is bit-exact against cv2's matcher."""
+    rng = np.random.default_rng(0)
+    q = rng.integers(0, 256, (500, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (480, 32), dtype=np.uint8)
+    sel = rng.permutation(500)[:300]
+    t[:300] = q[sel]
+    flip = rng.random((300, 32)) < 0.05
+    t[:300] ^= (flip * rng.integers(0, 256, (300, 32))).astype(np.uint8)
+    t[5] = t[6]
+    got = po.featureMatching_hamming(q, t, 0.5, seed=3)
+    draws = po.rand(3, 600)
+    for name in ("BruteForce-HammingLUT", "BruteForce-Hamming"):
+        knn = cv2.DescriptorMatcher_create(name).knnMatch(q, t, k=2)
+        exp, seen = [], set()
+        for i, (a, b) in enumerate(knn):
+            r = np.float32(a.distance) / np.float32(b.distance)
+            if r < 0.5:
+                if a.trainIdx in seen:
+                    continue
+                seen.add(a.trainIdx)
+                exp.append((i, a.trainIdx, np.float32(float(r) + float(np.float32(draws[len(exp)])) / (1000.0 * 2147483647))))
+        assert len(got) == len(exp) > 100
+        assert [(int(m["queryIdx"]), int(m["trainIdx"])) for m in got] == [(e[0], e[1]) for e in exp]
+        assert np.array_equal(got["distance"], np.array([e[2] for e in exp], np.float32))
+
+
+def test_rootsift_vs_cv2_pipeline():
+    """squareroot_descriptor_space (src/node.cpp:1823-1837): cv::abs, cv::reduce(CV_REDUCE_SUM, CV_32FC1), sqrt(v / sum).
+    cv2 4.13's reduce accumulates the row sequentially in float, as the oracle does: bit-exact."""
+    rng = np.random.default_rng(1)
+    for dim in (64, 128):
+        d = (rng.normal(size=(200, dim)) * rng.choice([0.01, 1.0, 50.0], size=(200, 1))).astype(np.float32)
+        d[7] = 0
+        a = cv2.absdiff(d, np.zeros_like(d))
+        sums = cv2.reduce(a, 1, cv2.REDUCE_SUM, None, cv2.CV_32F)
+        exp = a.copy()
+        nz = sums[:, 0] != 0
+        exp[nz] = np.sqrt(a[nz] / sums[nz])
+        assert np.array_equal(po.rootsift(d), exp)
