@@ -8,10 +8,12 @@ previous step) and registered (500-iteration RANSAC + LM refinement) -> B pose r
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B]      the CUDA path through the C ABI
   python bench.py --impl reference ...                                 the reference's CPU path (oracle/)
+  python bench.py --workload cfg3|cfg4|cfg5 ...                        the other BASELINE configs (lines kept under profiles/)
 
 `value`  : device-resident inputs (already in HBM when the timed region starts).
-`e2e`    : same steps through the host-buffer entry point: pinned host RGB+depth -> H2D inside the timed
-           region, pose records D2H (what Node::Node + Node::matchNodePair callers see).
+`e2e`    : same steps through the host-buffer entry point: pinned host RGB u8 + the 16-bit depth the sensor / TUM PNG
+           delivers (lsl_extract_batch_u16; metres + NaN conversion on the device) -> H2D inside the timed region,
+           pose records D2H (what Node::Node + Node::matchNodePair callers see).
 Multi-GPU: one process per GPU (torchrun), the stream is sharded (rank r owns its own batches, weak scaling),
 no data-path collective; the pose records are all-gathered with NCCL at the end of every step (graph-insert time).
 Only the cpu_baseline / --impl reference legs touch oracle/.
@@ -68,10 +70,56 @@ def palindrome(u: int, n: int, phase: int = 0):
     return [period[(phase + k) % len(period)] for k in range(n)]
 
 
-def make_unique_frames(u: int, rank: int):
+def _render_one(args):
+    """Pool worker: one frame of a synthetic stream (+ SIFT point features for cfg 3)."""
     from lineslam_b200 import synth
-    imgs, deps, _ = synth.make_stream(u, scene_seed=2000, start=rank * 7)
-    return imgs, deps, synth.camera_K(W, H)
+    seed, idx, Wd, Hd, traj_name, want_sift = args
+    global _SCENE
+    if "_SCENE" not in globals() or _SCENE[0] != seed:
+        _SCENE = (seed, synth.Scene(seed))
+    traj = synth.trajectory_orbit if traj_name == "orbit" else synth.trajectory_xyz
+    img, dep, R, p = synth.make_frame(_SCENE[1], idx, seed, Wd, Hd, traj)
+    pts = None
+    if want_sift:   # cfg 3: cv2 SIFT on the rendered frame -> xyz from the depth map (SURVEY.md §8d); raw SIFT rows, RootSIFT on device
+        import cv2
+        K = synth.camera_K(Wd, Hd)
+        kp, desc = cv2.SIFT_create(nfeatures=600).detectAndCompute(cv2.cvtColor(img, cv2.COLOR_BGR2GRAY), None)
+        kp, desc = kp[:600], (desc[:600] if desc is not None else np.zeros((0, 128), np.float32))
+        uv = np.array([k.pt for k in kp], np.float64).reshape(-1, 2)
+        ui = np.clip(np.rint(uv[:, 0]).astype(int), 0, Wd - 1); vi = np.clip(np.rint(uv[:, 1]).astype(int), 0, Hd - 1)
+        z = dep[vi, ui].astype(np.float64)
+        xyz1 = np.ones((len(kp), 4), np.float32)
+        xyz1[:, 0] = ((uv[:, 0] - K[0, 2]) / K[0, 0] * z).astype(np.float32)
+        xyz1[:, 1] = ((uv[:, 1] - K[1, 2]) / K[1, 1] * z).astype(np.float32)
+        xyz1[:, 2] = z.astype(np.float32)
+        pts = (xyz1, np.ascontiguousarray(desc, np.float32))
+    return img, dep, pts
+
+
+def make_unique_frames(u: int, rank: int, world: int = 1, Wd: int = W, Hd: int = H, traj: str = "xyz", sift: bool = False,
+                       stride: int = 1):
+    """u distinct consecutive frames of the synthetic stream, rendered in a process pool (0.45 s per VGA frame per core).
+    Must run BEFORE CUDA is initialised in this process (the pool forks)."""
+    import multiprocessing as mp
+    from lineslam_b200 import synth
+    workers = max(1, min((os.cpu_count() or 1) // max(world, 1), u))
+    start = rank * 7
+    jobs = [(2000, start + k * stride, Wd, Hd, traj, sift) for k in range(u)]
+    if workers > 1:
+        with mp.get_context("fork").Pool(workers) as pool:
+            res = pool.map(_render_one, jobs, chunksize=max(1, u // (workers * 4)))
+    else:
+        res = [_render_one(j) for j in jobs]
+    imgs = np.stack([r[0] for r in res]); deps = np.stack([r[1] for r in res])
+    pts = [r[2] for r in res] if sift else None
+    K = synth.camera_K(Wd, Hd)
+    return (imgs, deps, K, pts) if sift else (imgs, deps, K)
+
+
+def depth_to_u16(deps: np.ndarray) -> np.ndarray:
+    """The 16-bit TUM depth the synthetic f32 planes came from (they are quantised to 1/5000 m; NaN = 0)."""
+    raw = np.nan_to_num(deps.astype(np.float64) * 5000.0, nan=0.0)
+    return np.rint(raw).astype(np.uint16)
 
 
 class ClockSampler:
@@ -167,15 +215,30 @@ def cpu_pairs_per_sec(imgs, deps, K, n_pairs: int, threads: int):
     return total / wall, time.perf_counter() - t0, total, sum(r[1] for r in res)
 
 
+def tum_depth_planes(deps):
+    """(u16 raw, f32 metres) as the reference's loader makes them from the 16-bit PNG (openni_listener.cpp:1233-1244)."""
+    raw = depth_to_u16(deps)
+    conv = np.where(raw == 0, np.float32(np.nan), raw.astype(np.float32) * np.float32(1.0 / 5000.0)).astype(np.float32)
+    return raw, conv
+
+
+WORKLOADS = {
+    "cfg2": "cfg2 fr1/xyz-shape synthetic stream 640x480, line-only odometry",
+    "cfg3": "cfg3 fr2/desk-shape synthetic stream 640x480, line + SIFT-point fusion (Node::matchNodePair both modalities)",
+    "cfg4": "cfg4 loop-closure batch: 1 query x 256 keyframes line matching + RANSAC, keyframes block-wise over the ranks",
+    "cfg5": "cfg5 1280x960 stream, line odometry + levmar refine (computeRelativeMotion_Ransac + optimizeRelmotion) per edge",
+}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    imgs, deps, K = make_unique_frames(args.unique, 0)
+    imgs, deps, K = make_unique_frames(min(args.unique, max(24, threads + 2)), 0)
+    _, deps = tum_depth_planes(deps)
     per_step = threads * 2
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_pairs_per_sec(imgs, deps, K, threads, threads)
-    t0 = time.perf_counter()
     tot_pairs, tot_time = 0, 0.0
     for _ in range(args.steps):
         pps, sec, pairs, _ = cpu_pairs_per_sec(imgs, deps, K, per_step, threads)
@@ -186,9 +249,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frame-pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_time / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg2 fr1/xyz-shape synthetic stream 640x480, line-only odometry (CPU reference path)",
-                   "pairs_per_step": per_step, "unique_frames": args.unique},
+        "config": {"workload": WORKLOADS["cfg2"] + " (CPU reference path)",
+                   "pairs_per_step": per_step, "unique_frames": len(imgs)},
         "cpu_baseline": {"value": value, "unit": "frame-pairs/s", "cores": threads, "kind": "port",
+                         "per_core": value / threads,
                          "sample": f"{per_step} pairs per step: {threads} independent single-thread streams x 2 pairs "
                                    f"(oracle restatement of detect3DLines + lineMatching + getTransform_PtsLines_ransac)"},
         "e2e": {"value": value, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -198,20 +262,57 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm ----
+# FP64-pipe / issue-slot utilisation of the dominant kernels from the committed ncu capture of this build
+# (profiles/r2_ncu_summary.md): what actually bounds the path (it is not HBM).
+NCU_PIPE = {}
+try:
+    NCU_PIPE = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_pipe.json")))
+except Exception:
+    pass
+
+
 def run_cuda(args, rank, world, local_rank):
+    wl = args.workload
+    big = wl == "cfg5"
+    Wd, Hd = (1280, 960) if big else (W, H)
+    b_frame = Wd * Hd * (3 + 4)
+    B = args.batch if args.batch > 0 else {"cfg2": 592, "cfg3": 148, "cfg4": 256, "cfg5": 74}[wl]
+    U = min(args.unique, B) if wl != "cfg4" else 257
+    # ---- inputs first: the render pool forks, CUDA must not be initialised yet
+    t_r = time.perf_counter()
+    pts = None
+    if wl == "cfg2":
+        imgs, deps, K = make_unique_frames(U, rank, world)
+    elif wl == "cfg3":
+        imgs, deps, K, pts = make_unique_frames(U, rank, world, traj="orbit", sift=True)
+    elif wl == "cfg4":   # 1 query + 256 keyframes sampled from the cfg-3 orbit; every rank renders only its block (+ the query on rank 0)
+        from lineslam_b200.shard import shard_pairs, pad_records
+        from lineslam_b200 import synth
+        lo, hi, per = shard_pairs(256, world, rank)
+        K = synth.camera_K(W, H)
+    else:
+        imgs, deps, K = make_unique_frames(U, rank, world, Wd, Hd, traj="orbit")
+    if wl == "cfg4":
+        import multiprocessing as mp
+        idxs = ([0] if rank == 0 else []) + [40 + 11 * k for k in range(lo, hi)]      # query = orbit frame 0, keyframes every 11th frame
+        workers = max(1, min((os.cpu_count() or 1) // max(world, 1), len(idxs)))
+        with mp.get_context("fork").Pool(workers) as pool:
+            res = pool.map(_render_one, [(2000, i, W, H, "orbit", False) for i in idxs])
+        imgs = np.stack([r[0] for r in res]); deps = np.stack([r[1] for r in res])
+    raw16, deps = tum_depth_planes(deps)
+    render_s = time.perf_counter() - t_r
+
     import torch
     import torch.distributed as dist
     from lineslam_b200 import api
-    from lineslam_b200.records import POSE_DTYPE
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    B, U = args.batch, args.unique
-    imgs, deps, K = make_unique_frames(U, rank)
-    ctx = api.Context(device=local_rank, max_batch=B, max_w=W, max_h=H)
+    p = api.default_params()
+    ctx = api.Context(params=p, device=local_rank, max_batch=max(B if wl != "cfg4" else len(imgs), 1), max_w=Wd, max_h=Hd)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
     if world > 1:  # library-owned NCCL communicator; the id travels over torch.distributed (plumbing)
@@ -219,54 +320,84 @@ def run_cuda(args, rank, world, local_rank):
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0], world, rank)
 
-    # host (pinned) and device copies of two batch layouts so that consecutive steps read different addresses
-    def batch_arrays(phase):
-        order = palindrome(U, B, phase)
-        return np.stack([imgs[i] for i in order]), np.stack([deps[i] for i in order])
-    nbuf = 2
-    host_i, host_d, dev_i, dev_d = [], [], [], []
-    for p in range(nbuf):
-        bi, bd = batch_arrays(p * B)
-        hi = torch.from_numpy(bi).pin_memory()
-        hd = torch.from_numpy(bd).pin_memory()
-        host_i.append(hi); host_d.append(hd)
-        dev_i.append(hi.cuda(non_blocking=False)); dev_d.append(hd.cuda(non_blocking=False))
-    torch.cuda.synchronize()
-
-    state = {"prev": None, "step": 0, "found": 0, "pairs": 0, "lines": 0}
+    state = {"prev": None, "step": 0, "found": 0, "pairs": 0, "lines": []}
     per_step = []
     ktime = {}
 
-    def one_step(e2e: bool):
-        s = state["step"]
-        b = s % nbuf
-        seeds = np.arange(1, B + 1, dtype=np.uint32) + s * B
-        if e2e:
-            frames = ctx.extract_batch(host_i[b].numpy(), host_d[b].numpy(), K, seeds)
-        else:
-            frames = ctx.extract_batch_dev(dev_i[b].data_ptr(), 3, dev_d[b].data_ptr(), B, W, H, K, seeds)
+    def note_ktimes(pair_stage):
         for k, v in ctx.kernel_times().items():
-            if v > 0 and not k.startswith(("match", "pose")):
+            if v > 0 and (k.startswith(("match", "pose", "relmotion")) == pair_stage):
                 ktime.setdefault(k, []).append(v)
-        trains = [state["prev"]] + frames[:-1] if state["prev"] is not None else [frames[0]] + frames[:-1]
-        ids = np.arange(B, dtype=np.int32) + s * B + 1
-        recs = ctx.match_pair_batch(frames, trains, ids, ids - 1, seeds)
-        for k, v in ctx.kernel_times().items():
-            if v > 0 and k.startswith(("match", "pose")):
-                ktime.setdefault(k, []).append(v)
-        if world > 1:
-            recs_all = ctx.allgather_poses(recs)     # graph-insert-time exchange
-            assert len(recs_all) == world * B
-        state["found"] += int(recs["found"].sum()); state["pairs"] += B
-        state["lines"] += sum(f.num_lines for f in frames[:4])
-        old = state["prev"]
-        state["prev"] = frames[-1]
-        for f in frames[:-1]:
-            f.free()
-        if old is not None:
-            old.free()
-        state["step"] += 1
-        return recs
+
+    if wl == "cfg4":
+        # ---- setup (untimed): every rank extracts its keyframe block once; rank 0 also the query
+        frames = ctx.extract_batch(imgs, deps, K, seeds=np.arange(1, len(imgs) + 1))
+        query0 = frames[0] if rank == 0 else None
+        keyframes = frames[1:] if rank == 0 else frames
+        n_loc = len(keyframes)
+        kf_ids = np.arange(lo, hi, dtype=np.int32) + 100
+        state["lines"] = [f.num_lines for f in frames]
+        pairs_per_step_total = 256
+
+        def one_step(e2e):
+            q = ctx.bcast_frame(query0, 0) if world > 1 else query0          # ncclBroadcast of the query record
+            recs = ctx.match_pair_batch([q] * n_loc, keyframes, np.full(n_loc, 1000, np.int32), kf_ids,
+                                        np.arange(n_loc, dtype=np.uint32) + 1 + lo)
+            note_ktimes(True)
+            if world > 1:
+                allr = ctx.allgather_poses(None, n_loc) if n_loc == per else ctx.allgather_poses(pad_records(recs, per))
+                assert len(allr) == world * per
+                if q is not query0:
+                    q.free()
+            state["found"] += int(recs["found"].sum()); state["pairs"] += n_loc
+            state["step"] += 1
+    else:
+        nbuf = 2
+        host_i, host_d16, dev_i, dev_d = [], [], [], []
+        for pb in range(nbuf):
+            order = palindrome(U, B, pb * B)
+            hi_ = torch.from_numpy(np.stack([imgs[i] for i in order])).pin_memory()
+            hd16 = torch.from_numpy(np.stack([raw16[i] for i in order]).view(np.int16)).pin_memory()
+            host_i.append(hi_); host_d16.append(hd16)
+            dev_i.append(hi_.cuda()); dev_d.append(torch.from_numpy(np.stack([deps[i] for i in order])).cuda())
+        orders = [palindrome(U, B, pb * B) for pb in range(nbuf)]
+        torch.cuda.synchronize()
+        pairs_per_step_total = world * B
+
+        def one_step(e2e):
+            s_ = state["step"]
+            b = s_ % nbuf
+            seeds = np.arange(1, B + 1, dtype=np.uint32) + s_ * B
+            if e2e:
+                frames = ctx.extract_batch(host_i[b].numpy(), host_d16[b].numpy().view(np.uint16), K, seeds)
+            else:
+                frames = ctx.extract_batch_dev(dev_i[b].data_ptr(), 3, dev_d[b].data_ptr(), B, Wd, Hd, K, seeds)
+            note_ktimes(False)
+            if pts is not None:      # cfg 3: the detectors' output enters as an input (Node::Node, src/node.cpp:219-310)
+                for f, i in zip(frames, orders[b]):
+                    f.set_points(pts[i][0], pts[i][1], root_sift=True)
+            trains = [state["prev"]] + frames[:-1] if state["prev"] is not None else [frames[0]] + frames[:-1]
+            ids = np.arange(B, dtype=np.int32) + s_ * B + 1
+            recs = ctx.match_pair_batch(frames, trains, ids, ids - 1, seeds)
+            note_ktimes(True)
+            if wl == "cfg5":         # levmar refine per edge (computeRelativeMotion_Ransac + optimizeRelmotion, motion.cpp:367-526)
+                for k in range(B):
+                    m = ctx.pair_matches(k, 0)
+                    if len(m) >= 3:
+                        ctx.relmotion_ransac(trains[k], frames[k], m, seed=int(seeds[k]))
+            if world > 1:
+                recs_all = ctx.allgather_poses(None, B)     # graph-insert-time exchange, from the device buffer
+                assert len(recs_all) == world * B
+            state["found"] += int(recs["found"].sum()); state["pairs"] += B
+            if len(state["lines"]) < 4 * B:
+                state["lines"] += [f.num_lines for f in frames]
+            old = state["prev"]
+            state["prev"] = frames[-1]
+            for f in frames[:-1]:
+                f.free()
+            if old is not None:
+                old.free()
+            state["step"] += 1
 
     def timed(e2e: bool, steps: int):
         for v in ktime.values():
@@ -294,31 +425,38 @@ def run_cuda(args, rank, world, local_rank):
             sampler.window(w0, time.time())
         gc.enable()
         ms = e0.elapsed_time(e1)
+        ms_rank = ms
         if world > 1:
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
             dist.barrier()
         st1 = ctx.stats()
-        return ms, wall, st0, st1
+        return ms, wall, st0, st1, ms_rank
 
     sampler = ClockSampler(local_rank) if rank == 0 and not os.environ.get("LSL_BENCH_NOCLOCKS") else None
     if sampler:
         sampler.start()
     for _ in range(max(args.warmup, 3)):
         one_step(False)
-    ms_dev, wall_dev, s0, s1 = timed(False, args.steps)
+    ms_dev, wall_dev, s0, s1, _ = timed(False, args.steps)
     steps_dev = list(per_step)
     kt = {k: float(np.mean(v)) for k, v in ktime.items() if v}
     found_frac = state["found"] / max(state["pairs"], 1)
     launches = int(s1.kernel_launches - s0.kernel_launches)
     one_step(True)  # warm the host-buffer path (pinned staging is the caller's here)
-    ms_e2e, wall_e2e, h0, h1 = timed(True, args.steps)
+    ms_e2e, wall_e2e, h0, h1, ms_e2e_rank = timed(True, args.steps)
     clocks = sampler.stop() if sampler else None
 
-    pairs_total = world * B * args.steps
+    pairs_total = pairs_per_step_total * args.steps
     value = pairs_total / (ms_dev / 1e3)
     e2e_value = pairs_total / (ms_e2e / 1e3)
+    h2d_step = int((h1.h2d_bytes - h0.h2d_bytes) // args.steps)
+    h2d_gbs = [h2d_step / (ms_e2e_rank / args.steps / 1e3) / 1e9]
+    if world > 1:   # per-rank H2D rate: shows a host-side (NUMA / PCIe root) limiter in the scaling run
+        g = [None] * world
+        dist.all_gather_object(g, h2d_gbs[0])
+        h2d_gbs = g
     if rank == 0:
         peaks = {}
         try:
@@ -327,36 +465,46 @@ def run_cuda(args, rank, world, local_rank):
             pass
         peak = _hbm_peak(peaks)
         dom = max(kt, key=kt.get) if kt else "lsd_region_kernel"
-        achieved = B * B_FRAME / (kt.get(dom, float("nan")) / 1e3) / 1e9
+        units = B if wl != "cfg4" else max(len(imgs) - (1 if rank == 0 else 0), 1)
+        alg_bytes = units * b_frame if wl != "cfg4" else int(np.sum(state["lines"])) * 1040
+        achieved = alg_bytes / (kt.get(dom, float("nan")) / 1e3) / 1e9
+        ln = np.array(state["lines"] if state["lines"] else [0])
         line = {
             "metric": METRIC, "value": value, "unit": "frame-pairs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak" if wl != "cfg4" else "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cfg2 fr1/xyz-shape synthetic stream 640x480, line-only odometry, 1 B200 per rank",
-                       "batch_frames_per_gpu": B, "unique_frames": U, "ransac_iters": 500,
-                       "l2": f"inputs larger than L2: {B * B_FRAME / 1e6:.0f} MB of RGB+depth per step per GPU, two alternating batch buffers",
-                       "pairs_found_frac": found_frac, "lines_per_frame": state["lines"] / max(4 * (state["step"]), 1)},
-            "e2e": {"value": e2e_value, "unit": "frame-pairs/s",
-                    "h2d_bytes_per_step": int((h1.h2d_bytes - h0.h2d_bytes) // args.steps),
-                    "d2h_bytes_per_step": int((h1.d2h_bytes - h0.d2h_bytes) // args.steps), "ms_per_step": ms_e2e / args.steps},
+            "config": {"workload": WORKLOADS[wl] + ", 1 B200 per rank", "image": f"{Wd}x{Hd}",
+                       ("batch_frames_per_gpu" if wl != "cfg4" else "pairs_per_step"): B, "unique_frames": U if wl != "cfg4" else 257,
+                       "ransac_iters": 500,
+                       "l2": (f"inputs larger than L2: {B * b_frame / 1e6:.0f} MB of RGB+depth per step per GPU, two alternating batch buffers"
+                              if wl != "cfg4" else "feature records of 256 keyframes + LM scratch (> 126 MB per step), flushed by the scratch writes"),
+                       "pairs_found_frac": found_frac, "lines_per_frame": float(ln.mean()),
+                       "lines_per_frame_spread": [int(ln.min()), int(np.percentile(ln, 50)), int(ln.max())],
+                       "render_s": round(render_s, 1)},
+            "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d_step,
+                    "d2h_bytes_per_step": int((h1.d2h_bytes - h0.d2h_bytes) // args.steps), "ms_per_step": ms_e2e / args.steps,
+                    "h2d_gbs_per_rank": [round(float(x), 2) for x in h2d_gbs],
+                    "input": "pinned host RGB u8 + 16-bit depth (TUM PNG values), converted on the device" if wl != "cfg4" else "features resident (pre-distributed keyframes); query record broadcast"},
             "gpu_launches": launches,
             "host_ms_each_step": {"value": steps_dev, "e2e": list(per_step)},
             "kernel_ms_per_step": kt,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
-                         "traffic": (NCU_DRAM_BYTES_PER_FRAME[dom] * B if dom in NCU_DRAM_BYTES_PER_FRAME else None),
-                         "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r1_final2_ncu_full_raw_b592.csv)",
-                         "algorithmic_bytes": B * B_FRAME,
-                         "note": f"algorithmic bytes = {B} frames x {B_FRAME} B (RGB u8 + depth f32) per launch / CUDA-event time of "
+                         "traffic": (NCU_PIPE.get(dom, {}).get("dram_bytes_per_frame", 0) * units or None) if wl != "cfg4" else None,
+                         "traffic_unit": "bytes per launch (ncu dram read + write of this build, profiles/r2_ncu_pipe.json)",
+                         "algorithmic_bytes": alg_bytes,
+                         "actual_bound": {"kind": "fp64 dependency latency", "kernel": dom, **{k: v for k, v in NCU_PIPE.get(dom, {}).items() if k != "dram_bytes_per_frame"},
+                                          "source": "profiles/r2_ncu_pipe.json (ncu --set full of this build, batch 592)"},
+                         "note": f"algorithmic bytes = {units} frames x {b_frame} B (RGB u8 + depth f32) per launch / CUDA-event time of "
                                  f"{dom}; peak = MEASURED_PEAKS.json hbm_gbs ({'measured' if peaks else 'fallback 6650 GB/s of B200_PROFILING.md'}); "
                                  f"the path is FP64-latency / dependency bound (100 LM iterations per line, sequential region "
-                                 f"growing), not HBM bound: see DESIGN.md section 4 and profiles/r1_summary.md"},
+                                 f"growing), not HBM bound: see DESIGN.md section 4 and profiles/r2_summary.md"},
             "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and wl == "cfg2":
             threads = os.cpu_count() or 1
             pps, sec, pairs, _ = cpu_pairs_per_sec(imgs, deps, K, threads * 8, threads)
-            line["cpu_baseline"] = {"value": pps, "unit": "frame-pairs/s", "cores": threads, "kind": "port",
+            line["cpu_baseline"] = {"value": pps, "unit": "frame-pairs/s", "cores": threads, "kind": "port", "per_core": pps / threads,
                                     "sample": f"{pairs} pairs of the same stream: {threads} independent single-thread streams "
                                               f"of the oracle restatement, {sec:.1f} s of wall time"}
         print(json.dumps(line), flush=True)
@@ -371,8 +519,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("LSL_BENCH_BATCH", 592)), help="frames per step per GPU")
-    ap.add_argument("--unique", type=int, default=12, help="distinct rendered frames (tiled palindromically into a batch)")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("LSL_BENCH_BATCH", 0)), help="frames per step per GPU (0: the workload's default, 592 for cfg2)")
+    ap.add_argument("--unique", type=int, default=148, help="distinct consecutive rendered frames of the stream (tiled palindromically into a batch)")
+    ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS), help="BASELINE.json config (cfg2 = the metric's config, the default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

@@ -182,7 +182,8 @@ int lsl_match_pair_batch(lsl_ctx* ctx, int npairs, const lsl_frame* const* queri
 int lsl_pair_matches(lsl_ctx* ctx, int pair, int what, lsl_match* out, int cap, int* n);
 
 /* Graph-insert-time exchange: all ranks contribute nlocal records and receive
- * nranks*nlocal. nccl_comm is an ncclComm_t created by the host; NCCL is resolved with dlopen. */
+ * nranks*nlocal. nccl_comm is an ncclComm_t created by the host; NCCL is resolved with dlopen. local_recs == NULL: the
+ * first nlocal records of the last lsl_match_pair_batch are sent straight from the device buffer the pose kernel wrote. */
 int lsl_allgather_poses(lsl_ctx* ctx, void* nccl_comm, int nranks, const lsl_pose_rec* local_recs, int nlocal,
                         lsl_pose_rec* all_recs);
 /* Communicator owned by the library (the reference has no communication layer; this is the plumbing the
@@ -191,6 +192,13 @@ int lsl_allgather_poses(lsl_ctx* ctx, void* nccl_comm, int nranks, const lsl_pos
  * then uses it. */
 int lsl_comm_unique_id(void* id128);
 int lsl_comm_init(lsl_ctx* ctx, const void* id128, int nranks, int rank);
+
+/* Loop-closure batches sharded over ranks (BASELINE config 4): the keyframes' features are pre-distributed
+ * block-wise, the ONE query frame's line records (~0.27 MB) are broadcast from `root` to every rank with ncclBroadcast over
+ * the library's communicator (lsl_comm_init). On the root `frame` is the extracted query and *out == frame; on the other
+ * ranks `frame` is ignored and *out is a new frame holding the records (free it with lsl_frame_free). Point features are
+ * not carried. Device to device: the records never visit the host. */
+int lsl_bcast_frame(lsl_ctx* ctx, int root, lsl_frame* frame, lsl_frame** out);
 
 /* Stage counters of the last call (segments, lines, matches, LM iterations, kernel launches). */
 typedef struct lsl_stats {

@@ -124,7 +124,12 @@ class Context:
         _check(lib().lsl_comm_init(self._h, C.c_char_p(uid), nranks, rank), self._h)
         self.nranks, self.rank = nranks, rank
 
-    def allgather_poses(self, local_recs):
+    def allgather_poses(self, local_recs=None, nlocal=None):
+        """All ranks' pose records. local_recs None: the records of the last match_pair_batch, gathered from the device."""
+        if local_recs is None:
+            out = np.zeros(nlocal * self.nranks, POSE_DTYPE)
+            _check(lib().lsl_allgather_poses(self._h, None, 0, None, nlocal, ptr(out)), self._h)
+            return out
         loc = np.ascontiguousarray(local_recs, POSE_DTYPE)
         out = np.zeros(len(loc) * self.nranks, POSE_DTYPE)
         _check(lib().lsl_allgather_poses(self._h, None, 0, ptr(loc), len(loc), ptr(out)), self._h)
@@ -190,6 +195,14 @@ class Context:
         n = C.c_int(0)
         _check(lib().lsl_match_points(self._h, query._h, train._h, C.c_uint32(seed), ptr(out), cap, C.byref(n)), self._h)
         return out[:n.value].copy()
+
+    def bcast_frame(self, frame, root: int = 0):
+        """ncclBroadcast of the query frame's line records from `root` (loop-closure batches sharded over ranks)."""
+        out = C.c_void_p()
+        _check(lib().lsl_bcast_frame(self._h, root, frame._h if frame is not None else None, C.byref(out)), self._h)
+        if frame is not None and out.value == frame._h.value:
+            return frame
+        return Frame(self, out)
 
     def set_camera(self, fx: float, dt: float = 0.0):
         _check(lib().lsl_ctx_set_camera(self._h, C.c_double(fx), C.c_double(dt)), self._h)

@@ -127,6 +127,7 @@ extern "C" int lsl_ctx_create(lsl_ctx** out, const lsl_params* params, int cuda_
   ctx->cam_fx = 525.0; ctx->cam_dt = 0.0;   // K(0,0) of src/openni_listener.cpp:1256; replaced by the K of the last extract call
   ctx->h_pin = nullptr; ctx->h_pin_bytes = 0;
   ctx->d_depth16 = nullptr; ctx->d_depth16_bytes = 0;
+  ctx->d_gather = nullptr; ctx->d_gather_bytes = 0;
   memset(&ctx->stats, 0, sizeof(ctx->stats));
   memset(&ctx->dims, 0, sizeof(ctx->dims));
   memset(ctx->kran, 0, sizeof(ctx->kran));
@@ -179,6 +180,7 @@ extern "C" void lsl_ctx_destroy(lsl_ctx* ctx) {
   free_pair_ws(ctx);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   if (ctx->d_depth16) cudaFree(ctx->d_depth16);
+  if (ctx->d_gather) cudaFree(ctx->d_gather);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev3);
   for (int k = 0; k < LSL_K_COUNT; ++k) { cudaEventDestroy(ctx->kev[k][0]); cudaEventDestroy(ctx->kev[k][1]); }
   cudaStreamDestroy(ctx->own_stream);
@@ -979,30 +981,78 @@ static void nccl_teardown(lsl_ctx* ctx) {
 }
 extern "C" int lsl_allgather_poses(lsl_ctx* ctx, void* nccl_comm, int nranks, const lsl_pose_rec* local_recs, int nlocal,
                                    lsl_pose_rec* all_recs) {
-  if (!ctx || !local_recs || !all_recs || nlocal < 1) return LSL_ERR_ARG;
+  if (!ctx || !all_recs || nlocal < 1) return LSL_ERR_ARG;
+  LSL_ENTER(ctx);
   void* comm = nccl_comm ? nccl_comm : ctx->nccl_comm;
   if (!nccl_comm) nranks = ctx->nccl_nranks;
   if (!comm || nranks < 1) { ctx->err = "no communicator: call lsl_comm_init or pass an ncclComm_t"; return LSL_ERR_NCCL; }
-  LSL_ENTER(ctx);
+  // local_recs == NULL: the records of the last lsl_match_pair_batch are gathered straight from the device buffer the
+  // pose kernel wrote (no host round trip on the send side)
+  if (!local_recs && (size_t)nlocal > ctx->pw.h_pairs.size()) { ctx->err = "no device-resident records of that count"; return LSL_ERR_ARG; }
   void* h = nccl_open(ctx);
   if (!h) return LSL_ERR_NCCL;
   nccl_allgather_fn ag = (nccl_allgather_fn)dlsym(h, "ncclAllGather");
   if (!ag) return LSL_ERR_NCCL;
   const size_t lb = sizeof(lsl_pose_rec) * (size_t)nlocal;
-  uint8_t* d = nullptr;
-  LSL_CUDA(cudaMallocAsync((void**)&d, lb * (size_t)(nranks + 1), ctx->stream));
-  LSL_CUDA(cudaMemcpyAsync(d, local_recs, lb, cudaMemcpyHostToDevice, ctx->stream));
-  int rc = ag(d, d + lb, lb, /* ncclChar */ 0, comm, ctx->stream);
+  const size_t need = lb * (size_t)(nranks + 1);
+  if (ctx->d_gather_bytes < need) {   // persistent exchange buffer (grown, never shrunk)
+    LSL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_gather) cudaFree(ctx->d_gather);
+    ctx->d_gather = nullptr; ctx->d_gather_bytes = 0;
+    LSL_CUDA(cudaMalloc((void**)&ctx->d_gather, need * 2));
+    ctx->d_gather_bytes = need * 2;
+  }
+  uint8_t* d = ctx->d_gather;
+  const void* src = ctx->pw.recs;
+  if (local_recs) { LSL_CUDA(cudaMemcpyAsync(d, local_recs, lb, cudaMemcpyHostToDevice, ctx->stream)); src = d; ctx->stats.h2d_bytes += lb; }
+  int rc = ag(src, d + lb, lb, /* ncclChar */ 0, comm, ctx->stream);
   if (rc != 0) {
     nccl_errstr_fn es = (nccl_errstr_fn)dlsym(h, "ncclGetErrorString");
     ctx->err = std::string("ncclAllGather: ") + (es ? es(rc) : "error");
-    cudaFreeAsync(d, ctx->stream);
     return LSL_ERR_NCCL;
   }
   LSL_CUDA(cudaMemcpyAsync(all_recs, d + lb, lb * (size_t)nranks, cudaMemcpyDeviceToHost, ctx->stream));
-  LSL_CUDA(cudaFreeAsync(d, ctx->stream));
   LSL_CUDA(cudaStreamSynchronize(ctx->stream));
-  ctx->stats.h2d_bytes += lb; ctx->stats.d2h_bytes += lb * nranks;
+  ctx->stats.d2h_bytes += lb * nranks;
+  return LSL_OK;
+}
+
+typedef int (*nccl_bcast_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+extern "C" int lsl_bcast_frame(lsl_ctx* ctx, int root, lsl_frame* frame, lsl_frame** out) {
+  if (!ctx || !out) return LSL_ERR_ARG;
+  LSL_ENTER(ctx);
+  if (!ctx->nccl_comm) { ctx->err = "no communicator: call lsl_comm_init first"; return LSL_ERR_NCCL; }
+  if (root < 0 || root >= ctx->nccl_nranks) return LSL_ERR_ARG;
+  const bool is_root = ctx->nccl_rank == root;
+  if (is_root && !frame) return LSL_ERR_ARG;
+  void* h = nccl_open(ctx);
+  nccl_bcast_fn bc = h ? (nccl_bcast_fn)dlsym(h, "ncclBroadcast") : nullptr;
+  if (!bc) return LSL_ERR_NCCL;
+  cudaStream_t st = ctx->stream;
+  int32_t* d_n = nullptr;
+  LSL_CUDA(cudaMallocAsync((void**)&d_n, sizeof(int32_t), st));
+  int32_t n = is_root ? frame->nlines : 0;
+  if (is_root) LSL_CUDA(cudaMemcpyAsync(d_n, &n, sizeof(n), cudaMemcpyHostToDevice, st));
+  int rc = bc(d_n, d_n, sizeof(int32_t), /* ncclChar */ 0, root, ctx->nccl_comm, st);
+  if (rc == 0) {
+    LSL_CUDA(cudaMemcpyAsync(&n, d_n, sizeof(n), cudaMemcpyDeviceToHost, st));
+    LSL_CUDA(cudaStreamSynchronize(st));
+  }
+  cudaFreeAsync(d_n, st);
+  if (rc != 0 || n < 0 || n > LSL_MAX_LINES) { ctx->err = "ncclBroadcast (line count) failed"; return LSL_ERR_NCCL; }
+  lsl_frame* fr = frame;
+  if (!is_root) {
+    fr = new (std::nothrow) lsl_frame();
+    if (!fr) return LSL_ERR_ARG;
+    fr->ctx = ctx; fr->nlines = n; fr->nsegs = 0; fr->d_lines = nullptr; fr->blk = nullptr; fr->have_dbg = false; fr->have_host = false;
+    if (n) LSL_CUDA(cudaMalloc((void**)&fr->d_lines, sizeof(lsl_line_rec) * (size_t)n));
+  }
+  if (n) {
+    rc = bc(fr->d_lines, fr->d_lines, sizeof(lsl_line_rec) * (size_t)n, 0, root, ctx->nccl_comm, st);
+    if (rc != 0) { ctx->err = "ncclBroadcast (line records) failed"; if (!is_root) lsl_frame_free(fr); return LSL_ERR_NCCL; }
+    LSL_CUDA(cudaStreamSynchronize(st));
+  }
+  *out = fr;
   return LSL_OK;
 }
 

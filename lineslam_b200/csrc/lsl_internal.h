@@ -216,6 +216,7 @@ struct lsl_ctx {
   LslHybWork hw;
   double cam_fx, cam_dt;     // focal length / asynch time used by the point-edge information (compPt3dCov)
   uint8_t* h_pin; size_t h_pin_bytes;   // pinned staging
+  uint8_t* d_gather; size_t d_gather_bytes;      // pose exchange buffer of lsl_allgather_poses
   uint16_t* d_depth16; size_t d_depth16_bytes;   // raw 16-bit depth planes of lsl_extract_batch_u16 (allocated on first use)
   std::string err;
   lsl_stats stats;
