@@ -170,13 +170,15 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
   }
   __syncthreads();
   const double w = PP.line_weight_g2o;
-  double lambda = 0, ni = 2;
+  double lambda = 0, ni = 2, currentChi = 0;
   const double tau = 1e-5, lowS = 1. / 3., upS = 2. / 3.;
   const double del = 1e-9, scalar = 1 / (2 * del);
   for (int it = 0; it < iterations; ++it) {
     Iso w2n;
     iso_inv(cam1, w2n);
-    chi2_terms(V, md_all, n, w2n, ident, V.L, PP);
+    // chi2 of the current estimate: iteration 0 computes it; every later iteration follows an accepted step, whose trial
+    // chi2 (tempChi) IS this sum — same L, same pose, same edge order, same adds — so it is carried over, not recomputed
+    if (it == 0) chi2_terms(V, md_all, n, w2n, ident, V.L, PP);
     PT(4);
     // the twelve perturbed camera poses (cam1 (+) +-delta e_d)^-1 are the same for every match: once per iteration
     if (tid < 12) {
@@ -285,14 +287,14 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
     // ordered sums over the matches: Hpp (36), bp (6) on threads 0..41; chi2 on thread 64
     if (tid < 36) s_S[tid] = chain_sum<false>(0.0, V.contrib + (size_t)tid * V.cap, 1, n);
     else if (tid < 42) s_S[tid] = chain_sum<true>(0.0, V.contrib + (size_t)tid * V.cap, 1, n);
-    else if (tid == 64) s_red[0] = chain_sum<false>(0.0, V.chi, 1, 2 * n);
+    else if (tid == 64 && it == 0) s_red[0] = chain_sum<false>(0.0, V.chi, 1, 2 * n);
     __syncthreads();
     double Hpp[36], bp[6];
 #pragma unroll
     for (int k = 0; k < 36; ++k) Hpp[k] = s_S[k];
 #pragma unroll
     for (int k = 0; k < 6; ++k) bp[k] = s_S[36 + k];
-    double currentChi = s_red[0];
+    if (it == 0) currentChi = s_red[0];
     __syncthreads();
     if (it == 0) {  // computeLambdaInit: tau * max |diagonal entry|
       double md_ = 0;
