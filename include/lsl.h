@@ -213,6 +213,11 @@ int lsl_last_timing(const lsl_ctx* ctx, float* ms_total, float* ms_region_grow);
 int lsl_kernel_times(const lsl_ctx* ctx, float* ms, int cap, int* n);
 const char* lsl_kernel_name(int i);
 
+/* Tensor-core pre-filter of lsl_match_points / the point half of lsl_match_pair_batch (f32 rows of 8..128 floats, multiple
+ * of 8; LSL_MATCH_TC=0 in the environment selects the exact scalar kernel): out[0] exact distance evaluations made by the
+ * refine step, out[1] query rows that overflowed their candidate list and were rescanned in full, out[2] query rows. */
+int lsl_match_tc_stats(lsl_ctx* ctx, int64_t out[3], int reset);
+
 /* Stage-wise read-back for parity tests (frame 0 of the last extract call):
  * what: 0 gray u8[H*W], 1 scaled f64[sh*sw], 2 angles f64, 3 modgrad f64, 4 seeds i32 (x|y<<16),
  *       5 gx i16[H*W], 6 gy i16[H*W]. Returns the number of elements copied (or <0). */

@@ -204,6 +204,12 @@ class Context:
             return frame
         return Frame(self, out)
 
+    def match_tc_stats(self, reset: bool = True):
+        """(exact evaluations, rows rescanned in full, rows) of the tensor-core pre-filtered point matcher."""
+        out = np.zeros(3, np.int64)
+        _check(lib().lsl_match_tc_stats(self._h, ptr(out), int(reset)), self._h)
+        return tuple(int(v) for v in out)
+
     def set_camera(self, fx: float, dt: float = 0.0):
         _check(lib().lsl_ctx_set_camera(self._h, C.c_double(fx), C.c_double(dt)), self._h)
 

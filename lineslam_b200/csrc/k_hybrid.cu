@@ -12,6 +12,7 @@
 // The operation order follows oracle/oracle_pair.cpp (refine_pose_hybrid, getTransform_PtsLines_ransac); with no
 // point matches the result is identical to k_pair.cu's line-only pose_kernel.
 #include "pair_common.cuh"
+#include <stdlib.h>
 #include "shared/lsl_points.h"
 
 #define PMD_STRIDE 22   // doubles per point match: q xyz1 + t xyz1 (8 floats = 4 doubles) | Omega_q 9 | Omega_t 9
@@ -912,9 +913,17 @@ int lsl_launch_match_points(lsl_ctx* ctx, int npairs, int max_nq, int dim, int k
   LSL_KSTART(ctx, LSL_K_MATCHPTS);
   if (max_nq > 0) {
     dim3 g((max_nq + 7) / 8, npairs);
+    int tc_used = 0;
     if (kind == 1) match_points_hamming_kernel<<<g, 256, 8 * dim, ctx->stream>>>(h.d_ppairs, (Knn2*)h.knn);
-    else match_points_kernel<<<g, 256, 8 * dim * sizeof(float), ctx->stream>>>(h.d_ppairs, (Knn2*)h.knn);
-    ctx->stats.kernel_launches += 1;
+    else {
+      // f32 rows: the distance matrix goes through the tensor cores (tcgen05 tf32 pre-filter + exact re-evaluation of the
+      // candidates, k_match_tc.cu) unless LSL_MATCH_TC=0 or the row length does not fit that path
+      static int want_tc = -1;
+      if (want_tc < 0) { const char* e = getenv("LSL_MATCH_TC"); want_tc = (e && e[0] == '0') ? 0 : 1; }
+      if (want_tc) { int rc = lsl_launch_match_points_tc(ctx, npairs, max_nq, dim, &tc_used); if (rc) return rc; }
+      if (!tc_used) match_points_kernel<<<g, 256, 8 * dim * sizeof(float), ctx->stream>>>(h.d_ppairs, (Knn2*)h.knn);
+    }
+    if (!tc_used) ctx->stats.kernel_launches += 1;
   }
   match_points_accept_kernel<<<npairs, 32, 0, ctx->stream>>>(h.d_ppairs, ctx->pw.d_pairs, (const Knn2*)h.knn, h.pmatches, h.npmatch,
                                                             h.hs.rng, ctx->P.nn_distance_ratio);

@@ -105,6 +105,10 @@ static void free_pair_ws(lsl_ctx* ctx) {
   memset(&h.hs, 0, sizeof(h.hs));
   h.d_ppairs = nullptr; h.knn = nullptr; h.pmatches = nullptr; h.npmatch = nullptr;
   h.cap_pairs = h.cap_pm = h.cap_knn = 0; h.max_iter = 0; h.last_hybrid = false;
+  if (h.tc_cand) cudaFree(h.tc_cand);
+  if (h.tc_cnt) cudaFree(h.tc_cnt);
+  if (h.tc_stats) cudaFree(h.tc_stats);
+  h.tc_cand = nullptr; h.tc_cnt = nullptr; h.tc_stats = nullptr; h.cap_tc = 0;
 }
 
 extern "C" int lsl_ctx_create(lsl_ctx** out, const lsl_params* params, int cuda_device, int max_batch, int max_w, int max_h) {
@@ -124,6 +128,7 @@ extern "C" int lsl_ctx_create(lsl_ctx** out, const lsl_params* params, int cuda_
   memset(&ctx->hw.hs, 0, sizeof(ctx->hw.hs));
   ctx->hw.d_ppairs = nullptr; ctx->hw.knn = nullptr; ctx->hw.pmatches = nullptr; ctx->hw.npmatch = nullptr;
   ctx->hw.cap_pairs = ctx->hw.cap_pm = ctx->hw.cap_knn = 0; ctx->hw.max_iter = 0; ctx->hw.last_hybrid = false;
+  ctx->hw.tc_cand = nullptr; ctx->hw.tc_cnt = nullptr; ctx->hw.tc_stats = nullptr; ctx->hw.cap_tc = 0;
   ctx->cam_fx = 525.0; ctx->cam_dt = 0.0;   // K(0,0) of src/openni_listener.cpp:1256; replaced by the K of the last extract call
   ctx->h_pin = nullptr; ctx->h_pin_bytes = 0;
   ctx->d_depth16 = nullptr; ctx->d_depth16_bytes = 0;

@@ -138,6 +138,8 @@ struct LslHybWork {
   std::vector<LslPairPts> h_ppairs;
   std::vector<int32_t> h_npmatch, h_npinl, h_nprinl;
   bool last_hybrid;     // the last pair call ran the point + line path
+  // tensor-core pre-filter of featureMatching (k_match_tc.cu): candidate train rows per query row
+  int32_t* tc_cand; int32_t* tc_cnt; void* tc_stats; size_t cap_tc;
 };
 
 // ---- computeRelativeMotion_Ransac scratch (k_hybrid.cu:relmotion_kernel), allocated per call ----
@@ -251,5 +253,6 @@ int lsl_launch_match(lsl_ctx* ctx, int npairs);
 int lsl_launch_pose(lsl_ctx* ctx, int npairs);
 int lsl_launch_match_points(lsl_ctx* ctx, int npairs, int max_nq, int dim, int kind);
 int lsl_launch_rootsift(lsl_ctx* ctx, float* d_desc, int n, int dim);
+int lsl_launch_match_points_tc(lsl_ctx* ctx, int npairs, int max_nq, int dim, int* used);
 int lsl_launch_pose_hybrid(lsl_ctx* ctx, int npairs, double fx, double dt);
 int lsl_launch_relmotion(lsl_ctx* ctx, int npairs, RmScratch rs);

@@ -179,3 +179,58 @@ def test_orb_hamming_branch_and_device_rootsift(api, oracle, hyb):
     assert len(ref) > 100 and np.array_equal(got, ref)
     for f in (fq, ft, fa, fb):
         f.free()
+
+
+def test_tensor_core_prefilter_gives_the_exact_matches(api, oracle):
+    """N2 (north star: tensor cores for the descriptor-distance matrix): featureMatching runs G = Q T^T on tcgen05 (tf32, TMEM
+    accumulator) as a pre-filter and re-evaluates the surviving candidates in OpenCV's f32 summation order — the match lists
+    (indices, ratio + jitter distances) must equal the oracle's exhaustive scan, including on data built to sit inside the
+    tf32 error band: near-duplicate rows, exact ties, big norms, zero rows, ragged sizes."""
+    p = api.default_params()
+    p.nn_distance_ratio = 0.97          # accept nearly everything: exposes any error in the SECOND nearest distance too
+    ctx = api.Context(params=p, max_batch=1, max_w=64, max_h=64)
+    empty = np.zeros(0, api.LINE_DTYPE) if hasattr(api, "LINE_DTYPE") else None
+    rng = np.random.default_rng(77)
+
+    def frames(q, t):
+        from lineslam_b200.records import LINE_DTYPE
+        fq = ctx.frame_from_lines(np.zeros(0, LINE_DTYPE)).set_points(np.ones((len(q), 4), np.float32), q)
+        ft = ctx.frame_from_lines(np.zeros(0, LINE_DTYPE)).set_points(np.ones((len(t), 4), np.float32), t)
+        return fq, ft
+
+    def unit(x):
+        x = np.abs(x).astype(np.float32)
+        return np.sqrt(x / x.sum(1, keepdims=True)).astype(np.float32)
+
+    cases = []
+    for dim in (128, 64, 72, 8):
+        q = unit(rng.random((600, dim)) ** 3); t = unit(rng.random((600, dim)) ** 3)
+        t[:350] = unit(q[rng.permutation(600)[:350]] ** 2 + rng.normal(0, 0.003, (350, dim)) ** 2)
+        cases.append((f"rootsift{dim}", q, t))
+    # near duplicates far inside the tf32 band: 1e-6 .. 1e-4 perturbations of the same row, plus exact ties
+    base = unit(rng.random((1, 128)))
+    t = np.repeat(base, 300, 0) + (rng.normal(0, 1, (300, 128)) * np.logspace(-7, -4, 300)[:, None]).astype(np.float32)
+    t = np.abs(t).astype(np.float32); t[17] = t[4]; t[250] = t[3]
+    q = np.concatenate([base + np.float32(1e-5), unit(rng.random((130, 128)))]).astype(np.float32)
+    cases.append(("near_duplicates", q, t))
+    # big norms, mixed scales, zero rows, ragged sizes
+    q = (rng.normal(0, 1, (129, 128)) * rng.choice([0.01, 1.0, 100.0], (129, 1))).astype(np.float32); q[5] = 0
+    t = (rng.normal(0, 1, (131, 128)) * rng.choice([0.01, 1.0, 100.0], (131, 1))).astype(np.float32); t[7] = 0
+    t[:60] = q[:60] * np.float32(1.001)
+    cases.append(("mixed_scales", q, t))
+    cases.append(("tiny", unit(rng.random((1, 64))), unit(rng.random((2, 64)))))
+    cases.append(("one_train_row", unit(rng.random((5, 64))), unit(rng.random((1, 64)))))
+    ctx.match_tc_stats(reset=True)
+    total_pairs = 0
+    for name, q, t in cases:
+        fq, ft = frames(q, t)
+        for seed in (1, 9):
+            got = ctx.match_points(fq, ft, seed)
+            ref = oracle.featureMatching(q, t, p.nn_distance_ratio, seed)
+            assert len(got) == len(ref), (name, len(got), len(ref))
+            assert np.array_equal(got, ref), name
+        total_pairs += 2 * len(q) * len(t)
+        fq.free(); ft.free()
+    evals, full_rows, rows = ctx.match_tc_stats()
+    assert rows > 0 and evals < 0.5 * total_pairs        # the pre-filter removed most exact evaluations even on this adversarial mix
+    ctx.close()
