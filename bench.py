@@ -374,17 +374,14 @@ def run_cuda(args, rank, world, local_rank):
                 frames = ctx.extract_batch_dev(dev_i[b].data_ptr(), 3, dev_d[b].data_ptr(), B, Wd, Hd, K, seeds)
             note_ktimes(False)
             if pts is not None:      # cfg 3: the detectors' output enters as an input (Node::Node, src/node.cpp:219-310)
-                for f, i in zip(frames, orders[b]):
-                    f.set_points(pts[i][0], pts[i][1], root_sift=True)
+                ctx.set_points_batch(frames, [pts[i][0] for i in orders[b]], [pts[i][1] for i in orders[b]], root_sift=True)
             trains = [state["prev"]] + frames[:-1] if state["prev"] is not None else [frames[0]] + frames[:-1]
             ids = np.arange(B, dtype=np.int32) + s_ * B + 1
             recs = ctx.match_pair_batch(frames, trains, ids, ids - 1, seeds)
             note_ktimes(True)
             if wl == "cfg5":         # levmar refine per edge (computeRelativeMotion_Ransac + optimizeRelmotion, motion.cpp:367-526)
-                for k in range(B):
-                    m = ctx.pair_matches(k, 0)
-                    if len(m) >= 3:
-                        ctx.relmotion_ransac(trains[k], frames[k], m, seed=int(seeds[k]))
+                ctx.relmotion_batch(B)
+                note_ktimes(True)
             if world > 1:
                 recs_all = ctx.allgather_poses(None, B)     # graph-insert-time exchange, from the device buffer
                 assert len(recs_all) == world * B

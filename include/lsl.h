@@ -137,6 +137,10 @@ int lsl_frame_set_points(lsl_ctx* ctx, lsl_frame* f, const float* xyz1, const fl
  *                   SIFT / SURF rows. Ignored for u8 rows (the reference does not condition ORB). */
 int lsl_frame_set_points_ex(lsl_ctx* ctx, lsl_frame* f, const float* xyz1, const void* desc, int n, int dim, int desc_is_u8,
                             int root_sift);
+/* The same for n frames at once (the Node constructors of a batch): xyz1 / desc hold the frames' rows back to back,
+ * counts[i] rows for frames[i]. One device block and two uploads for the whole batch. */
+int lsl_frames_set_points_batch(lsl_ctx* ctx, int n, lsl_frame* const* frames, const float* xyz1, const void* desc,
+                                const int32_t* counts, int dim, int desc_is_u8, int root_sift);
 /* Copies the frame's (conditioned) descriptor rows back: n x dim floats, or n x dim bytes for u8 rows. */
 int lsl_frame_descriptors(lsl_ctx* ctx, const lsl_frame* f, void* dst, int64_t cap_bytes);
 int lsl_frame_num_points(const lsl_frame* f);
@@ -167,6 +171,11 @@ int lsl_pose_ransac(lsl_ctx* ctx, const lsl_frame* train, const lsl_frame* query
 int lsl_relmotion_ransac(lsl_ctx* ctx, const lsl_frame* train, const lsl_frame* query, const lsl_match* ln_matches, int nln,
                          uint32_t seed, double R[9], double t[3], int32_t* conset, int cap, int* n_conset, int* lm_calls,
                          int* have);
+
+/* lsl_relmotion_ransac for every pair of the last lsl_match_pair_batch, on the line matches that call left on the device
+ * ("levmar LM refine per edge", BASELINE config 5): Rt[i] = R (9, row-major) then t (3), info[i] = {consensus size,
+ * optimizeRelmotion calls, have, 0}; seeds are the pairs' seeds. One launch. */
+int lsl_relmotion_batch(lsl_ctx* ctx, int npairs, double* Rt, int32_t* info);
 
 /* Node::matchNodePair (src/node.h:107, src/node.cpp:1494-1545) for npairs independent pairs, the
  * unit GraphManager::nodeComparisons maps over (src/graph_manager.cpp:555): featureMatching (when both frames

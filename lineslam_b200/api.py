@@ -236,6 +236,24 @@ class Context:
                                           ptr(R), ptr(t), ptr(con), len(con), C.byref(n), C.byref(calls), C.byref(have)), self._h)
         return dict(R=R.reshape(3, 3), t=t, conset=con[:n.value].copy(), lm_calls=calls.value, have=bool(have.value))
 
+    def set_points_batch(self, frames, xyz1_list, desc_list, root_sift: bool = False):
+        """lsl_frames_set_points_batch: point features of many frames in one device block / two uploads."""
+        n = len(frames)
+        counts = np.array([len(x) for x in xyz1_list], np.int32)
+        u8 = np.asarray(desc_list[0]).dtype == np.uint8
+        x = np.ascontiguousarray(np.concatenate([np.asarray(a, np.float32).reshape(-1, 4) for a in xyz1_list]), np.float32)
+        d = np.ascontiguousarray(np.concatenate([np.asarray(a).reshape(len(a), -1) for a in desc_list]), np.uint8 if u8 else np.float32)
+        fr = (C.c_void_p * n)(*[f._h.value for f in frames])
+        _check(lib().lsl_frames_set_points_batch(self._h, n, fr, ptr(x), ptr(d), ptr(counts), d.shape[1], int(u8), int(root_sift)), self._h)
+        for f in frames:
+            f._pdim, f._pu8 = d.shape[1], bool(u8)
+
+    def relmotion_batch(self, npairs: int):
+        """lsl_relmotion_batch on the pairs of the last match_pair_batch: (R [n,3,3], t [n,3], info [n,4])."""
+        Rt = np.zeros((npairs, 12)); info = np.zeros((npairs, 4), np.int32)
+        _check(lib().lsl_relmotion_batch(self._h, npairs, ptr(Rt), ptr(info)), self._h)
+        return Rt[:, :9].reshape(npairs, 3, 3), Rt[:, 9:], info
+
     def match_pair_batch(self, queries, trains, id_query, id_train, seeds):
         """Node::matchNodePair for a batch of independent pairs (graph_manager.cpp:555). Returns POSE_DTYPE[n]."""
         n = len(queries)

@@ -124,7 +124,7 @@ extern "C" int lsl_ctx_create(lsl_ctx** out, const lsl_params* params, int cuda_
   ctx->wk_block = nullptr;
   memset(&ctx->pw.sc, 0, sizeof(ctx->pw.sc));
   ctx->pw.d_pairs = nullptr; ctx->pw.D = nullptr; ctx->pw.matches = nullptr; ctx->pw.nmatch = nullptr; ctx->pw.recs = nullptr;
-  ctx->pw.cap_pairs = ctx->pw.cap_m = ctx->pw.cap_d = 0;
+  ctx->pw.cap_pairs = ctx->pw.cap_m = ctx->pw.cap_d = 0; ctx->pw.last_tot_m = 0;
   memset(&ctx->hw.hs, 0, sizeof(ctx->hw.hs));
   ctx->hw.d_ppairs = nullptr; ctx->hw.knn = nullptr; ctx->hw.pmatches = nullptr; ctx->hw.npmatch = nullptr;
   ctx->hw.cap_pairs = ctx->hw.cap_pm = ctx->hw.cap_knn = 0; ctx->hw.max_iter = 0; ctx->hw.last_hybrid = false;
@@ -463,6 +463,17 @@ extern "C" int lsl_frame_from_lines(lsl_ctx* ctx, const lsl_line_rec* recs, int 
   *out = fr;
   return LSL_OK;
 }
+static void release_points(lsl_frame* f) {
+  if (f->pblk) {
+    if (--f->pblk->refs == 0) { cudaFree(f->pblk->d_xyz1); cudaFree(f->pblk->d_desc); delete f->pblk; }
+    f->pblk = nullptr;
+  } else {
+    if (f->d_xyz1) cudaFree(f->d_xyz1);
+    if (f->d_desc) cudaFree(f->d_desc);
+  }
+  f->d_xyz1 = nullptr; f->d_desc = nullptr; f->npoints = 0;
+}
+
 extern "C" void lsl_frame_free(lsl_frame* f) {
   if (!f) return;
   if (f->d_lines) {
@@ -471,8 +482,7 @@ extern "C" void lsl_frame_free(lsl_frame* f) {
       if (--f->blk->refs == 0) { cudaFreeAsync(f->blk->d, f->ctx->stream); delete f->blk; }
     } else cudaFree(f->d_lines);
   }
-  if (f->d_xyz1) cudaFree(f->d_xyz1);
-  if (f->d_desc) cudaFree(f->d_desc);
+  { LSL_LOCK(f->ctx); cudaSetDevice(f->ctx->device); release_points(f); }
   delete f;
 }
 extern "C" int lsl_frame_clear_lines(lsl_frame* f) {
@@ -494,8 +504,7 @@ extern "C" int lsl_frame_set_points_ex(lsl_ctx* ctx, lsl_frame* f, const float* 
   if (!ctx || !f || n < 0 || n > LSL_MAX_POINTS || (n && (!xyz1 || !desc)) || dim < 1 || dim > 512) return LSL_ERR_ARG;
   if (desc_is_u8 && (dim & 3)) { ctx->err = "binary descriptor rows must be a multiple of 4 bytes"; return LSL_ERR_ARG; }
   LSL_ENTER(ctx);
-  if (f->d_xyz1) { cudaFree(f->d_xyz1); f->d_xyz1 = nullptr; }
-  if (f->d_desc) { cudaFree(f->d_desc); f->d_desc = nullptr; }
+  release_points(f);
   f->npoints = n; f->pdim = dim; f->pkind = desc_is_u8 ? 1 : 0;
   if (n) {
     const size_t row = desc_is_u8 ? (size_t)dim : sizeof(float) * (size_t)dim;
@@ -512,6 +521,84 @@ extern "C" int lsl_frame_set_points_ex(lsl_ctx* ctx, lsl_frame* f, const float* 
 extern "C" int lsl_frame_set_points(lsl_ctx* ctx, lsl_frame* f, const float* xyz1, const float* desc, int n, int dim) {
   return lsl_frame_set_points_ex(ctx, f, xyz1, desc, n, dim, 0, 0);
 }
+// Point features of n frames in one go (the Node constructors of a batch): ONE device block, two uploads, one optional
+// RootSIFT launch over all rows — instead of two cudaMalloc + a synchronisation per frame.
+extern "C" int lsl_frames_set_points_batch(lsl_ctx* ctx, int n, lsl_frame* const* frames, const float* xyz1, const void* desc,
+                                           const int32_t* counts, int dim, int desc_is_u8, int root_sift) {
+  if (!ctx || n < 1 || !frames || !counts || dim < 1 || dim > 512) return LSL_ERR_ARG;
+  if (desc_is_u8 && (dim & 3)) return LSL_ERR_ARG;
+  size_t tot = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!frames[i] || counts[i] < 0 || counts[i] > LSL_MAX_POINTS) return LSL_ERR_ARG;
+    tot += (size_t)counts[i];
+  }
+  if (tot && (!xyz1 || !desc)) return LSL_ERR_ARG;
+  LSL_ENTER(ctx);
+  const size_t row = desc_is_u8 ? (size_t)dim : sizeof(float) * (size_t)dim;
+  LslPointBlock* blk = nullptr;
+  if (tot) {
+    blk = new (std::nothrow) LslPointBlock();
+    if (!blk) return LSL_ERR_ARG;
+    blk->refs = 0; blk->d_xyz1 = nullptr; blk->d_desc = nullptr;
+    LSL_CUDA(cudaMalloc((void**)&blk->d_xyz1, sizeof(float) * 4 * tot));
+    LSL_CUDA(cudaMalloc((void**)&blk->d_desc, row * tot));
+    LSL_CUDA(cudaMemcpyAsync(blk->d_xyz1, xyz1, sizeof(float) * 4 * tot, cudaMemcpyHostToDevice, ctx->stream));
+    LSL_CUDA(cudaMemcpyAsync(blk->d_desc, desc, row * tot, cudaMemcpyHostToDevice, ctx->stream));
+    if (root_sift && !desc_is_u8) { int rc = lsl_launch_rootsift(ctx, (float*)blk->d_desc, (int)tot, dim); if (rc) return rc; }
+    ctx->stats.h2d_bytes += sizeof(float) * 4 * tot + row * tot;
+  }
+  size_t off = 0;
+  for (int i = 0; i < n; ++i) {
+    lsl_frame* f = frames[i];
+    release_points(f);
+    f->npoints = counts[i]; f->pdim = dim; f->pkind = desc_is_u8 ? 1 : 0;
+    if (counts[i]) {
+      f->pblk = blk; blk->refs += 1;
+      f->d_xyz1 = blk->d_xyz1 + 4 * off;
+      f->d_desc = (float*)((uint8_t*)blk->d_desc + row * off);
+    }
+    off += (size_t)counts[i];
+  }
+  if (tot) LSL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return LSL_OK;
+}
+
+// computeRelativeMotion_Ransac + optimizeRelmotion for EVERY pair of the last lsl_match_pair_batch, on the line matches that
+// call left on the device (BASELINE config 5: "levmar refine per edge"): one launch, one CTA per pair.
+extern "C" int lsl_relmotion_batch(lsl_ctx* ctx, int npairs, double* Rt /* [npairs][12]: R row-major, t */, int32_t* info /* [npairs][4]: consensus size, LM calls, have, 0 */) {
+  if (!ctx || npairs < 1 || !Rt || !info) return LSL_ERR_ARG;
+  LSL_ENTER(ctx);
+  if ((size_t)npairs > ctx->pw.h_pairs.size()) { ctx->err = "no pair batch of that size on the device"; return LSL_ERR_ARG; }
+  cudaStream_t st = ctx->stream;
+  const size_t M = ctx->pw.last_tot_m > 0 ? ctx->pw.last_tot_m : 1, it = ctx->P.ransac_iters_line_motion, np = (size_t)npairs;
+  const size_t bytes = align_up(M * RM_STRIDE * 8) + align_up(M * 4 * 8) + align_up(M * RM_M * 8) + align_up(M * 4) + align_up(M * 2 * 4) +
+                       align_up(np * it * 12 * 8) + align_up(np * it * 4) + align_up(np * it * 3 * 2) + align_up(np * 12 * 8) + align_up(np * 16);
+  uint8_t* blk = nullptr;
+  LSL_CUDA(cudaMallocAsync((void**)&blk, bytes, st));
+  RmScratch rs;
+  size_t off = 0;
+  rs.g = (double*)(blk + off); off += align_up(M * RM_STRIDE * 8);
+  rs.hx = (double*)(blk + off); off += align_up(M * 4 * 8);
+  rs.jac = (double*)(blk + off); off += align_up(M * RM_M * 8);
+  rs.flag = (int32_t*)(blk + off); off += align_up(M * 4);
+  rs.cur = (int32_t*)(blk + off); off += align_up(M * 2 * 4);
+  rs.hyp = (double*)(blk + off); off += align_up(np * it * 12 * 8);
+  rs.cnts = (int32_t*)(blk + off); off += align_up(np * it * 4);
+  rs.trip = (uint16_t*)(blk + off); off += align_up(np * it * 3 * 2);
+  rs.outRt = (double*)(blk + off); off += align_up(np * 12 * 8);
+  rs.outn = (int32_t*)(blk + off);
+  rs.max_iter = (int)it;
+  int rc = lsl_launch_relmotion(ctx, npairs, rs);
+  if (rc) { cudaFreeAsync(blk, st); return rc; }
+  LSL_CUDA(cudaMemcpyAsync(Rt, rs.outRt, np * 12 * 8, cudaMemcpyDeviceToHost, st));
+  LSL_CUDA(cudaMemcpyAsync(info, rs.outn, np * 16, cudaMemcpyDeviceToHost, st));
+  LSL_CUDA(cudaFreeAsync(blk, st));
+  LSL_CUDA(cudaStreamSynchronize(st));
+  collect_ktimes(ctx, LSL_K_RELMOTION, LSL_K_RELMOTION + 1);
+  ctx->stats.d2h_bytes += np * (12 * 8 + 16);
+  return LSL_OK;
+}
+
 extern "C" int lsl_frame_descriptors(lsl_ctx* ctx, const lsl_frame* f, void* dst, int64_t cap_bytes) {
   if (!ctx || !f || (f->npoints && !dst)) return LSL_ERR_ARG;
   const size_t bytes = (f->pkind ? (size_t)f->pdim : sizeof(float) * (size_t)f->pdim) * (size_t)f->npoints;
@@ -599,6 +686,7 @@ static int setup_pairs(lsl_ctx* ctx, int npairs, const lsl_frame* const* queries
     m_off += (size_t)(d.cap_m > 0 ? d.cap_m : 1);
     d_off += (size_t)d.nq * d.nt;
   }
+  p.last_tot_m = m_off;
   int rc = ensure_pair_ws(ctx, npairs, m_off, d_off);
   if (rc) return rc;
   LSL_CUDA(cudaMemcpyAsync(p.d_pairs, p.h_pairs.data(), sizeof(LslPairDesc) * npairs, cudaMemcpyHostToDevice, ctx->stream));

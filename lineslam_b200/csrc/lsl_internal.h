@@ -101,6 +101,7 @@ struct LslPairWork {
   lsl_pose_rec* recs;  // [pairs]
   LslPairScratch sc;
   size_t cap_pairs, cap_m, cap_d;
+  size_t last_tot_m;                  // match slots of the last batch (sum of cap_m)
   std::vector<LslPairDesc> h_pairs;   // descriptors of the last batch (host copy)
   std::vector<int32_t> h_nmatch, h_ninl, h_nrinl;
 };
@@ -172,6 +173,12 @@ struct LslLineBlock {
   int refs;
 };
 
+// Point features of all frames of one lsl_frames_set_points_batch call live in one device allocation; frames reference-count it.
+struct LslPointBlock {
+  float* d_xyz1; void* d_desc;
+  int refs;
+};
+
 struct lsl_frame {
   lsl_ctx* ctx;
   int nlines, nsegs;
@@ -187,6 +194,7 @@ struct lsl_frame {
   int npoints, pdim, pkind;    // pkind 0: f32 descriptors, 1: u8 (ORB) rows of pdim bytes
   float* d_xyz1;   // [npoints][4]
   float* d_desc;   // [npoints][pdim]
+  LslPointBlock* pblk;   // non-null: d_xyz1 / d_desc point into a shared block
 };
 
 struct lsl_ctx {

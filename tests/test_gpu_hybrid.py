@@ -234,3 +234,26 @@ def test_tensor_core_prefilter_gives_the_exact_matches(api, oracle):
     evals, full_rows, rows = ctx.match_tc_stats()
     assert rows > 0 and evals < 0.5 * total_pairs        # the pre-filter removed most exact evaluations even on this adversarial mix
     ctx.close()
+
+
+def test_batched_entry_points_equal_the_per_call_ones(api, oracle, hyb):
+    """lsl_frames_set_points_batch == per-frame lsl_frame_set_points_ex, lsl_relmotion_batch == per-pair lsl_relmotion_ransac
+    (which test_relmotion_ransac_levmar pins to the oracle): same bits, one launch / one device block instead of one per call."""
+    ctx, frames, lines, pts, poses = hyb
+    from lineslam_b200.records import LINE_DTYPE
+    fb = [ctx.frame_from_lines(lines[i]) for i in range(3)]
+    ctx.set_points_batch(fb, [p[0] for p in pts], [p[1] for p in pts])
+    for (q, t, seed) in [(1, 0, 1), (2, 1, 7)]:
+        assert np.array_equal(ctx.match_points(fb[q], fb[t], seed), ctx.match_points(frames[q], frames[t], seed))
+    assert np.array_equal(fb[2].descriptors(), pts[2][1])
+    # relmotion: batch of two pairs vs the single-pair entry on the same line matches and seeds
+    recs = ctx.match_pair_batch([frames[1], frames[2]], [frames[0], frames[1]], [1, 2], [0, 1], [5, 6])
+    ms = [ctx.pair_matches(k, 0) for k in range(2)]
+    R, t, info = ctx.relmotion_batch(2)
+    for k, (q, tr) in enumerate([(1, 0), (2, 1)]):
+        one = ctx.relmotion_ransac(frames[tr], frames[q], ms[k], seed=5 + k)
+        assert bool(info[k, 2]) == one["have"] and int(info[k, 0]) == len(one["conset"]) and int(info[k, 1]) == one["lm_calls"]
+        if one["have"]:
+            assert np.array_equal(R[k], one["R"]) and np.array_equal(t[k], one["t"])
+    for f in fb:
+        f.free()
