@@ -314,6 +314,107 @@ __global__ void sobel5_kernel(const uint8_t* __restrict__ gray, int16_t* __restr
   gy[(size_t)f * W * H + (size_t)y * W + x] = (int16_t)sy;
 }
 
+// cv::Sobel ksize 5 with TMA tile staging: one CTA = 128 x 32 output pixels; the (16 + 128 + 16) x 36 byte halo tile of
+// the gray plane (the innermost box coordinate of a TMA tile must be 16-byte aligned: measured with tools/ubench/tma_probe.cu,
+// a start at x0 - 2 raises an illegal-instruction fault) arrives in shared memory by ONE cp.async.bulk.tensor.3d (tensor map over [batch][H][W] u8, out-of-image
+// bytes zero-filled by the copy engine, completion on an mbarrier; UTMALDG in SASS). BORDER_REFLECT_101 only concerns CTAs
+// on the image border: the mirrored pixel always lies inside the same tile, so those CTAs remap the tile index instead
+// of touching global memory. Each thread produces a 4 x 4 micro-tile from eight aligned 8-byte row segments (separable:
+// horizontal [-1 -2 0 2 1] / [1 4 6 4 1] per row, then the vertical taps) and stores 8 bytes per row and plane: exact
+// integer arithmetic, so the planes equal sobel5_kernel's bit for bit.
+#define SB_W 128
+#define SB_H 32
+#define SB_TW 160   // tile row pitch in bytes, columns x0 - 16 .. x0 + 143
+#define SB_X0 16    // tile column of image column x0
+#define SB_TH 36
+__global__ void __launch_bounds__(256) sobel5_tma_kernel(const __grid_constant__ CUtensorMap tmap, int16_t* __restrict__ gx,
+                                                        int16_t* __restrict__ gy, int W, int H, int f0) {
+  __shared__ __align__(128) uint8_t t[SB_TH][SB_TW];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * SB_W, y0 = blockIdx.y * SB_H, f = blockIdx.z;
+  const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar), t_a = (uint32_t)__cvta_generic_to_shared(&t[0][0]);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;\n");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar_a), "r"(SB_TH * SB_TW));
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+                 ::"r"(t_a), "l"(&tmap), "r"(x0 - SB_X0), "r"(y0 - 2), "r"(f0 + f), "r"(bar_a) : "memory");
+  }
+  __syncthreads();   // the barrier is initialised for everybody
+  {
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar_a) : "memory");
+  }
+  const int cx = (tid & 31) * 4, cy = (tid >> 5) * 4;      // micro-tile origin inside the CTA tile
+  if (x0 + cx >= W || y0 + cy >= H) return;                // micro-tile entirely outside the image (ragged sizes)
+  const bool border = x0 == 0 || y0 == 0 || x0 + SB_W + 2 > W || y0 + SB_H + 2 > H;
+  int hd[8][4], hs[8][4];                                  // horizontal derivative / smoothing sums of the 8 rows
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    int v[8];
+    if (!border) {
+      // pixels x0 + cx - 2 .. x0 + cx + 5 = tile columns cx + 14 .. cx + 21: three aligned words
+      const uint32_t w0 = *reinterpret_cast<const uint32_t*>(&t[cy + r][cx + 12]), w1 = *reinterpret_cast<const uint32_t*>(&t[cy + r][cx + 16]),
+                     w2 = *reinterpret_cast<const uint32_t*>(&t[cy + r][cx + 20]);
+      v[0] = (w0 >> 16) & 0xff; v[1] = w0 >> 24;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[2 + k] = (w1 >> (8 * k)) & 0xff;
+      v[6] = w2 & 0xff; v[7] = (w2 >> 8) & 0xff;
+    } else {
+      // mirrored coordinates of pixels an in-image output needs lie inside the tile; the clamps only touch inputs of
+      // outputs beyond the image edge, which are never stored
+      const int ty = min(max(reflect101(y0 + cy + r - 2, H) - (y0 - 2), 0), SB_TH - 1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = t[ty][min(max(reflect101(x0 + cx + k - 2, W) - (x0 - SB_X0), 0), SB_TW - 1)];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      hd[r][c] = -v[c] - 2 * v[c + 1] + 2 * v[c + 3] + v[c + 4];
+      hs[r][c] = v[c] + 4 * v[c + 1] + 6 * v[c + 2] + 4 * v[c + 3] + v[c + 4];
+    }
+  }
+  const int x = x0 + cx;
+#pragma unroll
+  for (int yy = 0; yy < 4; ++yy) {
+    const int y = y0 + cy + yy;
+    if (y >= H) break;
+    short ox[4], oy[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      ox[c] = (short)(hd[yy][c] + 4 * hd[yy + 1][c] + 6 * hd[yy + 2][c] + 4 * hd[yy + 3][c] + hd[yy + 4][c]);
+      oy[c] = (short)(-hs[yy][c] - 2 * hs[yy + 1][c] + 2 * hs[yy + 3][c] + hs[yy + 4][c]);
+    }
+    const size_t o = (size_t)f * W * H + (size_t)y * W + x;
+    *reinterpret_cast<uint2*>(gx + o) = make_uint2((uint16_t)ox[0] | ((uint32_t)(uint16_t)ox[1] << 16), (uint16_t)ox[2] | ((uint32_t)(uint16_t)ox[3] << 16));
+    *reinterpret_cast<uint2*>(gy + o) = make_uint2((uint16_t)oy[0] | ((uint32_t)(uint16_t)oy[1] << 16), (uint16_t)oy[2] | ((uint32_t)(uint16_t)oy[3] << 16));
+  }
+}
+
+// Tensor map of the context's gray planes: rank 3 {W, H, max_batch} u8, box {160, 36, 1}; (re)encoded when the frame size
+// changes. cuTensorMapEncodeTiled is taken from the driver through the runtime (no link-time dependency on libcuda).
+int lsl_prepare_tmaps(lsl_ctx* ctx) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  ctx->tmap_gray_ok = false;
+  const LslDims& d = ctx->dims;
+  if ((d.W & 15) || d.W < SB_TW || d.H < SB_TH) return LSL_OK;       // TMA stride rule (multiples of 16 bytes): such sizes keep the plain kernel
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn || q != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return LSL_OK;
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)ctx->max_batch};
+  const cuuint64_t strides[2] = {(cuuint64_t)d.W, (cuuint64_t)d.W * d.H};
+  const cuuint32_t box[3] = {SB_TW, SB_TH, 1}, estr[3] = {1, 1, 1};
+  CUresult r = ((encode_fn)fn)(&ctx->tmap_gray, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ctx->wk.gray, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ctx->tmap_gray_ok = (r == CUDA_SUCCESS);
+  return LSL_OK;
+}
+
 // Image stage for the frames [f0, f0 + n) of the batch (the host-buffer path calls it per upload chunk so that
 // the RGB upload of the next chunk overlaps these kernels). channels == 1: the caller already has a gray plane.
 int lsl_launch_image(lsl_ctx* ctx, int f0, int n, const uint8_t* d_img, int channels) {
@@ -352,9 +453,14 @@ int lsl_launch_image(lsl_ctx* ctx, int f0, int n, const uint8_t* d_img, int chan
   ll_angle_kernel<<<gla, bla, 0, st>>>(w.scaled + f0 * spix, w.angles + f0 * spix, w.modgrad + f0 * spix, w.cs + f0 * spix,
                                       w.binT + f0 * spix, d.sw, d.sh, rho, P.lsd_n_bins, P.lsd_max_grad);
   LSL_KSTOP(ctx, LSL_K_LLANGLE);
-  dim3 bs(32, 16), gs((d.W + 31) / 32, (d.H + 15) / 16, n);
   LSL_KSTART(ctx, LSL_K_SOBEL);
-  sobel5_kernel<<<gs, bs, 0, st>>>(gray, w.gx + f0 * npix, w.gy + f0 * npix, d.W, d.H);
+  if (ctx->tmap_gray_ok) {
+    dim3 gt((d.W + SB_W - 1) / SB_W, (d.H + SB_H - 1) / SB_H, n);
+    sobel5_tma_kernel<<<gt, 256, 0, st>>>(ctx->tmap_gray, w.gx + f0 * npix, w.gy + f0 * npix, d.W, d.H, f0);
+  } else {
+    dim3 bs(32, 16), gs((d.W + 31) / 32, (d.H + 15) / 16, n);
+    sobel5_kernel<<<gs, bs, 0, st>>>(gray, w.gx + f0 * npix, w.gy + f0 * npix, d.W, d.H);
+  }
   LSL_KSTOP(ctx, LSL_K_SOBEL);
   LSL_CUDA(cudaGetLastError());
   return LSL_OK;

@@ -133,6 +133,7 @@ extern "C" int lsl_ctx_create(lsl_ctx** out, const lsl_params* params, int cuda_
   ctx->h_pin = nullptr; ctx->h_pin_bytes = 0;
   ctx->d_depth16 = nullptr; ctx->d_depth16_bytes = 0;
   ctx->d_gather = nullptr; ctx->d_gather_bytes = 0;
+  ctx->tmap_gray_ok = false;
   memset(&ctx->stats, 0, sizeof(ctx->stats));
   memset(&ctx->dims, 0, sizeof(ctx->dims));
   memset(ctx->kran, 0, sizeof(ctx->kran));
@@ -216,7 +217,9 @@ static int set_dims(lsl_ctx* ctx, int W, int H) {
   ctx->dims.sh = (int)floor(H * ctx->P.lsd_scale);
   ctx->dims.msld_s = (int)(5 * W / 800.0);
   if (ctx->dims.sw >= 65536 || ctx->dims.sh >= 32768) return LSL_ERR_ARG;
-  return lsl_prepare_taps(ctx);
+  int rc = lsl_prepare_taps(ctx);
+  if (rc) return rc;
+  return lsl_prepare_tmaps(ctx);
 }
 
 static int ensure_pinned(lsl_ctx* ctx, size_t bytes) {

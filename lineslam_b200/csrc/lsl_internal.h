@@ -1,5 +1,6 @@
 // lsl_internal.h — context / frame / workspace layout of liblsl_b200 (product code, CUDA only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <mutex>
@@ -218,6 +219,7 @@ struct lsl_ctx {
   int debug;
   int32_t* d_goff;           // [max_batch] gather offsets
   void* nccl_lib; void* nccl_comm; int nccl_rank, nccl_nranks; bool nccl_own;
+  CUtensorMap tmap_gray; bool tmap_gray_ok;   // TMA tile map of the gray planes (sobel5_tma_kernel), valid for `dims`
   LslDims dims;   // dims the workspace / taps were last prepared for
   LslTaps taps;
   LslWork wk;
@@ -255,6 +257,7 @@ int lsl_launch_seeds(lsl_ctx* ctx, int n);
 int lsl_launch_lsd(lsl_ctx* ctx, int n);
 int lsl_launch_lines(lsl_ctx* ctx, int n, const float* d_depth, const double K[9], double dt);
 int lsl_prepare_taps(lsl_ctx* ctx);
+int lsl_prepare_tmaps(lsl_ctx* ctx);
 int lsl_launch_gather(lsl_ctx* ctx, int n, lsl_line_rec* dst);
 int lsl_launch_depth_u16(lsl_ctx* ctx, cudaStream_t st, const uint16_t* d_in, float* d_out, size_t count, float scale);
 int lsl_launch_match(lsl_ctx* ctx, int npairs);
