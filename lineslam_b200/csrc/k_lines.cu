@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(128, RANSAC_MINB) line3d_ransac_kernel(LslWork
         for (int wd = 0; wd < 4; ++wd) {
           int i = wd * 32 + lane;
           bool in = false;
-          if (i < n && !degenerate) in = mah_dist3d_pt_line(s_pos + 3 * i, s_DU + 9 * i, A, B) < P.mah_thres;
+          if (i < n && !degenerate) in = mah_dist3d_pt_line_lt(s_pos + 3 * i, s_DU + 9 * i, A, B, P.mah_thres);
           unsigned m = __ballot_sync(FULL, in);
           if (lane == 0) s_hmask[h][wd] = m;
           cnt += __popc(m);
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(128, RANSAC_MINB) line3d_ransac_kernel(LslWork
           for (int wd = 0; wd < 4; ++wd) {
             int i = wd * 32 + lane;
             bool in = false;
-            if (i < n) in = mah_dist3d_pt_line(s_pos + 3 * i, s_DU + 9 * i, tm, q2) < P.mah_thres;
+            if (i < n) in = mah_dist3d_pt_line_lt(s_pos + 3 * i, s_DU + 9 * i, tm, q2, P.mah_thres);
             nm[wd] = __ballot_sync(FULL, in);
             cnt += __popc(nm[wd]);
           }

@@ -573,9 +573,7 @@ __global__ void __launch_bounds__(POSE_THREADS, POSE_MINB) pose_kernel(const Lsl
       int i = i0 + lane;
       bool in = false;
       if (i < nm) {
-        double da, db;
-        score_match(md_all + (size_t)i * MD_STRIDE, tf, &da, &db);
-        in = da < PP.thr && db < PP.thr;
+        in = score_match_inlier(md_all + (size_t)i * MD_STRIDE, tf, PP.thr);
       }
       c += __popc(__ballot_sync(FULL, in));
     }

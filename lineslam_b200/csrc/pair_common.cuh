@@ -122,6 +122,16 @@ __device__ __forceinline__ void score_match(const double* md, const float* tf, d
   *db = mah_dist3d_pt_line(md + 9, md + 21, qA, qB);
 }
 
+// inlier decision of a match under tf (motion.cpp:688-699): da < thr && db < thr, with the division / square root only near
+// the threshold (mah_dist3d_pt_line_lt); identical decisions to score_match + compare
+__device__ __forceinline__ bool score_match_inlier(const double* md, const float* tf, double thr) {
+  float qa[3] = {(float)md[0], (float)md[1], (float)md[2]}, qb[3] = {(float)md[3], (float)md[4], (float)md[5]};
+  double qA[3], qB[3];
+  tf_apply_f(tf, qa, qA);
+  tf_apply_f(tf, qb, qB);
+  return mah_dist3d_pt_line_lt(md + 6, md + 12, qA, qB, thr) && mah_dist3d_pt_line_lt(md + 9, md + 21, qA, qB, thr);
+}
+
 // ------------------------------------------------- g2o-style refinement ----
 __device__ __forceinline__ void iso_mul(const Iso& a, const Iso& b, Iso& c) {
   for (int r = 0; r < 3; ++r) {

@@ -146,6 +146,36 @@ LSL_HD double mah_dist3d_pt_line(const double pos[3], const double DU[9], const 
               (term4 * term4 + term5 * term5 + term6 * term6));
 }
 
+// Decision form of the same distance: mah_dist3d_pt_line(pos, DU, q1, q2) < thr, bit for bit, without paying for the
+// division and the square root in the clear cases. num and den are the very sums above; with q = RN(num / den) and
+// s = RN(sqrt(q)) the computed s differs from the real sqrt(num / den) by less than 2^-52 relative, so
+// num < den * thr^2 * (1 - 1e-9) implies s < thr and num > den * thr^2 * (1 + 1e-9) implies s > thr (margins seven orders
+// of magnitude above the rounding); everything else — including NaN and den == 0 — takes the exact path.
+LSL_HD bool mah_dist3d_pt_line_lt(const double pos[3], const double DU[9], const double q1[3], const double q2[3], double thr) {
+  double xa = q1[0], ya = q1[1], za = q1[2], xb = q2[0], yb = q2[1], zb = q2[2];
+  double c1 = DU[0], c2 = DU[1], c3 = DU[2], c4 = DU[3], c5 = DU[4], c6 = DU[5], c7 = DU[6],
+         c8 = DU[7], c9 = DU[8];
+  double x1 = pos[0], x2 = pos[1], x3 = pos[2];
+  double a1 = c1 * (x1 - xa) + c2 * (x2 - ya) + c3 * (x3 - za);
+  double a2 = c4 * (x1 - xa) + c5 * (x2 - ya) + c6 * (x3 - za);
+  double a3 = c7 * (x1 - xa) + c8 * (x2 - ya) + c9 * (x3 - za);
+  double b1 = c1 * (x1 - xb) + c2 * (x2 - yb) + c3 * (x3 - zb);
+  double b2 = c4 * (x1 - xb) + c5 * (x2 - yb) + c6 * (x3 - zb);
+  double b3 = c7 * (x1 - xb) + c8 * (x2 - yb) + c9 * (x3 - zb);
+  double term1 = a1 * b2 - a2 * b1;
+  double term2 = a1 * b3 - a3 * b1;
+  double term3 = a2 * b3 - a3 * b2;
+  double term4 = c1 * (x1 - xa) - c1 * (x1 - xb) + c2 * (x2 - ya) - c2 * (x2 - yb) + c3 * (x3 - za) - c3 * (x3 - zb);
+  double term5 = c4 * (x1 - xa) - c4 * (x1 - xb) + c5 * (x2 - ya) - c5 * (x2 - yb) + c6 * (x3 - za) - c6 * (x3 - zb);
+  double term6 = c7 * (x1 - xa) - c7 * (x1 - xb) + c8 * (x2 - ya) - c8 * (x2 - yb) + c9 * (x3 - za) - c9 * (x3 - zb);
+  const double num = term1 * term1 + term2 * term2 + term3 * term3;
+  const double den = term4 * term4 + term5 * term5 + term6 * term6;
+  const double t2 = thr * thr;
+  if (thr > 0.0 && num < den * (t2 * (1.0 - 1e-9))) return true;
+  if (thr > 0.0 && num > den * (t2 * (1.0 + 1e-9))) return false;
+  return sqrt(num / den) < thr;
+}
+
 // compPt3dCov (src/line/utils.cpp:690-722): cov = J diag(s^2, s^2, sz^2) J^T with
 // J = [[z/f,0,x/z],[0,z/f,y/z],[0,0,1]], products evaluated as (J*S)*J^T, zeros included
 // as in the dense 3x3 Armadillo products (adding +0.0 terms is exact).

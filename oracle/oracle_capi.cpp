@@ -301,4 +301,11 @@ void orc_get_gradient(const double* xG, const double* yG, int W, int H, const do
   orc::get_gradient_probe(xG, yG, W, H, pq, r);
 }
 
+// decision form of the Mahalanobis point-to-line test (shared/lsl_linalg.h) against the plain formula: both results
+void orc_mah_lt(const double* pos, const double* DU, const double* q1, const double* q2, double thr, int* fast, int* plain) {
+  *fast = lslm::mah_dist3d_pt_line_lt(pos, DU, q1, q2, thr) ? 1 : 0;
+  *plain = (lslm::mah_dist3d_pt_line(pos, DU, q1, q2) < thr) ? 1 : 0;
+}
+double orc_mah_dist(const double* pos, const double* DU, const double* q1, const double* q2) { return lslm::mah_dist3d_pt_line(pos, DU, q1, q2); }
+
 }  // extern "C"

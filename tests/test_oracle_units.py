@@ -153,3 +153,36 @@ def test_error_free_product_is_exact(oracle):
         L.orc_m_two_prod(float(a), float(b), pe)
         assert pe[0] == a * b
         assert Fraction(pe[0]) + Fraction(pe[1]) == Fraction(float(a)) * Fraction(float(b)), (a, b)
+
+
+def test_mahalanobis_decision_form_is_exact(oracle):
+    """mah_dist3d_pt_line_lt (the division- and sqrt-free fast path of the 3D-line RANSAC and of the pose scoring) takes the
+    same decision as `mah_dist3d_pt_line(...) < thr` — on random geometry and on points moved onto the threshold to the
+    last bits (where it must fall back to the exact formula)."""
+    import ctypes as C
+    L = oracle.lib()
+    L.orc_mah_dist.restype = C.c_double
+    rng = np.random.default_rng(3)
+    fast, plain = C.c_int(0), C.c_int(0)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    n_in = n_edge = 0
+    for k in range(4000):
+        pos = rng.normal(0, 1, 3); q1 = rng.normal(0, 1, 3); q2 = q1 + rng.normal(0, 1, 3)
+        A = rng.normal(0, 1, (3, 3)) * rng.choice([0.3, 3.0, 30.0])
+        DU = np.ascontiguousarray(A.reshape(9))
+        thr = float(rng.choice([1.5, 3.0]))
+        if k % 2:   # move the point so that the distance sits on the threshold, then nudge by a few ulps
+            d = L.orc_mah_dist(P(pos), P(DU), P(q1), P(q2))
+            if np.isfinite(d) and d > 0:
+                foot = q1 + (q2 - q1) * np.dot(pos - q1, q2 - q1) / np.dot(q2 - q1, q2 - q1)
+                pos = foot + (pos - foot) * (thr / d)
+                pos = np.nextafter(pos, pos + rng.choice([-1, 1]) * 1e9) if k % 4 == 1 else pos
+                n_edge += 1
+        L.orc_mah_lt(P(pos), P(DU), P(q1), P(q2), C.c_double(thr), C.byref(fast), C.byref(plain))
+        assert fast.value == plain.value, k
+        n_in += plain.value
+    assert 200 < n_in < 3800 and n_edge > 1500
+    # degenerate line (q1 == q2): 0 / 0 -> NaN -> not an inlier on both paths
+    z = np.zeros(3)
+    L.orc_mah_lt(P(z), P(np.eye(3).reshape(9).copy()), P(z), P(z), C.c_double(1.5), C.byref(fast), C.byref(plain))
+    assert fast.value == plain.value == 0
