@@ -165,12 +165,85 @@ __global__ void __launch_bounds__(1024) png_unfilter_kernel(const uint8_t* __res
   }
 }
 
+// Integrity of what was just decoded (cv::imread rejects a PNG whose chunk CRC or zlib check value is wrong): one CTA
+// per image. (1) CRC-32 of every IDAT chunk (type + data, PNG §5.3) over the gathered payload pieces, slice-by-4 tables
+// built in shared memory, one thread per piece; (2) Adler-32 of the inflated stream (RFC 1950) as 256 contiguous
+// segments: per segment A = sum d, B = sum (len - k) d_k, combined in stream order by one thread, against the trailer.
+struct PngPiece { uint32_t off_lo, off_hi, len, crc; };   // offset of the piece inside the staging block, stored CRC
+__global__ void __launch_bounds__(256) png_check_kernel(const uint8_t* __restrict__ z_all, const PngPiece* __restrict__ pieces,
+                                                        const uint32_t* __restrict__ piece_begin, const uint32_t* __restrict__ adler_want,
+                                                        const uint8_t* __restrict__ filt_all, size_t filt_img_bytes, int* __restrict__ status) {
+  __shared__ uint32_t T[4][256];
+  __shared__ uint32_t sA[256];
+  __shared__ unsigned long long sB[256];
+  const int img = blockIdx.x, tid = threadIdx.x;
+  {  // CRC tables (polynomial 0xEDB88320)
+    uint32_t c = (uint32_t)tid;
+    for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+    T[0][tid] = c;
+  }
+  __syncthreads();
+  for (int t = 1; t < 4; ++t) { const uint32_t c = T[t - 1][tid]; T[t][tid] = T[0][c & 255u] ^ (c >> 8); }
+  __syncthreads();
+  if (status[img] != 0) return;          // not decoded: the earlier error stands (uniform per CTA)
+  bool bad_crc = false;
+  for (uint32_t pi = piece_begin[img] + tid; pi < piece_begin[img + 1]; pi += blockDim.x) {
+    const PngPiece P = pieces[pi];
+    const uint8_t* d = z_all + (((size_t)P.off_hi << 32) | P.off_lo);
+    uint32_t c = 0xFFFFFFFFu;
+    const uint8_t ty[4] = {'I', 'D', 'A', 'T'};
+    for (int k = 0; k < 4; ++k) c = T[0][(c ^ ty[k]) & 255u] ^ (c >> 8);
+    uint32_t i = 0;
+    for (; i < P.len && ((reinterpret_cast<uintptr_t>(d + i)) & 3); ++i) c = T[0][(c ^ d[i]) & 255u] ^ (c >> 8);
+    for (; i + 4 <= P.len; i += 4) {
+      c ^= __ldg(reinterpret_cast<const uint32_t*>(d + i));
+      c = T[3][c & 255u] ^ T[2][(c >> 8) & 255u] ^ T[1][(c >> 16) & 255u] ^ T[0][c >> 24];
+    }
+    for (; i < P.len; ++i) c = T[0][(c ^ d[i]) & 255u] ^ (c >> 8);
+    if ((c ^ 0xFFFFFFFFu) != P.crc) bad_crc = true;
+  }
+  // Adler-32 segments
+  const uint8_t* f = filt_all + (size_t)img * filt_img_bytes;
+  const size_t seg = (filt_img_bytes + 255) / 256;
+  const size_t b0 = (size_t)tid * seg, b1 = b0 + seg < filt_img_bytes ? b0 + seg : filt_img_bytes;
+  uint32_t A = 0; unsigned long long B = 0;
+  if (b0 < filt_img_bytes) {
+    const unsigned long long L = b1 - b0;
+    for (size_t k = b0; k < b1; ++k) { const uint32_t v = f[k]; A += v; B += (L - (k - b0)) * v; }
+  }
+  sA[tid] = A; sB[tid] = B;
+  const int any_bad = __syncthreads_or(bad_crc ? 1 : 0);
+  if (tid == 0) {
+    unsigned long long s1 = 1, s2 = 0;
+    for (int t = 0; t < 256; ++t) {
+      const size_t t0 = (size_t)t * seg;
+      if (t0 >= filt_img_bytes) break;
+      const unsigned long long L = (t0 + seg < filt_img_bytes ? t0 + seg : filt_img_bytes) - t0;
+      s2 = (s2 + (L % 65521ull) * s1 + sB[t] % 65521ull) % 65521ull;
+      s1 = (s1 + sA[t]) % 65521ull;
+    }
+    const uint32_t got = (uint32_t)((s2 << 16) | s1);
+    if (any_bad) status[img] = -10;
+    else if (got != adler_want[img]) status[img] = -11;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host ----
+// CRC-32 of the small non-IDAT chunks on the host (the IDAT payload is checked on the device, png_check_kernel)
+uint32_t crc32_host(const uint8_t* p, size_t n) {
+  static uint32_t T[256];
+  static bool init = false;
+  if (!init) { for (uint32_t i = 0; i < 256; ++i) { uint32_t c = i; for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1; T[i] = c; } init = true; }
+  uint32_t c = 0xFFFFFFFFu;
+  for (size_t i = 0; i < n; ++i) c = T[(c ^ p[i]) & 255u] ^ (c >> 8);
+  return c ^ 0xFFFFFFFFu;
+}
 uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
 
 struct PngView {
   int W = 0, H = 0, ch = 0, bits = 0;
   std::vector<std::pair<const uint8_t*, size_t>> idat;
+  std::vector<uint32_t> idat_crc;   // stored CRC of each IDAT chunk (verified on the device)
 };
 
 bool png_parse(const uint8_t* p, size_t len, PngView* v, std::string* err) {
@@ -196,7 +269,9 @@ bool png_parse(const uint8_t* p, size_t len, PngView* v, std::string* err) {
       have_ihdr = true;
     } else if (!std::memcmp(type, "IDAT", 4)) {
       v->idat.emplace_back(data, (size_t)clen);
+      v->idat_crc.push_back(be32(data + clen));
     } else if (!std::memcmp(type, "IEND", 4)) end = true;
+    if (std::memcmp(type, "IDAT", 4) != 0 && crc32_host(type, 4 + (size_t)clen) != be32(data + clen)) { *err = "PNG chunk CRC mismatch"; return false; }
     off += 12 + (size_t)clen;
   }
   if (!have_ihdr || v->idat.empty()) { *err = "PNG without IHDR / IDAT"; return false; }
@@ -207,6 +282,7 @@ struct TumScratch {   // staging per list kind (0 colour, 1 depth) so that the t
   uint8_t* h_z[2] = {nullptr, nullptr}; size_t h_cap[2] = {0, 0};     // pinned: [offsets (n + 1) size_t | status n int | compressed streams]
   uint8_t* d_z[2] = {nullptr, nullptr}; size_t dz_cap[2] = {0, 0};    // the same block on the device
   uint8_t* d_filt[2] = {nullptr, nullptr}; size_t d_cap[2] = {0, 0};  // inflated (still filtered) scan lines
+  uint8_t* h_meta[2] = {nullptr, nullptr}; uint8_t* d_meta[2] = {nullptr, nullptr}; size_t meta_cap[2] = {0, 0};   // IDAT piece table + Adler-32 trailers
   uint8_t* d_bgr = nullptr; size_t bgr_cap = 0;  // lsl_extract_tum_batch only
   float* d_depth = nullptr; size_t depth_cap = 0;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -243,6 +319,8 @@ const char* inflate_error(int rc) {
     case -7: return "truncated data stream";
     case -8: return "short data stream (fewer bytes than W x H needs)";
     case -9: return "bad PNG filter type";
+    case -10: return "IDAT chunk CRC mismatch";
+    case -11: return "zlib Adler-32 mismatch";
     default: return "corrupt data stream";
   }
 }
@@ -288,16 +366,40 @@ int decode_list(lsl_ctx* ctx, TumScratch& S, cudaStream_t st, int n, const uint8
   uint8_t* const dfilt = S.d_filt[kind];
   size_t* h_off = reinterpret_cast<size_t*>(hz);
   int* h_status = reinterpret_cast<int*>(hz + (size_t)(n + 1) * sizeof(size_t));
+  size_t npieces = 0;
+  for (int i = 0; i < n; ++i) npieces += views[(size_t)i].idat.size();
+  const size_t meta_bytes = sizeof(PngPiece) * npieces + sizeof(uint32_t) * (size_t)(n + 1) + sizeof(uint32_t) * (size_t)n;
+  if (S.meta_cap[kind] < meta_bytes) {
+    if (S.h_meta[kind]) cudaFreeHost(S.h_meta[kind]);
+    if (S.d_meta[kind]) cudaFree(S.d_meta[kind]);
+    S.h_meta[kind] = nullptr; S.d_meta[kind] = nullptr; S.meta_cap[kind] = 0;
+    LSL_CUDA(cudaHostAlloc((void**)&S.h_meta[kind], meta_bytes * 2, cudaHostAllocDefault));
+    LSL_CUDA(cudaMalloc((void**)&S.d_meta[kind], meta_bytes * 2));
+    S.meta_cap[kind] = meta_bytes * 2;
+  }
+  PngPiece* h_pieces = reinterpret_cast<PngPiece*>(S.h_meta[kind]);
+  uint32_t* h_pbegin = reinterpret_cast<uint32_t*>(S.h_meta[kind] + sizeof(PngPiece) * npieces);
+  uint32_t* h_adler = h_pbegin + (n + 1);
+  size_t pi = 0;
   size_t off = head;
   for (int i = 0; i < n; ++i) {
     h_off[i] = off;
-    for (const auto& c : views[(size_t)i].idat) { std::memcpy(hz + off, c.first, c.second); off += c.second; }
+    h_pbegin[i] = (uint32_t)pi;
+    const PngView& vw = views[(size_t)i];
+    for (size_t c = 0; c < vw.idat.size(); ++c) {
+      PngPiece& P = h_pieces[pi++];
+      P.off_lo = (uint32_t)(off & 0xffffffffu); P.off_hi = (uint32_t)(off >> 32); P.len = (uint32_t)vw.idat[c].second; P.crc = vw.idat_crc[c];
+      std::memcpy(hz + off, vw.idat[c].first, vw.idat[c].second); off += vw.idat[c].second;
+    }
+    h_adler[i] = (off - h_off[i] >= 4) ? be32(hz + off - 4) : 0u;     // zlib trailer: the last four payload bytes (RFC 1950)
     const size_t pad = (16 - (off & 15)) & 15;      // < 16 zero bytes behind the Adler-32 trailer: never decoded, the
     std::memset(hz + off, 0, pad);                  // final block ends the stream before them
     off += pad;
     h_status[i] = 0;
   }
   h_off[n] = off;
+  h_pbegin[n] = (uint32_t)pi;
+  LSL_CUDA(cudaMemcpyAsync(S.d_meta[kind], S.h_meta[kind], meta_bytes, cudaMemcpyHostToDevice, st));
   LSL_CUDA(cudaMemcpyAsync(dz, hz, total, cudaMemcpyHostToDevice, st));
   ctx->stats.h2d_bytes += (int64_t)total;
   const size_t* d_off = reinterpret_cast<const size_t*>(dz);
@@ -313,6 +415,12 @@ int decode_list(lsl_ctx* ctx, TumScratch& S, cudaStream_t st, int n, const uint8
   }
   png_inflate_kernel<<<n, 32, LSL_INF_RING, st>>>(dz, d_off, dfilt, img_bytes, d_status);
   cudaEventRecord(ctx->kev[k_inf][1], st);
+  {
+    const PngPiece* d_pieces = reinterpret_cast<const PngPiece*>(S.d_meta[kind]);
+    const uint32_t* d_pbegin = reinterpret_cast<const uint32_t*>(S.d_meta[kind] + sizeof(PngPiece) * npieces);
+    png_check_kernel<<<n, 256, 0, st>>>(dz, d_pieces, d_pbegin, d_pbegin + (n + 1), dfilt, img_bytes, d_status);
+    ctx->stats.kernel_launches += 1;
+  }
   cudaEventRecord(ctx->kev[k_unf][0], st);
   uint8_t* o = (uint8_t*)d_out;
   const size_t out_img = kind == 1 ? (size_t)W * H * sizeof(float) : (size_t)W * H * 3;
@@ -448,6 +556,8 @@ extern "C" void lsl_tum_release(lsl_ctx* ctx) {
     if (S.h_z[k]) cudaFreeHost(S.h_z[k]);
     if (S.d_z[k]) cudaFree(S.d_z[k]);
     if (S.d_filt[k]) cudaFree(S.d_filt[k]);
+    if (S.h_meta[k]) cudaFreeHost(S.h_meta[k]);
+    if (S.d_meta[k]) cudaFree(S.d_meta[k]);
   }
   if (S.ev_fork) cudaEventDestroy(S.ev_fork);
   if (S.ev_join) cudaEventDestroy(S.ev_join);

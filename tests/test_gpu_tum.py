@@ -93,7 +93,20 @@ def test_rejects(api, ctx):
         except api.LslError as e:
             assert "image 1" in str(e)
             n_err += 1
-    assert n_err > 20
+    assert n_err == 40          # every flipped bit inside an IDAT chunk breaks its CRC-32 (checked on the device)
+    # the zlib check value: a wrong Adler-32 trailer inside a chunk whose CRC is right -> rejected by the Adler check
+    import struct
+    import zlib
+    ln = struct.unpack(">I", good[i0 - 8:i0 - 4])[0]
+    bad = bytearray(good)
+    bad[i0 + ln - 1] ^= 0x5a                                            # last byte of the zlib stream = Adler-32 low byte
+    bad[i0 + ln:i0 + ln + 4] = struct.pack(">I", zlib.crc32(bytes(bad[i0 - 4:i0 + ln])) & 0xffffffff)
+    with pytest.raises(api.LslError, match="Adler"):
+        tum.decode_batch(ctx, [good, bytes(bad)], None, 32, 24, out.data_ptr(), 0)
+    # a damaged ancillary / IEND chunk CRC is caught by the host walk
+    bad = bytearray(good); bad[-1] ^= 1
+    with pytest.raises(api.LslError, match="CRC"):
+        tum.decode_batch(ctx, [bytes(bad)], None, 32, 24, out.data_ptr(), 0)
     tum.decode_batch(ctx, [good, good], None, 32, 24, out.data_ptr(), 0)     # the context is still usable
     torch.cuda.synchronize()
     assert np.array_equal(out[1].cpu().numpy(), OP.imread_bgr(good))
