@@ -143,6 +143,16 @@ int lsl_frames_set_points_batch(lsl_ctx* ctx, int n, lsl_frame* const* frames, c
                                 const int32_t* counts, int dim, int desc_is_u8, int root_sift);
 /* Copies the frame's (conditioned) descriptor rows back: n x dim floats, or n x dim bytes for u8 rows. */
 int lsl_frame_descriptors(lsl_ctx* ctx, const lsl_frame* f, void* dst, int64_t cap_bytes);
+/* The point-feature half of Node::Node on the device (src/node.cpp:219-310, 952-1018): when a detector
+ * is selected, every lsl_extract* call also runs detector->detect (SIFT as OpenCV implements it), removeDepthless,
+ * KeyPointsFilter::retainBest(max_keypoints), extractor->compute, projectTo3D and (root_sift) squareroot_descriptor_space on
+ * the frames' gray / depth planes already in HBM and attaches the result as the frames' point features — what
+ * lsl_frame_set_points would upload, without a host round trip. kind: 0 none (default), 1 SIFT. Needs 3-channel or gray
+ * input through the extract call; Tier-T against cv2's SIFT (tests/test_gpu_sift.py). */
+int lsl_ctx_set_point_detector(lsl_ctx* ctx, int kind, int max_keypoints, int root_sift);
+/* Read-back of a frame's point features: xyz1 [n][4], desc [n][dim] (f32 rows), kp [n][6] = x, y, size, angle, response,
+ * octave + 256 * layer (device-detected points only); any of the three may be NULL. */
+int lsl_frame_points(lsl_ctx* ctx, const lsl_frame* f, float* xyz1, float* desc, float* kp, int cap, int* n);
 int lsl_frame_num_points(const lsl_frame* f);
 /* fx = K(0,0) and Node::asynch_time_diff_sec_ used by the point-edge information matrices of the refinement
  * (compPt3dCov, src/transformation_estimation.cpp:243-262). Every extract call sets them from its K / dt. */

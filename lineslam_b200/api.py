@@ -204,6 +204,10 @@ class Context:
             return frame
         return Frame(self, out)
 
+    def set_point_detector(self, kind: str = "SIFT", max_keypoints: int = 600, root_sift: bool = True):
+        """Point detector run by every extract call (the other half of Node::Node): 'SIFT' or None."""
+        _check(lib().lsl_ctx_set_point_detector(self._h, 1 if kind else 0, max_keypoints, int(root_sift)), self._h)
+
     def match_tc_stats(self, reset: bool = True):
         """(exact evaluations, rows rescanned in full, rows) of the tensor-core pre-filtered point matcher."""
         out = np.zeros(3, np.int64)
@@ -325,6 +329,20 @@ class Frame:
         _check(lib().lsl_frame_set_points_ex(self.ctx._h, self._h, ptr(x), ptr(d), len(x), d.shape[1], int(u8), int(root_sift)), self.ctx._h)
         self._pdim, self._pu8 = d.shape[1], bool(u8)
         return self
+
+    def points(self):
+        """(xyz1 [n,4], desc [n,dim], kp [n,6] or None) of the frame's point features, read back from the device."""
+        n = self.num_points
+        xyz = np.zeros((max(n, 1), 4), np.float32); kp = np.zeros((max(n, 1), 6), np.float32)
+        k = C.c_int(0)
+        rc = lib().lsl_frame_points(self.ctx._h, self._h, ptr(xyz), None, ptr(kp), max(n, 1), C.byref(k))
+        have_kp = rc == 0
+        if not have_kp:
+            _check(lib().lsl_frame_points(self.ctx._h, self._h, ptr(xyz), None, None, max(n, 1), C.byref(k)), self.ctx._h)
+        dim = 128 if have_kp else getattr(self, "_pdim", 128)
+        desc = np.zeros((max(n, 1), dim), np.float32)
+        _check(lib().lsl_frame_points(self.ctx._h, self._h, None, ptr(desc), None, max(n, 1), C.byref(k)), self.ctx._h)
+        return xyz[:n], desc[:n], (kp[:n] if have_kp else None)
 
     def descriptors(self) -> np.ndarray:
         """The frame's descriptor rows as the device holds them (after the optional RootSIFT conditioning)."""

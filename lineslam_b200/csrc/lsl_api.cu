@@ -28,7 +28,7 @@ extern "C" const char* lsl_last_error(const lsl_ctx* ctx) { return ctx ? ctx->er
 static const char* const kKernelNames[LSL_K_COUNT] = {
     "gray_kernel", "xpass_kernel", "ypass_kernel", "ll_angle_kernel", "seed_list_kernel", "sobel5_kernel",
     "lsd_region_kernel", "lsd_nfa_kernel", "line3d_ransac_kernel", "line_msld_kernel", "msld_randfill_kernel", "line_mle_kernel",
-    "gather_lines_kernel", "match_lines_kernel", "pose_kernel", "match_points_kernel", "pose_hybrid_kernel", "relmotion_kernel", "png_unfilter_kernel", "png_inflate_kernel", "png_unfilter_kernel(depth)", "png_inflate_kernel(depth)"};
+    "gather_lines_kernel", "match_lines_kernel", "pose_kernel", "match_points_kernel", "pose_hybrid_kernel", "relmotion_kernel", "png_unfilter_kernel", "png_inflate_kernel", "png_unfilter_kernel(depth)", "png_inflate_kernel(depth)", "sift_kernels"};
 extern "C" const char* lsl_kernel_name(int i) { return (i >= 0 && i < LSL_K_COUNT) ? kKernelNames[i] : ""; }
 
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -134,6 +134,7 @@ extern "C" int lsl_ctx_create(lsl_ctx** out, const lsl_params* params, int cuda_
   ctx->d_depth16 = nullptr; ctx->d_depth16_bytes = 0;
   ctx->d_gather = nullptr; ctx->d_gather_bytes = 0;
   ctx->tmap_gray_ok = false;
+  ctx->sift.block = nullptr; ctx->sift.bytes = 0; ctx->sift_kind = 0; ctx->sift_max_kp = 600; ctx->sift_root = 1;
   memset(&ctx->stats, 0, sizeof(ctx->stats));
   memset(&ctx->dims, 0, sizeof(ctx->dims));
   memset(ctx->kran, 0, sizeof(ctx->kran));
@@ -187,6 +188,7 @@ extern "C" void lsl_ctx_destroy(lsl_ctx* ctx) {
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   if (ctx->d_depth16) cudaFree(ctx->d_depth16);
   if (ctx->d_gather) cudaFree(ctx->d_gather);
+  if (ctx->sift.block) cudaFree(ctx->sift.block);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev3);
   for (int k = 0; k < LSL_K_COUNT; ++k) { cudaEventDestroy(ctx->kev[k][0]); cudaEventDestroy(ctx->kev[k][1]); }
   cudaStreamDestroy(ctx->own_stream);
@@ -316,6 +318,11 @@ static int extract_device(lsl_ctx* ctx, int n, const uint8_t* d_imgs, int channe
     out[f] = fr;
   }
   LSL_CUDA(cudaStreamSynchronize(st));
+  ctx->kran[LSL_K_SIFT] = false; ctx->kms[LSL_K_SIFT] = 0.f;
+  if (ctx->sift_kind == 1 && channels >= 1) {   // the other half of Node::Node: point features of the same frames (src/node.cpp:219-310)
+    if ((rc = lsl_launch_sift(ctx, n, d_depths, W, H, K, out))) return rc;
+    collect_ktimes(ctx, LSL_K_SIFT, LSL_K_SIFT + 1);
+  }
   ctx->stats.frames += n;
   cudaEventElapsedTime(&ctx->ms_total, ctx->ev0, ctx->ev3);
   collect_ktimes(ctx, 0, LSL_K_MATCH);
@@ -468,13 +475,13 @@ extern "C" int lsl_frame_from_lines(lsl_ctx* ctx, const lsl_line_rec* recs, int 
 }
 static void release_points(lsl_frame* f) {
   if (f->pblk) {
-    if (--f->pblk->refs == 0) { cudaFree(f->pblk->d_xyz1); cudaFree(f->pblk->d_desc); delete f->pblk; }
+    if (--f->pblk->refs == 0) { cudaFree(f->pblk->d_xyz1); cudaFree(f->pblk->d_desc); if (f->pblk->d_kp) cudaFree(f->pblk->d_kp); delete f->pblk; }
     f->pblk = nullptr;
   } else {
     if (f->d_xyz1) cudaFree(f->d_xyz1);
     if (f->d_desc) cudaFree(f->d_desc);
   }
-  f->d_xyz1 = nullptr; f->d_desc = nullptr; f->npoints = 0;
+  f->d_xyz1 = nullptr; f->d_desc = nullptr; f->d_kp = nullptr; f->npoints = 0;
 }
 
 extern "C" void lsl_frame_free(lsl_frame* f) {
@@ -542,7 +549,7 @@ extern "C" int lsl_frames_set_points_batch(lsl_ctx* ctx, int n, lsl_frame* const
   if (tot) {
     blk = new (std::nothrow) LslPointBlock();
     if (!blk) return LSL_ERR_ARG;
-    blk->refs = 0; blk->d_xyz1 = nullptr; blk->d_desc = nullptr;
+    blk->refs = 0; blk->d_xyz1 = nullptr; blk->d_desc = nullptr; blk->d_kp = nullptr;
     LSL_CUDA(cudaMalloc((void**)&blk->d_xyz1, sizeof(float) * 4 * tot));
     LSL_CUDA(cudaMalloc((void**)&blk->d_desc, row * tot));
     LSL_CUDA(cudaMemcpyAsync(blk->d_xyz1, xyz1, sizeof(float) * 4 * tot, cudaMemcpyHostToDevice, ctx->stream));
@@ -611,6 +618,31 @@ extern "C" int lsl_frame_descriptors(lsl_ctx* ctx, const lsl_frame* f, void* dst
   LSL_CUDA(cudaMemcpyAsync(dst, f->d_desc, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   LSL_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->stats.d2h_bytes += bytes;
+  return LSL_OK;
+}
+// Point detector of the context: kind 0 = none (point features enter through lsl_frame_set_points), 1 = SIFT on the device.
+extern "C" int lsl_ctx_set_point_detector(lsl_ctx* ctx, int kind, int max_keypoints, int root_sift) {
+  if (!ctx || kind < 0 || kind > 1 || max_keypoints < 1 || max_keypoints > LSL_MAX_POINTS) return LSL_ERR_ARG;
+  LSL_LOCK(ctx);
+  ctx->sift_kind = kind; ctx->sift_max_kp = max_keypoints; ctx->sift_root = root_sift ? 1 : 0;
+  return LSL_OK;
+}
+// xyz1 [n][4], descriptor rows [n][dim] (f32 rows only) and, for device-detected points, kp [n][6] back to the host
+extern "C" int lsl_frame_points(lsl_ctx* ctx, const lsl_frame* f, float* xyz1, float* desc, float* kp, int cap, int* n) {
+  if (!ctx || !f || !n) return LSL_ERR_ARG;
+  *n = f->npoints;
+  if (f->npoints > cap) return LSL_ERR_CAPACITY;
+  if (!f->npoints) return LSL_OK;
+  if (f->pkind != 0 && desc) return LSL_ERR_ARG;
+  LSL_ENTER(ctx);
+  const size_t np = (size_t)f->npoints;
+  if (xyz1) LSL_CUDA(cudaMemcpyAsync(xyz1, f->d_xyz1, sizeof(float) * 4 * np, cudaMemcpyDeviceToHost, ctx->stream));
+  if (desc) LSL_CUDA(cudaMemcpyAsync(desc, f->d_desc, sizeof(float) * (size_t)f->pdim * np, cudaMemcpyDeviceToHost, ctx->stream));
+  if (kp) {
+    if (!f->d_kp) return LSL_ERR_ARG;
+    LSL_CUDA(cudaMemcpyAsync(kp, f->d_kp, sizeof(float) * 6 * np, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  LSL_CUDA(cudaStreamSynchronize(ctx->stream));
   return LSL_OK;
 }
 extern "C" int lsl_frame_num_points(const lsl_frame* f) { return f ? f->npoints : LSL_ERR_ARG; }

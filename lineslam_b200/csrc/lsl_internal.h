@@ -144,6 +144,9 @@ struct LslHybWork {
   int32_t* tc_cand; int32_t* tc_cnt; void* tc_stats; size_t cap_tc;
 };
 
+// ---- point-feature detection workspace (k_sift.cu): pyramid of a few frames + candidate lists + dense output tables ----
+struct LslSiftWork { void* block; size_t bytes; };
+
 // ---- computeRelativeMotion_Ransac scratch (k_hybrid.cu:relmotion_kernel), allocated per call ----
 #define RM_STRIDE 52   // aA aB bA bB (12) | a.DU_A a.DU_B b.DU_A b.DU_B (36) | a.u (3) | pad
 #define RM_M 7
@@ -164,7 +167,7 @@ struct RmScratch {
 // Kernel ids for the per-kernel device timers (CUDA events on the context stream)
 enum LslKernelId {
   LSL_K_GRAY = 0, LSL_K_XPASS, LSL_K_YPASS, LSL_K_LLANGLE, LSL_K_SEEDS, LSL_K_SOBEL, LSL_K_REGION, LSL_K_NFA, LSL_K_RANSAC3D,
-  LSL_K_MSLD, LSL_K_RANDFILL, LSL_K_MLE, LSL_K_GATHER, LSL_K_MATCH, LSL_K_POSE, LSL_K_MATCHPTS, LSL_K_POSEHYB, LSL_K_RELMOTION, LSL_K_PNG, LSL_K_INFLATE, LSL_K_PNG_D, LSL_K_INFLATE_D, LSL_K_COUNT
+  LSL_K_MSLD, LSL_K_RANDFILL, LSL_K_MLE, LSL_K_GATHER, LSL_K_MATCH, LSL_K_POSE, LSL_K_MATCHPTS, LSL_K_POSEHYB, LSL_K_RELMOTION, LSL_K_PNG, LSL_K_INFLATE, LSL_K_PNG_D, LSL_K_INFLATE_D, LSL_K_SIFT, LSL_K_COUNT
 };
 
 // Line records of all frames of one extract call live in ONE device allocation (stream-ordered pool);
@@ -177,6 +180,7 @@ struct LslLineBlock {
 // Point features of all frames of one lsl_frames_set_points_batch call live in one device allocation; frames reference-count it.
 struct LslPointBlock {
   float* d_xyz1; void* d_desc;
+  float* d_kp;      // [n][6] x, y, size, angle, response, octave + 256 layer — only for points detected on the device (k_sift.cu)
   int refs;
 };
 
@@ -196,6 +200,7 @@ struct lsl_frame {
   float* d_xyz1;   // [npoints][4]
   float* d_desc;   // [npoints][pdim]
   LslPointBlock* pblk;   // non-null: d_xyz1 / d_desc point into a shared block
+  float* d_kp;           // keypoint geometry of device-detected points (inside pblk), else nullptr
 };
 
 struct lsl_ctx {
@@ -219,6 +224,7 @@ struct lsl_ctx {
   int debug;
   int32_t* d_goff;           // [max_batch] gather offsets
   void* nccl_lib; void* nccl_comm; int nccl_rank, nccl_nranks; bool nccl_own;
+  LslSiftWork sift; int sift_kind, sift_max_kp, sift_root;   // point detector run by every extract call (0: none, 1: SIFT)
   CUtensorMap tmap_gray; bool tmap_gray_ok;   // TMA tile map of the gray planes (sobel5_tma_kernel), valid for `dims`
   LslDims dims;   // dims the workspace / taps were last prepared for
   LslTaps taps;
@@ -265,5 +271,6 @@ int lsl_launch_pose(lsl_ctx* ctx, int npairs);
 int lsl_launch_match_points(lsl_ctx* ctx, int npairs, int max_nq, int dim, int kind);
 int lsl_launch_rootsift(lsl_ctx* ctx, float* d_desc, int n, int dim);
 int lsl_launch_match_points_tc(lsl_ctx* ctx, int npairs, int max_nq, int dim, int* used);
+int lsl_launch_sift(lsl_ctx* ctx, int n, const float* d_depth, int W, int H, const double K[9], lsl_frame** frames);
 int lsl_launch_pose_hybrid(lsl_ctx* ctx, int npairs, double fx, double dt);
 int lsl_launch_relmotion(lsl_ctx* ctx, int npairs, RmScratch rs);

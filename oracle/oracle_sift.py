@@ -99,7 +99,8 @@ def build_pyramid(gray_u8: np.ndarray):
             if o == 0 and i == 0:
                 layers.append(base)
             elif i == 0:
-                layers.append(np.ascontiguousarray(gauss[o - 1][N_LAYERS][::2, ::2]))   # INTER_NEAREST by 2
+                prev = gauss[o - 1][N_LAYERS]                                  # resize(Size(cols / 2, rows / 2), INTER_NEAREST)
+                layers.append(np.ascontiguousarray(prev[::2, ::2][:prev.shape[0] // 2, :prev.shape[1] // 2]))
             else:
                 layers.append(gaussian_blur(layers[i - 1], float(sig[i])))
         gauss.append(layers)
@@ -124,6 +125,21 @@ def fast_atan2(y, x):
     return a.astype(np.float32)
 
 
+def _solve3(A, b):
+    """Matx33f::solve(b, DECOMP_LU): cv::solve's closed form for 3 x 3 (Cramer's rule, products and determinant in double,
+    result cast to float); zeros if the determinant is exactly 0."""
+    S = A.astype(np.float64); bf = b.astype(np.float64)
+    d = (S[0, 0] * (S[1, 1] * S[2, 2] - S[1, 2] * S[2, 1]) - S[0, 1] * (S[1, 0] * S[2, 2] - S[1, 2] * S[2, 0]) +
+         S[0, 2] * (S[1, 0] * S[2, 1] - S[1, 1] * S[2, 0]))
+    if d == 0.0:
+        return np.zeros(3, np.float32)
+    d = 1.0 / d
+    t0 = d * (bf[0] * (S[1, 1] * S[2, 2] - S[1, 2] * S[2, 1]) - S[0, 1] * (bf[1] * S[2, 2] - S[1, 2] * bf[2]) + S[0, 2] * (bf[1] * S[2, 1] - S[1, 1] * bf[2]))
+    t1 = d * (S[0, 0] * (bf[1] * S[2, 2] - S[1, 2] * bf[2]) - bf[0] * (S[1, 0] * S[2, 2] - S[1, 2] * S[2, 0]) + S[0, 2] * (S[1, 0] * bf[2] - bf[1] * S[2, 0]))
+    t2 = d * (S[0, 0] * (S[1, 1] * bf[2] - bf[1] * S[2, 1]) - S[0, 1] * (S[1, 0] * bf[2] - bf[1] * S[2, 0]) + bf[0] * (S[1, 0] * S[2, 1] - S[1, 1] * S[2, 0]))
+    return np.array([t0, t1, t2]).astype(np.float32)
+
+
 def _adjust(dog_o, layer, r, c):
     """adjustLocalExtrema; returns None or (layer, r, c, xi, xr, xc, contr)."""
     img_scale = np.float32(1.0 / 255)
@@ -141,10 +157,7 @@ def _adjust(dog_o, layer, r, c):
         dxs = (nxt[r, c + 1] - nxt[r, c - 1] - prv[r, c + 1] + prv[r, c - 1]) * cs
         dys = (nxt[r + 1, c] - nxt[r - 1, c] - prv[r + 1, c] + prv[r - 1, c]) * cs
         Hm = np.array([[dxx, dxy, dxs], [dxy, dyy, dys], [dxs, dys, dss]], np.float32)
-        try:
-            X = np.linalg.solve(Hm.astype(np.float64), dD.astype(np.float64)).astype(np.float32)
-        except np.linalg.LinAlgError:
-            X = np.zeros(3, np.float32)
+        X = _solve3(Hm, dD)
         xi, xr, xc = -X[2], -X[1], -X[0]
         if abs(xi) < 0.5 and abs(xr) < 0.5 and abs(xc) < 0.5:
             break
