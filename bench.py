@@ -276,7 +276,8 @@ def run_cuda(args, rank, world, local_rank):
     big = wl == "cfg5"
     Wd, Hd = (1280, 960) if big else (W, H)
     b_frame = Wd * Hd * (3 + 4)
-    B = args.batch if args.batch > 0 else {"cfg2": 592, "cfg3": 148, "cfg4": 256, "cfg5": 74}[wl]
+    B = args.batch if args.batch > 0 else {"cfg2": 1184, "cfg3": 148, "cfg4": 256, "cfg5": 74}[wl]
+    dev_sift = wl == "cfg3" and args.points == "device"
     U = min(args.unique, B) if wl != "cfg4" else 257
     # ---- inputs first: the render pool forks, CUDA must not be initialised yet
     t_r = time.perf_counter()
@@ -284,7 +285,10 @@ def run_cuda(args, rank, world, local_rank):
     if wl == "cfg2":
         imgs, deps, K = make_unique_frames(U, rank, world)
     elif wl == "cfg3":
-        imgs, deps, K, pts = make_unique_frames(U, rank, world, traj="orbit", sift=True)
+        if dev_sift:   # point features detected on the device inside every extract call (k_sift.cu)
+            imgs, deps, K = make_unique_frames(U, rank, world, traj="orbit")
+        else:
+            imgs, deps, K, pts = make_unique_frames(U, rank, world, traj="orbit", sift=True)
     elif wl == "cfg4":   # 1 query + 256 keyframes sampled from the cfg-3 orbit; every rank renders only its block (+ the query on rank 0)
         from lineslam_b200.shard import shard_pairs, pad_records
         from lineslam_b200 import synth
@@ -315,6 +319,8 @@ def run_cuda(args, rank, world, local_rank):
     ctx = api.Context(params=p, device=local_rank, max_batch=max(B if wl != "cfg4" else len(imgs), 1), max_w=Wd, max_h=Hd)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
+    if dev_sift:
+        ctx.set_point_detector("SIFT", p.max_keypoints if hasattr(p, "max_keypoints") else 600, root_sift=True)
     if world > 1:  # library-owned NCCL communicator; the id travels over torch.distributed (plumbing)
         uid = [api.Context.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -477,7 +483,9 @@ def run_cuda(args, rank, world, local_rank):
                               if wl != "cfg4" else "feature records of 256 keyframes + LM scratch (> 126 MB per step), flushed by the scratch writes"),
                        "pairs_found_frac": found_frac, "lines_per_frame": float(ln.mean()),
                        "lines_per_frame_spread": [int(ln.min()), int(np.percentile(ln, 50)), int(ln.max())],
-                       "render_s": round(render_s, 1)},
+                       "render_s": round(render_s, 1),
+                       **({"point_features": "SIFT detected on the device inside lsl_extract_batch (k_sift.cu), max 600, RootSIFT" if dev_sift
+                           else "cv2 SIFT on the host, uploaded with lsl_frames_set_points_batch, RootSIFT on the device"} if wl == "cfg3" else {})},
             "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d_step,
                     "d2h_bytes_per_step": int((h1.d2h_bytes - h0.d2h_bytes) // args.steps), "ms_per_step": ms_e2e / args.steps,
                     "h2d_gbs_per_rank": [round(float(x), 2) for x in h2d_gbs],
@@ -516,8 +524,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("LSL_BENCH_BATCH", 0)), help="frames per step per GPU (0: the workload's default, 592 for cfg2)")
-    ap.add_argument("--unique", type=int, default=148, help="distinct consecutive rendered frames of the stream (tiled palindromically into a batch)")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("LSL_BENCH_BATCH", 0)), help="frames per step per GPU (0: the workload's default, 1184 = 8 x 148 SMs for cfg2)")
+    ap.add_argument("--points", default="device", choices=["device", "host"], help="cfg3: SIFT on the device inside the extract call (default) or cv2 SIFT on the host, uploaded with lsl_frames_set_points_batch")
+    ap.add_argument("--unique", type=int, default=296, help="distinct consecutive rendered frames of the stream (tiled palindromically into a batch)")
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS), help="BASELINE.json config (cfg2 = the metric's config, the default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
