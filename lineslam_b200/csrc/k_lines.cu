@@ -24,7 +24,7 @@ using namespace lslm;
 
 #define FULL 0xffffffffu
 #ifndef RANSAC_CH
-#define RANSAC_CH 8  // hypotheses evaluated per round
+#define RANSAC_CH 12  // hypotheses evaluated per round
 #endif
 
 struct LineParams {
@@ -158,13 +158,14 @@ __global__ void __launch_bounds__(128, RANSAC_MINB) line3d_ransac_kernel(LslWork
   __shared__ double s_pos[LSL_MAX_SMP * 3];
   __shared__ double s_DU[LSL_MAX_SMP * 9];
   __shared__ int s_idx[LSL_MAX_SMP];
-  __shared__ int s_hA[RANSAC_CH], s_hB[RANSAC_CH], s_hcnt[RANSAC_CH];
+  __shared__ int s_hA[2][RANSAC_CH], s_hB[2][RANSAC_CH], s_hcnt[RANSAC_CH];   // sample pairs double-buffered: the next round's are drawn under this round's scoring
+  __shared__ int s_next;                                                      // next hypothesis of the round to score (warps pull)
   __shared__ uint32_t s_hmask[RANSAC_CH][4];
   // 16-byte aligned: the compiler merges neighbouring 4-byte reads into LDS.128 and would otherwise straddle two arrays
   __shared__ __align__(16) uint32_t s_best[4];
   __shared__ __align__(16) int s_wcnt[4];
   __shared__ __align__(16) int s_flag[4];  // 0: done, 1: accepted
-  __shared__ GRand s_rng, s_snap;
+  __shared__ GRand s_rng, s_snap[2];
 
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = P.W, H = P.H;
@@ -244,24 +245,51 @@ __global__ void __launch_bounds__(128, RANSAC_MINB) line3d_ransac_kernel(LslWork
     const int maxIter = min(P.ransac_iters, (int)(n * (n - 1) * 0.5));
     int best_cnt = 0, bestA = -1, bestB = -1;  // maintained uniformly by warp 0
     bool done = false;
-    for (int it0 = 0; it0 < maxIter && !done; it0 += RANSAC_CH) {
-      const int nch = min(RANSAC_CH, maxIter - it0);
-      if (tid == 0) {
-        s_snap = s_rng;
-        for (int h = 0; h < nch; ++h) {
-          int left = n;
-          for (int k = 0; k < 2; ++k) {  // random_unique(begin, end, 2), utils.h:49-60
-            int r = grand_next(&s_rng) % left;
-            int t = s_idx[k]; s_idx[k] = s_idx[k + r]; s_idx[k + r] = t;
-            --left;
-          }
-          s_hA[h] = s_idx[0]; s_hB[h] = s_idx[1];
+    // One round = RANSAC_CH hypotheses. Thread 0 draws the sample pairs (one rand() stream, cumulative shuffle:
+    // random_unique, utils.h:49-60) of round c + 1 while the other warps already score round c; the warps pull
+    // hypotheses from a shared counter, so warp 0 joins the scoring when its draws are done. The scan that follows
+    // is the reference's loop in hypothesis order; when it stops early, the rand() state is rewound to the round's
+    // snapshot and advanced by exactly the draws the reference consumed.
+    // r % left without the division sequence: q = umulhi(r, ceil(2^32 / left)) is floor(r / left) or one more
+    // (r < 2^31, left <= 128), corrected by the sign of the remainder.
+    uint32_t mg0 = 0, mg1 = 0;
+    auto draw_round = [&](int buf, int cnt) {
+      s_snap[buf] = s_rng;
+      for (int h = 0; h < cnt; ++h) {
+        {
+          const uint32_t v = (uint32_t)grand_next(&s_rng);
+          int r = (int)(v - __umulhi(v, mg0) * (uint32_t)n);
+          if (r < 0) r += n;
+          int t = s_idx[0]; s_idx[0] = s_idx[r]; s_idx[r] = t;
         }
+        {
+          const uint32_t v = (uint32_t)grand_next(&s_rng);
+          int r = (int)(v - __umulhi(v, mg1) * (uint32_t)(n - 1));
+          if (r < 0) r += n - 1;
+          int t = s_idx[1]; s_idx[1] = s_idx[1 + r]; s_idx[1 + r] = t;
+        }
+        s_hA[buf][h] = s_idx[0]; s_hB[buf][h] = s_idx[1];
       }
-      __syncthreads();
-      for (int h = warp; h < nch; h += 4) {
-        const double* A = s_pos + 3 * s_hA[h];
-        const double* B = s_pos + 3 * s_hB[h];
+    };
+    if (tid == 0) {
+      mg0 = 0xFFFFFFFFu / (uint32_t)n + 1u; mg1 = 0xFFFFFFFFu / (uint32_t)(n - 1) + 1u;
+      s_next = 0;
+      if (maxIter > 0) draw_round(0, min(RANSAC_CH, maxIter));
+    }
+    __syncthreads();
+    for (int it0 = 0, rnd = 0; it0 < maxIter && !done; it0 += RANSAC_CH, ++rnd) {
+      const int nch = min(RANSAC_CH, maxIter - it0), buf = rnd & 1;
+      if (warp == 0) {
+        if (lane == 0 && it0 + RANSAC_CH < maxIter) draw_round(buf ^ 1, min(RANSAC_CH, maxIter - it0 - RANSAC_CH));
+        __syncwarp();
+      }
+      while (true) {
+        int h = 0;
+        if (lane == 0) h = atomicAdd(&s_next, 1);
+        h = __shfl_sync(FULL, h, 0);
+        if (h >= nch) break;
+        const double* A = s_pos + 3 * s_hA[buf][h];
+        const double* B = s_pos + 3 * s_hB[buf][h];
         double BA[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]};
         bool degenerate = norm3(BA) < 1e-10;
         int cnt = 0;
@@ -283,8 +311,8 @@ __global__ void __launch_bounds__(128, RANSAC_MINB) line3d_ransac_kernel(LslWork
           int c = s_hcnt[h];
           if (c < 0) continue;
           if (c > best_cnt) {
-            if (verify3dLine(s_pos, s_hmask[h], s_pos + 3 * s_hA[h], s_pos + 3 * s_hB[h], P.ncells, P.support_ratio)) {
-              best_cnt = c; bestA = s_hA[h]; bestB = s_hB[h];
+            if (verify3dLine(s_pos, s_hmask[h], s_pos + 3 * s_hA[buf][h], s_pos + 3 * s_hB[buf][h], P.ncells, P.support_ratio)) {
+              best_cnt = c; bestA = s_hA[buf][h]; bestB = s_hB[buf][h];
               if (lane < 4) s_best[lane] = s_hmask[h][lane];
               __syncwarp();
             }
@@ -293,12 +321,12 @@ __global__ void __launch_bounds__(128, RANSAC_MINB) line3d_ransac_kernel(LslWork
         }
         if (hexit >= 0) {
           done = true;
-          if (lane == 0 && hexit != nch - 1) {  // give back the draws of the hypotheses never visited
-            s_rng = s_snap;
+          if (lane == 0) {  // give back the draws of the hypotheses never visited (and of the round drawn ahead)
+            s_rng = s_snap[buf];
             for (int k = 0; k < 2 * (hexit + 1); ++k) grand_next(&s_rng);
           }
         }
-        if (lane == 0) s_flag[0] = done ? 1 : 0;
+        if (lane == 0) { s_flag[0] = done ? 1 : 0; s_next = 0; }
       }
       __syncthreads();
       done = s_flag[0] != 0;
@@ -620,7 +648,8 @@ __device__ __noinline__ int ax_eq_b_lu6(const MleSmemT<CAP>& S, double mu, doubl
   const int lane = threadIdx.x & 31;
   double* a = W; double* work = W + 36; double* xs = W + 42;
   __syncwarp();
-  for (int e = lane; e < 36; e += 32) { const int r = e / 6, c = e - 6 * r; a[e] = (r == c) ? S.JtJ[e] + mu : S.JtJ[e]; }
+  a[lane] = (lane % 7 == 0) ? S.JtJ[lane] + mu : S.JtJ[lane];                   // elements 0..31; the diagonal is e = 0, 7, .., 35
+  if (lane < 4) a[32 + lane] = (lane == 3) ? S.JtJ[35] + mu : S.JtJ[32 + lane];
   double mx = 0.0, tmp;
   if (lane < 6) {
     xs[lane] = S.Jte[lane];
@@ -637,15 +666,24 @@ __device__ __noinline__ int ax_eq_b_lu6(const MleSmemT<CAP>& S, double mu, doubl
   const int ui = 1 + lane / 5, uc = 1 + lane % 5;   // lanes 0..24 <-> element (ui, uc) of the trailing 5 x 5 block
 #pragma unroll 1
   for (int j = 0; j < 6; ++j) {
-    // pivot: the reference's scan over the rows i >= j (`>=`: the last maximum wins, NaNs never do), run redundantly
-    // by every lane on the shared-memory column (six independent loads) instead of a shuffle reduction
+    // pivot: the reference's scan over the rows i >= j (`>=`: the last maximum wins, NaNs never do). The candidates
+    // work[i] |a[i][j]| are non-negative or NaN, so their bit patterns order like the values: lane i forms its row's
+    // candidate, two REDUX.MAX (high word, then low word among the lanes holding the high maximum) give the maximum and a
+    // ballot its last holder — 16 instructions instead of the 54 of the six-step select chain every lane ran redundantly.
     {
-      double pmax = 0.0;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const double t = work[i] * fabs(a[i * 6 + j]);
-        if (i >= j && t >= pmax) { pmax = t; maxi = i; }
+      bool valid = false;
+      unsigned khi = 0u, klo = 0u;
+      if (lane < 6) {
+        const double t = work[lane] * fabs(a[lane * 6 + j]);
+        valid = lane >= j && t == t;                       // t >= pmax is false for a NaN at any pmax
+        const long long kb = __double_as_longlong(t);
+        khi = valid ? (unsigned)(kb >> 32) : 0u; klo = (unsigned)kb;
       }
+      const unsigned mhi = __reduce_max_sync(FULL, khi);
+      const bool top = valid && khi == mhi;
+      const unsigned mlo = __reduce_max_sync(FULL, top ? klo : 0u);
+      const unsigned win = __ballot_sync(FULL, top && klo == mlo);
+      if (win) maxi = 31 - __clz(win);
     }
     if (j != maxi) {                         // uniform
       __syncwarp();                          // every lane has read the column and the weights
@@ -811,15 +849,20 @@ __global__ void __launch_bounds__(32, MINB) line_mle_kernel(LslWork w, LineParam
         const double* ja; const double* jb; int sb;
         if (lane < 21) { ja = S.jac + tri_j; jb = S.jac + tri_i; sb = MLE_JS; }
         else { ja = S.jac + (lane - 21); jb = Ecur; sb = 1; }
-        int l = n - 1;
+        // running pointers (one bump each per four points) instead of index products; the three extra offsets of the
+        // lane's second operand (row stride MLE_JS, or 1 for the J^T e lanes) are loop invariants
+        const double* pa = ja + (n - 1) * MLE_JS;
+        const double* pb = jb + (n - 1) * sb;
+        const int o1 = -sb, o2 = -2 * sb, o3 = -3 * sb, sb4 = 4 * sb;
+        int l = n;
 #pragma unroll 1
-        for (; l >= 3; l -= 4) {
-          double t0 = ja[l * MLE_JS] * jb[l * sb], t1 = ja[(l - 1) * MLE_JS] * jb[(l - 1) * sb], t2 = ja[(l - 2) * MLE_JS] * jb[(l - 2) * sb],
-                 t3 = ja[(l - 3) * MLE_JS] * jb[(l - 3) * sb];
+        for (; l >= 4; l -= 4) {
+          double t0 = pa[0] * pb[0], t1 = pa[-MLE_JS] * pb[o1], t2 = pa[-2 * MLE_JS] * pb[o2], t3 = pa[-3 * MLE_JS] * pb[o3];
           acc += t0; acc += t1; acc += t2; acc += t3;
+          pa -= 4 * MLE_JS; pb -= sb4;
         }
 #pragma unroll 1
-        for (; l >= 0; --l) acc += ja[l * MLE_JS] * jb[l * sb];
+        for (; l > 0; --l) { acc += pa[0] * pb[0]; pa -= MLE_JS; pb -= sb; }
         if (lane < 21) { S.JtJ[tri_i * m + tri_j] = acc; S.JtJ[tri_j * m + tri_i] = acc; }
         else S.Jte[lane - 21] = acc;
       }

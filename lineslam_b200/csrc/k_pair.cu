@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) match_lines_kernel(const LslPairDesc* __r
 // column / block row); sums over the matches run as ordered chains on dedicated threads.
 // tf (12 floats, shared memory) in/out.
 __device__ void refine_pose(const LmView& V, const double* md_all, int n, float* tf, int iterations, const PoseParams& PP,
-                            double* s_red /* >= 64 doubles shared */, double* s_S /* 96 doubles shared */, Iso* s_ci /* 12, shared */, long long& t_last_) {
+                            double* s_red /* >= 64 doubles shared */, double* s_S /* 144 doubles shared */, Iso* s_ci /* 12, shared */, long long& t_last_) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   if (n == 0) return;
   Iso tfd, cam1, ident;
@@ -289,9 +289,11 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
     else if (tid < 42) s_S[tid] = chain_sum<true>(0.0, V.contrib + (size_t)tid * V.cap, 1, n);
     else if (tid == 64 && it == 0) s_red[0] = chain_sum<false>(0.0, V.chi, 1, 2 * n);
     __syncthreads();
-    double Hpp[36], bp[6];
-#pragma unroll
-    for (int k = 0; k < 36; ++k) Hpp[k] = s_S[k];
+    // Hpp | bp stay in shared memory (s_S[96..137]) for the damping retries: a per-thread copy indexed by tid lived in
+    // local memory (42 doubles of stack per thread, read back through L1 / L2 on every retry)
+    double* const s_H = s_S + 96;
+    if (tid < 42) s_H[tid] = s_S[tid];
+    double bp[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) bp[k] = s_S[36 + k];
     if (it == 0) currentChi = s_red[0];
@@ -304,7 +306,7 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
       __syncthreads();
       double maxDiag = 0;
 #pragma unroll
-      for (int a = 0; a < 6; ++a) maxDiag = fmax(fabs(Hpp[a * 6 + a]), maxDiag);
+      for (int a = 0; a < 6; ++a) maxDiag = fmax(fabs(s_H[a * 6 + a]), maxDiag);
       for (int k = 0; k < nthr / 32; ++k) maxDiag = fmax(maxDiag, s_red[1 + k]);
       __syncthreads();
       lambda = tau * maxDiag;
@@ -353,7 +355,7 @@ __device__ void refine_pose(const LmView& V, const double* md_all, int n, float*
       __syncthreads();
       PT(9);
       if (tid < 42) {
-        double s0 = tid < 36 ? Hpp[tid] : bp[tid - 36];
+        double s0 = s_H[tid];
         if (tid < 36 && (tid / 6 == tid % 6)) s0 += lambda;
         s_S[tid] = chain_sum<true>(s0, V.contrib + (size_t)tid * V.cap, 1, n);
       } else if (tid == 64) {
@@ -479,7 +481,7 @@ __global__ void __launch_bounds__(POSE_THREADS, POSE_MINB) pose_kernel(const Lsl
                                                             lsl_pose_rec* __restrict__ out) {
   __shared__ float s_tf[16];
   __shared__ double s_red[64];
-  __shared__ double s_S[96];
+  __shared__ double s_S[144];   // S | bp (42) .. inverse (48..83) .. Hpp | bp of the iteration (96..137)
   __shared__ Iso s_ci[12];
   __shared__ int s_i[4];
   __shared__ double s_d[2];

@@ -20,6 +20,8 @@
 //   sift_pack_kernel       xyz1 + descriptor rows of the batch block
 #include "lsl_internal.h"
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <float.h>
 #include <limits.h>
 #include <mutex>
@@ -32,7 +34,7 @@
 #define SF_BORDER 5
 #define SF_MAX_CAND 16384
 #define SF_MAX_KP 16384
-#define SF_CHUNK 8            // frames per pyramid pass
+#define SF_CHUNK 32           // frames per pyramid pass (39 MB of pyramid per VGA frame)
 #define SF_FIX 16777216.0f    // 2^24: fixed-point scale of the histogram accumulators
 
 struct SiftOct { int W, H; size_t off; };                       // off: floats from the frame's pyramid base to layer 0
@@ -63,26 +65,80 @@ __global__ void sift_upsample_kernel(const uint8_t* __restrict__ gray, float* __
   pyr[(size_t)f * G.frame_floats + (size_t)Y * (2 * W) + X] = h0 * (1.0f - wy) + h1 * wy;   // staged in octave 0, layer 1 (scratch)
 }
 
-// horizontal / vertical pass of cv::GaussianBlur (float, taps in order, BORDER_REFLECT_101)
-__global__ void sift_blur_row_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t fstride_src, size_t fstride_dst, int W, int H, int kidx) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
-  if (x >= W) return;
+// horizontal / vertical pass of cv::GaussianBlur (float, taps summed in tap order from 0, BORDER_REFLECT_101).
+// Row pass: a CTA stages SF_ROW_T + 2 r input values of one image row in shared memory (coalesced, reflected at the borders)
+// and every thread sums its 2 r + 1 taps from there — each input value crosses L2 once instead of 2 r + 1 times.
+#define SF_ROW_T 256          // outputs per CTA: 64 threads x 4 consecutive pixels
+template <int R>
+__global__ void __launch_bounds__(SF_ROW_T / 4) sift_blur_row_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t fstride_src,
+                                                                     size_t fstride_dst, int W, int H, int kidx) {
+  __shared__ __align__(16) float s_in[SF_ROW_T + 2 * R + 6];
+  const int x0 = blockIdx.x * SF_ROW_T, y = blockIdx.y, f = blockIdx.z, tid = threadIdx.x;
   const float* s = src + (size_t)f * fstride_src + (size_t)y * W;
-  const int r = c_rad[kidx];
-  float acc = 0.f;
-  if (x >= r && x + r < W) { for (int t = 0; t <= 2 * r; ++t) acc += c_taps[kidx][t] * s[x - r + t]; }
-  else { for (int t = 0; t <= 2 * r; ++t) acc += c_taps[kidx][t] * s[reflect101g(x - r + t, W)]; }
-  dst[(size_t)f * fstride_dst + (size_t)y * W + x] = acc;
-}
-__global__ void sift_blur_col_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t fstride_src, size_t fstride_dst, int W, int H, int kidx) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+  for (int e = tid; e < SF_ROW_T + 2 * R; e += SF_ROW_T / 4) {
+    const int x = x0 - R + e;
+    s_in[e] = (x >= 0 && x < W) ? s[x] : s[reflect101g(x, W)];
+  }
+  __syncthreads();
+  const int x = x0 + 4 * tid;
   if (x >= W) return;
+  float v[4 + 2 * R + 2];                                   // window of the four outputs, read as float4 (16-byte aligned: 4 tid)
+#pragma unroll
+  for (int k = 0; k < (4 + 2 * R + 3) / 4; ++k) {
+    const float4 q = *reinterpret_cast<const float4*>(s_in + 4 * tid + 4 * k);
+    if (4 * k < 4 + 2 * R + 2) v[4 * k] = q.x;
+    if (4 * k + 1 < 4 + 2 * R + 2) v[4 * k + 1] = q.y;
+    if (4 * k + 2 < 4 + 2 * R + 2) v[4 * k + 2] = q.z;
+    if (4 * k + 3 < 4 + 2 * R + 2) v[4 * k + 3] = q.w;
+  }
+  float* d = dst + (size_t)f * fstride_dst + (size_t)y * W + x;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t <= 2 * R; ++t) acc += c_taps[kidx][t] * v[k + t];
+    if (x + k < W) d[k] = acc;
+  }
+}
+// Column pass: a thread owns one column of a SF_COL_RUN-row strip and slides a register window down it: RUN + 2 R loads
+// (each a coalesced row segment across the warp) for RUN outputs instead of (2 R + 1) RUN.
+#define SF_COL_RUN 16
+template <int R>
+__global__ void __launch_bounds__(256) sift_blur_col_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t fstride_src,
+                                                            size_t fstride_dst, int W, int H, int kidx) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), f = blockIdx.z;
+  const int y0 = (blockIdx.y * 8 + (threadIdx.x >> 5)) * SF_COL_RUN;
+  if (x >= W || y0 >= H) return;
   const float* s = src + (size_t)f * fstride_src + x;
-  const int r = c_rad[kidx];
-  float acc = 0.f;
-  if (y >= r && y + r < H) { for (int t = 0; t <= 2 * r; ++t) acc += c_taps[kidx][t] * s[(size_t)(y - r + t) * W]; }
-  else { for (int t = 0; t <= 2 * r; ++t) acc += c_taps[kidx][t] * s[(size_t)reflect101g(y - r + t, H) * W]; }
-  dst[(size_t)f * fstride_dst + (size_t)y * W + x] = acc;
+  float v[SF_COL_RUN + 2 * R];
+#pragma unroll
+  for (int k = 0; k < SF_COL_RUN + 2 * R; ++k) {
+    const int y = y0 - R + k;
+    v[k] = s[(size_t)((y >= 0 && y < H) ? y : reflect101g(y, H)) * W];
+  }
+  float* d = dst + (size_t)f * fstride_dst + x;
+#pragma unroll
+  for (int k = 0; k < SF_COL_RUN; ++k) {
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t <= 2 * R; ++t) acc += c_taps[kidx][t] * v[k + t];
+    if (y0 + k < H) d[(size_t)(y0 + k) * W] = acc;
+  }
+}
+// one separable blur: rows src -> tmp, columns tmp -> dst (the instance of the kernel's radius)
+template <int R>
+static void sift_blur_R(cudaStream_t st, int nf, const float* src, size_t fs_src, float* tmp, size_t fs_tmp, float* dst, size_t fs_dst, int W, int H, int kidx) {
+  sift_blur_row_kernel<R><<<dim3((W + SF_ROW_T - 1) / SF_ROW_T, H, nf), SF_ROW_T / 4, 0, st>>>(src, tmp, fs_src, fs_tmp, W, H, kidx);
+  sift_blur_col_kernel<R><<<dim3((W + 31) / 32, (H + 8 * SF_COL_RUN - 1) / (8 * SF_COL_RUN), nf), 256, 0, st>>>(tmp, dst, fs_tmp, fs_dst, W, H, kidx);
+}
+static void sift_blur(int r, cudaStream_t st, int nf, const float* src, size_t fs_src, float* tmp, size_t fs_tmp, float* dst, size_t fs_dst, int W, int H, int kidx) {
+  switch (r) {
+    case 5: sift_blur_R<5>(st, nf, src, fs_src, tmp, fs_tmp, dst, fs_dst, W, H, kidx); break;
+    case 6: sift_blur_R<6>(st, nf, src, fs_src, tmp, fs_tmp, dst, fs_dst, W, H, kidx); break;
+    case 8: sift_blur_R<8>(st, nf, src, fs_src, tmp, fs_tmp, dst, fs_dst, W, H, kidx); break;
+    case 10: sift_blur_R<10>(st, nf, src, fs_src, tmp, fs_tmp, dst, fs_dst, W, H, kidx); break;
+    default: sift_blur_R<13>(st, nf, src, fs_src, tmp, fs_tmp, dst, fs_dst, W, H, kidx); break;   // r == 13 (checked by the caller)
+  }
 }
 __global__ void sift_down_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t fstride, int Ws, int Wd, int Hd) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
@@ -453,10 +509,11 @@ int lsl_launch_sift(lsl_ctx* ctx, int n, const float* d_depth, int W, int H, con
   int* slot2kp = (int*)base; base += (size_t)SF_CHUNK * LSL_MAX_POINTS * sizeof(int);
   int* counters = (int*)base;                            // [0..C) ncand, [C..2C) nkp, [2C..2C+B) nout, then goff [B]
   int* d_ncand = counters; int* d_nkp = counters + SF_CHUNK; int* d_nout = counters + 2 * SF_CHUNK; int* d_goff = d_nout + B;
+  int rad[SF_NIMG];
   {
     static std::mutex mu;
     std::lock_guard<std::mutex> lk(mu);
-    float taps[SF_NIMG][40]; int rad[SF_NIMG];
+    float taps[SF_NIMG][40];
     const double sigma = 1.6, k = pow(2.0, 1.0 / SF_LAYERS);
     sift_taps((double)(float)sqrt(fmax(sigma * sigma - 0.5 * 0.5 * 4, 0.01)), taps[0], &rad[0]);       // createInitialImage
     for (int i = 1; i < SF_NIMG; ++i) { const double sp = pow(k, (double)(i - 1)) * sigma, stt = sp * k; sift_taps(sqrt(stt * stt - sp * sp), taps[i], &rad[i]); }
@@ -464,22 +521,29 @@ int lsl_launch_sift(lsl_ctx* ctx, int n, const float* d_depth, int W, int H, con
     LSL_CUDA(cudaMemcpyToSymbolAsync(c_rad, rad, sizeof(rad), 0, cudaMemcpyHostToDevice, st));
     LSL_CUDA(cudaStreamSynchronize(st));   // the host arrays go out of scope
   }
+  for (int i = 0; i < SF_NIMG; ++i)
+    if (rad[i] != 5 && rad[i] != 6 && rad[i] != 8 && rad[i] != 10 && rad[i] != 13) { ctx->err = "SIFT blur radius without a column-pass instance"; return LSL_ERR_ARG; }
   LSL_CUDA(cudaMemsetAsync(d_nout, 0, sizeof(int) * n, st));
   const float inv_fx = (float)(1.0 / K[0]), inv_fy = (float)(1.0 / K[4]), cx = (float)K[2], cy = (float)K[5];
+  // LSL_SIFT_PROFILE=1: device time per phase (pyramid | extrema | orientation | flag + rank | descriptors) on stderr
+  static const bool prof = getenv("LSL_SIFT_PROFILE") != nullptr;
+  cudaEvent_t pe[6]; float pms[5] = {0, 0, 0, 0, 0};
+  if (prof) for (int i = 0; i < 6; ++i) cudaEventCreate(&pe[i]);
+#define SF_MARK(i) do { if (prof) cudaEventRecord(pe[i], st); } while (0)
   LSL_KSTART(ctx, LSL_K_SIFT);
   for (int f0 = 0; f0 < n; f0 += SF_CHUNK) {
     const int nf = n - f0 < SF_CHUNK ? n - f0 : SF_CHUNK;
     const uint8_t* gray = ctx->wk.gray + (size_t)f0 * W * H;
     const float* dep = d_depth + (size_t)f0 * W * H;
     LSL_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * 2 * SF_CHUNK, st));
+    SF_MARK(0);
     // base image: up-sample into layer 1 (scratch), blur rows -> tmp, columns -> layer 0
     {
       const SiftOct O = G.o[0];
       const size_t L = (size_t)O.W * O.H;
       dim3 g((O.W + 127) / 128, O.H, nf);
       sift_upsample_kernel<<<g, 128, 0, st>>>(gray, pyr + L, G, W, H);
-      sift_blur_row_kernel<<<g, 128, 0, st>>>(pyr + L, tmp, G.frame_floats, L, O.W, O.H, 0);
-      sift_blur_col_kernel<<<g, 128, 0, st>>>(tmp, pyr, L, G.frame_floats, O.W, O.H, 0);
+      sift_blur(rad[0], st, nf, pyr + L, G.frame_floats, tmp, L, pyr, G.frame_floats, O.W, O.H, 0);
       ctx->stats.kernel_launches += 3;
     }
     for (int o = 0; o < G.n_oct; ++o) {
@@ -492,8 +556,7 @@ int lsl_launch_sift(lsl_ctx* ctx, int n, const float* d_depth, int W, int H, con
         ctx->stats.kernel_launches += 1;
       }
       for (int i = 1; i < SF_NIMG; ++i) {
-        sift_blur_row_kernel<<<g, 128, 0, st>>>(pyr + O.off + (size_t)(i - 1) * L, tmp, G.frame_floats, L, O.W, O.H, i);
-        sift_blur_col_kernel<<<g, 128, 0, st>>>(tmp, pyr + O.off + (size_t)i * L, L, G.frame_floats, O.W, O.H, i);
+        sift_blur(rad[i], st, nf, pyr + O.off + (size_t)(i - 1) * L, G.frame_floats, tmp, L, pyr + O.off + (size_t)i * L, G.frame_floats, O.W, O.H, i);
         ctx->stats.kernel_launches += 2;
       }
       if (O.W > 2 * SF_BORDER && O.H > 2 * SF_BORDER) {
@@ -502,13 +565,26 @@ int lsl_launch_sift(lsl_ctx* ctx, int n, const float* d_depth, int W, int H, con
         ctx->stats.kernel_launches += 1;
       }
     }
+    SF_MARK(1);
     sift_orient_kernel<<<dim3(256, nf), 128, 0, st>>>(pyr, G, cand, d_ncand, kps, d_nkp);
+    SF_MARK(2);
     sift_flag_kernel<<<dim3(32, nf), 256, 0, st>>>(kps, d_nkp, dep, W, H);
     sift_rank_kernel<<<dim3(32, nf), 256, 0, st>>>(kps, d_nkp, max_kp, d_nout + f0, slot2kp);
+    SF_MARK(3);
     sift_describe_kernel<<<dim3(max_kp, nf), 128, 0, st>>>(pyr, G, kps, slot2kp, d_nout + f0, dep, W, H, inv_fx, inv_fy, cx, cy,
                                                            t_xyz1 + (size_t)f0 * LSL_MAX_POINTS * 4, t_desc + (size_t)f0 * LSL_MAX_POINTS * 128,
                                                            t_kp + (size_t)f0 * LSL_MAX_POINTS * 6);
     ctx->stats.kernel_launches += 4;
+    SF_MARK(4);
+    if (prof) {
+      cudaEventSynchronize(pe[4]);
+      for (int i = 0; i < 4; ++i) { float ms = 0; cudaEventElapsedTime(&ms, pe[i], pe[i + 1]); pms[i] += ms; }
+    }
+  }
+#undef SF_MARK
+  if (prof) {
+    fprintf(stderr, "sift phases (%d frames): pyramid+extrema %.2f ms, orientation %.2f ms, flag+rank %.2f ms, descriptors %.2f ms\n", n, pms[0], pms[1], pms[2], pms[3]);
+    for (int i = 0; i < 6; ++i) cudaEventDestroy(pe[i]);
   }
   LSL_CUDA(cudaGetLastError());
   // ---- counts back (4 bytes per frame), one block for the batch, pack, optional RootSIFT, attach
