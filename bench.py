@@ -282,8 +282,12 @@ def run_cuda(args, rank, world, local_rank):
     # ---- inputs first: the render pool forks, CUDA must not be initialised yet
     t_r = time.perf_counter()
     pts = None
+    split = wl == "cfg2" and world > 1 and args.split == "stream"
+    if split:   # ONE stream dealt block-wise to the ranks: every block must start at the same phase of the palindromic tiling
+        U = B // 4 + 1 if B % 4 == 0 and B >= 8 else U
+        assert B % (2 * U - 2) == 0, "--split stream needs a batch that is a multiple of the tiling period 2 * unique - 2"
     if wl == "cfg2":
-        imgs, deps, K = make_unique_frames(U, rank, world)
+        imgs, deps, K = make_unique_frames(U, 0 if split else rank, world)
     elif wl == "cfg3":
         if dev_sift:   # point features detected on the device inside every extract call (k_sift.cu)
             imgs, deps, K = make_unique_frames(U, rank, world, traj="orbit")
@@ -373,7 +377,8 @@ def run_cuda(args, rank, world, local_rank):
         def one_step(e2e):
             s_ = state["step"]
             b = s_ % nbuf
-            seeds = np.arange(1, B + 1, dtype=np.uint32) + s_ * B
+            blk = s_ * world + rank if split else s_          # block of the (shared or own) stream this step extracts
+            seeds = np.arange(1, B + 1, dtype=np.uint32) + blk * B
             if e2e:
                 frames = ctx.extract_batch(host_i[b].numpy(), host_d16[b].numpy().view(np.uint16), K, seeds)
             else:
@@ -381,8 +386,20 @@ def run_cuda(args, rank, world, local_rank):
             note_ktimes(False)
             if pts is not None:      # cfg 3: the detectors' output enters as an input (Node::Node, src/node.cpp:219-310)
                 ctx.set_points_batch(frames, [pts[i][0] for i in orders[b]], [pts[i][1] for i in orders[b]], root_sift=True)
-            trains = [state["prev"]] + frames[:-1] if state["prev"] is not None else [frames[0]] + frames[:-1]
-            ids = np.arange(B, dtype=np.int32) + s_ * B + 1
+            recv = None
+            if split:   # the head pair of this block needs the tail record of the previous block: ring shift over NVLink
+                recv = ctx.shift_frame(frames[-1])
+                if s_ == 0:   # once, untimed warm-up: what arrived is bit for bit what the neighbour extracted
+                    import hashlib
+                    hs = [None] * world
+                    dist.all_gather_object(hs, (hashlib.sha1(frames[-1].lines().tobytes()).hexdigest(), hashlib.sha1(recv.lines().tobytes()).hexdigest()))
+                    assert all(hs[r][1] == hs[(r - 1) % world][0] for r in range(world)), "lsl_shift_frame: records differ from the sender's"
+                    state["shift_checked"] = True
+                head = recv if rank > 0 else state["prev"]
+            else:
+                head = state["prev"]
+            trains = [head] + frames[:-1] if head is not None else [frames[0]] + frames[:-1]
+            ids = np.arange(B, dtype=np.int32) + blk * B + 1
             recs = ctx.match_pair_batch(frames, trains, ids, ids - 1, seeds)
             note_ktimes(True)
             if wl == "cfg5":         # levmar refine per edge (computeRelativeMotion_Ransac + optimizeRelmotion, motion.cpp:367-526)
@@ -395,7 +412,13 @@ def run_cuda(args, rank, world, local_rank):
             if len(state["lines"]) < 4 * B:
                 state["lines"] += [f.num_lines for f in frames]
             old = state["prev"]
-            state["prev"] = frames[-1]
+            if split:   # rank 0 keeps what it received (the last rank's tail precedes the head of its next block)
+                state["prev"] = recv if rank == 0 else None
+                if rank > 0:
+                    recv.free()
+                frames[-1].free()
+            else:
+                state["prev"] = frames[-1]
             for f in frames[:-1]:
                 f.free()
             if old is not None:
@@ -484,6 +507,7 @@ def run_cuda(args, rank, world, local_rank):
                        "pairs_found_frac": found_frac, "lines_per_frame": float(ln.mean()),
                        "lines_per_frame_spread": [int(ln.min()), int(np.percentile(ln, 50)), int(ln.max())],
                        "render_s": round(render_s, 1),
+                       **({"split": "one stream, blocks of %d frames dealt round-robin to the ranks, tail records shifted rank to rank by ncclSend / ncclRecv (lsl_shift_frame); received == sent checked: %s" % (B, state.get("shift_checked", False))} if split else {}),
                        **({"point_features": "SIFT detected on the device inside lsl_extract_batch (k_sift.cu), max 600, RootSIFT" if dev_sift
                            else "cv2 SIFT on the host, uploaded with lsl_frames_set_points_batch, RootSIFT on the device"} if wl == "cfg3" else {})},
             "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d_step,
@@ -525,6 +549,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("LSL_BENCH_BATCH", 0)), help="frames per step per GPU (0: the workload's default, 1184 = 8 x 148 SMs for cfg2)")
+    ap.add_argument("--split", default="streams", choices=["streams", "stream"], help="cfg2 on N > 1 GPUs: one independent stream per rank (default), or ONE stream dealt block-wise to the ranks with the block tails shifted rank to rank (lsl_shift_frame)")
     ap.add_argument("--points", default="device", choices=["device", "host"], help="cfg3: SIFT on the device inside the extract call (default) or cv2 SIFT on the host, uploaded with lsl_frames_set_points_batch")
     ap.add_argument("--unique", type=int, default=296, help="distinct consecutive rendered frames of the stream (tiled palindromically into a batch)")
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS), help="BASELINE.json config (cfg2 = the metric's config, the default)")

@@ -218,6 +218,13 @@ int lsl_comm_init(lsl_ctx* ctx, const void* id128, int nranks, int rank);
  * ranks `frame` is ignored and *out is a new frame holding the records (free it with lsl_frame_free). Point features are
  * not carried. Device to device: the records never visit the host. */
 int lsl_bcast_frame(lsl_ctx* ctx, int root, lsl_frame* frame, lsl_frame** out);
+/* One stream split block-wise over the ranks (the map of src/graph_manager.cpp:555 sharded): the pair
+ * (t-1, t) at the head of rank r's block needs the record of frame t-1, which rank r-1 extracted as the tail of its block.
+ * Every rank sends `frame` (its tail) to rank (r + 1) % nranks and receives the tail of rank (r - 1 + nranks) % nranks in
+ * *out (a new frame; free it with lsl_frame_free): ncclSend / ncclRecv in one group over the library's communicator,
+ * peer to peer over NVLink, device to device. Rank 0 receives the tail of the last rank, i.e. the predecessor of the head
+ * of its NEXT block. Line records only (point features are not carried). Collective: every rank must call it. */
+int lsl_shift_frame(lsl_ctx* ctx, const lsl_frame* frame, lsl_frame** out);
 
 /* Stage counters of the last call (segments, lines, matches, LM iterations, kernel launches). */
 typedef struct lsl_stats {

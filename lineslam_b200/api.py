@@ -204,6 +204,13 @@ class Context:
             return frame
         return Frame(self, out)
 
+    def shift_frame(self, frame):
+        """Ring shift of the block tails of one stream split over the ranks: sends `frame` to rank + 1, returns the frame
+        received from rank - 1 (ncclSend / ncclRecv, device to device). Collective."""
+        out = C.c_void_p()
+        _check(lib().lsl_shift_frame(self._h, frame._h, C.byref(out)), self._h)
+        return Frame(self, out)
+
     def set_point_detector(self, kind: str = "SIFT", max_keypoints: int = 600, root_sift: bool = True):
         """Point detector run by every extract call (the other half of Node::Node): 'SIFT' or None."""
         _check(lib().lsl_ctx_set_point_detector(self._h, 1 if kind else 0, max_keypoints, int(root_sift)), self._h)

@@ -1184,6 +1184,51 @@ extern "C" int lsl_bcast_frame(lsl_ctx* ctx, int root, lsl_frame* frame, lsl_fra
   return LSL_OK;
 }
 
+// Ring shift of the block tails of a stream split over the ranks: send `frame` to the next rank, receive the previous
+// rank's in *out. Two grouped ncclSend / ncclRecv rounds (line count, then the records), device to device.
+typedef int (*nccl_send_fn)(const void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_recv_fn)(void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_group_fn)(void);
+extern "C" int lsl_shift_frame(lsl_ctx* ctx, const lsl_frame* frame, lsl_frame** out) {
+  if (!ctx || !frame || !out) return LSL_ERR_ARG;
+  LSL_ENTER(ctx);
+  if (!ctx->nccl_comm) { ctx->err = "no communicator: call lsl_comm_init first"; return LSL_ERR_NCCL; }
+  void* h = nccl_open(ctx);
+  nccl_send_fn snd = h ? (nccl_send_fn)dlsym(h, "ncclSend") : nullptr;
+  nccl_recv_fn rcv = h ? (nccl_recv_fn)dlsym(h, "ncclRecv") : nullptr;
+  nccl_group_fn gs = h ? (nccl_group_fn)dlsym(h, "ncclGroupStart") : nullptr;
+  nccl_group_fn ge = h ? (nccl_group_fn)dlsym(h, "ncclGroupEnd") : nullptr;
+  if (!snd || !rcv || !gs || !ge) return LSL_ERR_NCCL;
+  const int nr = ctx->nccl_nranks, next = (ctx->nccl_rank + 1) % nr, prev = (ctx->nccl_rank + nr - 1) % nr;
+  cudaStream_t st = ctx->stream;
+  int32_t* d_n = nullptr;
+  LSL_CUDA(cudaMallocAsync((void**)&d_n, 2 * sizeof(int32_t), st));
+  int32_t n[2] = {frame->nlines, 0};
+  LSL_CUDA(cudaMemcpyAsync(d_n, n, sizeof(n), cudaMemcpyHostToDevice, st));
+  int rc = gs();
+  rc |= snd(d_n, sizeof(int32_t), /* ncclChar */ 0, next, ctx->nccl_comm, st);
+  rc |= rcv(d_n + 1, sizeof(int32_t), 0, prev, ctx->nccl_comm, st);
+  rc |= ge();
+  if (rc == 0) {
+    LSL_CUDA(cudaMemcpyAsync(&n[1], d_n + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    LSL_CUDA(cudaStreamSynchronize(st));
+  }
+  cudaFreeAsync(d_n, st);
+  if (rc != 0 || n[1] < 0 || n[1] > LSL_MAX_LINES) { ctx->err = "ncclSend / ncclRecv (line count) failed"; return LSL_ERR_NCCL; }
+  lsl_frame* fr = new (std::nothrow) lsl_frame();
+  if (!fr) return LSL_ERR_ARG;
+  fr->ctx = ctx; fr->nlines = n[1]; fr->nsegs = 0; fr->d_lines = nullptr; fr->blk = nullptr; fr->have_dbg = false; fr->have_host = false;
+  if (n[1]) LSL_CUDA(cudaMalloc((void**)&fr->d_lines, sizeof(lsl_line_rec) * (size_t)n[1]));
+  rc = gs();
+  if (n[0]) rc |= snd(frame->d_lines, sizeof(lsl_line_rec) * (size_t)n[0], 0, next, ctx->nccl_comm, st);
+  if (n[1]) rc |= rcv(fr->d_lines, sizeof(lsl_line_rec) * (size_t)n[1], 0, prev, ctx->nccl_comm, st);
+  rc |= ge();
+  if (rc != 0) { ctx->err = "ncclSend / ncclRecv (line records) failed"; lsl_frame_free(fr); return LSL_ERR_NCCL; }
+  LSL_CUDA(cudaStreamSynchronize(st));
+  *out = fr;
+  return LSL_OK;
+}
+
 // ------------------------------------------------------------------ introspection ----
 extern "C" int lsl_get_stats(const lsl_ctx* ctx, lsl_stats* out) {
   if (!ctx || !out) return LSL_ERR_ARG;
