@@ -400,7 +400,32 @@ def run_cuda(args, rank, world, local_rank):
                 head = state["prev"]
             trains = [head] + frames[:-1] if head is not None else [frames[0]] + frames[:-1]
             ids = np.arange(B, dtype=np.int32) + blk * B + 1
-            recs = ctx.match_pair_batch(frames, trains, ids, ids - 1, seeds)
+            if pipelined:   # the pair stage of the PREVIOUS batch ran under this batch's extraction: collect it, then start this one
+                finish_pairs()
+                ctx.match_pair_batch_begin(frames, trains, ids, ids - 1, seeds)
+                state["pending"] = (frames, head if not split or rank == 0 else None, recv if split and rank > 0 else None)
+                if split:
+                    state["prev"] = recv if rank == 0 else None
+                else:
+                    state["prev"] = frames[-1]
+            else:
+                recs = ctx.match_pair_batch(frames, trains, ids, ids - 1, seeds)
+                after_pairs(recs, frames)
+                old = state["prev"]
+                if split:   # rank 0 keeps what it received (the last rank's tail precedes the head of its next block)
+                    state["prev"] = recv if rank == 0 else None
+                    if rank > 0:
+                        recv.free()
+                    frames[-1].free()
+                else:
+                    state["prev"] = frames[-1]
+                for f in frames[:-1]:
+                    f.free()
+                if old is not None:
+                    old.free()
+            state["step"] += 1
+
+        def after_pairs(recs, frames):
             note_ktimes(True)
             if wl == "cfg5":         # levmar refine per edge (computeRelativeMotion_Ransac + optimizeRelmotion, motion.cpp:367-526)
                 ctx.relmotion_batch(B)
@@ -411,19 +436,23 @@ def run_cuda(args, rank, world, local_rank):
             state["found"] += int(recs["found"].sum()); state["pairs"] += B
             if len(state["lines"]) < 4 * B:
                 state["lines"] += [f.num_lines for f in frames]
-            old = state["prev"]
-            if split:   # rank 0 keeps what it received (the last rank's tail precedes the head of its next block)
-                state["prev"] = recv if rank == 0 else None
-                if rank > 0:
-                    recv.free()
-                frames[-1].free()
-            else:
-                state["prev"] = frames[-1]
-            for f in frames[:-1]:
-                f.free()
-            if old is not None:
-                old.free()
-            state["step"] += 1
+
+        def finish_pairs():
+            """Collects the batch in flight (records, exchange, statistics) and releases its frames."""
+            pend = state.get("pending")
+            if pend is None:
+                return
+            frames_p, head_p, recv_p = pend
+            recs = ctx.match_pair_batch_end()
+            after_pairs(recs, frames_p)
+            keep = state["prev"]
+            for f in frames_p:
+                if f is not keep:
+                    f.free()
+            for f in (head_p, recv_p):
+                if f is not None and f is not keep and f not in frames_p:
+                    f.free()
+            state["pending"] = None
 
     def timed(e2e: bool, steps: int):
         for v in ktime.values():
@@ -444,6 +473,8 @@ def run_cuda(args, rank, world, local_rank):
             ts = time.perf_counter()
             one_step(e2e)
             per_step.append(round(1e3 * (time.perf_counter() - ts), 2))
+        if wl != "cfg4" and pipelined:
+            finish_pairs()        # the last batch's pair stage completes inside the timed region
         e1.record(stream)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -460,17 +491,22 @@ def run_cuda(args, rank, world, local_rank):
         st1 = ctx.stats()
         return ms, wall, st0, st1, ms_rank
 
+    pipelined = wl != "cfg4" and not args.no_pipeline
     sampler = ClockSampler(local_rank) if rank == 0 and not os.environ.get("LSL_BENCH_NOCLOCKS") else None
     if sampler:
         sampler.start()
     for _ in range(max(args.warmup, 3)):
         one_step(False)
+    if pipelined:
+        finish_pairs()
     ms_dev, wall_dev, s0, s1, _ = timed(False, args.steps)
     steps_dev = list(per_step)
     kt = {k: float(np.mean(v)) for k, v in ktime.items() if v}
     found_frac = state["found"] / max(state["pairs"], 1)
     launches = int(s1.kernel_launches - s0.kernel_launches)
     one_step(True)  # warm the host-buffer path (pinned staging is the caller's here)
+    if pipelined:
+        finish_pairs()
     ms_e2e, wall_e2e, h0, h1, ms_e2e_rank = timed(True, args.steps)
     clocks = sampler.stop() if sampler else None
 
@@ -507,6 +543,7 @@ def run_cuda(args, rank, world, local_rank):
                        "pairs_found_frac": found_frac, "lines_per_frame": float(ln.mean()),
                        "lines_per_frame_spread": [int(ln.min()), int(np.percentile(ln, 50)), int(ln.max())],
                        "render_s": round(render_s, 1),
+                       **({"pipeline": "pair stage of batch k on the pair stream under the extraction of batch k + 1 (lsl_match_pair_batch_begin / _end); all K pair batches complete inside the timed region"} if pipelined else {}),
                        **({"split": "one stream, blocks of %d frames dealt round-robin to the ranks, tail records shifted rank to rank by ncclSend / ncclRecv (lsl_shift_frame); received == sent checked: %s" % (B, state.get("shift_checked", False))} if split else {}),
                        **({"point_features": "SIFT detected on the device inside lsl_extract_batch (k_sift.cu), max 600, RootSIFT" if dev_sift
                            else "cv2 SIFT on the host, uploaded with lsl_frames_set_points_batch, RootSIFT on the device"} if wl == "cfg3" else {})},
@@ -549,6 +586,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("LSL_BENCH_BATCH", 0)), help="frames per step per GPU (0: the workload's default, 1184 = 8 x 148 SMs for cfg2)")
+    ap.add_argument("--no-pipeline", action="store_true", help="run the pair stage of a batch to completion before the next extraction (default: lsl_match_pair_batch_begin / _end, the pair stage of batch k runs under the extraction of batch k + 1)")
     ap.add_argument("--split", default="streams", choices=["streams", "stream"], help="cfg2 on N > 1 GPUs: one independent stream per rank (default), or ONE stream dealt block-wise to the ranks with the block tails shifted rank to rank (lsl_shift_frame)")
     ap.add_argument("--points", default="device", choices=["device", "host"], help="cfg3: SIFT on the device inside the extract call (default) or cv2 SIFT on the host, uploaded with lsl_frames_set_points_batch")
     ap.add_argument("--unique", type=int, default=296, help="distinct consecutive rendered frames of the stream (tiled palindromically into a batch)")

@@ -29,7 +29,8 @@ typedef enum lsl_status {
   LSL_ERR_CUDA = -2,       /* CUDA runtime error (lsl_last_error has the text) */
   LSL_ERR_CAPACITY = -3,   /* caller buffer or internal table too small */
   LSL_ERR_NO_DEVICE = -4,  /* no CUDA device: there is NO CPU fallback */
-  LSL_ERR_NCCL = -5
+  LSL_ERR_NCCL = -5,
+  LSL_ERR_BUSY = -6        /* a pair batch is in flight (lsl_match_pair_batch_begin): finish it with lsl_match_pair_batch_end first */
 } lsl_status;
 
 /* Parameters: src/parameter_server.cpp:160-199 + SystemParameters::init (src/line/lineslam.cpp:577-640)
@@ -194,6 +195,16 @@ int lsl_match_pair_batch(lsl_ctx* ctx, int npairs, const lsl_frame* const* queri
                          const int32_t* id_query, const int32_t* id_train, const uint32_t* seeds,
                          lsl_pose_rec* out);
 
+/* The same batch in two halves, for a stream of batches: _begin enqueues matching + registration of the pairs on the
+ * context's PAIR STREAM and returns at once; _end waits for it and delivers the records. Between the two the caller may
+ * run lsl_extract* of the NEXT batch on the same context: its image / LSD / 3D-line kernels (latency-bound, few warps per
+ * SM) then share the GPU with the registration of the previous batch (register-bound, 16 warps per SM) instead of
+ * running after it — the two stages touch disjoint workspaces. While a batch is in flight every other entry point that
+ * uses the pair workspace returns LSL_ERR_BUSY, and the frames of the batch must stay alive (lsl_frame_free of any frame
+ * waits for the pair stream first). lsl_match_pair_batch == _begin immediately followed by _end. */
+int lsl_match_pair_batch_begin(lsl_ctx* ctx, int npairs, const lsl_frame* const* queries, const lsl_frame* const* trains,
+                               const int32_t* id_query, const int32_t* id_train, const uint32_t* seeds);
+int lsl_match_pair_batch_end(lsl_ctx* ctx, lsl_pose_rec* out, int cap);
 /* Match lists of pair `pair` of the last lsl_match_pair_batch / lsl_pose_ransac call: what = 0 all line
  * matches (Node::lineMatching output), 1 refined inliers (output_line_inlier_matches), 2 inliers of the best
  * RANSAC hypothesis (max_line_inlier_set, motion.cpp:714-721); 3, 4, 5 the same three lists for points

@@ -277,6 +277,25 @@ class Context:
         _check(lib().lsl_match_pair_batch(self._h, n, q, t, ptr(iq), ptr(it), ptr(sd), ptr(out)), self._h)
         return out
 
+    def match_pair_batch_begin(self, queries, trains, id_query, id_train, seeds):
+        """First half of match_pair_batch: enqueues the batch on the context's pair stream and returns at once, so that
+        the extraction of the next batch can run underneath it. The frames must stay alive until match_pair_batch_end."""
+        n = len(queries)
+        qa = (C.c_void_p * n)(*[q._h.value for q in queries])
+        ta = (C.c_void_p * n)(*[t._h.value for t in trains])
+        iq = np.ascontiguousarray(id_query, np.int32); it = np.ascontiguousarray(id_train, np.int32)
+        sd = np.ascontiguousarray(seeds, np.uint32)
+        _check(lib().lsl_match_pair_batch_begin(self._h, n, qa, ta, ptr(iq), ptr(it), ptr(sd)), self._h)
+        self._pending_pairs = n
+
+    def match_pair_batch_end(self):
+        """Second half: waits for the pair stream and returns POSE_DTYPE[n]."""
+        n = getattr(self, "_pending_pairs", 0)
+        out = np.zeros(max(n, 1), POSE_DTYPE)
+        _check(lib().lsl_match_pair_batch_end(self._h, ptr(out), max(n, 1)), self._h)
+        self._pending_pairs = 0
+        return out[:n]
+
     def pair_matches(self, pair: int, what: int):
         """Lists of the last pair call: what 0 = all line matches, 1 = refined line inliers, 2 = line inliers of the
         best RANSAC hypothesis; 3, 4, 5 = the same lists for point matches."""

@@ -20,6 +20,7 @@ extern "C" const char* lsl_strerror(int s) {
     case LSL_ERR_CAPACITY: return "capacity exceeded";
     case LSL_ERR_NO_DEVICE: return "no CUDA device (liblsl_b200 has no CPU fallback)";
     case LSL_ERR_NCCL: return "NCCL error";
+    case LSL_ERR_BUSY: return "a pair batch is in flight";
     default: return "unknown status";
   }
 }
@@ -134,6 +135,10 @@ extern "C" int lsl_ctx_create(lsl_ctx** out, const lsl_params* params, int cuda_
   ctx->d_depth16 = nullptr; ctx->d_depth16_bytes = 0;
   ctx->d_gather = nullptr; ctx->d_gather_bytes = 0;
   ctx->tmap_gray_ok = false;
+  ctx->pair_inflight = 0; ctx->pair_hybrid = false;
+  // (an extraction stream of higher priority than this one was measured: 202 instead of 198 ms per 1184-frame step)
+  cudaStreamCreateWithFlags(&ctx->pair_stream, cudaStreamNonBlocking);
+  cudaEventCreate(&ctx->ev0p); cudaEventCreate(&ctx->ev3p);
   ctx->sift.block = nullptr; ctx->sift.bytes = 0; ctx->sift_kind = 0; ctx->sift_max_kp = 600; ctx->sift_root = 1;
   memset(&ctx->stats, 0, sizeof(ctx->stats));
   memset(&ctx->dims, 0, sizeof(ctx->dims));
@@ -189,6 +194,8 @@ extern "C" void lsl_ctx_destroy(lsl_ctx* ctx) {
   if (ctx->d_depth16) cudaFree(ctx->d_depth16);
   if (ctx->d_gather) cudaFree(ctx->d_gather);
   if (ctx->sift.block) cudaFree(ctx->sift.block);
+  cudaStreamSynchronize(ctx->pair_stream); cudaStreamDestroy(ctx->pair_stream);
+  cudaEventDestroy(ctx->ev0p); cudaEventDestroy(ctx->ev3p);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev3);
   for (int k = 0; k < LSL_K_COUNT; ++k) { cudaEventDestroy(ctx->kev[k][0]); cudaEventDestroy(ctx->kev[k][1]); }
   cudaStreamDestroy(ctx->own_stream);
@@ -486,6 +493,7 @@ static void release_points(lsl_frame* f) {
 
 extern "C" void lsl_frame_free(lsl_frame* f) {
   if (!f) return;
+  if (f->ctx && f->ctx->pair_inflight) { LSL_ENTER(f->ctx); cudaStreamSynchronize(f->ctx->pair_stream); }   // the batch in flight may read this frame
   if (f->d_lines) {
     LSL_ENTER(f->ctx);
     if (f->blk) {
@@ -497,6 +505,7 @@ extern "C" void lsl_frame_free(lsl_frame* f) {
 }
 extern "C" int lsl_frame_clear_lines(lsl_frame* f) {
   if (!f) return LSL_ERR_ARG;
+  if (f->ctx && f->ctx->pair_inflight) { LSL_ENTER(f->ctx); cudaStreamSynchronize(f->ctx->pair_stream); }
   if (f->d_lines) {
     LSL_ENTER(f->ctx);
     if (f->blk) {
@@ -578,6 +587,7 @@ extern "C" int lsl_frames_set_points_batch(lsl_ctx* ctx, int n, lsl_frame* const
 extern "C" int lsl_relmotion_batch(lsl_ctx* ctx, int npairs, double* Rt /* [npairs][12]: R row-major, t */, int32_t* info /* [npairs][4]: consensus size, LM calls, have, 0 */) {
   if (!ctx || npairs < 1 || !Rt || !info) return LSL_ERR_ARG;
   LSL_ENTER(ctx);
+  if (ctx->pair_inflight) { ctx->err = "a pair batch is in flight: call lsl_match_pair_batch_end first"; return LSL_ERR_BUSY; }
   if ((size_t)npairs > ctx->pw.h_pairs.size()) { ctx->err = "no pair batch of that size on the device"; return LSL_ERR_ARG; }
   cudaStream_t st = ctx->stream;
   const size_t M = ctx->pw.last_tot_m > 0 ? ctx->pw.last_tot_m : 1, it = ctx->P.ransac_iters_line_motion, np = (size_t)npairs;
@@ -704,6 +714,7 @@ static int ensure_pair_ws(lsl_ctx* ctx, size_t npairs, size_t tot_m, size_t tot_
 static int setup_pairs(lsl_ctx* ctx, int npairs, const lsl_frame* const* queries, const lsl_frame* const* trains,
                        const int32_t* id_query, const int32_t* id_train, const uint32_t* seeds, const int* adjacent,
                        int cap_override) {
+  if (ctx->pair_inflight) { ctx->err = "a pair batch is in flight: call lsl_match_pair_batch_end first"; return LSL_ERR_BUSY; }
   LslPairWork& p = ctx->pw;
   p.h_pairs.resize(npairs);
   size_t m_off = 0, d_off = 0;
@@ -993,10 +1004,21 @@ extern "C" int lsl_relmotion_ransac(lsl_ctx* ctx, const lsl_frame* train, const 
   return rcap;
 }
 
-extern "C" int lsl_match_pair_batch(lsl_ctx* ctx, int npairs, const lsl_frame* const* queries, const lsl_frame* const* trains,
-                                    const int32_t* id_query, const int32_t* id_train, const uint32_t* seeds, lsl_pose_rec* out) {
-  if (!ctx || npairs < 1 || !queries || !trains || !out) return LSL_ERR_ARG;
+// Runs `body` with the context's launches, copies and kernel timers directed to the pair stream.
+struct PairStreamScope {
+  lsl_ctx* c; cudaStream_t saved;
+  explicit PairStreamScope(lsl_ctx* ctx) : c(ctx), saved(ctx->stream) { ctx->stream = ctx->pair_stream; }
+  ~PairStreamScope() { c->stream = saved; }
+};
+
+extern "C" int lsl_match_pair_batch_begin(lsl_ctx* ctx, int npairs, const lsl_frame* const* queries, const lsl_frame* const* trains,
+                                          const int32_t* id_query, const int32_t* id_train, const uint32_t* seeds) {
+  if (!ctx || npairs < 1 || !queries || !trains) return LSL_ERR_ARG;
   LSL_ENTER(ctx);
+  if (ctx->pair_inflight) { ctx->err = "a pair batch is in flight: call lsl_match_pair_batch_end first"; return LSL_ERR_BUSY; }
+  // the frames' records were written on the context stream (extract calls return synchronised; uploads of
+  // lsl_frame_from_lines / set_points are synchronised too), so the pair stream needs no event to see them
+  PairStreamScope scope(ctx);
   int rc = setup_pairs(ctx, npairs, queries, trains, id_query, id_train, seeds, nullptr, -1);
   if (rc) return rc;
   bool hybrid = false;   // any frame with point features -> Node::matchNodePair with both modalities
@@ -1005,26 +1027,49 @@ extern "C" int lsl_match_pair_batch(lsl_ctx* ctx, int npairs, const lsl_frame* c
   int mq = 0, dim = 1, kind = 0;
   if (hybrid && (rc = setup_ppairs(ctx, npairs, queries, trains, -1, &mq, &dim, &kind))) return rc;
   clear_ktimes(ctx, LSL_K_MATCH, LSL_K_PNG);
-  cudaEventRecord(ctx->ev0, ctx->stream);
+  cudaEventRecord(ctx->ev0p, ctx->stream);
   if (hybrid && (rc = lsl_launch_match_points(ctx, npairs, mq, dim, kind))) return rc;   // featureMatching first (node.cpp:1504)
   if ((rc = lsl_launch_match(ctx, npairs))) return rc;
   if (hybrid) { if ((rc = lsl_launch_pose_hybrid(ctx, npairs, ctx->cam_fx, ctx->cam_dt))) return rc; }
   else if ((rc = lsl_launch_pose(ctx, npairs))) return rc;
-  cudaEventRecord(ctx->ev3, ctx->stream);
+  cudaEventRecord(ctx->ev3p, ctx->stream);
+  ctx->pair_inflight = npairs; ctx->pair_hybrid = hybrid;
+  return LSL_OK;
+}
+
+extern "C" int lsl_match_pair_batch_end(lsl_ctx* ctx, lsl_pose_rec* out, int cap) {
+  if (!ctx || !out) return LSL_ERR_ARG;
+  LSL_ENTER(ctx);
+  const int npairs = ctx->pair_inflight;
+  if (!npairs) { ctx->err = "no pair batch in flight"; return LSL_ERR_ARG; }
+  if (cap < npairs) return LSL_ERR_CAPACITY;
+  PairStreamScope scope(ctx);
+  int rc;
   if ((rc = fetch_counts(ctx, npairs))) return rc;
-  if (hybrid && (rc = fetch_counts_hyb(ctx, npairs))) return rc;
+  if (ctx->pair_hybrid && (rc = fetch_counts_hyb(ctx, npairs))) return rc;
   LSL_CUDA(cudaMemcpyAsync(out, ctx->pw.recs, sizeof(lsl_pose_rec) * npairs, cudaMemcpyDeviceToHost, ctx->stream));
   LSL_CUDA(cudaStreamSynchronize(ctx->stream));
-  cudaEventElapsedTime(&ctx->ms_total, ctx->ev0, ctx->ev3);
+  ctx->pair_inflight = 0;
+  cudaEventElapsedTime(&ctx->ms_total, ctx->ev0p, ctx->ev3p);
   collect_ktimes(ctx, LSL_K_MATCH, LSL_K_PNG);
   ctx->stats.pairs += npairs; ctx->stats.d2h_bytes += (sizeof(lsl_pose_rec) + 12) * npairs;
   for (int i = 0; i < npairs; ++i) ctx->stats.matches += ctx->pw.h_nmatch[i];
   return LSL_OK;
 }
 
+extern "C" int lsl_match_pair_batch(lsl_ctx* ctx, int npairs, const lsl_frame* const* queries, const lsl_frame* const* trains,
+                                    const int32_t* id_query, const int32_t* id_train, const uint32_t* seeds, lsl_pose_rec* out) {
+  if (!ctx || npairs < 1 || !queries || !trains || !out) return LSL_ERR_ARG;
+  LSL_ENTER(ctx);
+  int rc = lsl_match_pair_batch_begin(ctx, npairs, queries, trains, id_query, id_train, seeds);
+  if (rc) return rc;
+  return lsl_match_pair_batch_end(ctx, out, npairs);
+}
+
 extern "C" int lsl_pair_matches(lsl_ctx* ctx, int pair, int what, lsl_match* out, int cap, int* n) {
   if (!ctx || !n || pair < 0 || pair >= (int)ctx->pw.h_nmatch.size() || what < 0 || what > 5) return LSL_ERR_ARG;
   LSL_ENTER(ctx);
+  if (ctx->pair_inflight) { ctx->err = "a pair batch is in flight: call lsl_match_pair_batch_end first"; return LSL_ERR_BUSY; }
   if (what >= 3) {   // point lists: 3 all point matches, 4 refined point inliers, 5 point inliers of the best hypothesis
     const LslHybWork& h = ctx->hw;
     if (!h.last_hybrid || pair >= (int)h.h_npmatch.size()) { *n = 0; return LSL_OK; }
@@ -1116,6 +1161,7 @@ extern "C" int lsl_allgather_poses(lsl_ctx* ctx, void* nccl_comm, int nranks, co
   if (!comm || nranks < 1) { ctx->err = "no communicator: call lsl_comm_init or pass an ncclComm_t"; return LSL_ERR_NCCL; }
   // local_recs == NULL: the records of the last lsl_match_pair_batch are gathered straight from the device buffer the
   // pose kernel wrote (no host round trip on the send side)
+  if (!local_recs && ctx->pair_inflight) { ctx->err = "a pair batch is in flight: call lsl_match_pair_batch_end first"; return LSL_ERR_BUSY; }
   if (!local_recs && (size_t)nlocal > ctx->pw.h_pairs.size()) { ctx->err = "no device-resident records of that count"; return LSL_ERR_ARG; }
   void* h = nccl_open(ctx);
   if (!h) return LSL_ERR_NCCL;

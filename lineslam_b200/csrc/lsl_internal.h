@@ -224,6 +224,7 @@ struct lsl_ctx {
   int debug;
   int32_t* d_goff;           // [max_batch] gather offsets
   void* nccl_lib; void* nccl_comm; int nccl_rank, nccl_nranks; bool nccl_own;
+  cudaStream_t pair_stream; cudaEvent_t ev0p, ev3p; int pair_inflight; bool pair_hybrid;   // lsl_match_pair_batch_begin / _end
   LslSiftWork sift; int sift_kind, sift_max_kp, sift_root;   // point detector run by every extract call (0: none, 1: SIFT)
   CUtensorMap tmap_gray; bool tmap_gray_ok;   // TMA tile map of the gray planes (sobel5_tma_kernel), valid for `dims`
   LslDims dims;   // dims the workspace / taps were last prepared for
