@@ -37,13 +37,6 @@ sys.path.insert(0, ROOT)
 W, H = 640, 480
 B_FRAME = W * H * (3 + 4)          # compulsory HBM bytes per extracted frame: RGB u8 + depth f32
 METRIC = "frame-pairs/sec (extract+match+RANSAC pose) on 640x480 RGB-D"
-# dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture at batch 592
-# (profiles/r1_final2_ncu_full_raw_b592.csv for the first three kernels, profiles/r1_end_ncu_full_raw_b592.csv for the
-# others), per frame of the launch
-NCU_DRAM_BYTES_PER_FRAME = {"line_mle_kernel": (0.1764e9 + 0.1708e9) / 592, "lsd_region_kernel": (1.4525e9 + 0.0903e9) / 592,
-                            "line3d_ransac_kernel": (0.3238e9 + 0.1165e9) / 592, "lsd_nfa_kernel": (0.2759e9 + 0.0110e9) / 592,
-                            "ll_angle_kernel": (0.9328e9 + 3.925e9) / 592, "line_msld_kernel": (0.6691e9 + 0.0586e9) / 592}
-
 
 def _hbm_peak(peaks, fallback: float = 6650.0) -> float:
     """HBM GB/s out of the driver-written MEASURED_PEAKS.json (key `hbm_gbs`; any numeric entry whose key names HBM /
@@ -560,7 +553,7 @@ def run_cuda(args, rank, world, local_rank):
                          "traffic_unit": "bytes per launch (ncu dram read + write of this build, profiles/r2_ncu_pipe.json)",
                          "algorithmic_bytes": alg_bytes,
                          "actual_bound": {"kind": "fp64 dependency latency", "kernel": dom, **{k: v for k, v in NCU_PIPE.get(dom, {}).items() if k != "dram_bytes_per_frame"},
-                                          "source": "profiles/r2_ncu_pipe.json (ncu --set full of this build, batch 592)"},
+                                          "source": NCU_PIPE.get("_source", "profiles/r2_ncu_pipe.json")},
                          "note": f"algorithmic bytes = {units} frames x {b_frame} B (RGB u8 + depth f32) per launch / CUDA-event time of "
                                  f"{dom}; peak = MEASURED_PEAKS.json hbm_gbs ({'measured' if peaks else 'fallback 6650 GB/s of B200_PROFILING.md'}); "
                                  f"the path is FP64-latency / dependency bound (100 LM iterations per line, sequential region "

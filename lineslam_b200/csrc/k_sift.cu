@@ -511,15 +511,19 @@ int lsl_launch_sift(lsl_ctx* ctx, int n, const float* d_depth, int W, int H, con
   int* d_ncand = counters; int* d_nkp = counters + SF_CHUNK; int* d_nout = counters + 2 * SF_CHUNK; int* d_goff = d_nout + B;
   int rad[SF_NIMG];
   {
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lk(mu);
     float taps[SF_NIMG][40];
     const double sigma = 1.6, k = pow(2.0, 1.0 / SF_LAYERS);
     sift_taps((double)(float)sqrt(fmax(sigma * sigma - 0.5 * 0.5 * 4, 0.01)), taps[0], &rad[0]);       // createInitialImage
     for (int i = 1; i < SF_NIMG; ++i) { const double sp = pow(k, (double)(i - 1)) * sigma, stt = sp * k; sift_taps(sqrt(stt * stt - sp * sp), taps[i], &rad[i]); }
-    LSL_CUDA(cudaMemcpyToSymbolAsync(c_taps, taps, sizeof(taps), 0, cudaMemcpyHostToDevice, st));
-    LSL_CUDA(cudaMemcpyToSymbolAsync(c_rad, rad, sizeof(rad), 0, cudaMemcpyHostToDevice, st));
-    LSL_CUDA(cudaStreamSynchronize(st));   // the host arrays go out of scope
+    static std::mutex mu;
+    static bool uploaded[64] = {false};
+    std::lock_guard<std::mutex> lk(mu);
+    if (!uploaded[ctx->device & 63]) {   // the tap tables are constants of the algorithm: once per device
+      LSL_CUDA(cudaMemcpyToSymbolAsync(c_taps, taps, sizeof(taps), 0, cudaMemcpyHostToDevice, st));
+      LSL_CUDA(cudaMemcpyToSymbolAsync(c_rad, rad, sizeof(rad), 0, cudaMemcpyHostToDevice, st));
+      LSL_CUDA(cudaStreamSynchronize(st));   // the host arrays go out of scope
+      uploaded[ctx->device & 63] = true;
+    }
   }
   for (int i = 0; i < SF_NIMG; ++i)
     if (rad[i] != 5 && rad[i] != 6 && rad[i] != 8 && rad[i] != 10 && rad[i] != 13) { ctx->err = "SIFT blur radius without a column-pass instance"; return LSL_ERR_ARG; }
@@ -598,10 +602,13 @@ int lsl_launch_sift(lsl_ctx* ctx, int n, const float* d_depth, int W, int H, con
   if (tot) {
     blk = new (std::nothrow) LslPointBlock();
     if (!blk) return LSL_ERR_ARG;
-    blk->refs = 0; blk->d_xyz1 = nullptr; blk->d_desc = nullptr; blk->d_kp = nullptr;
-    LSL_CUDA(cudaMalloc((void**)&blk->d_xyz1, sizeof(float) * 4 * tot));
-    LSL_CUDA(cudaMalloc((void**)&blk->d_desc, sizeof(float) * 128 * tot));
-    LSL_CUDA(cudaMalloc((void**)&blk->d_kp, sizeof(float) * 6 * tot));
+    blk->refs = 0; blk->d_xyz1 = nullptr; blk->d_desc = nullptr; blk->d_kp = nullptr; blk->pooled = true;
+    // one stream-ordered allocation per batch in 4 MB size classes (consecutive batches reuse each other's blocks; a plain
+    // cudaMalloc / cudaFree pair per call synchronises the device — and with it the pair stream of the previous batch)
+    const size_t rows = (tot + tot / 8 + 7167) / 7168 * 7168;
+    uint8_t* pb = nullptr;
+    LSL_CUDA(cudaMallocAsync((void**)&pb, rows * (4 + 128 + 6) * sizeof(float), st));
+    blk->d_xyz1 = (float*)pb; blk->d_desc = pb + rows * 4 * sizeof(float); blk->d_kp = (float*)(pb + rows * (4 + 128) * sizeof(float));
     LSL_CUDA(cudaMemcpyAsync(d_goff, goff.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
     sift_pack_kernel<<<dim3(64, n), 256, 0, st>>>(t_xyz1, t_desc, t_kp, d_nout, d_goff, blk->d_xyz1, (float*)blk->d_desc, blk->d_kp);
     ctx->stats.kernel_launches += 1;

@@ -482,7 +482,11 @@ extern "C" int lsl_frame_from_lines(lsl_ctx* ctx, const lsl_line_rec* recs, int 
 }
 static void release_points(lsl_frame* f) {
   if (f->pblk) {
-    if (--f->pblk->refs == 0) { cudaFree(f->pblk->d_xyz1); cudaFree(f->pblk->d_desc); if (f->pblk->d_kp) cudaFree(f->pblk->d_kp); delete f->pblk; }
+    if (--f->pblk->refs == 0) {
+      if (f->pblk->pooled) cudaFreeAsync(f->pblk->d_xyz1, f->ctx->stream);
+      else { cudaFree(f->pblk->d_xyz1); cudaFree(f->pblk->d_desc); if (f->pblk->d_kp) cudaFree(f->pblk->d_kp); }
+      delete f->pblk;
+    }
     f->pblk = nullptr;
   } else {
     if (f->d_xyz1) cudaFree(f->d_xyz1);
@@ -558,7 +562,7 @@ extern "C" int lsl_frames_set_points_batch(lsl_ctx* ctx, int n, lsl_frame* const
   if (tot) {
     blk = new (std::nothrow) LslPointBlock();
     if (!blk) return LSL_ERR_ARG;
-    blk->refs = 0; blk->d_xyz1 = nullptr; blk->d_desc = nullptr; blk->d_kp = nullptr;
+    blk->refs = 0; blk->d_xyz1 = nullptr; blk->d_desc = nullptr; blk->d_kp = nullptr; blk->pooled = false;
     LSL_CUDA(cudaMalloc((void**)&blk->d_xyz1, sizeof(float) * 4 * tot));
     LSL_CUDA(cudaMalloc((void**)&blk->d_desc, row * tot));
     LSL_CUDA(cudaMemcpyAsync(blk->d_xyz1, xyz1, sizeof(float) * 4 * tot, cudaMemcpyHostToDevice, ctx->stream));

@@ -181,6 +181,7 @@ struct LslLineBlock {
 struct LslPointBlock {
   float* d_xyz1; void* d_desc;
   float* d_kp;      // [n][6] x, y, size, angle, response, octave + 256 layer — only for points detected on the device (k_sift.cu)
+  bool pooled;      // one stream-ordered allocation (cudaMallocAsync) starting at d_xyz1 holds all three tables
   int refs;
 };
 
