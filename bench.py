@@ -306,6 +306,7 @@ def run_cuda(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from lineslam_b200 import api
+    from lineslam_b200 import shard as shard_mod
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
@@ -370,7 +371,7 @@ def run_cuda(args, rank, world, local_rank):
         def one_step(e2e):
             s_ = state["step"]
             b = s_ % nbuf
-            blk = s_ * world + rank if split else s_          # block of the (shared or own) stream this step extracts
+            blk = shard_mod.stream_block(s_, world, rank, B)[0] if split else s_   # block of the (shared or own) stream this step extracts
             seeds = np.arange(1, B + 1, dtype=np.uint32) + blk * B
             if e2e:
                 frames = ctx.extract_batch(host_i[b].numpy(), host_d16[b].numpy().view(np.uint16), K, seeds)

@@ -22,6 +22,41 @@ def shard_stream(n_frames: int, world: int, rank: int, batch: int):
     return out
 
 
+def stream_block(step: int, world: int, rank: int, batch: int):
+    """ONE stream dealt block-wise: at `step` rank r extracts block g = step * world + r, frames [g * batch, (g + 1) * batch).
+    Returns (g, first_frame, prev_owner_rank, prev_owner_step): the head pair (first - 1, first) needs the tail record of
+    block g - 1, extracted by rank r - 1 at the same step, or — for rank 0 — by the last rank at the previous step
+    (None, None for the very first block). On the GPUs the tails travel with lsl_shift_frame (ncclSend / ncclRecv ring)."""
+    g = step * world + rank
+    if g == 0:
+        return g, 0, None, None
+    return g, g * batch, (rank - 1) % world, step if rank > 0 else step - 1
+
+
+def ring_shift_bytes(payload: bytes, group=None) -> bytes:
+    """Host-side stand-in for lsl_shift_frame (any torch.distributed backend): every rank sends `payload` to rank + 1 and
+    returns what rank - 1 sent. Collective."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    nxt, prv = (rank + 1) % world, (rank - 1) % world
+    n_out = torch.tensor([len(payload)], dtype=torch.int64)
+    n_in = torch.zeros(1, dtype=torch.int64)
+    reqs = [dist.isend(n_out, nxt, group=group), dist.irecv(n_in, prv, group=group)]
+    for r in reqs:
+        r.wait()
+    out = torch.frombuffer(bytearray(payload), dtype=torch.uint8) if payload else torch.zeros(0, dtype=torch.uint8)
+    inn = torch.zeros(int(n_in.item()), dtype=torch.uint8)
+    reqs = []
+    if len(payload):
+        reqs.append(dist.isend(out, nxt, group=group))
+    if inn.numel():
+        reqs.append(dist.irecv(inn, prv, group=group))
+    for r in reqs:
+        r.wait()
+    return inn.numpy().tobytes()
+
+
 def shard_pairs(n_pairs: int, world: int, rank: int):
     """Block-wise split of a loop-closure batch (1 query x n keyframes): rank r gets [lo, hi); blocks are padded
     to equal length `per` so that the all-gather moves the same record count from every rank."""

@@ -127,3 +127,48 @@ def test_sharded_candidates_give_the_unsharded_graph():
         assert e == gm.edges().tobytes() and n == gm.nodes().tobytes()
         assert k == [int(x) for x in gm.keyframe_ids()]
     assert len(gm.edges()) > 60
+
+
+def _stream_worker(rank, world, port, batch, steps, q):
+    """One stream dealt block-wise: every rank 'extracts' its block (a record = a function of the frame id), the block tails
+    are ring-shifted, the head pair of every block is registered against the received tail."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lineslam_b200 import shard
+    pairs, kept = [], None
+    for s in range(steps):
+        g, first, own_rank, own_step = shard.stream_block(s, world, rank, batch)
+        frames = [np.full(3 + (f % 5), f, np.int64) for f in range(first, first + batch)]       # ragged fake line records
+        recv = np.frombuffer(shard.ring_shift_bytes(frames[-1].tobytes()), np.int64)            # lsl_shift_frame
+        head = recv if rank > 0 else kept
+        if own_rank is None:
+            assert head is None
+        else:
+            assert own_rank == (rank - 1) % world and own_step == (s if rank > 0 else s - 1)
+            assert len(head) == 3 + ((first - 1) % 5) and head[0] == first - 1                    # the neighbour's tail, intact
+            pairs.append((int(head[0]), first))
+        pairs += [(f - 1, f) for f in range(first + 1, first + batch)]
+        if rank == 0:
+            kept = recv                     # the last rank's tail precedes the head of rank 0's next block
+    q.put((rank, pairs))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_one_stream_dealt_blockwise_with_shifted_tails_covers_every_pair_once():
+    world, batch, steps = 2, 7, 3
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_stream_worker, args=(r, world, port, batch, steps, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    got = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    allp = sorted(sum((g[1] for g in got), []))
+    n = world * batch * steps
+    assert allp == [(f - 1, f) for f in range(1, n)]          # every consecutive pair of the stream exactly once

@@ -135,3 +135,49 @@ def test_sift_batch_feeds_the_hybrid_pair_path(api, stream4):
         T = synth.relative_pose_q2t(*poses[k + 1], *poses[k])
         assert np.abs(recs[k]["tf"].reshape(4, 4)[:3, 3] - T[:3, 3]).max() < 0.03
     ctx.close()
+
+
+def test_sift_edge_cases(api, oracle):
+    """Empty and degenerate inputs of the point half of Node::Node: a blank frame (no extrema), a frame whose depth is NaN
+    everywhere (removeDepthless drops every keypoint), a small max_keypoints (retainBest + resize), a tiny frame whose coarse
+    octaves shrink below the 5-pixel border, and two sizes in one context; each against the oracle."""
+    from lineslam_b200 import synth
+    from oracle import oracle_sift as S
+    tum, dep, K = _tum_inputs()
+    H, W = tum.shape[:2]
+    ctx = api.Context(max_batch=2, max_w=W, max_h=H)
+    ctx.set_point_detector("SIFT", 600, root_sift=False)
+    blank = np.full_like(tum, 117)
+    nodepth = np.full_like(dep, np.nan)
+    fr = ctx.extract_batch(np.stack([blank, tum]), np.stack([dep, nodepth]), K, seeds=[1, 2])
+    assert fr[0].num_points == 0 and fr[1].num_points == 0
+    xyz, desc, kp = fr[0].points()
+    assert xyz.shape == (0, 4) and desc.shape[0] == 0
+    # frames without points take the line-only branch of matchNodePair
+    recs = ctx.match_pair_batch([fr[1]], [fr[1]], [1], [0], [3])
+    assert recs.shape == (1,)
+    # retainBest(40): the 40 strongest of the oracle, in response order
+    ctx.set_point_detector("SIFT", 40, root_sift=False)
+    f40 = ctx.extract_batch(tum[None], dep[None], K, seeds=[9])[0]
+    kps, xyz_o, desc_o = _oracle_features(oracle.gray(tum), dep, K, 40)
+    _, d40, k40 = f40.points()
+    m, A = _pair_up(k40, kps)
+    assert f40.num_points == 40 and (m >= 0).sum() >= 39 and np.abs(d40[m >= 0] - desc_o[m[m >= 0]]).max() <= 1.0
+    # a tiny frame in the same context (octave sizes 160x120 ... 5x3; the last ones are smaller than the border)
+    imgs, deps, _ = synth.make_stream(1, scene_seed=2004, W=80, H=60)
+    Ks = synth.camera_K(80, 60)
+    ctx.set_point_detector("SIFT", 600, root_sift=False)
+    small = ctx.extract_batch(imgs, deps, Ks, seeds=[4])[0]
+    kps_s, xyz_s, desc_s = _oracle_features(oracle.gray(imgs[0]), deps[0], Ks, 600)
+    _, ds, ks = small.points()
+    assert small.num_points == len(kps_s)
+    if len(kps_s):
+        ms, _ = _pair_up(ks, kps_s)
+        assert (ms >= 0).all() and np.abs(ds - desc_s[ms]).max() <= 1.0
+    # argument checks of the ABI
+    L = api.lib()
+    assert L.lsl_ctx_set_point_detector(ctx._h, 2, 600, 1) < 0 and L.lsl_ctx_set_point_detector(ctx._h, 1, 0, 1) < 0
+    import ctypes as C
+    n = C.c_int(0)
+    assert L.lsl_frame_points(ctx._h, f40._h, None, None, None, 10, C.byref(n)) < 0 and n.value == 40     # capacity error reports the count
+    ctx.close()
