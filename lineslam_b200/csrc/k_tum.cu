@@ -18,6 +18,8 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
+#include <algorithm>
 #include <vector>
 #include "lsl_internal.h"
 #include "shared/lsl_inflate.h"
@@ -30,7 +32,13 @@ namespace {
 // (DEFLATE matches reach at most 32 KB back), literals and match copies touch only the ring, and every completed
 // LSL_INF_CHUNK bytes leave for global memory as one coalesced 16-byte-per-lane store pass. Without the ring every
 // match copy was a round trip to L2 for bytes this warp had just written (357 ms per 2 x 592 VGA images).
-#define LSL_INF_RING 36864    // 18 chunks: >= 32768 + one chunk + the longest match, and a multiple of the chunk
+#define LSL_INF_RING 8192     // 4 chunks. Matches that reach further back than LSL_INF_NEAR bytes (rare in image data: the rows
+                              // a PNG filter refers to are 1.3 - 3.8 KB back) read their source from the output in global memory,
+                              // where every chunk older than the one in progress already is. 8 KB instead of the full 32 KB window
+                              // + one chunk is what lets 16 instead of 5 streams be resident per SM.
+#define LSL_INF_NEAR (LSL_INF_RING - 768)   // dist <= NEAR: every source byte is still in the ring when it is read (the longest
+                                            // match writes 258 bytes ahead); dist > NEAR: every source byte is older than the
+                                            // chunk in progress (NEAR > chunk + longest match), i.e. flushed
 #define LSL_INF_CHUNK 2048
 // stores output bytes [first, first + LSL_INF_CHUNK) from the ring; rare (once per 2 KB), kept out of line (and free of
 // the ops object, which must stay in registers) so that the literal loop stays small
@@ -62,15 +70,74 @@ struct InflateOpsWarp {
     rp = (rp + 1 == LSL_INF_RING) ? 0 : rp + 1;
     if (pos + 1 == next_flush) flush_chunk(out);
   }
+  // Literal runs are 87 % of the decoder's instructions on image data (51 per literal in the general loop: an output-overflow
+  // test, a chunk test, a ring wrap and five reconvergence points per symbol). Here the three events (chunk complete, output
+  // full, ring end) are folded into ONE countdown computed per run, and a symbol costs a table load, the literal test, the
+  // shift, a predicated store and the countdown.
+  __device__ __forceinline__ uint32_t literal_run(lslm::BitIn* b, const lslm::HuffTable* h, uint8_t* out, uint32_t pos, uint32_t want) {
+    // 32-bit shared-window addresses once per run (the compiler otherwise rebuilds them from generic pointers per symbol)
+    const uint32_t fast_s = (uint32_t)__cvta_generic_to_shared(h->fast), ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    for (;;) {
+      uint32_t left = min(min(next_flush - pos, want - pos), (uint32_t)LSL_INF_RING - rp);
+      if (left == 0) return pos;                    // output full: the general loop decides what the next symbol means
+      const uint32_t n0 = left;
+      bool stop = false;
+      // three symbols per refill test: after bits_fill there are >= 33 valid bits and a first-level code has <= 9
+      while (left >= 3) {
+        if (b->cnt <= 32) lslm::bits_fill(b);
+        uint64_t buf = b->buf;
+        uint32_t e0, e1, e2;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e0) : "r"(fast_s + 2u * ((uint32_t)buf & ((1u << LSL_INF_FAST) - 1u))));
+        if (e0 - 1u >= 4095u) { stop = true; break; }   // 0: long code; >= 256 << 4: length / end-of-block symbol
+        const int l0 = (int)(e0 & 15u);
+        buf >>= l0;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e1) : "r"(fast_s + 2u * ((uint32_t)buf & ((1u << LSL_INF_FAST) - 1u))));
+        if (lane == 0) asm volatile("st.shared.u8 [%0], %1;" :: "r"(ring_s + rp), "r"(e0 >> 4) : "memory");
+        if (e1 - 1u >= 4095u) { b->buf = buf; b->cnt -= l0; rp += 1; left -= 1; stop = true; break; }
+        const int l1 = (int)(e1 & 15u);
+        buf >>= l1;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e2) : "r"(fast_s + 2u * ((uint32_t)buf & ((1u << LSL_INF_FAST) - 1u))));
+        if (lane == 0) asm volatile("st.shared.u8 [%0], %1;" :: "r"(ring_s + rp + 1u), "r"(e1 >> 4) : "memory");
+        if (e2 - 1u >= 4095u) { b->buf = buf; b->cnt -= l0 + l1; rp += 2; left -= 2; stop = true; break; }
+        const int l2 = (int)(e2 & 15u);
+        buf >>= l2;
+        if (lane == 0) asm volatile("st.shared.u8 [%0], %1;" :: "r"(ring_s + rp + 2u), "r"(e2 >> 4) : "memory");
+        b->buf = buf; b->cnt -= l0 + l1 + l2; rp += 3; left -= 3;
+      }
+      while (left && !stop) {
+        if (b->cnt <= 32) lslm::bits_fill(b);
+        uint32_t e;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(fast_s + 2u * ((uint32_t)b->buf & ((1u << LSL_INF_FAST) - 1u))));
+        if (e - 1u >= 4095u) { stop = true; break; }
+        const int l = (int)(e & 15u);
+        b->buf >>= l; b->cnt -= l;
+        if (lane == 0) asm volatile("st.shared.u8 [%0], %1;" :: "r"(ring_s + rp), "r"(e >> 4) : "memory");
+        ++rp; --left;
+      }
+      pos += n0 - left;
+      if (rp == LSL_INF_RING) rp = 0;
+      if (pos == next_flush) flush_chunk(out);
+      if (stop) return pos;
+    }
+  }
   __device__ __forceinline__ void copy(uint8_t* out, uint32_t pos, int dist, int n) {
     __syncwarp();                                   // the bytes the match refers to are visible to every lane
-    const uint32_t sbase = rp + LSL_INF_RING - (uint32_t)dist;    // < 2 * LSL_INF_RING
-    for (int i = lane; i < n; i += 32) {
-      uint32_t s = sbase + (uint32_t)(dist >= n ? i : i % dist);
-      if (s >= LSL_INF_RING) s -= LSL_INF_RING;
-      uint32_t d = rp + (uint32_t)i;
-      if (d >= LSL_INF_RING) d -= LSL_INF_RING;
-      ring[d] = ring[s];
+    if (dist <= LSL_INF_NEAR) {
+      const uint32_t sbase = rp + LSL_INF_RING - (uint32_t)dist;    // < 2 * LSL_INF_RING
+      for (int i = lane; i < n; i += 32) {
+        uint32_t s = sbase + (uint32_t)(dist >= n ? i : i % dist);
+        if (s >= LSL_INF_RING) s -= LSL_INF_RING;
+        uint32_t d = rp + (uint32_t)i;
+        if (d >= LSL_INF_RING) d -= LSL_INF_RING;
+        ring[d] = ring[s];
+      }
+    } else {                                        // far match: the source left the ring, read it back from the output (L2)
+      const uint8_t* src = out + (pos - (uint32_t)dist);
+      for (int i = lane; i < n; i += 32) {          // dist > n here (NEAR > 258): no overlap
+        uint32_t d = rp + (uint32_t)i;
+        if (d >= LSL_INF_RING) d -= LSL_INF_RING;
+        ring[d] = __ldcg(src + i);
+      }
     }
     __syncwarp();
     rp += (uint32_t)n;
@@ -382,20 +449,33 @@ int decode_list(lsl_ctx* ctx, TumScratch& S, cudaStream_t st, int n, const uint8
   uint32_t* h_adler = h_pbegin + (n + 1);
   size_t pi = 0;
   size_t off = head;
-  for (int i = 0; i < n; ++i) {
+  for (int i = 0; i < n; ++i) {                    // layout first (serial, a few words per chunk) ...
     h_off[i] = off;
     h_pbegin[i] = (uint32_t)pi;
     const PngView& vw = views[(size_t)i];
     for (size_t c = 0; c < vw.idat.size(); ++c) {
       PngPiece& P = h_pieces[pi++];
       P.off_lo = (uint32_t)(off & 0xffffffffu); P.off_hi = (uint32_t)(off >> 32); P.len = (uint32_t)vw.idat[c].second; P.crc = vw.idat_crc[c];
-      std::memcpy(hz + off, vw.idat[c].first, vw.idat[c].second); off += vw.idat[c].second;
+      off += vw.idat[c].second;
     }
-    h_adler[i] = (off - h_off[i] >= 4) ? be32(hz + off - 4) : 0u;     // zlib trailer: the last four payload bytes (RFC 1950)
-    const size_t pad = (16 - (off & 15)) & 15;      // < 16 zero bytes behind the Adler-32 trailer: never decoded, the
-    std::memset(hz + off, 0, pad);                  // final block ends the stream before them
-    off += pad;
+    off += (16 - (off & 15)) & 15;
     h_status[i] = 0;
+  }
+  {                                                // ... then the payload copies on a few host threads (0.4 - 0.5 MB per image:
+    const int T = std::max(1, std::min(8, std::min(n / 16, (int)std::thread::hardware_concurrency())));   // 1 GB per 1184 frames)
+    auto work = [&](int t) {
+      for (int i = t; i < n; i += T) {
+        const PngView& vw = views[(size_t)i];
+        size_t o = h_off[i];
+        for (size_t c = 0; c < vw.idat.size(); ++c) { std::memcpy(hz + o, vw.idat[c].first, vw.idat[c].second); o += vw.idat[c].second; }
+        h_adler[i] = (o - h_off[i] >= 4) ? be32(hz + o - 4) : 0u;     // zlib trailer: the last four payload bytes (RFC 1950)
+        std::memset(hz + o, 0, (16 - (o & 15)) & 15);                 // < 16 zero bytes behind the Adler-32 trailer: never decoded,
+      }                                                               // the final block ends the stream before them
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
   }
   h_off[n] = off;
   h_pbegin[n] = (uint32_t)pi;

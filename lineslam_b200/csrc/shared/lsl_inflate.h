@@ -130,6 +130,10 @@ struct InflateOpsSerial {
   LSL_HDM void sync() const {}                   // all threads of the group have passed this point, writes visible
   LSL_HDM void finish(uint8_t*, uint32_t) const {} // everything handed to put / copy / stored is in `out` afterwards
   LSL_HDM void put(uint8_t* out, uint32_t pos, uint8_t v) const { out[pos] = v; }
+  // optional fast path: decodes a run of literals whose codes hit the first-level table and returns the new position; it
+  // stops (without consuming it) at the first symbol that is not such a literal or when `want` is reached. The serial
+  // variant leaves everything to the general loop.
+  LSL_HDM uint32_t literal_run(BitIn*, const HuffTable*, uint8_t*, uint32_t pos, uint32_t) const { return pos; }
   LSL_HDM void copy(uint8_t* out, uint32_t pos, int dist, int n) const { for (int i = 0; i < n; ++i) out[pos + i] = out[pos + i - dist]; }
   LSL_HDM void stored(uint8_t* out, uint32_t pos, const uint8_t* src, uint32_t n) const { for (uint32_t i = 0; i < n; ++i) out[pos + i] = src[i]; }
 };
@@ -218,6 +222,7 @@ LSL_HD int inflate_zlib(const uint8_t* in, size_t len, uint8_t* out, size_t want
       if (S->status) return -4;
     }
     for (;;) {                                          // compressed data of the block
+      pos = ops.literal_run(&b, &S->lit, out, pos, want);
       bits_fill(&b);
       int sym = huff_decode(&b, &S->lit);
       if (sym < 0) return -5;

@@ -145,3 +145,20 @@ def test_raw_directory_to_frames(api, ctx, stream4, tmp_path):
     assert frames[3].lines().tobytes() == ref2[0].lines().tobytes()
     kt = ctx.kernel_times()
     assert kt.get("png_unfilter_kernel", 0) > 0 and kt.get("png_inflate_kernel", 0) > 0
+
+
+@pytest.mark.parametrize("W,period", [(463, 16), (464, 16), (640, 24), (511, 16)])
+def test_far_matches_beyond_the_shared_memory_ring(ctx, W, period):
+    """Matches that reach further back than the 8 KB shared-memory ring (LSL_INF_NEAR = 7424 bytes) read their source from the
+    flushed output: incompressible rows repeated with a period of 7424 (W = 463, the last distance served by the ring), 7440,
+    15 384 and 8 192 bytes, unfiltered so that zlib finds the repeats at exactly that distance."""
+    rng = np.random.default_rng(W + period)
+    tile = rng.integers(0, 256, (period, W), dtype=np.uint8)
+    H = period * 5 + 3
+    a = np.tile(tile, (6, 1))[:H]
+    f = OP.png_encode(a, filters=0, level=9)
+    assert len(f) < 0.45 * a.size                       # the repeats were found: the stream is mostly far matches
+    # the decoder contract (shared header compiled for the host) and the device agree with the pixels
+    got, _ = _decode(ctx, [f, f], None, W, H)
+    want = np.repeat(a[:, :, None], 3, axis=2)
+    assert np.array_equal(got[0], want) and np.array_equal(got[1], want)
