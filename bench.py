@@ -269,7 +269,7 @@ def run_cuda(args, rank, world, local_rank):
     big = wl == "cfg5"
     Wd, Hd = (1280, 960) if big else (W, H)
     b_frame = Wd * Hd * (3 + 4)
-    B = args.batch if args.batch > 0 else {"cfg2": 1184, "cfg3": 148, "cfg4": 256, "cfg5": 74}[wl]
+    B = args.batch if args.batch > 0 else {"cfg2": 1184, "cfg3": 592, "cfg4": 256, "cfg5": 148}[wl]
     dev_sift = wl == "cfg3" and args.points == "device"
     U = min(args.unique, B) if wl != "cfg4" else 257
     # ---- inputs first: the render pool forks, CUDA must not be initialised yet

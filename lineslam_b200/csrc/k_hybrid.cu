@@ -86,14 +86,23 @@ __global__ void __launch_bounds__(256) match_points_hamming_kernel(const LslPair
 }
 
 // squareroot_descriptor_space (src/node.cpp:1823-1837) in place: thread per row (the L1 sum is a sequential float chain)
-__global__ void __launch_bounds__(128) rootsift_kernel(float* __restrict__ desc, int n, int dim) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
-  float* d = desc + (size_t)r * dim;
-  float sum = 0.f;
-  for (int c = 0; c < dim; ++c) { const float v = fabsf(d[c]); d[c] = v; sum = __fadd_rn(sum, v); }
-  if (sum == 0.f) return;
-  for (int c = 0; c < dim; ++c) d[c] = __fsqrt_rn(__fdiv_rn(d[c], sum));
+// up to 32 rows per CTA staged through shared memory (coalesced 128-byte loads and stores; row stride dim + 1 keeps the
+// per-thread walks conflict-free); the row sum is the sequential float sum of cv::reduce(SUM), one thread per row.
+__global__ void __launch_bounds__(128) rootsift_kernel(float* __restrict__ desc, int n, int dim, int rpc) {
+  extern __shared__ float s_rows[];                 // [rpc][dim + 1], rpc <= 32 rows per CTA
+  const int r0 = blockIdx.x * rpc, nr = min(rpc, n - r0), ld = dim + 1;
+  float* base = desc + (size_t)r0 * dim;
+  for (int e = threadIdx.x; e < nr * dim; e += blockDim.x) s_rows[(e / dim) * ld + e % dim] = fabsf(base[e]);
+  __syncthreads();
+  if (threadIdx.x < nr) {
+    float* d = s_rows + threadIdx.x * ld;
+    float sum = 0.f;
+    for (int c = 0; c < dim; ++c) sum = __fadd_rn(sum, d[c]);
+    if (sum != 0.f)
+      for (int c = 0; c < dim; ++c) d[c] = __fsqrt_rn(__fdiv_rn(d[c], sum));
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nr * dim; e += blockDim.x) base[e] = s_rows[(e / dim) * ld + e % dim];
 }
 
 // serial acceptance pass (row order): ratio test, unique trainIdx, distance jitter from rand()
@@ -933,7 +942,9 @@ int lsl_launch_match_points(lsl_ctx* ctx, int npairs, int max_nq, int dim, int k
 }
 
 int lsl_launch_rootsift(lsl_ctx* ctx, float* d_desc, int n, int dim) {
-  rootsift_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_desc, n, dim);
+  if (n <= 0) return LSL_OK;
+  const int rpc = dim <= 256 ? 32 : 8;              // <= 33 KB of shared memory either way (dim <= 512)
+  rootsift_kernel<<<(n + rpc - 1) / rpc, 128, (size_t)rpc * (dim + 1) * sizeof(float), ctx->stream>>>(d_desc, n, dim, rpc);
   ctx->stats.kernel_launches += 1;
   LSL_CUDA(cudaGetLastError());
   return LSL_OK;

@@ -34,7 +34,10 @@
 #define SF_BORDER 5
 #define SF_MAX_CAND 16384
 #define SF_MAX_KP 16384
-#define SF_CHUNK 32           // frames per pyramid pass (39 MB of pyramid per VGA frame)
+#ifndef SF_CHUNK
+#define SF_CHUNK 148          // frames per pyramid pass at most (39 MB of pyramid per VGA frame: 5.8 GB). The stage is a chain of
+#endif                        // ~110 small launches per pass (9 octaves x 11), so fewer, larger passes win: 148 frames per step
+                              // took 29.6 / 22.0 / 17.4 / 15.6 / 13.8 ms with passes of 8 / 16 / 32 / 64 / 148 frames
 #define SF_FIX 16777216.0f    // 2^24: fixed-point scale of the histogram accumulators
 
 struct SiftOct { int W, H; size_t off; };                       // off: floats from the frame's pyramid base to layer 0
@@ -66,43 +69,58 @@ __global__ void sift_upsample_kernel(const uint8_t* __restrict__ gray, float* __
 }
 
 // horizontal / vertical pass of cv::GaussianBlur (float, taps summed in tap order from 0, BORDER_REFLECT_101).
-// Row pass: a CTA stages SF_ROW_T + 2 r input values of one image row in shared memory (coalesced, reflected at the borders)
-// and every thread sums its 2 r + 1 taps from there — each input value crosses L2 once instead of 2 r + 1 times.
-#define SF_ROW_T 256          // outputs per CTA: 64 threads x 4 consecutive pixels
+// Row pass: a CTA stages SF_ROW_T + 2 R4 input values of one image row in shared memory (R4 = R rounded up to 4: interior
+// tiles of 16-byte aligned rows are staged with float4 loads, border tiles element-wise with the reflection) and every thread
+// computes EIGHT consecutive outputs from a register window read as float4 — each input value crosses L2 once instead of
+// 2 R + 1 times and the staging / addressing overhead is shared by eight outputs (92 -> ~45 instructions per output at R = 5).
+#define SF_ROW_T 512          // outputs per CTA: 64 threads x 8 consecutive pixels
 template <int R>
-__global__ void __launch_bounds__(SF_ROW_T / 4) sift_blur_row_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t fstride_src,
+__global__ void __launch_bounds__(SF_ROW_T / 8) sift_blur_row_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t fstride_src,
                                                                      size_t fstride_dst, int W, int H, int kidx) {
-  __shared__ __align__(16) float s_in[SF_ROW_T + 2 * R + 6];
+  constexpr int R4 = (R + 3) / 4 * 4, NT = SF_ROW_T / 8, SW = SF_ROW_T + 2 * R4;
+  __shared__ __align__(16) float s_in[SW];
   const int x0 = blockIdx.x * SF_ROW_T, y = blockIdx.y, f = blockIdx.z, tid = threadIdx.x;
   const float* s = src + (size_t)f * fstride_src + (size_t)y * W;
-  for (int e = tid; e < SF_ROW_T + 2 * R; e += SF_ROW_T / 4) {
-    const int x = x0 - R + e;
-    s_in[e] = (x >= 0 && x < W) ? s[x] : s[reflect101g(x, W)];
+  const bool vec = (W & 3) == 0 && (((size_t)f * fstride_src) & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  if (vec && x0 - R4 >= 0 && x0 + SF_ROW_T + R4 <= W) {      // interior tile of an aligned row: s_in[e] = row[x0 - R4 + e]
+    const float4* s4 = reinterpret_cast<const float4*>(s + x0 - R4);
+    for (int e = tid; e < SW / 4; e += NT) reinterpret_cast<float4*>(s_in)[e] = s4[e];
+  } else {
+    for (int e = tid; e < SW; e += NT) {
+      const int x = x0 - R4 + e;
+      s_in[e] = (x >= 0 && x < W) ? s[x] : s[reflect101g(x, W)];
+    }
   }
   __syncthreads();
-  const int x = x0 + 4 * tid;
+  const int x = x0 + 8 * tid;
   if (x >= W) return;
-  float v[4 + 2 * R + 2];                                   // window of the four outputs, read as float4 (16-byte aligned: 4 tid)
+  float v[8 + 2 * R4];                                       // window of the eight outputs: v[k] = row[x - R4 + k]
 #pragma unroll
-  for (int k = 0; k < (4 + 2 * R + 3) / 4; ++k) {
-    const float4 q = *reinterpret_cast<const float4*>(s_in + 4 * tid + 4 * k);
-    if (4 * k < 4 + 2 * R + 2) v[4 * k] = q.x;
-    if (4 * k + 1 < 4 + 2 * R + 2) v[4 * k + 1] = q.y;
-    if (4 * k + 2 < 4 + 2 * R + 2) v[4 * k + 2] = q.z;
-    if (4 * k + 3 < 4 + 2 * R + 2) v[4 * k + 3] = q.w;
+  for (int k = 0; k < (8 + 2 * R4) / 4; ++k) {
+    const float4 q = *reinterpret_cast<const float4*>(s_in + 8 * tid + 4 * k);
+    v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
   }
-  float* d = dst + (size_t)f * fstride_dst + (size_t)y * W + x;
+  float o[8];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < 8; ++k) {
     float acc = 0.f;
 #pragma unroll
-    for (int t = 0; t <= 2 * R; ++t) acc += c_taps[kidx][t] * v[k + t];
-    if (x + k < W) d[k] = acc;
+    for (int t = 0; t <= 2 * R; ++t) acc += c_taps[kidx][t] * v[k + (R4 - R) + t];
+    o[k] = acc;
+  }
+  float* d = dst + (size_t)f * fstride_dst + (size_t)y * W + x;
+  if (vec && (((size_t)f * fstride_dst) & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && x + 8 <= W) {
+    reinterpret_cast<float4*>(d)[0] = make_float4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<float4*>(d)[1] = make_float4(o[4], o[5], o[6], o[7]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if (x + k < W) d[k] = o[k];
   }
 }
 // Column pass: a thread owns one column of a SF_COL_RUN-row strip and slides a register window down it: RUN + 2 R loads
-// (each a coalesced row segment across the warp) for RUN outputs instead of (2 R + 1) RUN.
-#define SF_COL_RUN 16
+// (each a coalesced row segment across the warp) for RUN outputs instead of (2 R + 1) RUN; strips that do not touch the image
+// border walk a pointer without any bounds logic.
+#define SF_COL_RUN 32
 template <int R>
 __global__ void __launch_bounds__(256) sift_blur_col_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t fstride_src,
                                                             size_t fstride_dst, int W, int H, int kidx) {
@@ -111,24 +129,31 @@ __global__ void __launch_bounds__(256) sift_blur_col_kernel(const float* __restr
   if (x >= W || y0 >= H) return;
   const float* s = src + (size_t)f * fstride_src + x;
   float v[SF_COL_RUN + 2 * R];
+  if (y0 - R >= 0 && y0 + SF_COL_RUN + R <= H) {
+    const float* p = s + (size_t)(y0 - R) * W;
 #pragma unroll
-  for (int k = 0; k < SF_COL_RUN + 2 * R; ++k) {
-    const int y = y0 - R + k;
-    v[k] = s[(size_t)((y >= 0 && y < H) ? y : reflect101g(y, H)) * W];
+    for (int k = 0; k < SF_COL_RUN + 2 * R; ++k) { v[k] = *p; p += W; }
+  } else {
+#pragma unroll
+    for (int k = 0; k < SF_COL_RUN + 2 * R; ++k) {
+      const int y = y0 - R + k;
+      v[k] = s[(size_t)((y >= 0 && y < H) ? y : reflect101g(y, H)) * W];
+    }
   }
-  float* d = dst + (size_t)f * fstride_dst + x;
+  float* d = dst + (size_t)f * fstride_dst + (size_t)y0 * W + x;
 #pragma unroll
   for (int k = 0; k < SF_COL_RUN; ++k) {
     float acc = 0.f;
 #pragma unroll
     for (int t = 0; t <= 2 * R; ++t) acc += c_taps[kidx][t] * v[k + t];
-    if (y0 + k < H) d[(size_t)(y0 + k) * W] = acc;
+    if (y0 + k < H) *d = acc;
+    d += W;
   }
 }
 // one separable blur: rows src -> tmp, columns tmp -> dst (the instance of the kernel's radius)
 template <int R>
 static void sift_blur_R(cudaStream_t st, int nf, const float* src, size_t fs_src, float* tmp, size_t fs_tmp, float* dst, size_t fs_dst, int W, int H, int kidx) {
-  sift_blur_row_kernel<R><<<dim3((W + SF_ROW_T - 1) / SF_ROW_T, H, nf), SF_ROW_T / 4, 0, st>>>(src, tmp, fs_src, fs_tmp, W, H, kidx);
+  sift_blur_row_kernel<R><<<dim3((W + SF_ROW_T - 1) / SF_ROW_T, H, nf), SF_ROW_T / 8, 0, st>>>(src, tmp, fs_src, fs_tmp, W, H, kidx);
   sift_blur_col_kernel<R><<<dim3((W + 31) / 32, (H + 8 * SF_COL_RUN - 1) / (8 * SF_COL_RUN), nf), 256, 0, st>>>(tmp, dst, fs_tmp, fs_dst, W, H, kidx);
 }
 static void sift_blur(int r, cudaStream_t st, int nf, const float* src, size_t fs_src, float* tmp, size_t fs_tmp, float* dst, size_t fs_dst, int W, int H, int kidx) {
@@ -202,28 +227,52 @@ __device__ bool sift_adjust(const OctView& V, int o, int layer, int r, int c, Si
   return true;
 }
 
-__global__ void __launch_bounds__(256) sift_extrema_kernel(const float* __restrict__ pyr, SiftGeom G, int o, SiftCand* __restrict__ cand,
-                                                           int* __restrict__ ncand) {
+// DoG extrema of all three layers of one octave for a 32 x 8 pixel tile: the five DoG planes of the tile (+ 1 pixel of halo)
+// are formed once in shared memory from the six Gaussian planes (each Gaussian value is loaded once and serves two
+// differences), the 26-neighbour tests then read shared memory only. (One kernel per layer that differenced on the fly read
+// every Gaussian plane 3.6 times through L2: 9 GB per 64 VGA frames, a quarter of the SIFT time.)
+#define SF_ET_W 32
+#define SF_ET_H 8
+__global__ void __launch_bounds__(SF_ET_W * SF_ET_H) sift_extrema_kernel(const float* __restrict__ pyr, SiftGeom G, int o, SiftCand* __restrict__ cand,
+                                                                         int* __restrict__ ncand) {
+  __shared__ float s_dog[SF_NIMG - 1][SF_ET_H + 2][SF_ET_W + 2];
   const SiftOct O = G.o[o];
-  const int c = SF_BORDER + blockIdx.x * 32 + (threadIdx.x & 31), r = SF_BORDER + blockIdx.y * 8 + (threadIdx.x >> 5);
-  const int f = blockIdx.z / SF_LAYERS, layer = 1 + blockIdx.z % SF_LAYERS;
+  const int f = blockIdx.z, tx = threadIdx.x & (SF_ET_W - 1), ty = threadIdx.x / SF_ET_W;
+  const int c0 = SF_BORDER + blockIdx.x * SF_ET_W, r0 = SF_BORDER + blockIdx.y * SF_ET_H;
+  const float* g = pyr + (size_t)f * G.frame_floats + O.off;
+  const size_t L = (size_t)O.W * O.H;
+  for (int e = threadIdx.x; e < (SF_ET_H + 2) * (SF_ET_W + 2); e += SF_ET_W * SF_ET_H) {
+    const int yy = e / (SF_ET_W + 2), xx = e - yy * (SF_ET_W + 2);
+    const int r = min(r0 - 1 + yy, O.H - 1), c = min(c0 - 1 + xx, O.W - 1);     // clamped positions are never a tested pixel's neighbour
+    const float* p = g + (size_t)r * O.W + c;
+    float prev = p[0];
+#pragma unroll
+    for (int d = 0; d < SF_NIMG - 1; ++d) { const float cur = p[(size_t)(d + 1) * L]; s_dog[d][yy][xx] = cur - prev; prev = cur; }
+  }
+  __syncthreads();
+  const int c = c0 + tx, r = r0 + ty;
   if (c >= O.W - SF_BORDER || r >= O.H - SF_BORDER) return;
-  OctView V; V.g = pyr + (size_t)f * G.frame_floats + O.off; V.W = O.W; V.H = O.H;
-  const float v = V.dog(layer, r, c);
-  if (!(fabsf(v) > 1.0f)) return;                    // threshold = cvFloor(0.5 * 0.04 / 3 * 255) = 1
-  bool ismax = v > 0, ismin = v < 0;
+  OctView V; V.g = g; V.W = O.W; V.H = O.H;
 #pragma unroll 1
-  for (int di = -1; di <= 1 && (ismax || ismin); ++di)
-    for (int dy = -1; dy <= 1; ++dy)
-      for (int dx = -1; dx <= 1; ++dx) {
-        const float n = V.dog(layer + di, r + dy, c + dx);
-        ismax = ismax && v >= n; ismin = ismin && v <= n;
-      }
-  if (!(ismax || ismin)) return;
-  SiftCand cd;
-  if (!sift_adjust(V, o, layer, r, c, &cd)) return;
-  const int slot = atomicAdd(&ncand[f], 1);
-  if (slot < SF_MAX_CAND) cand[(size_t)f * SF_MAX_CAND + slot] = cd;
+  for (int layer = 1; layer <= SF_LAYERS; ++layer) {
+    const float v = s_dog[layer][ty + 1][tx + 1];
+    if (!(fabsf(v) > 1.0f)) continue;                  // threshold = cvFloor(0.5 * 0.04 / 3 * 255) = 1
+    bool ismax = v > 0, ismin = v < 0;
+#pragma unroll
+    for (int di = -1; di <= 1; ++di)
+#pragma unroll
+      for (int dy = 0; dy <= 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx <= 2; ++dx) {
+          const float n = s_dog[layer + di][ty + dy][tx + dx];
+          ismax = ismax && v >= n; ismin = ismin && v <= n;
+        }
+    if (!(ismax || ismin)) continue;
+    SiftCand cd;
+    if (!sift_adjust(V, o, layer, r, c, &cd)) continue;
+    const int slot = atomicAdd(&ncand[f], 1);
+    if (slot < SF_MAX_CAND) cand[(size_t)f * SF_MAX_CAND + slot] = cd;
+  }
 }
 
 // cv::fastAtan2 (degrees)
@@ -463,7 +512,7 @@ static void sift_geometry(int W, int H, SiftGeom* G) {
   G->n_oct = 0;
   for (int o = 0; o < n && w >= 1 && h >= 1; ++o) {
     G->o[o].W = w; G->o[o].H = h; G->o[o].off = off;
-    off += (size_t)SF_NIMG * w * h;
+    off += ((size_t)SF_NIMG * w * h + 3) & ~(size_t)3;      // octave bases (and the frame stride) stay 16-byte aligned: float4 staging
     G->n_oct = o + 1;
     w /= 2; h /= 2;
   }
@@ -485,11 +534,12 @@ int lsl_launch_sift(lsl_ctx* ctx, int n, const float* d_depth, int W, int H, con
   SiftGeom G;
   sift_geometry(W, H, &G);
   const int max_kp = ctx->sift_max_kp < LSL_MAX_POINTS ? ctx->sift_max_kp : LSL_MAX_POINTS;
-  // ---- workspace: pyramid of SF_CHUNK frames + one row-pass scratch plane per frame + lists + dense output tables for n frames
-  const size_t pyr_floats = G.frame_floats * SF_CHUNK, tmp_floats = (size_t)G.W0 * G.H0 * SF_CHUNK;
-  const size_t need = (pyr_floats + tmp_floats) * sizeof(float) + (size_t)SF_CHUNK * (SF_MAX_CAND * sizeof(SiftCand) + SF_MAX_KP * sizeof(SiftKp)) +
+  const int chunk = ctx->max_batch < SF_CHUNK ? ctx->max_batch : SF_CHUNK;   // frames per pyramid pass of this context
+  // ---- workspace: pyramid of `chunk` frames + one row-pass scratch plane per frame + lists + dense output tables for n frames
+  const size_t pyr_floats = G.frame_floats * chunk, tmp_floats = (size_t)G.W0 * G.H0 * chunk;
+  const size_t need = (pyr_floats + tmp_floats) * sizeof(float) + (size_t)chunk * (SF_MAX_CAND * sizeof(SiftCand) + SF_MAX_KP * sizeof(SiftKp)) +
                       (size_t)ctx->max_batch * ((size_t)LSL_MAX_POINTS * (4 + 128 + 6) * 4 + 8) +
-                      (size_t)SF_CHUNK * (LSL_MAX_POINTS * sizeof(int) + 8) + 4096;
+                      (size_t)chunk * (LSL_MAX_POINTS * sizeof(int) + 8) + 4096;
   if (S.bytes < need) {
     LSL_CUDA(cudaStreamSynchronize(st));
     if (S.block) cudaFree(S.block);
@@ -500,15 +550,15 @@ int lsl_launch_sift(lsl_ctx* ctx, int n, const float* d_depth, int W, int H, con
   uint8_t* base = (uint8_t*)S.block;
   float* pyr = (float*)base; base += pyr_floats * sizeof(float);
   float* tmp = (float*)base; base += tmp_floats * sizeof(float);
-  SiftCand* cand = (SiftCand*)base; base += (size_t)SF_CHUNK * SF_MAX_CAND * sizeof(SiftCand);
-  SiftKp* kps = (SiftKp*)base; base += (size_t)SF_CHUNK * SF_MAX_KP * sizeof(SiftKp);
+  SiftCand* cand = (SiftCand*)base; base += (size_t)chunk * SF_MAX_CAND * sizeof(SiftCand);
+  SiftKp* kps = (SiftKp*)base; base += (size_t)chunk * SF_MAX_KP * sizeof(SiftKp);
   const size_t B = (size_t)ctx->max_batch;
   float* t_xyz1 = (float*)base; base += B * LSL_MAX_POINTS * 4 * sizeof(float);
   float* t_desc = (float*)base; base += B * LSL_MAX_POINTS * 128 * sizeof(float);
   float* t_kp = (float*)base; base += B * LSL_MAX_POINTS * 6 * sizeof(float);
-  int* slot2kp = (int*)base; base += (size_t)SF_CHUNK * LSL_MAX_POINTS * sizeof(int);
+  int* slot2kp = (int*)base; base += (size_t)chunk * LSL_MAX_POINTS * sizeof(int);
   int* counters = (int*)base;                            // [0..C) ncand, [C..2C) nkp, [2C..2C+B) nout, then goff [B]
-  int* d_ncand = counters; int* d_nkp = counters + SF_CHUNK; int* d_nout = counters + 2 * SF_CHUNK; int* d_goff = d_nout + B;
+  int* d_ncand = counters; int* d_nkp = counters + chunk; int* d_nout = counters + 2 * chunk; int* d_goff = d_nout + B;
   int rad[SF_NIMG];
   {
     float taps[SF_NIMG][40];
@@ -535,11 +585,11 @@ int lsl_launch_sift(lsl_ctx* ctx, int n, const float* d_depth, int W, int H, con
   if (prof) for (int i = 0; i < 6; ++i) cudaEventCreate(&pe[i]);
 #define SF_MARK(i) do { if (prof) cudaEventRecord(pe[i], st); } while (0)
   LSL_KSTART(ctx, LSL_K_SIFT);
-  for (int f0 = 0; f0 < n; f0 += SF_CHUNK) {
-    const int nf = n - f0 < SF_CHUNK ? n - f0 : SF_CHUNK;
+  for (int f0 = 0; f0 < n; f0 += chunk) {
+    const int nf = n - f0 < chunk ? n - f0 : chunk;
     const uint8_t* gray = ctx->wk.gray + (size_t)f0 * W * H;
     const float* dep = d_depth + (size_t)f0 * W * H;
-    LSL_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * 2 * SF_CHUNK, st));
+    LSL_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * 2 * chunk, st));
     SF_MARK(0);
     // base image: up-sample into layer 1 (scratch), blur rows -> tmp, columns -> layer 0
     {
@@ -564,8 +614,8 @@ int lsl_launch_sift(lsl_ctx* ctx, int n, const float* d_depth, int W, int H, con
         ctx->stats.kernel_launches += 2;
       }
       if (O.W > 2 * SF_BORDER && O.H > 2 * SF_BORDER) {
-        dim3 ge((O.W - 2 * SF_BORDER + 31) / 32, (O.H - 2 * SF_BORDER + 7) / 8, nf * SF_LAYERS);
-        sift_extrema_kernel<<<ge, 256, 0, st>>>(pyr, G, o, cand, d_ncand);
+        dim3 ge((O.W - 2 * SF_BORDER + SF_ET_W - 1) / SF_ET_W, (O.H - 2 * SF_BORDER + SF_ET_H - 1) / SF_ET_H, nf);
+        sift_extrema_kernel<<<ge, SF_ET_W * SF_ET_H, 0, st>>>(pyr, G, o, cand, d_ncand);
         ctx->stats.kernel_launches += 1;
       }
     }
