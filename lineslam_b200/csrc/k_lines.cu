@@ -429,7 +429,11 @@ __device__ double cvnorm(const double* v, int len) {
 }
 
 #define MSLD_CHUNK 32
-__global__ void __launch_bounds__(128) line_msld_kernel(LslWork w, LineParams P, int32_t* __restrict__ msld_fail) {
+#ifndef MSLD_MINB
+#define MSLD_MINB 8   // 64 registers instead of 168: 32 instead of 12 warps per SM on a latency-bound gather (per 592 frames: 4.45 ms -> 3.63 / 3.15 / 2.74 ms at 5 / 6 / 8 CTAs per SM)
+#endif
+#define MSLD_BOUNDS __launch_bounds__(128, MSLD_MINB)
+__global__ void MSLD_BOUNDS line_msld_kernel(LslWork w, LineParams P, int32_t* __restrict__ msld_fail) {
   __shared__ double s_g[MSLD_CHUNK][36];
   __shared__ uint8_t s_ok[MSLD_CHUNK];
   __shared__ long long s_sum[2];

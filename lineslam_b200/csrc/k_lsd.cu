@@ -544,7 +544,11 @@ __global__ void __launch_bounds__(32) lsd_region_kernel(LslWork w, int xs, int y
   if (lane == 0) w.nrects[f] = nout;
 }
 
-__global__ void __launch_bounds__(128) lsd_nfa_kernel(LslWork w, int xs, int ys, double eps, double scale, double logNT) {
+#ifndef NFA_MINB
+#define NFA_MINB 8    // 64 registers instead of 126: 32 instead of 16 warps per SM (per 592 frames: 4.66 -> 4.49 / 4.21 ms at 6 / 8 CTAs per SM)
+#endif
+#define NFA_BOUNDS __launch_bounds__(128, NFA_MINB)
+__global__ void NFA_BOUNDS lsd_nfa_kernel(LslWork w, int xs, int ys, double eps, double scale, double logNT) {
   const int f = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t po = (size_t)f * xs * ys;
   FrameView V;
