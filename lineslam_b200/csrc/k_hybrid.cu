@@ -672,7 +672,10 @@ __device__ void score_all_hybrid(const double* pmd_all, int npm, const double* m
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(POSE_THREADS, 1) pose_hybrid_kernel(const LslPairDesc* __restrict__ pairs, const LslPairPts* __restrict__ ppairs,
+#ifndef HYB_MINB
+#define HYB_MINB 1
+#endif
+__global__ void __launch_bounds__(POSE_THREADS, HYB_MINB) pose_hybrid_kernel(const LslPairDesc* __restrict__ pairs, const LslPairPts* __restrict__ ppairs,
                                                                    const lsl_match* __restrict__ matches_all, const int32_t* __restrict__ nmatch,
                                                                    const lsl_match* __restrict__ pm_all, const int32_t* __restrict__ npmatch,
                                                                    LslPairScratch sc, LslHybScratch hs, PoseParams PP, HybParams HP,
@@ -1271,7 +1274,12 @@ __device__ int rm_compact(const int32_t* flag, int n, int32_t* out, int* s_cnt) 
   return c;
 }
 
-__global__ void __launch_bounds__(RM_THREADS) relmotion_kernel(const LslPairDesc* __restrict__ pairs, const lsl_match* __restrict__ matches_all,
+#ifdef RM_MINB
+#define RM_BOUNDS __launch_bounds__(RM_THREADS, RM_MINB)
+#else
+#define RM_BOUNDS __launch_bounds__(RM_THREADS)
+#endif
+__global__ void RM_BOUNDS relmotion_kernel(const LslPairDesc* __restrict__ pairs, const lsl_match* __restrict__ matches_all,
                                                                const int32_t* __restrict__ nmatch, RmScratch rs, double distThresh,
                                                                double angThresh, double cosDeg, int maxIters) {
   __shared__ RmLmShared S;

@@ -547,7 +547,10 @@ __global__ void __launch_bounds__(32) lsd_region_kernel(LslWork w, int xs, int y
 #ifndef NFA_MINB
 #define NFA_MINB 8    // 64 registers instead of 126: 32 instead of 16 warps per SM (per 592 frames: 4.66 -> 4.49 / 4.21 ms at 6 / 8 CTAs per SM)
 #endif
-#define NFA_BOUNDS __launch_bounds__(128, NFA_MINB)
+#ifndef NFA_WARPS
+#define NFA_WARPS 4   // warps (= candidate rectangles in flight) per CTA
+#endif
+#define NFA_BOUNDS __launch_bounds__(32 * NFA_WARPS, NFA_MINB * 4 / NFA_WARPS)
 __global__ void NFA_BOUNDS lsd_nfa_kernel(LslWork w, int xs, int ys, double eps, double scale, double logNT) {
   const int f = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t po = (size_t)f * xs * ys;
@@ -558,7 +561,7 @@ __global__ void NFA_BOUNDS lsd_nfa_kernel(LslWork w, int xs, int ys, double eps,
   const int nr = min(w.nrects[f], LSL_MAX_RECTS);
   double* rects = w.rects + (size_t)f * LSL_MAX_RECTS * 12;
   uint8_t* ok = w.rect_ok + (size_t)f * LSL_MAX_RECTS;
-  for (int c = blockIdx.x * 4 + warp; c < nr; c += gridDim.x * 4) {
+  for (int c = blockIdx.x * NFA_WARPS + warp; c < nr; c += gridDim.x * NFA_WARPS) {
     double* r = rects + (size_t)c * 12;
     Rect rec;
     rec.x1 = r[0]; rec.y1 = r[1]; rec.x2 = r[2]; rec.y2 = r[3]; rec.width = r[4]; rec.x = r[5]; rec.y = r[6];
@@ -612,8 +615,8 @@ int lsl_launch_lsd(lsl_ctx* ctx, int n) {
   lsd_region_kernel<<<n, 32, 0, ctx->stream>>>(w, d.sw, d.sh, P.lsd_ang_th, P.lsd_density_th, min_reg_size);
   LSL_KSTOP(ctx, LSL_K_REGION);
   LSL_KSTART(ctx, LSL_K_NFA);
-  dim3 g(64, n);
-  lsd_nfa_kernel<<<g, 128, 0, ctx->stream>>>(w, d.sw, d.sh, P.lsd_eps, P.lsd_scale, logNT);
+  dim3 g(256 / NFA_WARPS, n);
+  lsd_nfa_kernel<<<g, 32 * NFA_WARPS, 0, ctx->stream>>>(w, d.sw, d.sh, P.lsd_eps, P.lsd_scale, logNT);
   lsd_compact_kernel<<<n, 32, 0, ctx->stream>>>(w);
   ctx->stats.kernel_launches += 1;   // two launches inside one timing bracket
   LSL_KSTOP(ctx, LSL_K_NFA);
