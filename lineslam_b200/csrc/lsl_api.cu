@@ -1032,10 +1032,11 @@ extern "C" int lsl_match_pair_batch_begin(lsl_ctx* ctx, int npairs, const lsl_fr
   if (hybrid && (rc = setup_ppairs(ctx, npairs, queries, trains, -1, &mq, &dim, &kind))) return rc;
   clear_ktimes(ctx, LSL_K_MATCH, LSL_K_PNG);
   cudaEventRecord(ctx->ev0p, ctx->stream);
-  if (hybrid && (rc = lsl_launch_match_points(ctx, npairs, mq, dim, kind))) return rc;   // featureMatching first (node.cpp:1504)
-  if ((rc = lsl_launch_match(ctx, npairs))) return rc;
-  if (hybrid) { if ((rc = lsl_launch_pose_hybrid(ctx, npairs, ctx->cam_fx, ctx->cam_dt))) return rc; }
-  else if ((rc = lsl_launch_pose(ctx, npairs))) return rc;
+  rc = LSL_OK;
+  if (hybrid) rc = lsl_launch_match_points(ctx, npairs, mq, dim, kind);   // featureMatching first (node.cpp:1504)
+  if (!rc) rc = lsl_launch_match(ctx, npairs);
+  if (!rc) rc = hybrid ? lsl_launch_pose_hybrid(ctx, npairs, ctx->cam_fx, ctx->cam_dt) : lsl_launch_pose(ctx, npairs);
+  if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }   // nothing of a failed batch keeps running on the pair workspace
   cudaEventRecord(ctx->ev3p, ctx->stream);
   ctx->pair_inflight = npairs; ctx->pair_hybrid = hybrid;
   return LSL_OK;
@@ -1046,14 +1047,14 @@ extern "C" int lsl_match_pair_batch_end(lsl_ctx* ctx, lsl_pose_rec* out, int cap
   LSL_ENTER(ctx);
   const int npairs = ctx->pair_inflight;
   if (!npairs) { ctx->err = "no pair batch in flight"; return LSL_ERR_ARG; }
-  if (cap < npairs) return LSL_ERR_CAPACITY;
+  if (cap < npairs) return LSL_ERR_CAPACITY;     // the batch stays in flight: call again with room for npairs records
+  ctx->pair_inflight = 0;                        // consumed whatever happens below (a CUDA error must not leave the context fenced)
   PairStreamScope scope(ctx);
   int rc;
   if ((rc = fetch_counts(ctx, npairs))) return rc;
   if (ctx->pair_hybrid && (rc = fetch_counts_hyb(ctx, npairs))) return rc;
   LSL_CUDA(cudaMemcpyAsync(out, ctx->pw.recs, sizeof(lsl_pose_rec) * npairs, cudaMemcpyDeviceToHost, ctx->stream));
   LSL_CUDA(cudaStreamSynchronize(ctx->stream));
-  ctx->pair_inflight = 0;
   cudaEventElapsedTime(&ctx->ms_total, ctx->ev0p, ctx->ev3p);
   collect_ktimes(ctx, LSL_K_MATCH, LSL_K_PNG);
   ctx->stats.pairs += npairs; ctx->stats.d2h_bytes += (sizeof(lsl_pose_rec) + 12) * npairs;
