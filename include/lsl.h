@@ -154,6 +154,13 @@ int lsl_ctx_set_point_detector(lsl_ctx* ctx, int kind, int max_keypoints, int ro
 /* Read-back of a frame's point features: xyz1 [n][4], desc [n][dim] (f32 rows), kp [n][6] = x, y, size, angle, response,
  * octave + 256 * layer (device-detected points only); any of the three may be NULL. */
 int lsl_frame_points(lsl_ctx* ctx, const lsl_frame* f, float* xyz1, float* desc, float* kp, int cap, int* n);
+/* Node::computeInliersAndError (src/node.cpp:1019-1080; compiled but not called when the reference is built with USE_LINES — the
+ * hybrid RANSAC scores points itself — provided because ICP / point-only builds call it): inliers of `matches` (queryIdx into
+ * `query`'s points, trainIdx into `train`'s) under the float transform `tf` (row-major 4 x 4) with errorFunction2 <=
+ * squared_max_inlier_dist, in match order; *rmse = sqrt(mean squared Mahalanobis distance), 1e9 with fewer than 3 inliers. */
+int lsl_compute_inliers_and_error(lsl_ctx* ctx, const lsl_frame* query, const lsl_frame* train, const lsl_match* matches, int n,
+                                  const float tf[16], double squared_max_inlier_dist, lsl_match* inliers, int cap, int* n_inliers,
+                                  double* rmse);
 int lsl_frame_num_points(const lsl_frame* f);
 /* fx = K(0,0) and Node::asynch_time_diff_sec_ used by the point-edge information matrices of the refinement
  * (compPt3dCov, src/transformation_estimation.cpp:243-262). Every extract call sets them from its K / dt. */

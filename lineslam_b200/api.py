@@ -204,6 +204,16 @@ class Context:
             return frame
         return Frame(self, out)
 
+    def compute_inliers_and_error(self, query: "Frame", train: "Frame", matches, tf, squared_max_inlier_dist: float):
+        """Node::computeInliersAndError (src/node.cpp:1019-1080): (inlier matches in order, rmse Mahalanobis distance)."""
+        m = np.ascontiguousarray(matches, MATCH_DTYPE)
+        out = np.zeros(max(len(m), 1), MATCH_DTYPE)
+        t = np.ascontiguousarray(tf, np.float32).reshape(16)
+        k = C.c_int(0); rmse = C.c_double(0.0)
+        _check(lib().lsl_compute_inliers_and_error(self._h, query._h, train._h, ptr(m), len(m), ptr(t), C.c_double(squared_max_inlier_dist),
+                                                   ptr(out), len(out), C.byref(k), C.byref(rmse)), self._h)
+        return out[:k.value].copy(), rmse.value
+
     def shift_frame(self, frame):
         """Ring shift of the block tails of one stream split over the ranks: sends `frame` to rank + 1, returns the frame
         received from rank - 1 (ncclSend / ncclRecv, device to device). Collective."""

@@ -944,6 +944,44 @@ int lsl_launch_match_points(lsl_ctx* ctx, int npairs, int max_nq, int dim, int k
   return LSL_OK;
 }
 
+// Node::computeInliersAndError (src/node.cpp:1019-1080): squared Mahalanobis distance (errorFunction2) of every point match under
+// `tf`, matches with a zero depth on either side skipped, outliers (> squared_max) and non-finite values dropped; the inlier
+// list and the sum keep the match order (thread 0 walks the flags: the sum is one ordered chain of <= 2048 adds).
+__global__ void __launch_bounds__(256) inliers_error_kernel(const float* __restrict__ qx, const float* __restrict__ tx, const lsl_match* __restrict__ ms,
+                                                            int n, const float* __restrict__ tf16, double sigma_depth, double squared_max,
+                                                            double* __restrict__ dist, lsl_match* __restrict__ out, int32_t* __restrict__ n_out,
+                                                            double* __restrict__ rmse) {
+  __shared__ double s_tf[16];
+  if (threadIdx.x < 16) s_tf[threadIdx.x] = (double)tf16[threadIdx.x];      // transformation4f.cast<double>()
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float* o = qx + 4 * (size_t)ms[i].queryIdx;
+    const float* t = tx + 4 * (size_t)ms[i].trainIdx;
+    double d = -1.0;                                                          // -1: skipped
+    if (!(o[2] == 0.0f || t[2] == 0.0f)) {                                    // does NOT trigger on NaN (node.cpp:1046)
+      const double m = error_function2(o, t, s_tf, sigma_depth);
+      if (!(m > squared_max) && m >= 0.0) d = m;
+    }
+    dist[i] = d;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double mean = 0.0;
+    int k = 0;
+    for (int i = 0; i < n; ++i)
+      if (dist[i] >= 0.0) { mean += dist[i]; out[k++] = ms[i]; }
+    *n_out = k;
+    *rmse = k < 3 ? 1e9 : sqrt(mean / (double)k);
+  }
+}
+int lsl_launch_inliers_error(lsl_ctx* ctx, const float* qx, const float* tx, const lsl_match* d_ms, int n, const float* d_tf, double squared_max,
+                             double* d_dist, lsl_match* d_out, int32_t* d_n, double* d_rmse) {
+  inliers_error_kernel<<<1, 256, 0, ctx->stream>>>(qx, tx, d_ms, n, d_tf, ctx->P.sigma_depth, squared_max, d_dist, d_out, d_n, d_rmse);
+  ctx->stats.kernel_launches += 1;
+  LSL_CUDA(cudaGetLastError());
+  return LSL_OK;
+}
+
 int lsl_launch_rootsift(lsl_ctx* ctx, float* d_desc, int n, int dim) {
   if (n <= 0) return LSL_OK;
   const int rpc = dim <= 256 ? 32 : 8;              // <= 33 KB of shared memory either way (dim <= 512)

@@ -659,6 +659,41 @@ extern "C" int lsl_frame_points(lsl_ctx* ctx, const lsl_frame* f, float* xyz1, f
   LSL_CUDA(cudaStreamSynchronize(ctx->stream));
   return LSL_OK;
 }
+extern "C" int lsl_compute_inliers_and_error(lsl_ctx* ctx, const lsl_frame* query, const lsl_frame* train, const lsl_match* matches, int n,
+                                             const float tf[16], double squared_max_inlier_dist, lsl_match* inliers, int cap, int* n_inliers,
+                                             double* rmse) {
+  if (!ctx || !query || !train || !tf || !n_inliers || !rmse || n < 0 || n > LSL_MAX_POINTS || (n && !matches)) return LSL_ERR_ARG;
+  *n_inliers = 0; *rmse = 1e9;
+  if (n == 0) return LSL_OK;                                   // (the reference asserts a non-empty list)
+  for (int i = 0; i < n; ++i)
+    if (matches[i].queryIdx < 0 || matches[i].queryIdx >= query->npoints || matches[i].trainIdx < 0 || matches[i].trainIdx >= train->npoints) {
+      ctx->err = "point match index outside the frames' point tables";
+      return LSL_ERR_ARG;
+    }
+  LSL_ENTER(ctx);
+  cudaStream_t st = ctx->stream;
+  const size_t mb = align_up(sizeof(lsl_match) * (size_t)n), db = align_up(sizeof(double) * (size_t)n);
+  uint8_t* blk = nullptr;
+  LSL_CUDA(cudaMallocAsync((void**)&blk, 2 * mb + db + 512, st));
+  lsl_match* d_ms = (lsl_match*)blk; lsl_match* d_out = (lsl_match*)(blk + mb);
+  double* d_dist = (double*)(blk + 2 * mb); double* d_rmse = (double*)(blk + 2 * mb + db);
+  int32_t* d_n = (int32_t*)(d_rmse + 1); float* d_tf = (float*)(d_rmse + 2);
+  LSL_CUDA(cudaMemcpyAsync(d_ms, matches, sizeof(lsl_match) * (size_t)n, cudaMemcpyHostToDevice, st));
+  LSL_CUDA(cudaMemcpyAsync(d_tf, tf, 16 * sizeof(float), cudaMemcpyHostToDevice, st));
+  int rc = lsl_launch_inliers_error(ctx, query->d_xyz1, train->d_xyz1, d_ms, n, d_tf, squared_max_inlier_dist, d_dist, d_out, d_n, d_rmse);
+  if (rc) { cudaFreeAsync(blk, st); return rc; }
+  int32_t k = 0;
+  LSL_CUDA(cudaMemcpyAsync(&k, d_n, sizeof(k), cudaMemcpyDeviceToHost, st));
+  LSL_CUDA(cudaMemcpyAsync(rmse, d_rmse, sizeof(double), cudaMemcpyDeviceToHost, st));
+  LSL_CUDA(cudaStreamSynchronize(st));
+  *n_inliers = k;
+  int ret = LSL_OK;
+  if (k > cap || (k && !inliers)) ret = LSL_ERR_CAPACITY;
+  else if (k) { LSL_CUDA(cudaMemcpyAsync(inliers, d_out, sizeof(lsl_match) * (size_t)k, cudaMemcpyDeviceToHost, st)); LSL_CUDA(cudaStreamSynchronize(st)); }
+  cudaFreeAsync(blk, st);
+  ctx->stats.h2d_bytes += sizeof(lsl_match) * (size_t)n + 64; ctx->stats.d2h_bytes += sizeof(lsl_match) * (size_t)k + 12;
+  return ret;
+}
 extern "C" int lsl_frame_num_points(const lsl_frame* f) { return f ? f->npoints : LSL_ERR_ARG; }
 extern "C" int lsl_ctx_set_camera(lsl_ctx* ctx, double fx, double asynch_dt_s) {
   if (!ctx || !(fx > 0)) return LSL_ERR_ARG;

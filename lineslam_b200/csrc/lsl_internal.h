@@ -272,6 +272,8 @@ int lsl_launch_match(lsl_ctx* ctx, int npairs);
 int lsl_launch_pose(lsl_ctx* ctx, int npairs);
 int lsl_launch_match_points(lsl_ctx* ctx, int npairs, int max_nq, int dim, int kind);
 int lsl_launch_rootsift(lsl_ctx* ctx, float* d_desc, int n, int dim);
+int lsl_launch_inliers_error(lsl_ctx* ctx, const float* qx, const float* tx, const lsl_match* d_ms, int n, const float* d_tf, double squared_max,
+                             double* d_dist, lsl_match* d_out, int32_t* d_n, double* d_rmse);
 int lsl_launch_match_points_tc(lsl_ctx* ctx, int npairs, int max_nq, int dim, int* used);
 int lsl_launch_sift(lsl_ctx* ctx, int n, const float* d_depth, int W, int H, const double K[9], lsl_frame** frames);
 int lsl_launch_pose_hybrid(lsl_ctx* ctx, int npairs, double fx, double dt);

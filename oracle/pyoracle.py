@@ -185,6 +185,22 @@ def error_function2(x1, x2, tf, sigma_depth=0.01):
     return lib().orc_error_function2(ptr(a), ptr(b), ptr(t), C.c_double(sigma_depth))
 
 
+def compute_inliers_and_error(matches, origins, earlier, tf, squared_max, sigma_depth=0.01):
+    """Node::computeInliersAndError (src/node.cpp:1019-1080) over errorFunction2: (indices of the inlier matches, rmse)."""
+    keep, mean = [], 0.0
+    for i, m in enumerate(matches):
+        o, t = origins[int(m["queryIdx"])], earlier[int(m["trainIdx"])]
+        if o[2] == 0.0 or t[2] == 0.0:            # does NOT trigger on NaN
+            continue
+        d = error_function2(o, t, tf, sigma_depth)
+        if d > squared_max or not (d >= 0.0):
+            continue
+        mean += d
+        keep.append(i)
+    import math
+    return keep, (1e9 if len(keep) < 3 else math.sqrt(mean / len(keep)))
+
+
 def kabsch(frm, to, w):
     f = np.ascontiguousarray(frm, np.float32); t = np.ascontiguousarray(to, np.float32); ww = np.ascontiguousarray(w, np.float32)
     tf = np.zeros(16, np.float32)

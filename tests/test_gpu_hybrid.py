@@ -257,3 +257,30 @@ def test_batched_entry_points_equal_the_per_call_ones(api, oracle, hyb):
             assert np.array_equal(R[k], one["R"]) and np.array_equal(t[k], one["t"])
     for f in fb:
         f.free()
+
+
+def test_computeInliersAndError(api, oracle, hyb):
+    """Node::computeInliersAndError (src/node.cpp:1019-1080): inlier list in match order and the rms Mahalanobis distance,
+    with zero-depth points (skipped), NaN-depth points (errorFunction2 = max: outliers), wrong matches and a loose / tight gate."""
+    ctx, frames, lines, pts, poses = hyb
+    from lineslam_b200 import synth
+    rng = np.random.default_rng(5)
+    xq, xt = pts[1][0].copy(), pts[0][0].copy()
+    xq[3::41, 2] = 0.0; xt[7::53, 2] = 0.0                     # zero depth: the match is skipped before the distance
+    fq = ctx.frame_from_lines(lines[1][:0]); ft = ctx.frame_from_lines(lines[0][:0])
+    fq.set_points(xq, pts[1][1]); ft.set_points(xt, pts[0][1])
+    pm = ctx.match_points(frames[1], frames[0], seed=3)
+    m = np.concatenate([pm, pm[:40]])
+    m["trainIdx"][-40:] = rng.integers(0, len(xt), 40)        # wrong correspondences
+    T = synth.relative_pose_q2t(*poses[1], *poses[0]).astype(np.float32)
+    for gate in (9.0, 0.5, 1e-6):
+        got, rmse = ctx.compute_inliers_and_error(fq, ft, m, T, gate)
+        keep, rmse_o = oracle.compute_inliers_and_error(m, xq, xt, T, gate)
+        assert np.array_equal(got, m[keep]) and rmse == rmse_o, (gate, len(got), len(keep), rmse, rmse_o)
+    assert len(keep) < 3 and rmse == 1e9                        # nothing passes the tightest gate
+    got, rmse = ctx.compute_inliers_and_error(fq, ft, m, T, 9.0)
+    assert 20 < len(got) < len(m)
+    bad = m[:3].copy(); bad["queryIdx"][1] = len(xq)
+    with pytest.raises(api.LslError):
+        ctx.compute_inliers_and_error(fq, ft, bad, T, 9.0)
+    fq.free(); ft.free()
